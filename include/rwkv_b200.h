@@ -1,0 +1,52 @@
+/* rwkv_b200.h -- additive entry points of the B200 engine that the reference ABI has no slot for.
+ * Nothing here is needed by a drop-in consumer; bench.py, the multi-GPU layer pipeline and the
+ * tests use them. All follow the conventions of rwkv.h (bool / NULL returns, flags readable with
+ * rwkv_get_last_error).
+ */
+#ifndef RWKV_B200_H
+#define RWKV_B200_H
+
+#include "rwkv.h"
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+/* Host-only summary of a model file (no GPU needed): what rwkv_init_from_file would load.
+ * Architecture detection as reference rwkv_model_loading.inc:319-340, head geometry :403-409. */
+struct rwkv_b200_file_info {
+    uint32_t version, n_vocab, n_embed, n_layer, data_type;
+    uint32_t arch_major, arch_minor, head_count, head_size;
+    uint64_t n_tensors, file_size;
+    uint64_t state_len;          /* floats, rwkv.cpp:171-179 */
+    uint64_t bytes_per_token;    /* SURVEY.md 8(d) byte model: all layer tensors + head + 1 emb row + 2x state */
+};
+RWKV_API bool rwkv_b200_inspect_file(const char * model_file_path, struct rwkv_b200_file_info * out);
+
+/* rwkv_init_from_file on an explicit CUDA device, keeping only layers [layer_begin, layer_end)
+ * resident (layer_end < 0 = n_layer). A context that lacks layer 0 takes its input activations
+ * from the previous pipeline stage, one that lacks the last layer cannot produce logits. */
+RWKV_API struct rwkv_context * rwkv_b200_init_from_file_ex(const char * model_file_path, int device, int layer_begin, int layer_end);
+
+/* Device-resident evaluation: the recurrent state stays in HBM between calls.
+ *   rwkv_b200_state_load : state_in (host, may be NULL = fresh) -> device
+ *   rwkv_b200_eval_resident: run n tokens from the resident state; logits stay on the device unless logits_out != NULL
+ *   rwkv_b200_state_store: device -> state_out (host) */
+RWKV_API bool rwkv_b200_state_load(struct rwkv_context * ctx, const float * state_in);
+RWKV_API bool rwkv_b200_eval_resident(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, bool want_logits, float * logits_out);
+RWKV_API bool rwkv_b200_state_store(struct rwkv_context * ctx, float * state_out);
+/* Blocks until everything enqueued on the context's stream has finished. */
+RWKV_API bool rwkv_b200_synchronize(struct rwkv_context * ctx);
+
+/* Measurement hooks. */
+RWKV_API float rwkv_b200_last_device_ms(const struct rwkv_context * ctx);     /* CUDA-event time of the last pass */
+RWKV_API uint64_t rwkv_b200_kernel_launch_count(void);                         /* kernels enqueued by this process */
+RWKV_API uint64_t rwkv_b200_bytes_per_token(const struct rwkv_context * ctx, bool with_logits);
+/* Times `iters` back-to-back resident evaluations of `n_tokens` tokens on the device with CUDA events on the
+ * context's own stream (after `warmup` untimed ones); returns total milliseconds or a negative value on error. */
+RWKV_API float rwkv_b200_time_resident(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, bool want_logits, int warmup, int iters);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif /* RWKV_B200_H */

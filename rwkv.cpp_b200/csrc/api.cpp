@@ -1,0 +1,239 @@
+// The rwkv.h C ABI over the B200 engine, plus the additive rwkv_b200_* entry points.
+// Argument checks, error categories and NULL conventions follow the reference entry points
+// (rwkv.cpp:71-258, rwkv_eval.inc:38-241) so its C tests run unchanged against this library.
+#include <cinttypes>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "../../include/rwkv.h"
+#include "../../include/rwkv_b200.h"
+#include "engine.h"
+#include "quantizer.h"
+
+using namespace rwkv;
+
+// The opaque handle of the C API is the engine's Context.
+struct rwkv_context : public rwkv::Context {};
+
+static inline Context * C(struct rwkv_context * c) { return static_cast<Context *>(c); }
+static inline const Context * C(const struct rwkv_context * c) { return static_cast<const Context *>(c); }
+
+static int default_device() {
+    const char * e = getenv("RWKV_B200_DEVICE");
+    return e ? atoi(e) : 0;
+}
+
+extern "C" {
+
+struct rwkv_context * rwkv_b200_init_from_file_ex(const char * file_path, int device, int layer_begin, int layer_end) {
+    g_last_error = RWKV_ERROR_NONE;
+    ErrorSink sink = global_sink();
+    RWKV_CHECK(sink, RWKV_ERROR_ARGS, nullptr, file_path != nullptr, "Model file path is NULL");
+    Model * model = load_model(file_path, device, layer_begin, layer_end, sink);
+    RWKV_PROPAGATE(sink, nullptr, model != nullptr);
+    Context * ctx = create_context(model, sink);   // deletes the model itself on failure
+    RWKV_PROPAGATE(sink, nullptr, ctx != nullptr);
+    return static_cast<struct rwkv_context *>(ctx);
+}
+
+struct rwkv_context * rwkv_init_from_file(const char * file_path, const uint32_t n_threads, const uint32_t n_gpu_layers) {
+    (void) n_gpu_layers;   // every layer always lives on the GPU
+    struct rwkv_context * ctx = rwkv_b200_init_from_file_ex(file_path, default_device(), 0, -1);
+    if (ctx) C(ctx)->n_threads = n_threads;
+    return ctx;
+}
+
+struct rwkv_context * rwkv_clone_context(struct rwkv_context * ctx, const uint32_t n_threads) {
+    if (!ctx) return nullptr;
+    bool print = C(ctx)->print_errors;
+    int flags = 0;
+    ErrorSink sink{&flags, &print};
+    Context * clone = create_context(C(ctx)->model, sink);
+    if (!clone) { g_last_error |= flags; return nullptr; }
+    clone->n_threads = n_threads;
+    clone->print_errors = C(ctx)->print_errors;
+    return static_cast<struct rwkv_context *>(clone);
+}
+
+bool rwkv_eval(struct rwkv_context * ctx, const uint32_t token, const float * state_in, float * state_out, float * logits_out) {
+    Context * c = C(ctx);
+    c->last_error = RWKV_ERROR_NONE;
+    const size_t n_vocab = (size_t) c->model->n_vocab;
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, token < n_vocab, "Token (%" PRIu32 ") is out of range (0 .. %zu)", token, n_vocab - 1);
+    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer,
+               "This context holds only a pipeline stage; use the rwkv_b200 stage API");
+    return upload_state(c, state_in) && forward(c, &token, 1, logits_out != nullptr) && download_outputs(c, state_out, logits_out);
+}
+
+bool rwkv_eval_sequence(struct rwkv_context * ctx, const uint32_t * sequence, const size_t sequence_len, const float * state_in, float * state_out, float * logits_out) {
+    Context * c = C(ctx);
+    c->last_error = RWKV_ERROR_NONE;
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, sequence_len > 0, "Sequence length is 0");
+    if (!sequence) return true;   // "build the graph only" in the reference (rwkv_eval.inc:122); nothing to build here
+    const size_t n_vocab = (size_t) c->model->n_vocab;
+    for (size_t i = 0; i < sequence_len; i++)
+        RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, sequence[i] < n_vocab, "Token at index %zu (%" PRIu32 ") is out of range (0 .. %zu)", i, sequence[i], n_vocab - 1);
+    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer,
+               "This context holds only a pipeline stage; use the rwkv_b200 stage API");
+    return upload_state(c, state_in) && forward(c, sequence, sequence_len, logits_out != nullptr) && download_outputs(c, state_out, logits_out);
+}
+
+bool rwkv_eval_sequence_in_chunks(struct rwkv_context * ctx, const uint32_t * tokens, const size_t sequence_len, const size_t chunk_size,
+                                  const float * state_in, float * state_out, float * logits_out) {
+    Context * c = C(ctx);
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, sequence_len > 0, "Sequence length is 0");
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, chunk_size > 0, "Chunk size is 0");
+    c->last_error = RWKV_ERROR_NONE;
+    if (!tokens) return true;
+    const size_t n_vocab = (size_t) c->model->n_vocab;
+    for (size_t i = 0; i < sequence_len; i++)
+        RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, tokens[i] < n_vocab, "Token at index %zu (%" PRIu32 ") is out of range (0 .. %zu)", i, tokens[i], n_vocab - 1);
+    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer,
+               "This context holds only a pipeline stage; use the rwkv_b200 stage API");
+    // Same chunk boundaries as the reference loop (rwkv_eval.inc:179-218); the state never leaves HBM
+    // between chunks, logits are computed for the final chunk only.
+    if (!upload_state(c, state_in)) return false;
+    size_t off = 0;
+    while (off < sequence_len) {
+        const size_t n = sequence_len - off < chunk_size ? sequence_len - off : chunk_size;
+        const bool last = off + n == sequence_len;
+        if (!forward(c, tokens + off, n, last && logits_out != nullptr)) return false;
+        off += n;
+    }
+    return download_outputs(c, state_out, logits_out);
+}
+
+size_t rwkv_get_n_vocab(const struct rwkv_context * ctx) { return (size_t) C(ctx)->model->n_vocab; }
+size_t rwkv_get_n_embed(const struct rwkv_context * ctx) { return (size_t) C(ctx)->model->n_embed; }
+size_t rwkv_get_n_layer(const struct rwkv_context * ctx) { return (size_t) C(ctx)->model->n_layer; }
+size_t rwkv_get_state_len(const struct rwkv_context * ctx) { return C(ctx)->model->state_len(); }
+size_t rwkv_get_logits_len(const struct rwkv_context * ctx) { return (size_t) C(ctx)->model->n_vocab; }
+uint32_t rwkv_get_state_buffer_element_count(const struct rwkv_context * ctx) { return (uint32_t) rwkv_get_state_len(ctx); }
+uint32_t rwkv_get_logits_buffer_element_count(const struct rwkv_context * ctx) { return (uint32_t) rwkv_get_logits_len(ctx); }
+
+void rwkv_init_state(const struct rwkv_context * ctx, float * state) { fill_init_state(*C(ctx)->model, state); }
+
+void rwkv_free(struct rwkv_context * ctx) {
+    if (!ctx) return;
+    destroy_context(C(ctx));
+}
+
+void rwkv_set_print_errors(struct rwkv_context * ctx, const bool print_errors) {
+    if (ctx) C(ctx)->print_errors = print_errors; else g_print_errors = print_errors;
+}
+bool rwkv_get_print_errors(const struct rwkv_context * ctx) { return ctx ? C(ctx)->print_errors : g_print_errors; }
+enum rwkv_error_flags rwkv_get_last_error(struct rwkv_context * ctx) {
+    int * p = ctx ? &C(ctx)->last_error : &g_last_error;
+    int v = *p;
+    *p = RWKV_ERROR_NONE;
+    return (enum rwkv_error_flags) v;
+}
+
+bool rwkv_quantize_model_file(const char * in_path, const char * out_path, const char * format_name) {
+    g_last_error = RWKV_ERROR_NONE;
+    return quantize_model_file(in_path, out_path, format_name, global_sink());
+}
+
+const char * rwkv_get_system_info_string(void) {
+    static std::string s;
+    if (s.empty()) {
+        s = "RWKV_B200=1 ARCH=sm_100a";
+        int n = 0;
+        if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) {
+            cudaDeviceProp p;
+            int drv = 0, rt = 0;
+            cudaDriverGetVersion(&drv); cudaRuntimeGetVersion(&rt);
+            if (cudaGetDeviceProperties(&p, default_device() < n ? default_device() : 0) == cudaSuccess) {
+                s += " CUDA_DEVICES=" + std::to_string(n) + " DEVICE=\"" + p.name + "\" SM=" + std::to_string(p.major) + std::to_string(p.minor) +
+                     " SMS=" + std::to_string(p.multiProcessorCount) + " HBM_GB=" + std::to_string((unsigned long long) (p.totalGlobalMem >> 30)) +
+                     " DRIVER=" + std::to_string(drv) + " RUNTIME=" + std::to_string(rt);
+            }
+        } else {
+            s += " CUDA_DEVICES=0";
+        }
+    }
+    return s.c_str();
+}
+
+// ---- additive entry points (include/rwkv_b200.h) ----------------------------------------------------
+
+bool rwkv_b200_inspect_file(const char * path, struct rwkv_b200_file_info * out) {
+    g_last_error = RWKV_ERROR_NONE;
+    ErrorSink sink = global_sink();
+    RWKV_CHECK(sink, RWKV_ERROR_ARGS, false, path && out, "NULL argument");
+    ModelFile mf;
+    RWKV_PROPAGATE(sink, false, scan_model_file(path, mf, sink));
+    memset(out, 0, sizeof(*out));
+    out->version = mf.header.version; out->n_vocab = mf.header.n_vocab; out->n_embed = mf.header.n_embed;
+    out->n_layer = mf.header.n_layer; out->data_type = mf.header.data_type;
+    out->n_tensors = mf.tensors.size(); out->file_size = mf.file_size;
+    out->arch_major = 4; out->arch_minor = 0;
+    if (mf.find("blocks.0.att.ln_x.weight")) { out->arch_major = 5; out->arch_minor = mf.find("blocks.0.att.gate.weight") ? 2 : 1; }
+    if (mf.find("blocks.0.att.time_maa_x")) { out->arch_major = 6; out->arch_minor = 0; }
+    if (mf.find("blocks.0.att.r_k")) { out->arch_major = 7; out->arch_minor = 0; }
+    if (out->arch_major == 7) out->head_count = (uint32_t) mf.find("blocks.0.att.r_k")->ne[1];
+    else if (out->arch_major >= 5) {
+        const TensorInfo * td = mf.find("blocks.0.att.time_decay");
+        RWKV_CHECK(sink, RWKV_ERROR_MODEL_PARAMS | RWKV_ERROR_PARAM_MISSING, false, td, "Model parameter blocks.0.att.time_decay not found");
+        out->head_count = (uint32_t) td->ne[2];
+    }
+    if (out->head_count) out->head_size = out->n_embed / out->head_count;
+    out->state_len = (uint64_t) out->n_embed * (out->arch_major >= 5 ? 2 + out->head_size : 5) * out->n_layer;
+    uint64_t bytes = 0;
+    for (const TensorInfo & t : mf.tensors) bytes += (t.name == "emb.weight") ? t.nbytes / t.ne[1] : t.nbytes;
+    out->bytes_per_token = bytes + 2 * 4 * out->state_len;
+    return true;
+}
+
+bool rwkv_b200_state_load(struct rwkv_context * ctx, const float * state_in) { C(ctx)->last_error = 0; return upload_state(C(ctx), state_in); }
+bool rwkv_b200_state_store(struct rwkv_context * ctx, float * state_out) { return download_outputs(C(ctx), state_out, nullptr); }
+bool rwkv_b200_synchronize(struct rwkv_context * ctx) { return download_outputs(C(ctx), nullptr, nullptr); }
+
+bool rwkv_b200_eval_resident(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, bool want_logits, float * logits_out) {
+    Context * c = C(ctx);
+    c->last_error = RWKV_ERROR_NONE;
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, tokens && n_tokens > 0, "No tokens");
+    const size_t n_vocab = (size_t) c->model->n_vocab;
+    for (size_t i = 0; i < n_tokens; i++)
+        RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, tokens[i] < n_vocab, "Token at index %zu (%" PRIu32 ") is out of range (0 .. %zu)", i, tokens[i], n_vocab - 1);
+    if (!forward(c, tokens, n_tokens, want_logits || logits_out)) return false;
+    if (logits_out) return download_outputs(c, nullptr, logits_out);
+    return true;
+}
+
+float rwkv_b200_last_device_ms(const struct rwkv_context * ctx) {
+    float ms = -1.f;
+    const Context * c = C(ctx);
+    if (cudaEventSynchronize(c->ev_stop) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+uint64_t rwkv_b200_kernel_launch_count(void) { return g_kernel_launches; }
+
+uint64_t rwkv_b200_bytes_per_token(const struct rwkv_context * ctx, bool with_logits) {
+    const Model & m = *C(ctx)->model;
+    return (uint64_t) (m.weight_bytes_per_token - (with_logits ? 0 : m.head_bytes) + 2 * 4 * m.state_len());
+}
+
+float rwkv_b200_time_resident(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, bool want_logits, int warmup, int iters) {
+    Context * c = C(ctx);
+    cudaEvent_t e0, e1;
+    if (cudaSetDevice(c->model->dev.device) != cudaSuccess) return -1.f;
+    for (int i = 0; i < warmup; i++) if (!rwkv_b200_eval_resident(ctx, tokens, n_tokens, want_logits, nullptr)) return -1.f;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1.f;
+    cudaStreamSynchronize(c->stream);
+    cudaEventRecord(e0, c->stream);
+    bool ok = true;
+    for (int i = 0; i < iters && ok; i++) ok = rwkv_b200_eval_resident(ctx, tokens, n_tokens, want_logits, nullptr);
+    cudaEventRecord(e1, c->stream);
+    float ms = -1.f;
+    if (ok && cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ok ? ms : -1.f;
+}
+
+}  // extern "C"

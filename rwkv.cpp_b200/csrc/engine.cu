@@ -1,0 +1,408 @@
+// Forward pass over a resident model: the per-architecture launch sequences.
+// Math follows rwkv_graph.inc (serial graph :611-720, sequence graph :744-866); every stage below
+// names the graph lines it covers. All launches go to ctx->stream; nothing here blocks the host
+// except the token upload.
+#include "engine.h"
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "kernels/gemv.h"
+#include "kernels/ops.h"
+
+namespace rwkv {
+
+namespace {
+
+struct Scratch {      // carve-up of ctx->scratch for T tokens
+    float * x, * xx, * sx;
+    float * mix[6];
+    float * r, * k, * v, * g, * w, * a, * vgate, * v_first, * y;
+    float * ffn_k, * ffn_r;
+    float * lora[4];
+};
+
+struct Dims { size_t C, F, R; };
+
+Dims model_dims(const Model & m) {
+    Dims d{(size_t) m.n_embed, 0, 0};
+    for (int i = m.layer_begin; i < m.layer_end; i++) {
+        const Layer & L = m.layers[i];
+        if ((size_t) L.ffn_key.M > d.F) d.F = L.ffn_key.M;
+        const int ranks[] = {L.att_maa_w1.M, L.att_decay_w1.M, L.att_w1.M, L.att_a1.M, L.att_g1.M, L.att_v1.M};
+        for (int r : ranks) if ((size_t) r > d.R) d.R = r;
+    }
+    if (d.R == 0) d.R = 1;
+    return d;
+}
+
+size_t scratch_floats_for(const Model & m, int T) {
+    Dims d = model_dims(m);
+    return ((size_t) 19 * d.C + d.F + 4 * d.R) * (size_t) T + 64;
+}
+
+Scratch carve(const Model & m, float * base, int T) {
+    Dims d = model_dims(m);
+    Scratch s;
+    float * p = base;
+    auto take = [&](size_t n) { float * q = p; p += n * (size_t) T; return q; };
+    s.x = take(d.C); s.xx = take(d.C); s.sx = take(d.C);
+    for (int i = 0; i < 6; i++) s.mix[i] = take(d.C);
+    s.r = take(d.C); s.k = take(d.C); s.v = take(d.C); s.g = take(d.C); s.w = take(d.C); s.a = take(d.C);
+    s.vgate = take(d.C); s.v_first = take(d.C); s.y = take(d.C);
+    s.ffn_r = take(d.C);
+    s.ffn_k = take(d.F);
+    for (int i = 0; i < 4; i++) s.lora[i] = take(d.R);
+    return s;
+}
+
+// ---- GEMV batch builder -------------------------------------------------------------------------
+struct Batch {
+    GemvBatch b;
+    explicit Batch(int T) { memset(&b, 0, sizeof(b)); b.T = T; }
+    GemvProblem & add(const DevMatrix & W, const float * x, float * y, int epi = EPI_NONE) {
+        GemvProblem & p = b.p[b.n++];
+        p.W = W.data; p.pitch = W.pitch; p.type = W.type; p.K = W.K; p.M = W.M;
+        p.x = x; p.ldx = W.K;
+        p.y = y; p.ldy = W.M;
+        p.epi = epi; p.pro = PRO_NONE;
+        return p;
+    }
+};
+
+#define CUDA_OK(ctx, call)                                                                               \
+    do { cudaError_t _e = (call);                                                                        \
+         RWKV_CHECK((ctx)->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, _e == cudaSuccess,       \
+                    "CUDA error: %s", cudaGetErrorString(_e)); } while (0)
+
+bool run_batch(Context * ctx, Batch & batch) {
+    CUDA_OK(ctx, gemv_launch(batch.b, ctx->model->dev, ctx->stream));
+    return true;
+}
+
+// Channel mixing, all versions (rwkv_ffn_v4_v5 :484-511, rwkv_ffn_v6 :513-531, rwkv_ffn_v7 :533-543).
+bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
+    const Model & m = *ctx->model;
+    const int C = m.n_embed;
+    LnMixParams lp{};
+    lp.x = s.x; lp.ln_w = L.ln2_w.data; lp.ln_b = L.ln2_b.data;
+    lp.state_in = st_in; lp.state_out = st_out; lp.C = C; lp.T = T;
+    if (m.arch_major == 7) {
+        lp.formula = 1; lp.n_out = 1; lp.coef[0] = L.ffn_x_k.data; lp.out[0] = s.mix[0];
+    } else if (m.arch_major == 6) {
+        lp.formula = 1; lp.n_out = 2;
+        lp.coef[0] = L.ffn_maa_k.data; lp.out[0] = s.mix[0];
+        lp.coef[1] = L.ffn_maa_r.data; lp.out[1] = s.mix[1];
+    } else {
+        lp.formula = 0; lp.n_out = 2;
+        lp.coef[0] = L.ffn_time_mix_k.data; lp.out[0] = s.mix[0];
+        lp.coef[1] = L.ffn_time_mix_r.data; lp.out[1] = s.mix[1];
+    }
+    CUDA_OK(ctx, launch_ln_mix(lp, ctx->stream));
+    {
+        Batch b(T);
+        b.add(L.ffn_key, s.mix[0], s.ffn_k, EPI_RELU_SQR);
+        if (m.arch_major != 7) b.add(L.ffn_receptance, s.mix[1], s.ffn_r, EPI_SIGMOID);
+        if (!run_batch(ctx, b)) return false;
+    }
+    {
+        Batch b(T);
+        GemvProblem & p = b.add(L.ffn_value, s.ffn_k, s.x, m.arch_major == 7 ? EPI_ADD : EPI_MUL_ADD);
+        p.res = s.x; p.ldres = C;
+        p.gate = s.ffn_r; p.ldgate = C;
+        if (!run_batch(ctx, b)) return false;
+    }
+    return true;
+}
+
+bool att_output(Context * ctx, const Layer & L, const Scratch & s, int T) {
+    Batch b(T);
+    GemvProblem & p = b.add(L.att_output, s.y, s.x, EPI_ADD);   // x + Wo.y  (:182/:291/:384/:481 + residual :667-679)
+    p.res = s.x; p.ldres = ctx->model->n_embed;
+    return run_batch(ctx, b);
+}
+
+bool att_v4(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
+    const int C = ctx->model->n_embed;
+    LnMixParams lp{};
+    lp.x = s.x; lp.ln_w = L.ln1_w.data; lp.ln_b = L.ln1_b.data;
+    lp.state_in = st_in + C; lp.state_out = st_out + C; lp.C = C; lp.T = T;
+    lp.formula = 0; lp.n_out = 3;
+    lp.coef[0] = L.att_time_mix_k.data; lp.out[0] = s.mix[0];
+    lp.coef[1] = L.att_time_mix_v.data; lp.out[1] = s.mix[1];
+    lp.coef[2] = L.att_time_mix_r.data; lp.out[2] = s.mix[2];
+    CUDA_OK(ctx, launch_ln_mix(lp, ctx->stream));
+    Batch b(T);
+    b.add(L.att_receptance, s.mix[2], s.r, EPI_SIGMOID);
+    b.add(L.att_key, s.mix[0], s.k);
+    b.add(L.att_value, s.mix[1], s.v);
+    if (!run_batch(ctx, b)) return false;
+    Wkv4Params wp{};
+    wp.k = s.k; wp.v = s.v; wp.r = s.r;
+    wp.time_first = L.att_time_first.data; wp.time_decay = L.att_time_decay.data;
+    wp.aa_in = st_in + 2 * C; wp.bb_in = st_in + 3 * C; wp.pp_in = st_in + 4 * C;
+    wp.aa_out = st_out + 2 * C; wp.bb_out = st_out + 3 * C; wp.pp_out = st_out + 4 * C;
+    wp.y = s.y; wp.C = C; wp.T = T;
+    CUDA_OK(ctx, launch_wkv4(wp, ctx->stream));
+    return att_output(ctx, L, s, T);
+}
+
+bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
+    const Model & m = *ctx->model;
+    const int C = m.n_embed;
+    const bool v52 = m.arch_minor >= 2;
+    LnMixParams lp{};
+    lp.x = s.x; lp.ln_w = L.ln1_w.data; lp.ln_b = L.ln1_b.data;
+    lp.state_in = st_in + C; lp.state_out = st_out + C; lp.C = C; lp.T = T;
+    lp.formula = 0; lp.n_out = v52 ? 4 : 3;
+    lp.coef[0] = L.att_time_mix_k.data; lp.out[0] = s.mix[0];
+    lp.coef[1] = L.att_time_mix_v.data; lp.out[1] = s.mix[1];
+    lp.coef[2] = L.att_time_mix_r.data; lp.out[2] = s.mix[2];
+    if (v52) { lp.coef[3] = L.att_time_mix_g.data; lp.out[3] = s.mix[3]; }
+    CUDA_OK(ctx, launch_ln_mix(lp, ctx->stream));
+    Batch b(T);
+    b.add(L.att_receptance, s.mix[2], s.r);
+    b.add(L.att_key, s.mix[0], s.k);
+    b.add(L.att_value, s.mix[1], s.v);
+    if (v52) b.add(L.att_gate, s.mix[3], s.g, EPI_SILU);
+    if (!run_batch(ctx, b)) return false;
+    Wkv6Params wp{};
+    wp.r = s.r; wp.k = s.k; wp.v = s.v;
+    wp.td = L.att_time_decay.data; wp.td_per_token = 0;
+    wp.tf = v52 ? L.att_time_faaaa.data : L.att_time_first.data;
+    wp.per_head_scalars = v52 ? 0 : 1;
+    wp.state_in = st_in + 2 * C; wp.state_out = st_out + 2 * C;
+    wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
+    wp.g = v52 ? s.g : nullptr;
+    wp.y = s.y; wp.eps = 1e-5f; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
+    CUDA_OK(ctx, launch_wkv6(wp, ctx->stream));
+    return att_output(ctx, L, s, T);
+}
+
+bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
+    const Model & m = *ctx->model;
+    const int C = m.n_embed;
+    LnMixParams lp{};   // :306-311
+    lp.x = s.x; lp.ln_w = L.ln1_w.data; lp.ln_b = L.ln1_b.data;
+    lp.state_in = st_in + C; lp.state_out = st_out + C; lp.C = C; lp.T = T;
+    lp.formula = 1; lp.n_out = 1; lp.coef[0] = L.att_maa_x.data; lp.out[0] = s.mix[0];
+    lp.out_xx = s.xx; lp.out_sx = s.sx;
+    CUDA_OK(ctx, launch_ln_mix(lp, ctx->stream));
+    {   // :313-321  tanh(W1 . xxx)
+        Batch b(T);
+        b.add(L.att_maa_w1, s.mix[0], s.lora[0], EPI_TANH);
+        if (!run_batch(ctx, b)) return false;
+    }
+    V6LerpParams vp{};   // :323-346
+    vp.w2 = L.att_maa_w2.data; vp.z = s.lora[0]; vp.xx = s.xx; vp.sx = s.sx;
+    vp.maa[0] = L.att_maa_w.data; vp.maa[1] = L.att_maa_k.data; vp.maa[2] = L.att_maa_v.data;
+    vp.maa[3] = L.att_maa_r.data; vp.maa[4] = L.att_maa_g.data;
+    for (int j = 0; j < 5; j++) vp.out[j] = s.mix[1 + j];   // w, k, v, r, g
+    vp.C = C; vp.T = T; vp.mix = L.maa_mix;
+    CUDA_OK(ctx, launch_v6_lerp(vp, ctx->stream));
+    {   // :349-363
+        Batch b(T);
+        b.add(L.att_receptance, s.mix[4], s.r);
+        b.add(L.att_key, s.mix[2], s.k);
+        b.add(L.att_value, s.mix[3], s.v);
+        b.add(L.att_gate, s.mix[5], s.g, EPI_SILU);
+        b.add(L.att_decay_w1, s.mix[1], s.lora[1], EPI_TANH);
+        if (!run_batch(ctx, b)) return false;
+    }
+    {   // :357-367  w = exp(-exp(Wd2 . tanh(..) + time_decay))
+        Batch b(T);
+        GemvProblem & p = b.add(L.att_decay_w2, s.lora[1], s.w, EPI_BIAS_EXPNEGEXP);
+        p.bias = L.att_time_decay.data;
+        if (!run_batch(ctx, b)) return false;
+    }
+    Wkv6Params wp{};   // :370-382
+    wp.r = s.r; wp.k = s.k; wp.v = s.v;
+    wp.td = s.w; wp.td_per_token = 1; wp.tf = L.att_time_faaaa.data; wp.per_head_scalars = 0;
+    wp.state_in = st_in + 2 * C; wp.state_out = st_out + 2 * C;
+    wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
+    wp.g = s.g; wp.y = s.y; wp.eps = 64e-5f; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
+    CUDA_OK(ctx, launch_wkv6(wp, ctx->stream));
+    return att_output(ctx, L, s, T);
+}
+
+bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T, const float * st_in, float * st_out) {
+    const Model & m = *ctx->model;
+    const int C = m.n_embed;
+    const bool first = layer == 0;
+    LnMixParams lp{};   // :400-413
+    lp.x = s.x; lp.ln_w = L.ln1_w.data; lp.ln_b = L.ln1_b.data;
+    lp.state_in = st_in + C; lp.state_out = st_out + C; lp.C = C; lp.T = T;
+    lp.formula = 1; lp.n_out = 6;
+    for (int j = 0; j < 6; j++) { lp.coef[j] = L.att_x_rwkvag.data + (size_t) j * C; lp.out[j] = s.mix[j]; }   // r w k v a g
+    CUDA_OK(ctx, launch_ln_mix(lp, ctx->stream));
+    float * v_dst = first ? s.v_first : s.v;
+    {   // :415-432, 439, 447 -- first halves of the LoRA pairs
+        Batch b(T);
+        b.add(L.att_receptance, s.mix[0], s.r);
+        b.add(L.att_key, s.mix[2], s.k);
+        b.add(L.att_value, s.mix[3], v_dst);
+        b.add(L.att_w1, s.mix[1], s.lora[0], EPI_TANH);
+        b.add(L.att_a1, s.mix[4], s.lora[1]);
+        b.add(L.att_g1, s.mix[5], s.lora[2], EPI_SIGMOID);
+        if (!first) b.add(L.att_v1, s.mix[3], s.lora[3]);
+        if (!run_batch(ctx, b)) return false;
+    }
+    {   // second halves
+        Batch b(T);
+        GemvProblem & pw = b.add(L.att_w2, s.lora[0], s.w, EPI_BIAS_W7);      pw.bias = L.att_w0.data;
+        GemvProblem & pa = b.add(L.att_a2, s.lora[1], s.a, EPI_BIAS_SIGMOID); pa.bias = L.att_a0.data;
+        b.add(L.att_g2, s.lora[2], s.g);
+        if (!first) { GemvProblem & pv = b.add(L.att_v2, s.lora[3], s.vgate, EPI_BIAS_SIGMOID); pv.bias = L.att_v0.data; }
+        if (!run_batch(ctx, b)) return false;
+    }
+    Wkv7Params wp{};   // :433-479
+    wp.r = s.r; wp.w = s.w; wp.k = s.k; wp.v = v_dst; wp.a = s.a; wp.g = s.g;
+    wp.vgate = first ? nullptr : s.vgate; wp.v_first = s.v_first; wp.v_out = nullptr;
+    wp.k_k = L.att_k_k.data; wp.k_a = L.att_k_a.data; wp.r_k = L.att_r_k.data;
+    wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
+    wp.state_in = st_in + 2 * C; wp.state_out = st_out + 2 * C;
+    wp.y = s.y; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
+    CUDA_OK(ctx, launch_wkv7(wp, ctx->stream));
+    return att_output(ctx, L, s, T);
+}
+
+bool ensure_capacity(Context * ctx, int T) {
+    if (T <= ctx->capacity_T) return true;
+    const Model & m = *ctx->model;
+    int cap = ctx->capacity_T ? ctx->capacity_T : 1;
+    while (cap < T) cap *= 2;
+    if (cap > MAX_TOKENS_PER_PASS) cap = MAX_TOKENS_PER_PASS;
+    if (ctx->scratch) { cudaFree(ctx->scratch); ctx->scratch = nullptr; }
+    if (ctx->tokens) { cudaFree(ctx->tokens); ctx->tokens = nullptr; }
+    if (ctx->tokens_host) { cudaFreeHost(ctx->tokens_host); ctx->tokens_host = nullptr; }
+    ctx->capacity_T = 0;
+    const size_t n = scratch_floats_for(m, cap);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ctx->scratch), n * sizeof(float));
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, false, e == cudaSuccess, "Failed to allocate %zu bytes of activation memory: %s", n * sizeof(float), cudaGetErrorString(e));
+    e = cudaMalloc(reinterpret_cast<void **>(&ctx->tokens), (size_t) cap * sizeof(int));
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, false, e == cudaSuccess, "Failed to allocate the token buffer: %s", cudaGetErrorString(e));
+    e = cudaMallocHost(reinterpret_cast<void **>(&ctx->tokens_host), (size_t) cap * sizeof(int));
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, false, e == cudaSuccess, "Failed to allocate pinned token staging: %s", cudaGetErrorString(e));
+    ctx->scratch_floats = n;
+    ctx->capacity_T = cap;
+    return true;
+}
+
+// One pass of at most MAX_TOKENS_PER_PASS tokens: state_a -> state_b, then swap.
+bool forward_pass(Context * ctx, const uint32_t * tokens, int T, bool want_logits) {
+    const Model & m = *ctx->model;
+    const int C = m.n_embed;
+    if (!ensure_capacity(ctx, T)) return false;
+    const Scratch s = carve(m, ctx->scratch, T);
+    for (int t = 0; t < T; t++) ctx->tokens_host[t] = (int) tokens[t];
+    // the previous pass may still be reading tokens_host through its async copy
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_OK(ctx, cudaMemcpyAsync(ctx->tokens, ctx->tokens_host, (size_t) T * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_OK(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    CUDA_OK(ctx, launch_embed_ln0(m.emb.data, m.emb.type, m.emb.pitch, ctx->tokens, T, C, m.ln0_w.data, m.ln0_b.data, s.x, ctx->stream));
+    const size_t per_layer = m.state_floats_per_layer();
+    for (int i = m.layer_begin; i < m.layer_end; i++) {
+        const Layer & L = m.layers[i];
+        const float * st_in = ctx->state_a + (size_t) i * per_layer;
+        float * st_out = ctx->state_b + (size_t) i * per_layer;
+        bool ok;
+        switch (m.arch_major) {
+            case 7: ok = att_v7(ctx, L, i, s, T, st_in, st_out); break;
+            case 6: ok = att_v6(ctx, L, s, T, st_in, st_out); break;
+            case 5: ok = att_v5(ctx, L, s, T, st_in, st_out); break;
+            default: ok = att_v4(ctx, L, s, T, st_in, st_out); break;
+        }
+        if (!ok || !ffn(ctx, L, s, T, st_in, st_out)) return false;
+    }
+    if (want_logits) {   // :705-708 / :851-854  head . LN(x_last; ln_out)
+        Batch b(1);
+        GemvProblem & p = b.add(m.head, s.x + (size_t) (T - 1) * C, ctx->logits);
+        p.pro = PRO_LAYERNORM; p.ln_w = m.ln_out_w.data; p.ln_b = m.ln_out_b.data;
+        if (!run_batch(ctx, b)) return false;
+    }
+    CUDA_OK(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+    float * tmp = ctx->state_a; ctx->state_a = ctx->state_b; ctx->state_b = tmp;
+    return true;
+}
+
+}  // namespace
+
+void fill_init_state(const Model & m, float * state) {
+    const size_t n = m.state_len();
+    memset(state, 0, n * sizeof(float));
+    if (m.arch_major >= 5) return;
+    const size_t C = m.n_embed;
+    for (int l = 0; l < m.n_layer; l++)
+        for (size_t c = 0; c < C; c++) state[(size_t) l * 5 * C + 4 * C + c] = -1e30f;
+}
+
+Context * create_context(Model * model, ErrorSink sink) {
+    Context * ctx = new (std::nothrow) Context();
+    RWKV_CHECK(sink, RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, nullptr, ctx, "Failed to allocate rwkv_context");
+    ctx->model = model;
+    model->refcount.fetch_add(1);
+    ctx->print_errors = *sink.print;
+    const size_t n = model->state_len();
+    bool ok = cudaSetDevice(model->dev.device) == cudaSuccess
+        && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess
+        && cudaEventCreate(&ctx->ev_start) == cudaSuccess && cudaEventCreate(&ctx->ev_stop) == cudaSuccess
+        && cudaMalloc(reinterpret_cast<void **>(&ctx->state_a), n * sizeof(float)) == cudaSuccess
+        && cudaMalloc(reinterpret_cast<void **>(&ctx->state_b), n * sizeof(float)) == cudaSuccess
+        && cudaMalloc(reinterpret_cast<void **>(&ctx->state_init), n * sizeof(float)) == cudaSuccess
+        && cudaMalloc(reinterpret_cast<void **>(&ctx->logits), (size_t) model->n_vocab * sizeof(float)) == cudaSuccess;
+    if (ok) {
+        std::vector<float> init(n);
+        fill_init_state(*model, init.data());
+        ok = cudaMemcpy(ctx->state_init, init.data(), n * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (!ok) {
+        cudaError_t e = cudaGetLastError();
+        destroy_context(ctx);
+        RWKV_CHECK(sink, RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, nullptr, false, "Failed to set up the context on the device: %s", cudaGetErrorString(e));
+    }
+    return ctx;
+}
+
+void destroy_context(Context * ctx) {
+    if (!ctx) return;
+    Model * model = ctx->model;
+    if (model) cudaSetDevice(model->dev.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->state_a); cudaFree(ctx->state_b); cudaFree(ctx->state_init); cudaFree(ctx->logits);
+    cudaFree(ctx->tokens); cudaFree(ctx->scratch);
+    if (ctx->tokens_host) cudaFreeHost(ctx->tokens_host);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (model && model->refcount.fetch_sub(1) == 1) delete model;
+    delete ctx;
+}
+
+bool upload_state(Context * ctx, const float * state_in) {
+    const size_t bytes = ctx->model->state_len() * sizeof(float);
+    if (state_in) CUDA_OK(ctx, cudaMemcpyAsync(ctx->state_a, state_in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    else CUDA_OK(ctx, cudaMemcpyAsync(ctx->state_a, ctx->state_init, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return true;
+}
+
+bool download_outputs(Context * ctx, float * state_out, float * logits_out) {
+    if (state_out) CUDA_OK(ctx, cudaMemcpyAsync(state_out, ctx->state_a, ctx->model->state_len() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (logits_out) CUDA_OK(ctx, cudaMemcpyAsync(logits_out, ctx->logits, (size_t) ctx->model->n_vocab * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return true;
+}
+
+bool forward(Context * ctx, const uint32_t * tokens, size_t T, bool want_logits) {
+    CUDA_OK(ctx, cudaSetDevice(ctx->model->dev.device));
+    size_t done = 0;
+    while (done < T) {
+        const size_t n = (T - done < (size_t) MAX_TOKENS_PER_PASS) ? T - done : (size_t) MAX_TOKENS_PER_PASS;
+        const bool last = done + n == T;
+        if (!forward_pass(ctx, tokens + done, (int) n, want_logits && last)) return false;
+        done += n;
+    }
+    return true;
+}
+
+}  // namespace rwkv

@@ -1,0 +1,57 @@
+// Per-context execution state and the forward pass (serial + sequence mode) over a resident Model.
+// Replaces rwkv_computation_graph + ggml_backend_sched (reference rwkv_graph.inc:16-54, 611-882;
+// rwkv_eval.inc:25-35): there is no graph IR -- the launch sequence is written out per architecture.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "model.h"
+
+namespace rwkv {
+
+struct Context {
+    Model * model = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+
+    // device buffers
+    float * state_a = nullptr;       // current input state
+    float * state_b = nullptr;       // output state of the running evaluation
+    float * state_init = nullptr;    // rwkv_init_state image, copied when state_in == NULL
+    float * logits = nullptr;        // [n_vocab]
+    int * tokens = nullptr;          // [capacity_T]
+    float * scratch = nullptr;       // activation arena for capacity_T tokens
+    size_t scratch_floats = 0;
+    int capacity_T = 0;
+    // pinned host staging for tokens
+    int * tokens_host = nullptr;
+
+    float last_device_ms = 0.f;      // CUDA-event time of the last forward (kernels only)
+    int last_error = 0;              // rwkv_error_flags
+    bool print_errors = true;
+    uint32_t n_threads = 1;
+
+    ErrorSink sink() { return ErrorSink{&last_error, &print_errors}; }
+};
+
+// Largest number of tokens pushed through the kernels in one go; longer sequences are cut into
+// pieces of this size with the state staying on the device.
+constexpr int MAX_TOKENS_PER_PASS = 512;
+
+Context * create_context(Model * model, ErrorSink sink);
+void destroy_context(Context * ctx);
+
+// Host image of a fresh state (rwkv_init_state, rwkv_eval.inc:224-241).
+void fill_init_state(const Model & m, float * state);
+
+// state_a <- host state (or the init image when NULL). Asynchronous on ctx->stream.
+bool upload_state(Context * ctx, const float * state_in);
+// host <- state_a / logits; synchronises the stream.
+bool download_outputs(Context * ctx, float * state_out, float * logits_out);
+
+// Runs T tokens (host pointer) through all resident layers: reads state_a, leaves the new state in
+// state_a (buffers are swapped internally), and, if want_logits, ln_out + head of the last token
+// into ctx->logits. Asynchronous except for the token upload.
+bool forward(Context * ctx, const uint32_t * tokens, size_t T, bool want_logits);
+
+}  // namespace rwkv
