@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- the north-star measurement: RWKV-6-World-7B-shape Q5_1, single-token decode and 128-token
+prefill through the rwkv.h C ABI of rwkv.cpp_b200/librwkv.so, on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload rwkv6-7b:Q5_1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one single-token evaluation (with logits) of the whole model. Prints ONE JSON line:
+  value        decode tokens/s, state resident in HBM, CUDA-event timed on the library's own stream
+  e2e          the same metric through rwkv_eval() with HOST state/logits buffers (H2D + D2H inside the timed region)
+  prefill      128-token rwkv_eval_sequence chunk: device-timed and e2e tokens/s
+  roofline     dominant kernel (fused dequant-GEMV): algorithmic weight bytes / CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline the UNMODIFIED reference (oracle/_ref) timed on this box's host cores on a bounded sample
+Weights are synthetic (random-init, exact shapes/dtypes; tools/synthetic_model.py); no checkpoints exist offline.
+The 6 GB of weights streamed per token exceed the 126 MB L2 48x, so no explicit L2 flush is needed between steps.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+PF = ctypes.POINTER(ctypes.c_float)
+PU = ctypes.POINTER(ctypes.c_uint32)
+CACHE_DIR = os.environ.get("RWKV_B200_BENCH_DIR", "/tmp/rwkv_b200_bench")
+PREFILL_TOKENS = 128
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rwkv6-7b:Q5_1", help="<preset>:<format>, presets in tools/synthetic_model.py")
+    ap.add_argument("--prefill-steps", type=int, default=8)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=25.0, help="CPU seconds the bounded reference sample may take per leg")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def workload_file(spec, rank=0, world=1, barrier=None):
+    import synthetic_model as sm
+    preset, fmt = spec.split(":")
+    os.makedirs(CACHE_DIR, exist_ok=True)
+    path = os.path.join(CACHE_DIR, f"{preset}-{fmt}-seed1.bin")
+    if rank == 0 and not os.path.isfile(path):
+        tmp = path + ".tmp"
+        sm.write_direct(tmp, preset, fmt, seed=1)
+        os.replace(tmp, path)
+    if barrier:
+        barrier()
+    return path, sm.PRESETS[preset]
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed regions (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, windows):
+        rows = [r for ts, r in self.rows if any(a <= ts <= b for a, b in windows)] or [r for _, r in self.rows]
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_buffers(n_state, n_logits):
+    """Pinned host buffers for the e2e leg (what a serving process would hold); falls back to pageable numpy."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            s = torch.zeros(n_state, dtype=torch.float32).pin_memory()
+            l = torch.zeros(n_logits, dtype=torch.float32).pin_memory()
+            return s, l, s.data_ptr(), l.data_ptr(), "pinned"
+    except Exception:
+        pass
+    s, l = np.zeros(n_state, np.float32), np.zeros(n_logits, np.float32)
+    return s, l, s.ctypes.data, l.ctypes.data, "pageable"
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_leg(path, preset, n_decode, budget_s, want_prefill=True):
+    """Times the unmodified reference (oracle/_ref) on the host cores: bounded sample of the same workload."""
+    import ref_lib
+    import synthetic_model as sm
+    ref = ref_lib.load_reference_library()
+    ref.rwkv_set_print_errors(None, False)
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, int(os.environ.get("RWKV_REF_THREADS", cores))))
+    t0 = time.time()
+    ctx = ref.rwkv_init_from_file(path.encode(), threads, 0)
+    if not ctx:
+        raise RuntimeError("reference failed to load " + path)
+    load_s = time.time() - t0
+    n_state, n_vocab = ref.rwkv_get_state_len(ctx), ref.rwkv_get_logits_len(ctx)
+    state, logits = np.zeros(n_state, np.float32), np.zeros(n_vocab, np.float32)
+    ref.rwkv_init_state(ctx, state.ctypes.data_as(PF))
+    toks = sm.synthetic_tokens(4096, n_vocab)
+    sp, lp = state.ctypes.data_as(PF), logits.ctypes.data_as(PF)
+    # warm-up (2 tokens: first call builds the scheduler) and a probe to size the sample
+    t0 = time.time()
+    for t in toks[:2]:
+        ref.rwkv_eval(ctx, t, sp, sp, lp)
+    probe = (time.time() - t0) / 2
+    n = int(max(4, min(n_decode, budget_s / max(probe, 1e-6))))
+    times = []
+    for t in toks[2:2 + n]:
+        t0 = time.perf_counter()
+        ref.rwkv_eval(ctx, t, sp, sp, lp)
+        times.append(time.perf_counter() - t0)
+    med = float(np.median(times))
+    out = {"decode_tokens_per_s": 1.0 / med, "decode_ms_per_token": med * 1e3, "decode_sample_tokens": n, "threads": threads, "cores": cores,
+           "load_s": load_s, "library": os.path.basename(ref_lib.reference_library_path())}
+    if want_prefill and med * PREFILL_TOKENS < 6 * budget_s:
+        arr = (ctypes.c_uint32 * PREFILL_TOKENS)(*toks[:PREFILL_TOKENS])
+        ref.rwkv_eval_sequence_in_chunks(ctx, arr, PREFILL_TOKENS, PREFILL_TOKENS, None, sp, lp)   # builds + caches the sequence graph
+        t0 = time.perf_counter()
+        ref.rwkv_eval_sequence_in_chunks(ctx, arr, PREFILL_TOKENS, PREFILL_TOKENS, None, sp, lp)
+        dt = time.perf_counter() - t0
+        out["prefill_tokens_per_s"] = PREFILL_TOKENS / dt
+        out["prefill_sample"] = "1 chunk of 128 tokens after one warm-up chunk"
+    ref.rwkv_free(ctx)
+    return out
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    path, preset = workload_file(args.workload)
+    r = cpu_reference_leg(path, preset, n_decode=args.steps, budget_s=max(args.cpu_budget_s, 10.0))
+    line = {
+        "impl": "reference", "metric": "decode_tokens_per_sec", "value": r["decode_tokens_per_s"], "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": r["decode_sample_tokens"], "warmup": 2, "ms_per_step": r["decode_ms_per_token"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "q5_1 weights x q8_1 activations (int8 dot, fp32 accumulate)" if "Q" in args.workload else "as file",
+        "data": "synthetic", "config": {"workload": args.workload + " single-token rwkv_eval, reference CPU path (oracle/_ref)", "cpu": cpu_model_name()},
+        "cpu_baseline": {"value": r["decode_tokens_per_s"], "unit": "tokens/s", "cores": r["threads"], "kind": "reference",
+                         "sample": f"{r['decode_sample_tokens']} rwkv_eval calls (median), {r['library']}, {r['threads']} threads of {r['cores']} logical CPUs"},
+        "e2e": {"value": r["decode_tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "prefill": {"tokens_per_s": r.get("prefill_tokens_per_s"), "chunk": PREFILL_TOKENS},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, dist):
+    import __graft_entry__
+    import synthetic_model as sm
+    pkg = __graft_entry__.load_package()
+    lib = pkg.load_rwkv_shared_library()
+    L = lib.library
+    barrier = (lambda: dist.barrier()) if dist else None
+    path, preset = workload_file(args.workload, rank, world, barrier)
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    t0 = time.time()
+    ctx = lib.rwkv_b200_init_from_file_ex(path, local, 0, -1)   # N > 1: one full replica per GPU (multi-GPU)
+    load_s = time.time() - t0
+    n_state, n_vocab = lib.rwkv_get_state_len(ctx), lib.rwkv_get_logits_len(ctx)
+    K, W = args.steps, args.warmup
+    toks = sm.synthetic_tokens(max(K + W + 8, (args.prefill_steps + 3) * PREFILL_TOKENS), n_vocab)
+    tok_arr = (ctypes.c_uint32 * len(toks))(*toks)
+    sampler = ClockSampler(local)
+    sampler.start()
+    windows = []
+
+    def sync_all():
+        L.rwkv_b200_synchronize(ctx.ptr)
+        if dist:
+            dist.barrier()
+
+    # ---- decode, state resident in HBM, CUDA events on the library's stream -------------------------------
+    L.rwkv_b200_state_load(ctx.ptr, None)
+    L.rwkv_b200_eval_resident(ctx.ptr, tok_arr, 1, True, None)   # lazy allocations, graph capture happens in warm-up
+    sync_all()
+    launches0 = L.rwkv_b200_kernel_launch_count()
+    w0 = time.time()
+    ms = L.rwkv_b200_time_resident(ctx.ptr, tok_arr, 1, K, W, True)
+    windows.append((w0, time.time()))
+    launches = (L.rwkv_b200_kernel_launch_count() - launches0) * K // (K + W)
+    assert ms > 0, "device timing failed"
+    ms_max = ms
+    if dist:
+        import torch
+        t = torch.tensor([ms], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+    decode_tps = world * K / (ms_max / 1e3)
+
+    # ---- decode end to end through rwkv_eval with host buffers ------------------------------------------------
+    sbuf, lbuf, sp, lp, kind = host_buffers(n_state, n_vocab)
+    lib.rwkv_init_state(ctx, sp)
+    for t in toks[:W]:
+        lib.rwkv_eval(ctx, t, sp, sp, lp)
+    sync_all()
+    w0 = time.time()
+    t0 = time.perf_counter()
+    for t in toks[W:W + K]:
+        lib.rwkv_eval(ctx, t, sp, sp, lp)
+    e2e_s = time.perf_counter() - t0
+    windows.append((w0, time.time()))
+    if dist:
+        import torch
+        t = torch.tensor([e2e_s], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_tps = world * K / e2e_s
+
+    # ---- prefill: 128-token chunk ----------------------------------------------------------------------------------
+    P = args.prefill_steps
+    L.rwkv_b200_state_load(ctx.ptr, None)
+    w0 = time.time()
+    pms = L.rwkv_b200_time_resident(ctx.ptr, tok_arr, PREFILL_TOKENS, P, 2, True)
+    windows.append((w0, time.time()))
+    arr128 = (ctypes.c_uint32 * PREFILL_TOKENS)(*toks[:PREFILL_TOKENS])
+    L.rwkv_eval_sequence_in_chunks(ctx.ptr, arr128, PREFILL_TOKENS, PREFILL_TOKENS, None, ctypes.cast(sp, PF), ctypes.cast(lp, PF))
+    t0 = time.perf_counter()
+    for _ in range(max(2, P // 2)):
+        L.rwkv_eval_sequence_in_chunks(ctx.ptr, arr128, PREFILL_TOKENS, PREFILL_TOKENS, None, ctypes.cast(sp, PF), ctypes.cast(lp, PF))
+    pe2e_s = (time.perf_counter() - t0) / max(2, P // 2)
+    if dist:
+        import torch
+        t = torch.tensor([pms, pe2e_s], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pms, pe2e_s = float(t[0].item()), float(t[1].item())
+
+    # ---- roofline leg: events around every GEMV launch of one decode pass ------------------------------------
+    prof = pkg.shared_library.ProfileResult()
+    L.rwkv_b200_state_load(ctx.ptr, None)
+    profs = []
+    for i in range(5):
+        L.rwkv_b200_profile_pass(ctx.ptr, ctypes.cast(ctypes.byref(tok_arr, 4 * i), PU), 1, True, ctypes.byref(prof))
+        profs.append((prof.gemv_ms, prof.gemv_bytes, prof.pass_ms, prof.gemv_launches, prof.total_launches, prof.top_ms, prof.top_bytes))
+    profs = profs[1:]
+    gemv_ms = float(np.median([p[0] for p in profs])); gemv_bytes = profs[0][1]; pass_ms = float(np.median([p[2] for p in profs]))
+    top = min(profs, key=lambda p: p[5])
+    peak, peak_src = measured_peaks()
+    bytes_tok = int(L.rwkv_b200_bytes_per_token(ctx.ptr, True))
+    step_ms = ms_max / K
+    sampler.stop()
+    clocks = sampler.summary(windows)
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "decode_tokens_per_sec", "value": decode_tps, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "q5_1 weights x q8_1 activations (int8 dp4a, fp32 accumulate); fp16 head" if "Q5_1" in args.workload else args.workload.split(":")[1],
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload} single-token rwkv_eval with logits ({preset['L']} layers, n_embed {preset['C']}, ffn {preset['F']}, vocab {preset['V']})",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas, one stream each (single-stream decode does not shard; DESIGN.md)",
+                       "l2": "6.1 GB of weights per step >> 126 MB L2, no flush needed", "bytes_per_token": bytes_tok, "load_s": round(load_s, 2),
+                       "cuda_graph": True},
+            "clocks": clocks,
+            "e2e": {"value": e2e_tps, "unit": "tokens/s", "h2d_bytes_per_step": n_state * 4 + 4, "d2h_bytes_per_step": n_state * 4 + n_vocab * 4,
+                    "host_buffers": kind, "ms_per_step": e2e_s / K * 1e3},
+            "gpu_launches": int(launches),
+            "prefill": {"tokens_per_s": world * P * PREFILL_TOKENS / (pms / 1e3), "ms_per_chunk": pms / P, "chunk": PREFILL_TOKENS, "steps": P,
+                        "e2e_tokens_per_s": world * PREFILL_TOKENS / pe2e_s},
+            "roofline": {"bound": "hbm", "kernel": "gemv_kernel (fused dequantize-GEMV, all launches of one decode step)",
+                         "achieved": gemv_bytes / (gemv_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": gemv_bytes / (gemv_ms * 1e-3) / 1e9 / peak,
+                         "peak_source": peak_src, "traffic": None, "bytes_per_step": gemv_bytes, "ms_per_step": gemv_ms,
+                         "launches_per_step": int(profs[0][3]), "share_of_step": gemv_ms / pass_ms,
+                         "largest_launch": {"bytes": top[6], "ms": top[5], "gbs": top[6] / (top[5] * 1e-3) / 1e9},
+                         "whole_step": {"bytes": bytes_tok, "ms": step_ms, "gbs": bytes_tok / (step_ms * 1e-3) / 1e9, "frac": bytes_tok / (step_ms * 1e-3) / 1e9 / peak}},
+        }
+    lib.rwkv_free(ctx)
+    if rank == 0:
+        if world == 1 and not args.skip_cpu_baseline:
+            try:
+                r = cpu_reference_leg(path, preset, n_decode=32, budget_s=args.cpu_budget_s)
+                line["cpu_baseline"] = {"value": r["decode_tokens_per_s"], "unit": "tokens/s", "cores": r["threads"], "kind": "reference",
+                                        "sample": f"{r['decode_sample_tokens']} rwkv_eval calls (median) on the same file, {r['library']}, {r['threads']} threads, {cpu_model_name()}",
+                                        "prefill_tokens_per_s": r.get("prefill_tokens_per_s")}
+            except Exception as e:   # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    dist = None
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist_mod.init_process_group("nccl")
+        dist = dist_mod
+    run_ours(args, rank, world, dist)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -42,9 +42,29 @@ RWKV_API bool rwkv_b200_synchronize(struct rwkv_context * ctx);
 RWKV_API float rwkv_b200_last_device_ms(const struct rwkv_context * ctx);     /* CUDA-event time of the last pass */
 RWKV_API uint64_t rwkv_b200_kernel_launch_count(void);                         /* kernels enqueued by this process */
 RWKV_API uint64_t rwkv_b200_bytes_per_token(const struct rwkv_context * ctx, bool with_logits);
-/* Times `iters` back-to-back resident evaluations of `n_tokens` tokens on the device with CUDA events on the
- * context's own stream (after `warmup` untimed ones); returns total milliseconds or a negative value on error. */
-RWKV_API float rwkv_b200_time_resident(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, bool want_logits, int warmup, int iters);
+/* Times `n_steps` back-to-back resident passes of `tokens_per_step` tokens each (after `warmup_steps` untimed ones)
+ * with CUDA events on the context's own stream. `tokens` holds (warmup_steps + n_steps) * tokens_per_step ids.
+ * Returns the milliseconds of the timed steps, or a negative value on error. Single-token passes replay a CUDA graph. */
+RWKV_API float rwkv_b200_time_resident(struct rwkv_context * ctx, const uint32_t * tokens, size_t tokens_per_step, int n_steps, int warmup_steps, bool want_logits);
+
+/* Roofline leg: runs ONE resident pass of n_tokens with CUDA events around every fused dequantize-GEMV launch (graphs off)
+ * and reports their summed duration, the algorithmic weight bytes they streamed (rwkv_tensor_nbytes of each matrix, reference
+ * rwkv_utilities.inc:1-3), their count, and the duration of the whole pass. */
+struct rwkv_b200_profile {
+    double gemv_ms, gemv_bytes, pass_ms;
+    double top_ms, top_bytes;      /* the single slowest GEMV launch of the pass */
+    uint32_t gemv_launches, total_launches;
+};
+RWKV_API bool rwkv_b200_profile_pass(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, bool want_logits, struct rwkv_b200_profile * out);
+
+/* Enables / disables CUDA-graph replay of single-token passes (on by default). */
+RWKV_API void rwkv_b200_set_graphs(struct rwkv_context * ctx, bool enabled);
+
+/* Test hook: one fused dequantize-GEMV on host buffers, y[M,T] = W[M,K] . x[K,T] (column-major activations),
+ * through exactly the kernel the eval path uses (csrc/kernels/gemv.cu). `weights` holds M rows in the file
+ * layout of `data_type` (rwkv_file_format.inc:5-24 ids; ggml quant blocks / f16 / f32, unpadded).
+ * epilogue: 0 none, 1 sigmoid, 2 silu, 3 tanh, 4 relu^2. */
+RWKV_API bool rwkv_b200_matvec(int data_type, int K, int M, int T, const void * weights, const float * x, float * y, int epilogue);
 
 #if defined(__cplusplus)
 }

@@ -219,21 +219,86 @@ uint64_t rwkv_b200_bytes_per_token(const struct rwkv_context * ctx, bool with_lo
     return (uint64_t) (m.weight_bytes_per_token - (with_logits ? 0 : m.head_bytes) + 2 * 4 * m.state_len());
 }
 
-float rwkv_b200_time_resident(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, bool want_logits, int warmup, int iters) {
+float rwkv_b200_time_resident(struct rwkv_context * ctx, const uint32_t * tokens, size_t tokens_per_step, int n_steps, int warmup_steps, bool want_logits) {
     Context * c = C(ctx);
     cudaEvent_t e0, e1;
-    if (cudaSetDevice(c->model->dev.device) != cudaSuccess) return -1.f;
-    for (int i = 0; i < warmup; i++) if (!rwkv_b200_eval_resident(ctx, tokens, n_tokens, want_logits, nullptr)) return -1.f;
+    if (!tokens || tokens_per_step == 0 || n_steps <= 0 || cudaSetDevice(c->model->dev.device) != cudaSuccess) return -1.f;
+    const uint32_t * t = tokens;
+    for (int i = 0; i < warmup_steps; i++, t += tokens_per_step) if (!rwkv_b200_eval_resident(ctx, t, tokens_per_step, want_logits, nullptr)) return -1.f;
     if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1.f;
     cudaStreamSynchronize(c->stream);
     cudaEventRecord(e0, c->stream);
     bool ok = true;
-    for (int i = 0; i < iters && ok; i++) ok = rwkv_b200_eval_resident(ctx, tokens, n_tokens, want_logits, nullptr);
+    for (int i = 0; i < n_steps && ok; i++, t += tokens_per_step) ok = rwkv_b200_eval_resident(ctx, t, tokens_per_step, want_logits, nullptr);
     cudaEventRecord(e1, c->stream);
     float ms = -1.f;
     if (ok && cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return ok ? ms : -1.f;
+}
+
+bool rwkv_b200_profile_pass(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, bool want_logits, struct rwkv_b200_profile * out) {
+    Context * c = C(ctx);
+    c->last_error = RWKV_ERROR_NONE;
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, tokens && out && n_tokens > 0 && n_tokens <= (size_t) MAX_TOKENS_PER_PASS, "Invalid profile arguments");
+    memset(out, 0, sizeof(*out));
+    c->profiling = true;
+    const unsigned long long before = g_kernel_launches;
+    bool ok = rwkv_b200_eval_resident(ctx, tokens, n_tokens, want_logits, nullptr) && cudaStreamSynchronize(c->stream) == cudaSuccess;
+    c->profiling = false;
+    out->total_launches = (uint32_t) (g_kernel_launches - before);
+    if (ok) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop);
+        out->pass_ms = ms;
+        for (auto & r : c->prof) {
+            cudaEventElapsedTime(&ms, r.start, r.stop);
+            out->gemv_ms += ms; out->gemv_bytes += r.bytes; out->gemv_launches++;
+            if (ms > out->top_ms) { out->top_ms = ms; out->top_bytes = r.bytes; }
+        }
+    }
+    for (auto & r : c->prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
+    c->prof.clear();
+    return ok;
+}
+
+void rwkv_b200_set_graphs(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_graphs = enabled; }
+
+bool rwkv_b200_matvec(int data_type, int K, int M, int T, const void * weights, const float * x, float * y, int epilogue) {
+    g_last_error = RWKV_ERROR_NONE;
+    ErrorSink sink = global_sink();
+    RWKV_CHECK(sink, RWKV_ERROR_ARGS, false, weights && x && y && K > 0 && M > 0 && T > 0 && dtype_supported(data_type) && K % dtype_block_elems(data_type) == 0 && epilogue >= 0 && epilogue <= EPI_RELU_SQR,
+               "Invalid matvec arguments");
+    int dev = default_device(), n_dev = 0;
+    RWKV_CHECK(sink, RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, cudaGetDeviceCount(&n_dev) == cudaSuccess && dev < n_dev && cudaSetDevice(dev) == cudaSuccess,
+               "No usable CUDA device; this engine has no CPU execution path");
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, dev);
+    DeviceInfo di{dev, prop.multiProcessorCount, (int) prop.sharedMemPerBlockOptin};
+    const size_t row_bytes = tensor_nbytes(data_type, (uint64_t) K, 1, 1);
+    size_t unit_bytes = row_bytes;
+    if (data_type == DT_Q4_0 || data_type == DT_Q5_0 || data_type == DT_Q8_0) unit_bytes = (size_t) ((K / 32 + 1) / 2 * 2) * dtype_block_bytes(data_type);
+    const size_t pitch = (unit_bytes + 15) / 16 * 16;
+    uint8_t * dW = nullptr; float * dx = nullptr, * dy = nullptr;
+    bool ok = cudaMalloc((void **) &dW, pitch * M + 256) == cudaSuccess && cudaMalloc((void **) &dx, sizeof(float) * K * T) == cudaSuccess &&
+              cudaMalloc((void **) &dy, sizeof(float) * M * T) == cudaSuccess;
+    ok = ok && cudaMemset(dW, 0, pitch * M + 256) == cudaSuccess &&
+         cudaMemcpy2D(dW, pitch, weights, row_bytes, row_bytes, M, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(dx, x, sizeof(float) * K * T, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok) {
+        GemvBatch b;
+        memset(&b, 0, sizeof(b));
+        b.n = 1; b.T = T;
+        GemvProblem & p = b.p[0];
+        p.W = dW; p.pitch = (long long) pitch; p.type = data_type; p.K = K; p.M = M;
+        p.x = dx; p.ldx = K; p.y = dy; p.ldy = M; p.epi = epilogue; p.pro = PRO_NONE;
+        ok = gemv_launch(b, di, 0) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess &&
+             cudaMemcpy(y, dy, sizeof(float) * M * T, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaFree(dW); cudaFree(dx); cudaFree(dy);
+    RWKV_CHECK(sink, RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, ok, "matvec failed on the device: %s", cudaGetErrorString(e));
+    return true;
 }
 
 }  // extern "C"

@@ -77,7 +77,19 @@ struct Batch {
                     "CUDA error: %s", cudaGetErrorString(_e)); } while (0)
 
 bool run_batch(Context * ctx, Batch & batch) {
+    if (!ctx->profiling) {
+        CUDA_OK(ctx, gemv_launch(batch.b, ctx->model->dev, ctx->stream));
+        return true;
+    }
+    Context::ProfRecord rec{};
+    CUDA_OK(ctx, cudaEventCreate(&rec.start));
+    CUDA_OK(ctx, cudaEventCreate(&rec.stop));
+    for (int i = 0; i < batch.b.n; i++)
+        rec.bytes += (double) tensor_nbytes(batch.b.p[i].type, (uint64_t) batch.b.p[i].K, (uint64_t) batch.b.p[i].M, 1);
+    CUDA_OK(ctx, cudaEventRecord(rec.start, ctx->stream));
     CUDA_OK(ctx, gemv_launch(batch.b, ctx->model->dev, ctx->stream));
+    CUDA_OK(ctx, cudaEventRecord(rec.stop, ctx->stream));
+    ctx->prof.push_back(rec);
     return true;
 }
 
@@ -275,31 +287,33 @@ bool ensure_capacity(Context * ctx, int T) {
     if (cap > MAX_TOKENS_PER_PASS) cap = MAX_TOKENS_PER_PASS;
     if (ctx->scratch) { cudaFree(ctx->scratch); ctx->scratch = nullptr; }
     if (ctx->tokens) { cudaFree(ctx->tokens); ctx->tokens = nullptr; }
-    if (ctx->tokens_host) { cudaFreeHost(ctx->tokens_host); ctx->tokens_host = nullptr; }
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 2; i++) {
+        if (ctx->tokens_host[i]) { cudaFreeHost(ctx->tokens_host[i]); ctx->tokens_host[i] = nullptr; }
+        ctx->slot_used[i] = false;
+    }
+    for (auto & row : ctx->graphs) for (auto & g : row) { if (g.exec) cudaGraphExecDestroy(g.exec); g = Context::GraphSlot(); }
     ctx->capacity_T = 0;
     const size_t n = scratch_floats_for(m, cap);
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ctx->scratch), n * sizeof(float));
     RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, false, e == cudaSuccess, "Failed to allocate %zu bytes of activation memory: %s", n * sizeof(float), cudaGetErrorString(e));
     e = cudaMalloc(reinterpret_cast<void **>(&ctx->tokens), (size_t) cap * sizeof(int));
     RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, false, e == cudaSuccess, "Failed to allocate the token buffer: %s", cudaGetErrorString(e));
-    e = cudaMallocHost(reinterpret_cast<void **>(&ctx->tokens_host), (size_t) cap * sizeof(int));
-    RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, false, e == cudaSuccess, "Failed to allocate pinned token staging: %s", cudaGetErrorString(e));
+    for (int i = 0; i < 2; i++) {
+        e = cudaMallocHost(reinterpret_cast<void **>(&ctx->tokens_host[i]), (size_t) cap * sizeof(int));
+        RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, false, e == cudaSuccess, "Failed to allocate pinned token staging: %s", cudaGetErrorString(e));
+    }
     ctx->scratch_floats = n;
     ctx->capacity_T = cap;
     return true;
 }
 
-// One pass of at most MAX_TOKENS_PER_PASS tokens: state_a -> state_b, then swap.
-bool forward_pass(Context * ctx, const uint32_t * tokens, int T, bool want_logits) {
+// Enqueues one pass (token upload + every kernel) on ctx->stream; pure stream work, so it can be captured.
+bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase) {
     const Model & m = *ctx->model;
     const int C = m.n_embed;
-    if (!ensure_capacity(ctx, T)) return false;
     const Scratch s = carve(m, ctx->scratch, T);
-    for (int t = 0; t < T; t++) ctx->tokens_host[t] = (int) tokens[t];
-    // the previous pass may still be reading tokens_host through its async copy
-    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    CUDA_OK(ctx, cudaMemcpyAsync(ctx->tokens, ctx->tokens_host, (size_t) T * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_OK(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    CUDA_OK(ctx, cudaMemcpyAsync(ctx->tokens, ctx->tokens_host[phase], (size_t) T * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_OK(ctx, launch_embed_ln0(m.emb.data, m.emb.type, m.emb.pitch, ctx->tokens, T, C, m.ln0_w.data, m.ln0_b.data, s.x, ctx->stream));
     const size_t per_layer = m.state_floats_per_layer();
     for (int i = m.layer_begin; i < m.layer_end; i++) {
@@ -321,8 +335,42 @@ bool forward_pass(Context * ctx, const uint32_t * tokens, int T, bool want_logit
         p.pro = PRO_LAYERNORM; p.ln_w = m.ln_out_w.data; p.ln_b = m.ln_out_b.data;
         if (!run_batch(ctx, b)) return false;
     }
+    return true;
+}
+
+// One pass of at most MAX_TOKENS_PER_PASS tokens: state_a -> state_b, then swap.
+bool forward_pass(Context * ctx, const uint32_t * tokens, int T, bool want_logits) {
+    if (!ensure_capacity(ctx, T)) return false;
+    const int phase = ctx->phase;
+    if (ctx->slot_used[phase]) CUDA_OK(ctx, cudaEventSynchronize(ctx->slot_free[phase]));   // pass n-2 has consumed this slot
+    for (int t = 0; t < T; t++) ctx->tokens_host[phase][t] = (int) tokens[t];
+    CUDA_OK(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    Context::GraphSlot * g = (T == 1 && ctx->use_graphs && !ctx->profiling) ? &ctx->graphs[want_logits ? 1 : 0][phase] : nullptr;
+    if (g && g->exec) {
+        CUDA_OK(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+        g_kernel_launches += g->launches;
+    } else if (g && g->uses >= 1) {
+        // second use of this (logits, phase) combination: capture the launch sequence once, replay from now on
+        const unsigned long long before = g_kernel_launches;
+        CUDA_OK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        const bool ok = enqueue_pass(ctx, T, want_logits, phase);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, ok && e == cudaSuccess && graph, "CUDA graph capture failed: %s", cudaGetErrorString(e));
+        g->launches = g_kernel_launches - before;
+        e = cudaGraphInstantiate(&g->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, e == cudaSuccess, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        CUDA_OK(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+    } else {
+        if (g) g->uses++;
+        if (!enqueue_pass(ctx, T, want_logits, phase)) return false;
+    }
     CUDA_OK(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+    CUDA_OK(ctx, cudaEventRecord(ctx->slot_free[phase], ctx->stream));
+    ctx->slot_used[phase] = true;
     float * tmp = ctx->state_a; ctx->state_a = ctx->state_b; ctx->state_b = tmp;
+    ctx->phase ^= 1;
     return true;
 }
 
@@ -347,6 +395,8 @@ Context * create_context(Model * model, ErrorSink sink) {
     bool ok = cudaSetDevice(model->dev.device) == cudaSuccess
         && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess
         && cudaEventCreate(&ctx->ev_start) == cudaSuccess && cudaEventCreate(&ctx->ev_stop) == cudaSuccess
+        && cudaEventCreateWithFlags(&ctx->slot_free[0], cudaEventDisableTiming) == cudaSuccess
+        && cudaEventCreateWithFlags(&ctx->slot_free[1], cudaEventDisableTiming) == cudaSuccess
         && cudaMalloc(reinterpret_cast<void **>(&ctx->state_a), n * sizeof(float)) == cudaSuccess
         && cudaMalloc(reinterpret_cast<void **>(&ctx->state_b), n * sizeof(float)) == cudaSuccess
         && cudaMalloc(reinterpret_cast<void **>(&ctx->state_init), n * sizeof(float)) == cudaSuccess
@@ -371,7 +421,12 @@ void destroy_context(Context * ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->state_a); cudaFree(ctx->state_b); cudaFree(ctx->state_init); cudaFree(ctx->logits);
     cudaFree(ctx->tokens); cudaFree(ctx->scratch);
-    if (ctx->tokens_host) cudaFreeHost(ctx->tokens_host);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->tokens_host[i]) cudaFreeHost(ctx->tokens_host[i]);
+        if (ctx->slot_free[i]) cudaEventDestroy(ctx->slot_free[i]);
+    }
+    for (auto & row : ctx->graphs) for (auto & g : row) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto & r : ctx->prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

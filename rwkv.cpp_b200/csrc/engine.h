@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <vector>
 
 #include "model.h"
 
@@ -23,8 +24,21 @@ struct Context {
     float * scratch = nullptr;       // activation arena for capacity_T tokens
     size_t scratch_floats = 0;
     int capacity_T = 0;
-    // pinned host staging for tokens
-    int * tokens_host = nullptr;
+    // Two pinned token slots, used alternately (`phase`): the host may prepare pass n+1 while pass n runs.
+    int * tokens_host[2] = {nullptr, nullptr};
+    cudaEvent_t slot_free[2] = {nullptr, nullptr};   // recorded after the pass that last read the slot
+    bool slot_used[2] = {false, false};
+    int phase = 0;                   // flips every pass together with the state_a/state_b swap
+
+    // CUDA graphs for single-token passes, keyed by [want_logits][phase]; captured on the second use.
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; int uses = 0; unsigned long long launches = 0; };
+    GraphSlot graphs[2][2];
+    bool use_graphs = true;
+
+    // Profiling mode (bench.py roofline leg): CUDA events around every GEMV launch, graphs off.
+    bool profiling = false;
+    struct ProfRecord { cudaEvent_t start, stop; double bytes; };
+    std::vector<ProfRecord> prof;
 
     float last_device_ms = 0.f;      // CUDA-event time of the last forward (kernels only)
     int last_error = 0;              // rwkv_error_flags

@@ -26,6 +26,11 @@ class FileInfo(ctypes.Structure):   # include/rwkv_b200.h: struct rwkv_b200_file
                [(n, ctypes.c_uint64) for n in ("n_tensors", "file_size", "state_len", "bytes_per_token")]
 
 
+class ProfileResult(ctypes.Structure):   # include/rwkv_b200.h: struct rwkv_b200_profile
+    _fields_ = [(n, ctypes.c_double) for n in ("gemv_ms", "gemv_bytes", "pass_ms", "top_ms", "top_bytes")] + \
+               [(n, ctypes.c_uint32) for n in ("gemv_launches", "total_launches")]
+
+
 class RWKVContext:
     def __init__(self, ptr: ctypes.c_void_p) -> None:
         self.ptr = ptr
@@ -91,8 +96,14 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_kernel_launch_count.restype = ctypes.c_uint64
         lib.rwkv_b200_bytes_per_token.argtypes = [vp, ctypes.c_bool]
         lib.rwkv_b200_bytes_per_token.restype = ctypes.c_uint64
-        lib.rwkv_b200_time_resident.argtypes = [vp, P_U32, ctypes.c_size_t, ctypes.c_bool, ctypes.c_int, ctypes.c_int]
+        lib.rwkv_b200_time_resident.argtypes = [vp, P_U32, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_bool]
         lib.rwkv_b200_time_resident.restype = ctypes.c_float
+        lib.rwkv_b200_profile_pass.argtypes = [vp, P_U32, ctypes.c_size_t, ctypes.c_bool, ctypes.POINTER(ProfileResult)]
+        lib.rwkv_b200_profile_pass.restype = ctypes.c_bool
+        lib.rwkv_b200_set_graphs.argtypes = [vp, ctypes.c_bool]
+        lib.rwkv_b200_set_graphs.restype = None
+        lib.rwkv_b200_matvec.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, P_FLOAT, P_FLOAT, ctypes.c_int]
+        lib.rwkv_b200_matvec.restype = ctypes.c_bool
 
     # --- rwkv.h -------------------------------------------------------------------------------
     def rwkv_init_from_file(self, model_file_path: str, thread_count: int, gpu_layer_count: int = 0) -> RWKVContext:

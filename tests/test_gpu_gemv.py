@@ -1,0 +1,87 @@
+"""Per-kernel parity: the fused dequantize-GEMV (csrc/kernels/gemv.cu) through the C-ABI test hook against the
+oracle's restatement of ggml_mul_mat for every weight type, ragged shapes, multi-column batches and epilogues.
+Single-op comparisons have no rounding-flip amplification, so the tolerances are tight."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import ggml_file as gf
+import rwkv_oracle as ro
+
+pytestmark = pytest.mark.gpu
+PF = ctypes.POINTER(ctypes.c_float)
+TYPES = ["FP32", "FP16", "Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q8_0"]
+
+
+def make_weights(fmt, M, K, rng):
+    w = (rng.standard_normal((M, K)) / np.sqrt(K)).astype(np.float32)
+    tid = gf.TYPE_IDS[fmt]
+    if fmt == "FP32":
+        raw = w.view(np.uint8).reshape(-1)
+    elif fmt == "FP16":
+        raw = w.astype(np.float16).view(np.uint8).reshape(-1)
+    else:
+        raw = ro.quantize_row_ref(tid, w.reshape(-1))
+    return tid, np.ascontiguousarray(raw)
+
+
+def run(lib, tid, K, M, T, raw, x, epi=0):
+    y = np.zeros((T, M), np.float32)
+    xc = np.ascontiguousarray(x.T)   # [T, K]: column t contiguous
+    ok = lib.library.rwkv_b200_matvec(tid, K, M, T, raw.ctypes.data, xc.ctypes.data_as(PF), y.ctypes.data_as(PF), epi)
+    assert ok
+    return y.T
+
+
+@pytest.mark.parametrize("fmt", TYPES)
+@pytest.mark.parametrize("shape", [(64, 64), (160, 128), (448, 128), (128, 448), (96, 32), (33, 96), (256, 4096), (64, 14336), (1000, 2048)])
+def test_gemv_matches_oracle(lib, fmt, shape):
+    M, K = shape
+    rng = np.random.default_rng(M * 131 + K)
+    tid, raw = make_weights(fmt, M, K, rng)
+    x = rng.standard_normal((K, 1)).astype(np.float32) * 2.0
+    got = run(lib, tid, K, M, 1, raw, x)
+    t = gf.Tensor("w", tid, (K, M), raw)
+    want = ro.Mat(t).mul(x)
+    scale = np.abs(want).max() + 1e-6
+    assert np.abs(got - want).max() / scale < 2e-5, (fmt, shape, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("fmt", TYPES)
+@pytest.mark.parametrize("T", [2, 3, 4, 7, 9])
+def test_gemv_columns_are_batch_invariant(lib, fmt, T):
+    """Each column of a multi-column call is bit-identical to the single-column call (serial == sequence)."""
+    M, K = 192, 320
+    rng = np.random.default_rng(T)
+    tid, raw = make_weights(fmt, M, K, rng)
+    x = rng.standard_normal((K, T)).astype(np.float32)
+    full = run(lib, tid, K, M, T, raw, x)
+    for t in range(T):
+        one = run(lib, tid, K, M, 1, raw, x[:, t:t + 1])
+        assert one.tobytes() == np.ascontiguousarray(full[:, t:t + 1]).tobytes()
+
+
+@pytest.mark.parametrize("epi,fn", [(1, lambda v: 1 / (1 + np.exp(-v))), (2, lambda v: v / (1 + np.exp(-v))), (3, np.tanh), (4, lambda v: np.maximum(v, 0) ** 2)])
+def test_gemv_epilogues(lib, epi, fn):
+    M, K = 128, 256
+    rng = np.random.default_rng(epi)
+    tid, raw = make_weights("Q5_1", M, K, rng)
+    x = rng.standard_normal((K, 1)).astype(np.float32)
+    base = run(lib, tid, K, M, 1, raw, x)
+    got = run(lib, tid, K, M, 1, raw, x, epi)
+    assert np.abs(got - fn(base.astype(np.float64))).max() < 1e-5
+
+
+def test_gemv_zero_and_extreme_activations(lib):
+    """All-zero blocks (amax == 0 -> id = 0, ggml-cpu-quants.c:806) and large magnitudes."""
+    M, K = 64, 128
+    rng = np.random.default_rng(5)
+    for fmt in ("Q4_0", "Q5_1", "Q8_0"):
+        tid, raw = make_weights(fmt, M, K, rng)
+        x = np.zeros((K, 1), np.float32)
+        assert not run(lib, tid, K, M, 1, raw, x).any()
+        x[40:44, 0] = [1e4, -3e4, 2.5e4, 1.0]
+        got = run(lib, tid, K, M, 1, raw, x)
+        want = ro.Mat(gf.Tensor("w", tid, (K, M), raw)).mul(x)
+        assert np.abs(got - want).max() / np.abs(want).max() < 2e-5

@@ -1,0 +1,185 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every declared symbol, the file
+reader / quantizer / error layer behave like the reference's, and the device code's bit twiddling is right (compiled
+for the host). No kernel is launched here."""
+import ctypes
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import QUANT_FORMATS, ROOT, VERSIONS, has_gpu, model_path
+import ggml_file as gf
+import rwkv_oracle as ro
+
+ERR = dict(ARGS=1 << 8, FILE=2 << 8, MODEL=3 << 8, MODEL_PARAMS=4 << 8, GRAPH=5 << 8, CTX=6 << 8, ALLOC=1, FILE_OPEN=2, FILE_STAT=3,
+           FILE_READ=4, FILE_WRITE=5, FILE_MAGIC=6, FILE_VERSION=7, DATA_TYPE=8, UNSUPPORTED=9, SHAPE=10, DIMENSION=11, KEY=12,
+           DATA=13, PARAM_MISSING=14)
+
+
+def test_exports_every_declared_symbol(lib):
+    declared = set()
+    for header in ("rwkv.h", "rwkv_b200.h"):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        declared |= set(re.findall(r"RWKV_API[^;(]*?\b(rwkv_[a-z0-9_]+)\s*\(", text))
+    assert len(declared) >= 29
+    out = subprocess.run(["nm", "-D", "--defined-only", lib.path], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (rwkv_[a-z0-9_]+)", out))
+    assert declared <= exported, declared - exported
+    for name in declared:
+        getattr(lib.library, name)
+    # nothing from the oracle or torch leaks into the product library
+    deps = subprocess.run(["ldd", lib.path], capture_output=True, text=True).stdout
+    assert "torch" not in deps and "rwkv_ref" not in deps
+
+
+def test_reference_abi_signatures_match():
+    """Same exported names as the reference library; compares against oracle/_ref when it is present."""
+    import ref_lib
+    path = ref_lib.reference_library_path()
+    if path is None:
+        pytest.skip("oracle/_ref not built")
+    ref_syms = set(re.findall(r" T (rwkv_[a-z0-9_]+)", subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout))
+    import __graft_entry__
+    ours = set(re.findall(r" T (rwkv_[a-z0-9_]+)", subprocess.run(["nm", "-D", "--defined-only", __graft_entry__.load_package().library_path()],
+                                                                 capture_output=True, text=True).stdout))
+    assert ref_syms <= ours, ref_syms - ours
+
+
+@pytest.mark.parametrize("ver", VERSIONS)
+def test_inspect_file_matches_oracle(lib, ver):
+    for fmt in ("FP32", "Q5_1"):
+        info = lib.rwkv_b200_inspect_file(model_path(ver, fmt))
+        m = ro.OracleModel(model_path(ver, fmt))
+        assert (info.n_vocab, info.n_embed, info.n_layer) == (m.n_vocab, m.n_embed, m.n_layer)
+        assert (info.arch_major, info.arch_minor) == (m.major, m.minor)
+        assert (info.head_count, info.head_size) == (m.head_count, m.head_size)
+        assert info.state_len == m.state_len
+        assert info.n_tensors == len(m.file.tensors)
+        assert info.bytes_per_token == ro.bytes_per_token(model_path(ver, fmt))
+
+
+def test_file_errors(lib, tmp_path):
+    from rwkv_cpp_b200.shared_library import FileInfo
+    lib.rwkv_set_print_errors(None, False)
+
+    def inspect(path):   # raw C call: returns (ok, flags)
+        ok = lib.library.rwkv_b200_inspect_file(str(path).encode(), ctypes.byref(FileInfo()))
+        return ok, lib.rwkv_get_last_error(None)
+
+    assert inspect("/nonexistent/model.bin") == (False, ERR["FILE"] | ERR["FILE_OPEN"])   # rwkv_model_loading.inc:295
+    assert lib.rwkv_get_last_error(None) == 0                                              # reading clears (rwkv.cpp:229-234)
+    assert inspect(model_path("4v0-660K", "FP32")) == (True, 0)
+    good = open(model_path("4v0-660K", "FP32"), "rb").read()
+    cases = {
+        "magic": (struct.pack("<I", 0x12345678) + good[4:], ERR["FILE"] | ERR["FILE_MAGIC"]),        # rwkv_file_format.inc:117
+        "version": (good[:4] + struct.pack("<I", 99) + good[8:], ERR["FILE"] | ERR["FILE_VERSION"]),  # :118
+        "dtype": (good[:20] + struct.pack("<I", 4) + good[24:], ERR["FILE"] | ERR["DATA_TYPE"]),     # Q4_1_O removed format, :123-130
+        "short": (good[:10], ERR["FILE"] | ERR["FILE_READ"]),                                         # :116
+    }
+    for name, (blob, want) in cases.items():
+        p = tmp_path / f"{name}.bin"
+        p.write_bytes(blob)
+        assert inspect(p) == (False, want), name
+    p = tmp_path / "truncated.bin"
+    p.write_bytes(good[:len(good) // 2])
+    ok, flags = inspect(p)
+    assert not ok and flags & ERR["MODEL_PARAMS"]
+    # quantised payload in a version-100 file is rejected (rwkv_file_format.inc:132-139)
+    q = open(model_path("4v0-660K", "Q5_1"), "rb").read()
+    p = tmp_path / "oldq.bin"
+    p.write_bytes(q[:4] + struct.pack("<I", 100) + q[8:])
+    assert inspect(p) == (False, ERR["FILE"] | ERR["DATA_TYPE"])
+    with pytest.raises(ValueError):
+        lib.rwkv_b200_inspect_file(str(p))
+
+
+def test_print_errors_flag(lib):
+    assert lib.rwkv_get_print_errors(None) is False
+    lib.rwkv_set_print_errors(None, True)
+    assert lib.rwkv_get_print_errors(None) is True
+    lib.rwkv_set_print_errors(None, False)
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the product must fail loudly -- there is no host execution path to fall back to."""
+    with pytest.raises(ValueError):
+        lib.rwkv_init_from_file(model_path("6v0-3m", "FP32"), 1, 0)
+    lib.rwkv_init_from_file  # noqa
+    ptr = lib.library.rwkv_init_from_file(model_path("6v0-3m", "FP32").encode(), 1, 0)
+    assert not ptr
+    assert lib.rwkv_get_last_error(None) == ERR["CTX"] | ERR["UNSUPPORTED"]
+    y = np.zeros(4, np.float32)
+    ok = lib.library.rwkv_b200_matvec(0, 4, 4, 1, np.eye(4, dtype=np.float32).ctypes.data, y.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                      y.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 0)
+    assert not ok
+
+
+@pytest.mark.parametrize("fmt", QUANT_FORMATS)
+def test_quantizer_bit_exact_vs_oracle(lib, fmt, tmp_path):
+    """rwkv_quantize_model_file (rwkv_quantize.inc:16-171) vs the numpy restatement of quantize_row_*_ref, tensor by tensor."""
+    for ver, src in (("6v0-3m", "FP32"), ("7v0-834K", "FP16"), ("5v1-730K", "FP32")):
+        out = tmp_path / f"{ver}-{src}-{fmt}.bin"
+        lib.rwkv_quantize_model_file(model_path(ver, src), str(out), fmt)
+        a, b = gf.read_model_file(model_path(ver, src)), gf.read_model_file(str(out))
+        assert b.version == 101 and b.data_type == gf.TYPE_IDS[fmt] and list(a.tensors) == list(b.tensors)
+        n_quant = 0
+        for name, ta in a.tensors.items():
+            tb = b.tensors[name]
+            assert ta.ne == tb.ne
+            skip = name in ("emb.weight", "head.weight") or any(s in name for s in ("att.v1", "att.v2", "att.g1", "att.g2", "att.a1", "att.a2", "att.w1", "att.w2", "att.r_k"))
+            if len(ta.ne) == 2 and not skip:
+                n_quant += 1
+                assert tb.dtype == gf.TYPE_IDS[fmt], name
+                x = ro.dequantize(ta.dtype, ta.raw, int(np.prod(ta.ne)))
+                assert np.array_equal(ro.quantize_row_ref(tb.dtype, x), tb.raw), name
+            else:
+                assert tb.dtype == ta.dtype and np.array_equal(ta.raw, tb.raw), name
+        assert n_quant > 0
+
+
+def test_quantizer_matches_compiled_reference(lib, tmp_path):
+    import filecmp
+    import ref_lib
+    if ref_lib.reference_library_path() is None:
+        pytest.skip("oracle/_ref not built")
+    ref = ref_lib.load_reference_library()
+    ref.rwkv_set_print_errors(None, False)
+    for ver in ("4v0-660K", "6v0-3m"):
+        for fmt in QUANT_FORMATS:
+            a, b = tmp_path / "a.bin", tmp_path / "b.bin"
+            lib.rwkv_quantize_model_file(model_path(ver, "FP16"), str(a), fmt)
+            assert ref.rwkv_quantize_model_file(model_path(ver, "FP16").encode(), str(b).encode(), fmt.encode())
+            assert filecmp.cmp(a, b, shallow=False), (ver, fmt)
+
+
+def test_quantizer_errors(lib, tmp_path):
+    with pytest.raises(ValueError):
+        lib.rwkv_quantize_model_file(model_path("4v0-660K", "FP32"), str(tmp_path / "x.bin"), "Q3_K")
+    assert not lib.library.rwkv_quantize_model_file(model_path("4v0-660K", "FP32").encode(), str(tmp_path / "x.bin").encode(), b"FP16")
+    assert lib.rwkv_get_last_error(None) == ERR["ARGS"] | ERR["DATA_TYPE"]          # rwkv_quantize.inc:20-25
+    assert not lib.library.rwkv_quantize_model_file(model_path("4v0-660K", "Q5_1").encode(), str(tmp_path / "x.bin").encode(), b"Q4_0")
+    assert lib.rwkv_get_last_error(None) == ERR["FILE"]                              # input must be FP32/FP16 (rwkv_quantize.inc:45-50)
+
+
+def test_device_bit_twiddling_on_host(tmp_path):
+    """Compiles the __host__ __device__ quant decoding of the GEMV kernel for the CPU and checks it against a scalar decode."""
+    exe = tmp_path / "host_kernels_check"
+    cmd = ["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-ffp-contract=off,-Wno-unknown-pragmas",
+           "-o", str(exe), os.path.join(ROOT, "tests", "host_kernels_check.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+
+
+def test_synthetic_model_loads_in_oracle(tmp_path):
+    import synthetic_model as sm
+    p = tmp_path / "syn.bin"
+    sm.write_direct(str(p), "rwkv6-small", "Q5_1", seed=3)
+    m = ro.OracleModel(str(p))
+    logits, state = m.eval_sequence(sm.synthetic_tokens(4, m.n_vocab))
+    assert np.isfinite(logits).all() and 0.3 < logits.std() < 3.0
