@@ -57,6 +57,13 @@ struct rwkv_b200_profile {
 };
 RWKV_API bool rwkv_b200_profile_pass(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, bool want_logits, struct rwkv_b200_profile * out);
 
+/* In-kernel timeline (stand-in for nsys): after rwkv_b200_trace_enable every kernel of a pass folds %globaltimer of its first
+ * and last CTA into one record, also inside CUDA-graph replays. rwkv_b200_trace_read returns the records of the most recent
+ * pass (microseconds relative to the first kernel's start, names up to 31 chars) and re-arms the buffer. */
+RWKV_API bool rwkv_b200_trace_enable(struct rwkv_context * ctx);
+RWKV_API void rwkv_b200_trace_set_marks_buffer(double * marks_us);   /* optional [max_records][4]: intra-kernel marks of CTA 0 */
+RWKV_API int rwkv_b200_trace_read(struct rwkv_context * ctx, double * start_us, double * end_us, char (*names)[32], int max_records);
+
 /* Enables / disables CUDA-graph replay of single-token passes (on by default). */
 RWKV_API void rwkv_b200_set_graphs(struct rwkv_context * ctx, bool enabled);
 

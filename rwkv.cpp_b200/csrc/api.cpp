@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -263,6 +264,44 @@ bool rwkv_b200_profile_pass(struct rwkv_context * ctx, const uint32_t * tokens, 
 }
 
 void rwkv_b200_set_graphs(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_graphs = enabled; }
+
+static bool trace_rearm(Context * c) {
+    std::vector<TraceRec> init(1024);
+    for (auto & r : init) { r.start = ~0ull; r.end = 0; for (auto & m : r.mark) m = 0; }
+    return cudaMemcpy(c->trace_buf, init.data(), init.size() * sizeof(TraceRec), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
+bool rwkv_b200_trace_enable(struct rwkv_context * ctx) {
+    Context * c = C(ctx);
+    if (cudaSetDevice(c->model->dev.device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
+    if (!c->trace_buf && cudaMalloc((void **) &c->trace_buf, 1024 * sizeof(TraceRec)) != cudaSuccess) return false;
+    // graphs captured so far carry no trace slots: drop them so they are re-captured
+    for (auto & row : c->graphs) for (auto & g : row) { if (g.exec) cudaGraphExecDestroy(g.exec); g = Context::GraphSlot(); }
+    return trace_rearm(c);
+}
+
+// marks_us: optional [max_records][4] intra-kernel marks of CTA 0 (-1 when absent)
+static double * g_trace_marks_out = nullptr;
+void rwkv_b200_trace_set_marks_buffer(double * marks_us) { g_trace_marks_out = marks_us; }
+
+int rwkv_b200_trace_read(struct rwkv_context * ctx, double * start_us, double * end_us, char (*names)[32], int max_records) {
+    Context * c = C(ctx);
+    if (!c->trace_buf || cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    std::vector<TraceRec> recs(1024);
+    if (cudaMemcpy(recs.data(), c->trace_buf, recs.size() * sizeof(TraceRec), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    const int n = c->trace_count < max_records ? c->trace_count : max_records;
+    unsigned long long t0 = ~0ull;
+    for (int i = 0; i < n; i++) if (recs[i].start < t0) t0 = recs[i].start;
+    for (int i = 0; i < n; i++) {
+        start_us[i] = recs[i].start == ~0ull ? -1.0 : (double) (recs[i].start - t0) * 1e-3;
+        end_us[i] = recs[i].end == 0 ? -1.0 : (double) (recs[i].end - t0) * 1e-3;
+        if (g_trace_marks_out) for (int k = 0; k < 4; k++) g_trace_marks_out[i * 4 + k] = recs[i].mark[k] ? (double) (recs[i].mark[k] - t0) * 1e-3 : -1.0;
+        const char * nm = g_trace_names[i] ? g_trace_names[i] : "?";
+        strncpy(names[i], nm, 31); names[i][31] = 0;
+    }
+    trace_rearm(c);
+    return n;
+}
 
 bool rwkv_b200_matvec(int data_type, int K, int M, int T, const void * weights, const float * x, float * y, int epilogue) {
     g_last_error = RWKV_ERROR_NONE;

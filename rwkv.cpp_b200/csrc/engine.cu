@@ -311,6 +311,8 @@ bool ensure_capacity(Context * ctx, int T) {
 // Enqueues one pass (token upload + every kernel) on ctx->stream; pure stream work, so it can be captured.
 bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase) {
     const Model & m = *ctx->model;
+    g_trace_base = ctx->trace_buf;
+    g_trace_next = 0;
     const int C = m.n_embed;
     const Scratch s = carve(m, ctx->scratch, T);
     CUDA_OK(ctx, cudaMemcpyAsync(ctx->tokens, ctx->tokens_host[phase], (size_t) T * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -335,6 +337,8 @@ bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase) {
         p.pro = PRO_LAYERNORM; p.ln_w = m.ln_out_w.data; p.ln_b = m.ln_out_b.data;
         if (!run_batch(ctx, b)) return false;
     }
+    if (ctx->trace_buf) ctx->trace_count = g_trace_next;
+    g_trace_base = nullptr;
     return true;
 }
 
@@ -420,7 +424,7 @@ void destroy_context(Context * ctx) {
     if (model) cudaSetDevice(model->dev.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->state_a); cudaFree(ctx->state_b); cudaFree(ctx->state_init); cudaFree(ctx->logits);
-    cudaFree(ctx->tokens); cudaFree(ctx->scratch);
+    cudaFree(ctx->tokens); cudaFree(ctx->scratch); cudaFree(ctx->trace_buf);
     for (int i = 0; i < 2; i++) {
         if (ctx->tokens_host[i]) cudaFreeHost(ctx->tokens_host[i]);
         if (ctx->slot_free[i]) cudaEventDestroy(ctx->slot_free[i]);

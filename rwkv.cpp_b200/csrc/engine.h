@@ -40,6 +40,9 @@ struct Context {
     struct ProfRecord { cudaEvent_t start, stop; double bytes; };
     std::vector<ProfRecord> prof;
 
+    TraceRec * trace_buf = nullptr;  // in-kernel timeline records (rwkv_b200_trace_*), 1024 slots
+    int trace_count = 0;             // slots used by the last enqueued / captured pass
+
     float last_device_ms = 0.f;      // CUDA-event time of the last forward (kernels only)
     int last_error = 0;              // rwkv_error_flags
     bool print_errors = true;

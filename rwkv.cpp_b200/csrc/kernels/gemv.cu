@@ -17,10 +17,14 @@
 #include "quant_decode.cuh"
 
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace rwkv {
 
 unsigned long long g_kernel_launches = 0;
+TraceRec * g_trace_base = nullptr;
+int g_trace_next = 0;
+const char * g_trace_names[1024];
 
 namespace {
 
@@ -241,6 +245,8 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvBatch batc
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ double red[GEMV_WARPS + 1];
     __shared__ GemvProblem P;
+    trace_begin(batch.trace);
+    pdl_prologue();
 
     {   // which problem does this CTA serve?
         int pi = 0;
@@ -279,6 +285,7 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvBatch batc
             }
         }
     }
+    trace_end(batch.trace);
 }
 
 template <int NC>
@@ -289,15 +296,26 @@ cudaError_t launch_nc(const GemvBatch & batch, int grid, size_t smem, int max_op
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    gemv_kernel<NC><<<grid, GEMV_THREADS, smem, stream>>>(batch);
     g_kernel_launches++;
-    return cudaGetLastError();
+    return launch_pdl(gemv_kernel<NC>, dim3(grid), dim3(GEMV_THREADS), smem, stream, batch);
 }
 
 }  // namespace
 
 cudaError_t gemv_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream) {
     if (batch.n <= 0 || batch.T <= 0) return cudaSuccess;
+    static const bool force_generic = getenv("RWKV_B200_GENERIC_GEMV") != nullptr;
+    static const bool no_pdl = getenv("RWKV_B200_NO_PDL") != nullptr;
+    if (no_pdl) g_use_pdl = false;
+    if (!force_generic) {
+        cudaError_t e = gemv_tma_launch(batch, dev, stream);
+        if (e != cudaErrorNotSupported) return e;
+    }
+    return gemv_generic_launch(batch, dev, stream);
+}
+
+cudaError_t gemv_generic_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream) {
+    batch.trace = trace_slot("gemv_generic");
     // CTA budget split over the problems in proportion to their weight bytes.
     const int total_ctas = dev.num_sms * CTAS_PER_SM;
     double total_bytes = 0;

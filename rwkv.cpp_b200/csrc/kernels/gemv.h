@@ -34,18 +34,74 @@ struct GemvProblem {
     const float * ln_w; const float * ln_b;  // [K]
     int epi, pro;
     int first_cta, n_cta;                 // filled by gemv_launch
+    int wk, g, tile_rows;                 // streaming kernel only: warps sharing a row along K, lanes per row, rows per TMA tile
 };
+
+// In-kernel timeline (our stand-in for nsys, which this image lacks): when a trace slot is attached, thread 0 of every
+// CTA folds %globaltimer into [min start, max end] of the slot. Works inside CUDA-graph replays.
+struct TraceRec { unsigned long long start, end, mark[4]; };   // mark[]: optional intra-kernel points of CTA 0
+extern TraceRec * g_trace_base;        // device buffer, or nullptr when tracing is off
+extern int g_trace_next;               // next free slot of the current pass
+extern const char * g_trace_names[1024];
+inline TraceRec * trace_slot(const char * name) {
+    if (!g_trace_base || g_trace_next >= 1024) return nullptr;
+    g_trace_names[g_trace_next] = name;
+    return g_trace_base + g_trace_next++;
+}
 
 constexpr int GEMV_MAX_PROBLEMS = 8;
 struct GemvBatch {
     int n, T;
+    TraceRec * trace;
+    long long max_col_bytes, stage_bytes; // streaming kernel only: shared-memory carve-up
     GemvProblem p[GEMV_MAX_PROBLEMS];
 };
 
 struct DeviceInfo { int device; int num_sms; int max_smem_optin; };
 
 // Enqueues one kernel on `stream` covering all problems. Returns cudaSuccess or the launch error.
+// Uses the TMA streaming kernel (gemv_tma.cu) whenever every problem's shape fits it, else the generic
+// direct-load kernel (gemv.cu); the choice depends on the problem shapes only, never on T.
 cudaError_t gemv_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream);
+cudaError_t gemv_tma_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream);      // cudaErrorNotSupported if a shape does not fit
+cudaError_t gemv_generic_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream);
+
+// Programmatic dependent launch for every kernel of the eval path (RWKV_B200_NO_PDL=1 turns it off).
+extern bool g_use_pdl;
+
+// Launch with the PDL attribute: the kernel may start while its predecessor in the stream is still running; it must
+// execute griddepcontrol.wait before touching anything the predecessor writes.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#if defined(__CUDACC__)
+// First statement of every non-GEMV kernel: let the successor start (it will prefetch its weights), then wait for the
+// predecessor's results.
+__device__ __forceinline__ void trace_begin(TraceRec * t) {
+    if (t && threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); atomicMin(&t->start, g); }
+}
+__device__ __forceinline__ void trace_end(TraceRec * t) {
+    if (t && threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); atomicMax(&t->end, g); }
+}
+__device__ __forceinline__ void trace_mark(TraceRec * t, int i) {
+    if (t && threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); t->mark[i] = g; }
+}
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
 
 // Per-launch count of kernels this module has enqueued (bench.py reports it as gpu_launches).
 extern unsigned long long g_kernel_launches;

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(GLUE_THREADS) embed_ln0_kernel(const uint8_t *
                                                                   const float * ln_w, const float * ln_b, float * x) {
     extern __shared__ float sh[];
     __shared__ double scratch[GLUE_WARPS + 1];
+    pdl_prologue();
     const int t = blockIdx.x;
     const uint8_t * row = emb + (size_t) tokens[t] * (size_t) pitch;
     for (int c = threadIdx.x; c < C; c += GLUE_THREADS)
@@ -59,62 +60,148 @@ __global__ void __launch_bounds__(GLUE_THREADS) embed_ln0_kernel(const uint8_t *
     layer_norm_to(sh, ln_w, ln_b, C, x + (size_t) t * C, scratch);
 }
 
-__global__ void __launch_bounds__(GLUE_THREADS) ln_mix_kernel(const LnMixParams p) {
-    extern __shared__ float sh[];
-    __shared__ double scratch[GLUE_WARPS + 1];
-    const int C = p.C, t = blockIdx.x;
-    float * xx = sh;            // LN(x[:, t])
-    float * prev = sh + C;      // LN(x[:, t-1]) or the carried state
-    layer_norm_to(p.x + (size_t) t * C, p.ln_w, p.ln_b, C, xx, scratch);
-    if (t == 0) {
-        for (int c = threadIdx.x; c < C; c += GLUE_THREADS) prev[c] = p.state_in[c];
-        __syncthreads();
-    } else {
-        layer_norm_to(p.x + (size_t) (t - 1) * C, p.ln_w, p.ln_b, C, prev, scratch);
-    }
-    for (int c = threadIdx.x; c < C; c += GLUE_THREADS) {
-        const float a = xx[c], b = prev[c];
-        const size_t o = (size_t) t * C + c;
-        if (p.formula == 0) {
-#pragma unroll
-            for (int j = 0; j < 6; j++)
-                if (j < p.n_out) {
-                    const float m = p.coef[j][c];
-                    p.out[j][o] = __fadd_rn(__fmul_rn(a, m), __fsub_rn(b, __fmul_rn(b, m)));
-                }
-        } else {
-            const float sx = __fsub_rn(b, a);
-#pragma unroll
-            for (int j = 0; j < 6; j++)
-                if (j < p.n_out) p.out[j][o] = __fadd_rn(__fmul_rn(sx, p.coef[j][c]), a);
-            if (p.out_sx) p.out_sx[o] = sx;
-        }
-        if (p.out_xx) p.out_xx[o] = a;
-        if (t == p.T - 1) p.state_out[c] = a;
-    }
+constexpr int LN_THREADS = 1024;
+constexpr int LN_WARPS = LN_THREADS / 32;
+
+// CTA-wide sum, one barrier: warp shuffle, 32 warp partials in `slots`, then every warp reduces the 32 slots again.
+__device__ __forceinline__ double block_sum_ln(double v, double * slots) {
+    v = warp_sum_d(v);
+    if ((threadIdx.x & 31) == 0) slots[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return warp_sum_d(slots[threadIdx.x & 31]);
 }
 
-// 8 lanes per channel, 32 channels per CTA: each (j, channel) row of W2 is `mix` contiguous floats.
+// Latency-optimised LayerNorm + token shift + mixing. This stage is ONE CTA per token sitting on the critical path
+// between two weight-streaming kernels, so what matters is the length of its dependent instruction chain: 1024
+// threads, PER = C/1024 channels per thread in registers, loads that do not depend on the previous kernel (LayerNorm
+// weights, the carried state of the previous token) issued BEFORE the programmatic-dependency wait, the x loads
+// right after it, two barrier-separated reductions, rolled output loop (small code: instruction fetch is the other
+// cost of a run-once kernel). Statistics as ggml_compute_forward_norm_f32 (ggml-cpu.c:6906-6925, sums in double).
+template <int PER>
+__global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const LnMixParams p) {
+    __shared__ double slots[4][LN_WARPS];
+    trace_begin(p.trace);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int C = p.C, t = blockIdx.x, tid = threadIdx.x;
+    float lw[PER], lb[PER], pv[PER], xa[PER], xb[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int c = tid + i * LN_THREADS;
+        const bool live = c < C;
+        lw[i] = live ? p.ln_w[c] : 0.f;
+        lb[i] = live ? p.ln_b[c] : 0.f;
+        pv[i] = (live && t == 0) ? p.state_in[c] : 0.f;   // written by the previous token's pass: safe before the wait
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    double sa = 0, sb = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int c = tid + i * LN_THREADS;
+        const bool live = c < C;
+        xa[i] = live ? p.x[(size_t) t * C + c] : 0.f;
+        xb[i] = (live && t > 0) ? p.x[(size_t) (t - 1) * C + c] : 0.f;
+        sa += (double) xa[i];
+        sb += (double) xb[i];
+    }
+    const float mean_a = (float) (block_sum_ln(sa, slots[0]) / C);
+    const float mean_b = (t > 0) ? (float) (block_sum_ln(sb, slots[1]) / C) : 0.f;
+    double va = 0, vb = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const bool live = tid + i * LN_THREADS < C;
+        xa[i] = live ? xa[i] - mean_a : 0.f;
+        xb[i] = live ? xb[i] - mean_b : 0.f;
+        va += (double) (xa[i] * xa[i]);
+        vb += (double) (xb[i] * xb[i]);
+    }
+    const float scale_a = 1.0f / sqrtf((float) (block_sum_ln(va, slots[2]) / C) + 1e-5f);
+    const float scale_b = (t > 0) ? 1.0f / sqrtf((float) (block_sum_ln(vb, slots[3]) / C) + 1e-5f) : 0.f;
+    // normalised current / previous token, in place
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        xa[i] = __fadd_rn(__fmul_rn(__fmul_rn(xa[i], scale_a), lw[i]), lb[i]);                            // LN(x[:, t])
+        xb[i] = (t > 0) ? __fadd_rn(__fmul_rn(__fmul_rn(xb[i], scale_b), lw[i]), lb[i]) : pv[i];          // LN(x[:, t-1]) or the carry
+    }
+    const size_t o0 = (size_t) t * C + tid;
+#pragma unroll 1
+    for (int j = 0; j < p.n_out; j++) {     // rolled: kernel parameters are indexable in the constant bank
+        const float * coef = p.coef[j];
+        float * out = p.out[j];
+        if (p.formula == 0) {
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int c = tid + i * LN_THREADS;
+                if (c < C) { const float m = coef[c]; out[o0 + i * LN_THREADS] = __fadd_rn(__fmul_rn(xa[i], m), __fsub_rn(xb[i], __fmul_rn(xb[i], m))); }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int c = tid + i * LN_THREADS;
+                if (c < C) out[o0 + i * LN_THREADS] = __fadd_rn(__fmul_rn(__fsub_rn(xb[i], xa[i]), coef[c]), xa[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int c = tid + i * LN_THREADS;
+        if (c >= C) continue;
+        if (p.out_sx) p.out_sx[o0 + i * LN_THREADS] = __fsub_rn(xb[i], xa[i]);
+        if (p.out_xx) p.out_xx[o0 + i * LN_THREADS] = xa[i];
+        if (t == p.T - 1) p.state_out[c] = xa[i];
+    }
+    trace_end(p.trace);
+}
+
+// 8 lanes per channel, 32 channels per CTA: each (j, channel) row of W2 is `mix` contiguous floats. The W2 rows
+// (5.2 MB per layer at 7B, straight from HBM) are pulled into registers before the programmatic-dependency wait.
+constexpr int LERP_MAX_F4 = 4;   // float4 per lane per j held in registers: mix <= 128
 __global__ void __launch_bounds__(GLUE_THREADS) v6_lerp_kernel(const V6LerpParams p) {
     extern __shared__ float zs[];   // [5*mix]
+    trace_begin(p.trace);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int t = blockIdx.y, mix = p.mix, C = p.C;
-    for (int i = threadIdx.x; i < 5 * mix; i += GLUE_THREADS) zs[i] = p.z[(size_t) t * 5 * mix + i];
-    __syncthreads();
     const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
     const int c = blockIdx.x * 32 + grp;
     const bool live = c < C;
+    const bool vec = (mix & 3) == 0 && mix / 4 <= 8 * LERP_MAX_F4;
+    float4 wreg[5][LERP_MAX_F4];
+    float maa[5];
+    if (vec) {
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            const float4 * wrow = reinterpret_cast<const float4 *>(p.w2 + ((size_t) j * C + (live ? c : 0)) * mix);
+#pragma unroll
+            for (int q = 0; q < LERP_MAX_F4; q++) {
+                const int i4 = sub + 8 * q;
+                wreg[j][q] = (live && i4 < mix / 4) ? __ldg(wrow + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            maa[j] = live ? p.maa[j][c] : 0.f;
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int i = threadIdx.x; i < 5 * mix; i += GLUE_THREADS) zs[i] = p.z[(size_t) t * 5 * mix + i];
     const size_t o = (size_t) t * C + (live ? c : 0);
     const float sx = live ? p.sx[o] : 0.f, xx = live ? p.xx[o] : 0.f;
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < 5; j++) {
         float acc = 0.f;
-        if (live) {
+        const float * zj = zs + j * mix;
+        if (vec) {
+#pragma unroll
+            for (int q = 0; q < LERP_MAX_F4; q++) {
+                const int i4 = sub + 8 * q;
+                if (i4 < mix / 4) {
+                    const float4 w = wreg[j][q], z = reinterpret_cast<const float4 *>(zj)[i4];
+                    acc = __fmaf_rn(w.x, z.x, acc); acc = __fmaf_rn(w.y, z.y, acc);
+                    acc = __fmaf_rn(w.z, z.z, acc); acc = __fmaf_rn(w.w, z.w, acc);
+                }
+            }
+        } else if (live) {
             const float * wrow = p.w2 + ((size_t) j * C + c) * mix;
-            const float * zj = zs + j * mix;
             if ((mix & 3) == 0) {
                 for (int i4 = sub; i4 < mix / 4; i4 += 8) {
-                    float4 w = __ldg(reinterpret_cast<const float4 *>(wrow) + i4);
-                    float4 z = reinterpret_cast<const float4 *>(zj)[i4];
+                    const float4 w = __ldg(reinterpret_cast<const float4 *>(wrow) + i4), z = reinterpret_cast<const float4 *>(zj)[i4];
                     acc = __fmaf_rn(w.x, z.x, acc); acc = __fmaf_rn(w.y, z.y, acc);
                     acc = __fmaf_rn(w.z, z.z, acc); acc = __fmaf_rn(w.w, z.w, acc);
                 }
@@ -125,30 +212,38 @@ __global__ void __launch_bounds__(GLUE_THREADS) v6_lerp_kernel(const V6LerpParam
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (live && sub == 0) p.out[j][o] = __fadd_rn(__fmul_rn(__fadd_rn(acc, p.maa[j][c]), sx), xx);
+        if (live && sub == 0) p.out[j][o] = __fadd_rn(__fmul_rn(__fadd_rn(acc, vec ? maa[j] : p.maa[j][c]), sx), xx);
     }
+    trace_end(p.trace);
 }
 
 }  // namespace
 
 cudaError_t launch_embed_ln0(const void * emb, int emb_type, long long emb_pitch, const int * tokens, int T, int C,
                              const float * ln_w, const float * ln_b, float * x, cudaStream_t s) {
-    embed_ln0_kernel<<<T, GLUE_THREADS, (size_t) C * sizeof(float), s>>>(reinterpret_cast<const uint8_t *>(emb), emb_type, emb_pitch, tokens, C, ln_w, ln_b, x);
     g_kernel_launches++;
-    return cudaGetLastError();
+    return launch_pdl(embed_ln0_kernel, dim3(T), dim3(GLUE_THREADS), (size_t) C * sizeof(float), s, reinterpret_cast<const uint8_t *>(emb), emb_type, emb_pitch, tokens, C, ln_w, ln_b, x);
 }
 
-cudaError_t launch_ln_mix(const LnMixParams & p, cudaStream_t s) {
-    ln_mix_kernel<<<p.T, GLUE_THREADS, (size_t) 2 * p.C * sizeof(float), s>>>(p);
+cudaError_t launch_ln_mix(const LnMixParams & p_in, cudaStream_t s) {
+    LnMixParams p = p_in;
+    p.trace = trace_slot("ln_mix");
     g_kernel_launches++;
-    return cudaGetLastError();
+    const int per = (p.C + LN_THREADS - 1) / LN_THREADS;
+    if (per <= 1) return launch_pdl(ln_mix_kernel<1>, dim3(p.T), dim3(LN_THREADS), 0, s, p);
+    if (per <= 2) return launch_pdl(ln_mix_kernel<2>, dim3(p.T), dim3(LN_THREADS), 0, s, p);
+    if (per <= 4) return launch_pdl(ln_mix_kernel<4>, dim3(p.T), dim3(LN_THREADS), 0, s, p);
+    if (per <= 8) return launch_pdl(ln_mix_kernel<8>, dim3(p.T), dim3(LN_THREADS), 0, s, p);
+    if (per <= 16) return launch_pdl(ln_mix_kernel<16>, dim3(p.T), dim3(LN_THREADS), 0, s, p);
+    return cudaErrorInvalidValue;   // n_embed > 16384
 }
 
-cudaError_t launch_v6_lerp(const V6LerpParams & p, cudaStream_t s) {
+cudaError_t launch_v6_lerp(const V6LerpParams & p_in, cudaStream_t s) {
+    V6LerpParams p = p_in;
+    p.trace = trace_slot("v6_lerp");
     dim3 grid((p.C + 31) / 32, p.T);
-    v6_lerp_kernel<<<grid, GLUE_THREADS, (size_t) 5 * p.mix * sizeof(float), s>>>(p);
     g_kernel_launches++;
-    return cudaGetLastError();
+    return launch_pdl(v6_lerp_kernel, grid, dim3(GLUE_THREADS), (size_t) 5 * p.mix * sizeof(float), s, p);
 }
 
 }  // namespace rwkv

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "gemv.h"   // TraceRec
+
 namespace rwkv {
 
 // x[:, t] = LN(emb[tokens[t]]; ln0)     (rwkv_graph.inc:655-658, 787-790)
@@ -13,6 +15,7 @@ cudaError_t launch_embed_ln0(const void * emb, int emb_type, long long emb_pitch
 
 // LayerNorm + token shift (rwkv_carry_x, rwkv_graph.inc:56-82) + per-arch mixing.
 struct LnMixParams {
+    TraceRec * trace = nullptr;
     const float * x;          // [C, T] residual stream
     const float * ln_w, * ln_b;
     const float * state_in;   // [C] previous token's LN(x) (att_xx / ffn_xx slot of the input state)
@@ -32,6 +35,7 @@ cudaError_t launch_ln_mix(const LnMixParams & p, cudaStream_t s);
 // v6 data-dependent lerp (rwkv_graph.inc:323-346): for j in {w,k,v,r,g}
 //   m_j[c,t] = sum_i W2[j][c][i] * z[j*mix + i, t];   out_j = (m_j + maa_j[c]) * sx + xx
 struct V6LerpParams {
+    TraceRec * trace = nullptr;
     const float * w2;         // [5][C][mix] fp32 (ggml ne = [mix, C, 5])
     const float * z;          // [5*mix, T] = tanh(W1 . xxx)
     const float * xx, * sx;   // [C, T]
@@ -43,6 +47,7 @@ cudaError_t launch_v6_lerp(const V6LerpParams & p, cudaStream_t s);
 
 // v4 WKV (rwkv_att_wkv_v4, rwkv_graph.inc:119-161) fused with the r* multiply (:182,195).
 struct Wkv4Params {
+    TraceRec * trace = nullptr;
     const float * k, * v, * r;        // [C, T]; r already sigmoid-ed
     const float * time_first, * time_decay;   // [C]
     const float * aa_in, * bb_in, * pp_in;    // [C]
@@ -55,6 +60,7 @@ cudaError_t launch_wkv4(const Wkv4Params & p, cudaStream_t s);
 // v5/v6 WKV (ggml_compute_forward_rwkv_wkv6_f32, ggml-cpu.c:11803) + per-head norm + ln_x + gate
 // (rwkv_graph.inc:275-289, 370-382).
 struct Wkv6Params {
+    TraceRec * trace = nullptr;
     const float * r, * k, * v;        // [C, T]
     const float * td;                 // decay: [C, T] if td_per_token else per-channel [C] (v5.2) / per-head [H] (v5.1)
     const float * tf;                 // time_first / time_faaaa: [C] or per-head [H]
@@ -72,6 +78,7 @@ cudaError_t launch_wkv6(const Wkv6Params & p, cudaStream_t s);
 // v7 (rwkv_att_v7, rwkv_graph.inc:432-479 + rwkv_wkv_v7_impl, rwkv_operators_wkv_v7.inc:37-106):
 // kk/l2norm, k and v corrections, the recurrence, per-head norm, ln_x, the r*k*r_k bonus and the gate.
 struct Wkv7Params {
+    TraceRec * trace = nullptr;
     const float * r, * w, * k, * v, * a;   // [C, T]: r raw, w decay, k raw, v raw, a = sigmoid(..)
     const float * g;                  // [C, T] gate
     const float * vgate;              // [C, T] sigmoid(v0 + ...) or NULL for layer 0

@@ -12,6 +12,8 @@ namespace {
 // Every ggml node is its own rounding, so no FMA contraction here.
 // ---------------------------------------------------------------------------------------------
 __global__ void wkv4_kernel(const Wkv4Params p) {
+    trace_begin(p.trace);
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.C) return;
     float aa = p.aa_in[c], bb = p.bb_in[c], pp = p.pp_in[c];
@@ -34,6 +36,7 @@ __global__ void wkv4_kernel(const Wkv4Params p) {
         p.y[o] = __fmul_rn(p.r[o], __fdiv_rn(a, b));
     }
     p.aa_out[c] = aa; p.bb_out[c] = bb; p.pp_out[c] = pp;
+    trace_end(p.trace);
 }
 
 // Per-head normalisation of S values held one per thread: ggml_norm over a head
@@ -67,13 +70,18 @@ __device__ __forceinline__ float head_norm(float y, float eps, float * red) {
 template <int S>
 __global__ void __launch_bounds__(S) wkv6_kernel(const Wkv6Params p) {
     __shared__ float sk[S], sr[S], sd[S], sf[S], red[S];
+    trace_begin(p.trace);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int h = blockIdx.x, j = threadIdx.x, C = p.H * S;
+    // the recurrent state (written by the previous token's pass) and the parameters do not depend on the previous
+    // kernel: pull them in before the programmatic-dependency wait
     float st[S];
 #pragma unroll
     for (int i = 0; i < S; i++) st[i] = p.state_in[((size_t) h * S + i) * S + j];
     sf[j] = p.per_head_scalars ? p.tf[h] : p.tf[h * S + j];
     if (!p.td_per_token) sd[j] = p.per_head_scalars ? p.td[h] : p.td[h * S + j];
     const float lw = p.lnx_w[h * S + j], lb = p.lnx_b[h * S + j];
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int t = 0; t < p.T; t++) {
         const size_t o = (size_t) t * C + h * S + j;
         __syncthreads();
@@ -97,6 +105,7 @@ __global__ void __launch_bounds__(S) wkv6_kernel(const Wkv6Params p) {
     }
 #pragma unroll
     for (int i = 0; i < S; i++) p.state_out[((size_t) h * S + i) * S + j] = st[i];
+    trace_end(p.trace);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -106,12 +115,15 @@ __global__ void __launch_bounds__(S) wkv6_kernel(const Wkv6Params p) {
 template <int S>
 __global__ void __launch_bounds__(S) wkv7_kernel(const Wkv7Params p) {
     __shared__ float sr[S], sw[S], sk[S], sa[S], sb[S], red[S];
+    trace_begin(p.trace);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int h = blockIdx.x, i = threadIdx.x, C = p.H * S, c = h * S + i;
     float st[S];
 #pragma unroll
     for (int j = 0; j < S; j++) st[j] = p.state_in[((size_t) h * S + i) * S + j];
     const float kk_w = p.k_k[c], ka_w = p.k_a[c], rk_w = p.r_k[c];
     const float lw = p.lnx_w[c], lb = p.lnx_b[c];
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int t = 0; t < p.T; t++) {
         const size_t o = (size_t) t * C + c;
         const float r = p.r[o], w = p.w[o], k0 = p.k[o], a = p.a[o];
@@ -158,37 +170,41 @@ __global__ void __launch_bounds__(S) wkv7_kernel(const Wkv7Params p) {
     }
 #pragma unroll
     for (int j = 0; j < S; j++) p.state_out[((size_t) h * S + i) * S + j] = st[j];
+    trace_end(p.trace);
 }
 
 }  // namespace
 
-cudaError_t launch_wkv4(const Wkv4Params & p, cudaStream_t s) {
+cudaError_t launch_wkv4(const Wkv4Params & p_in, cudaStream_t s) {
+    Wkv4Params p = p_in;
+    p.trace = trace_slot("wkv4");
     const int threads = 128;
-    wkv4_kernel<<<(p.C + threads - 1) / threads, threads, 0, s>>>(p);
     g_kernel_launches++;
-    return cudaGetLastError();
+    return launch_pdl(wkv4_kernel, dim3((p.C + threads - 1) / threads), dim3(threads), 0, s, p);
 }
 
 #define RWKV_DISPATCH_HEAD_SIZE(S_, KERNEL, PARAMS, STREAM)                              \
     switch (S_) {                                                                        \
-        case 8: KERNEL<8><<<PARAMS.H, 8, 0, STREAM>>>(PARAMS); break;                    \
-        case 16: KERNEL<16><<<PARAMS.H, 16, 0, STREAM>>>(PARAMS); break;                 \
-        case 32: KERNEL<32><<<PARAMS.H, 32, 0, STREAM>>>(PARAMS); break;                 \
-        case 64: KERNEL<64><<<PARAMS.H, 64, 0, STREAM>>>(PARAMS); break;                 \
-        case 128: KERNEL<128><<<PARAMS.H, 128, 0, STREAM>>>(PARAMS); break;              \
+        case 8: return launch_pdl(KERNEL<8>, dim3(PARAMS.H), dim3(8), 0, STREAM, PARAMS);         \
+        case 16: return launch_pdl(KERNEL<16>, dim3(PARAMS.H), dim3(16), 0, STREAM, PARAMS);      \
+        case 32: return launch_pdl(KERNEL<32>, dim3(PARAMS.H), dim3(32), 0, STREAM, PARAMS);      \
+        case 64: return launch_pdl(KERNEL<64>, dim3(PARAMS.H), dim3(64), 0, STREAM, PARAMS);      \
+        case 128: return launch_pdl(KERNEL<128>, dim3(PARAMS.H), dim3(128), 0, STREAM, PARAMS);   \
         default: return cudaErrorInvalidValue;                                           \
     }
 
-cudaError_t launch_wkv6(const Wkv6Params & p, cudaStream_t s) {
-    RWKV_DISPATCH_HEAD_SIZE(p.S, wkv6_kernel, p, s)
+cudaError_t launch_wkv6(const Wkv6Params & p_in, cudaStream_t s) {
+    Wkv6Params p = p_in;
+    p.trace = trace_slot("wkv6");
     g_kernel_launches++;
-    return cudaGetLastError();
+    RWKV_DISPATCH_HEAD_SIZE(p.S, wkv6_kernel, p, s)
 }
 
-cudaError_t launch_wkv7(const Wkv7Params & p, cudaStream_t s) {
-    RWKV_DISPATCH_HEAD_SIZE(p.S, wkv7_kernel, p, s)
+cudaError_t launch_wkv7(const Wkv7Params & p_in, cudaStream_t s) {
+    Wkv7Params p = p_in;
+    p.trace = trace_slot("wkv7");
     g_kernel_launches++;
-    return cudaGetLastError();
+    RWKV_DISPATCH_HEAD_SIZE(p.S, wkv7_kernel, p, s)
 }
 
 }  // namespace rwkv

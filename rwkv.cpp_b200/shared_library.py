@@ -100,6 +100,10 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_time_resident.restype = ctypes.c_float
         lib.rwkv_b200_profile_pass.argtypes = [vp, P_U32, ctypes.c_size_t, ctypes.c_bool, ctypes.POINTER(ProfileResult)]
         lib.rwkv_b200_profile_pass.restype = ctypes.c_bool
+        lib.rwkv_b200_trace_enable.argtypes = [vp]
+        lib.rwkv_b200_trace_enable.restype = ctypes.c_bool
+        lib.rwkv_b200_trace_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_void_p, ctypes.c_int]
+        lib.rwkv_b200_trace_read.restype = ctypes.c_int
         lib.rwkv_b200_set_graphs.argtypes = [vp, ctypes.c_bool]
         lib.rwkv_b200_set_graphs.restype = None
         lib.rwkv_b200_matvec.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, P_FLOAT, P_FLOAT, ctypes.c_int]

@@ -50,9 +50,11 @@ def test_gemv_matches_oracle(lib, fmt, shape):
 
 @pytest.mark.parametrize("fmt", TYPES)
 @pytest.mark.parametrize("T", [2, 3, 4, 7, 9])
-def test_gemv_columns_are_batch_invariant(lib, fmt, T):
-    """Each column of a multi-column call is bit-identical to the single-column call (serial == sequence)."""
-    M, K = 192, 320
+@pytest.mark.parametrize("shape", [(192, 320), (200, 64), (72, 128), (40, 4096), (24, 14336)])
+def test_gemv_columns_are_batch_invariant(lib, fmt, T, shape):
+    """Each column of a multi-column call is bit-identical to the single-column call (serial == sequence), for long rows
+    (32 lanes per row, 1 / 4 warps per row) and short LoRA rows (lane groups)."""
+    M, K = shape
     rng = np.random.default_rng(T)
     tid, raw = make_weights(fmt, M, K, rng)
     x = rng.standard_normal((K, T)).astype(np.float32)
