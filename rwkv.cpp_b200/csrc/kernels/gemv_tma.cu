@@ -212,30 +212,43 @@ __device__ void stage_column(const GemvProblem & P, int col_index, uint8_t * col
         const int UB = has_min ? 1 : 2;
         const int nblk = K / 32, nunits = (nblk + UB - 1) / UB;
         const int sub = tid & 7;
-        for (int base = tid * 4; base < ((K + 127) & ~127); base += CONSUMER_THREADS * 4) {   // whole warps iterate together
-            const bool live = base < K;
-            float4 t = live ? *reinterpret_cast<const float4 *>(x + base) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ln && live) { t.x = norm(t.x, base); t.y = norm(t.y, base + 1); t.z = norm(t.z, base + 2); t.w = norm(t.w, base + 3); }
-            float amax = fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w)));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-            const float d32 = amax / 127.0f;
-            const float id = (amax != 0.0f) ? 127.0f / amax : 0.0f;
-            const int q0 = __float2int_rn(t.x * id), q1 = __float2int_rn(t.y * id), q2 = __float2int_rn(t.z * id), q3 = __float2int_rn(t.w * id);
-            int isum = q0 + q1 + q2 + q3;
-            isum += __shfl_xor_sync(0xffffffffu, isum, 1);
-            isum += __shfl_xor_sync(0xffffffffu, isum, 2);
-            isum += __shfl_xor_sync(0xffffffffu, isum, 4);
-            if (live) {
-                const int blk = base >> 5, u = blk / UB, bi = blk % UB, h = sub >> 2, i = sub & 3;
-                const int word = (q0 & 0xFF) | ((q1 & 0xFF) << 8) | ((q2 & 0xFF) << 16) | ((q3 & 0xFF) << 24);
-                *reinterpret_cast<int *>(col + ((size_t) (bi * 2 + h) * nunits + u) * 16 + i * 4) = word;
-                if (sub == 0) {
-                    ActScale a;
-                    a.d = round_to_half(d32);
-                    a.s = has_min ? round_to_half(d32 * (float) isum) : (float) isum;
-                    *reinterpret_cast<ActScale *>(col + (size_t) nunits * UB * 32 + ((size_t) bi * nunits + u) * 8) = a;
+        constexpr int UNR = 4;   // loads of UNR iterations are issued together: the loop is L2-latency bound, not math bound
+        const int kpad = (K + 127) & ~127;
+        for (int base0 = tid * 4; base0 < kpad; base0 += CONSUMER_THREADS * 4 * UNR) {
+            float4 tv[UNR];
+#pragma unroll
+            for (int q = 0; q < UNR; q++) {
+                const int base = base0 + q * CONSUMER_THREADS * 4;
+                tv[q] = (base < K) ? *reinterpret_cast<const float4 *>(x + base) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < UNR; q++) {
+                const int base = base0 + q * CONSUMER_THREADS * 4;
+                if (base >= kpad) break;                     // warp-uniform
+                const bool live = base < K;
+                float4 t = tv[q];
+                if (ln && live) { t.x = norm(t.x, base); t.y = norm(t.y, base + 1); t.z = norm(t.z, base + 2); t.w = norm(t.w, base + 3); }
+                float amax = fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w)));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+                const float d32 = amax / 127.0f;
+                const float id = (amax != 0.0f) ? 127.0f / amax : 0.0f;
+                const int q0 = __float2int_rn(t.x * id), q1 = __float2int_rn(t.y * id), q2 = __float2int_rn(t.z * id), q3 = __float2int_rn(t.w * id);
+                int isum = q0 + q1 + q2 + q3;
+                isum += __shfl_xor_sync(0xffffffffu, isum, 1);
+                isum += __shfl_xor_sync(0xffffffffu, isum, 2);
+                isum += __shfl_xor_sync(0xffffffffu, isum, 4);
+                if (live) {
+                    const int blk = base >> 5, u = blk / UB, bi = blk % UB, h = sub >> 2, i = sub & 3;
+                    const int word = (q0 & 0xFF) | ((q1 & 0xFF) << 8) | ((q2 & 0xFF) << 16) | ((q3 & 0xFF) << 24);
+                    *reinterpret_cast<int *>(col + ((size_t) (bi * 2 + h) * nunits + u) * 16 + i * 4) = word;
+                    if (sub == 0) {
+                        ActScale a;
+                        a.d = round_to_half(d32);
+                        a.s = has_min ? round_to_half(d32 * (float) isum) : (float) isum;
+                        *reinterpret_cast<ActScale *>(col + (size_t) nunits * UB * 32 + ((size_t) bi * nunits + u) * 8) = a;
+                    }
                 }
             }
         }
