@@ -66,6 +66,8 @@ RWKV_API int rwkv_b200_trace_read(struct rwkv_context * ctx, double * start_us, 
 
 /* Enables / disables CUDA-graph replay of single-token passes (on by default). */
 RWKV_API void rwkv_b200_set_graphs(struct rwkv_context * ctx, bool enabled);
+/* Enables / disables the tcgen05 tensor-core kernel for passes of >= 32 tokens (on by default; off = batch-invariant SIMT path). */
+RWKV_API void rwkv_b200_set_tensor_cores(struct rwkv_context * ctx, bool enabled);
 
 /* Test hook: one fused dequantize-GEMV on host buffers, y[M,T] = W[M,K] . x[K,T] (column-major activations),
  * through exactly the kernel the eval path uses (csrc/kernels/gemv.cu). `weights` holds M rows in the file

@@ -264,6 +264,7 @@ bool rwkv_b200_profile_pass(struct rwkv_context * ctx, const uint32_t * tokens, 
 }
 
 void rwkv_b200_set_graphs(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_graphs = enabled; }
+void rwkv_b200_set_tensor_cores(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_tensor_cores = enabled; }
 
 static bool trace_rearm(Context * c) {
     std::vector<TraceRec> init(1024);
@@ -331,8 +332,13 @@ bool rwkv_b200_matvec(int data_type, int K, int M, int T, const void * weights, 
         GemvProblem & p = b.p[0];
         p.W = dW; p.pitch = (long long) pitch; p.type = data_type; p.K = K; p.M = M;
         p.x = dx; p.ldx = K; p.y = dy; p.ldy = M; p.epi = epilogue; p.pro = PRO_NONE;
-        ok = gemv_launch(b, di, 0) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess &&
-             cudaMemcpy(y, dy, sizeof(float) * M * T, cudaMemcpyDeviceToHost) == cudaSuccess;
+        void * act16 = nullptr;
+        const size_t act16_bytes = (size_t) ((T + 15) / 16 * 16) * K * 2 + 256;
+        const bool use_tc = gemm_tc_supported(p, T) && !getenv("RWKV_B200_NO_TC");
+        if (use_tc) ok = cudaMalloc(&act16, act16_bytes) == cudaSuccess && gemm_tc_launch(b, di, 0, act16, act16_bytes) == cudaSuccess;
+        else ok = gemv_launch(b, di, 0) == cudaSuccess;
+        ok = ok && cudaDeviceSynchronize() == cudaSuccess && cudaMemcpy(y, dy, sizeof(float) * M * T, cudaMemcpyDeviceToHost) == cudaSuccess;
+        cudaFree(act16);
     }
     cudaError_t e = cudaGetLastError();
     cudaFree(dW); cudaFree(dx); cudaFree(dy);

@@ -76,18 +76,35 @@ struct Batch {
          RWKV_CHECK((ctx)->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, _e == cudaSuccess,       \
                     "CUDA error: %s", cudaGetErrorString(_e)); } while (0)
 
-bool run_batch(Context * ctx, Batch & batch) {
-    if (!ctx->profiling) {
-        CUDA_OK(ctx, gemv_launch(batch.b, ctx->model->dev, ctx->stream));
+// Passes of >= 32 tokens send every problem the tensor-core kernel can take (any weight type but F32, K % 64 == 0) to
+// gemm_tc.cu; the rest (and all shorter passes) use the batch-invariant GEMV, so serial == sequence stays bit-exact
+// wherever the reference's tests compare states.
+bool launch_batch(Context * ctx, GemvBatch & b) {
+    if (b.T >= 32 && ctx->use_tensor_cores && ctx->act16) {
+        GemvBatch tcb, rest;
+        memset(&tcb, 0, sizeof(tcb)); memset(&rest, 0, sizeof(rest));
+        tcb.T = rest.T = b.T;
+        for (int i = 0; i < b.n; i++) {
+            if (gemm_tc_supported(b.p[i], b.T)) tcb.p[tcb.n++] = b.p[i];
+            else rest.p[rest.n++] = b.p[i];
+        }
+        if (tcb.n) CUDA_OK(ctx, gemm_tc_launch(tcb, ctx->model->dev, ctx->stream, ctx->act16, ctx->act16_bytes));
+        if (rest.n) CUDA_OK(ctx, gemv_launch(rest, ctx->model->dev, ctx->stream));
         return true;
     }
+    CUDA_OK(ctx, gemv_launch(b, ctx->model->dev, ctx->stream));
+    return true;
+}
+
+bool run_batch(Context * ctx, Batch & batch) {
+    if (!ctx->profiling) return launch_batch(ctx, batch.b);
     Context::ProfRecord rec{};
     CUDA_OK(ctx, cudaEventCreate(&rec.start));
     CUDA_OK(ctx, cudaEventCreate(&rec.stop));
     for (int i = 0; i < batch.b.n; i++)
         rec.bytes += (double) tensor_nbytes(batch.b.p[i].type, (uint64_t) batch.b.p[i].K, (uint64_t) batch.b.p[i].M, 1);
     CUDA_OK(ctx, cudaEventRecord(rec.start, ctx->stream));
-    CUDA_OK(ctx, gemv_launch(batch.b, ctx->model->dev, ctx->stream));
+    if (!launch_batch(ctx, batch.b)) return false;
     CUDA_OK(ctx, cudaEventRecord(rec.stop, ctx->stream));
     ctx->prof.push_back(rec);
     return true;
@@ -286,6 +303,7 @@ bool ensure_capacity(Context * ctx, int T) {
     while (cap < T) cap *= 2;
     if (cap > MAX_TOKENS_PER_PASS) cap = MAX_TOKENS_PER_PASS;
     if (ctx->scratch) { cudaFree(ctx->scratch); ctx->scratch = nullptr; }
+    if (ctx->act16) { cudaFree(ctx->act16); ctx->act16 = nullptr; ctx->act16_bytes = 0; }
     if (ctx->tokens) { cudaFree(ctx->tokens); ctx->tokens = nullptr; }
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 2; i++) {
@@ -302,6 +320,13 @@ bool ensure_capacity(Context * ctx, int T) {
     for (int i = 0; i < 2; i++) {
         e = cudaMallocHost(reinterpret_cast<void **>(&ctx->tokens_host[i]), (size_t) cap * sizeof(int));
         RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, false, e == cudaSuccess, "Failed to allocate pinned token staging: %s", cudaGetErrorString(e));
+    }
+    if (cap >= 32) {   // fp16 staging for the tensor-core path: up to 8 distinct inputs of max(C, F) x round16(cap)
+        Dims d = model_dims(m);
+        const size_t kmax = d.F > d.C ? d.F : d.C;
+        ctx->act16_bytes = (size_t) GEMV_MAX_PROBLEMS * (kmax * (size_t) ((cap + 15) / 16 * 16) * 2 + 256);
+        e = cudaMalloc(&ctx->act16, ctx->act16_bytes);
+        RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, false, e == cudaSuccess, "Failed to allocate fp16 staging: %s", cudaGetErrorString(e));
     }
     ctx->scratch_floats = n;
     ctx->capacity_T = cap;
@@ -424,7 +449,7 @@ void destroy_context(Context * ctx) {
     if (model) cudaSetDevice(model->dev.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->state_a); cudaFree(ctx->state_b); cudaFree(ctx->state_init); cudaFree(ctx->logits);
-    cudaFree(ctx->tokens); cudaFree(ctx->scratch); cudaFree(ctx->trace_buf);
+    cudaFree(ctx->tokens); cudaFree(ctx->scratch); cudaFree(ctx->trace_buf); cudaFree(ctx->act16);
     for (int i = 0; i < 2; i++) {
         if (ctx->tokens_host[i]) cudaFreeHost(ctx->tokens_host[i]);
         if (ctx->slot_free[i]) cudaEventDestroy(ctx->slot_free[i]);

@@ -22,6 +22,9 @@ struct Context {
     float * logits = nullptr;        // [n_vocab]
     int * tokens = nullptr;          // [capacity_T]
     float * scratch = nullptr;       // activation arena for capacity_T tokens
+    void * act16 = nullptr;          // fp16 copies of GEMM inputs for the tensor-core prefill path
+    size_t act16_bytes = 0;
+    bool use_tensor_cores = true;
     size_t scratch_floats = 0;
     int capacity_T = 0;
     // Two pinned token slots, used alternately (`phase`): the host may prepare pass n+1 while pass n runs.
@@ -53,7 +56,7 @@ struct Context {
 
 // Largest number of tokens pushed through the kernels in one go; longer sequences are cut into
 // pieces of this size with the state staying on the device.
-constexpr int MAX_TOKENS_PER_PASS = 512;
+constexpr int MAX_TOKENS_PER_PASS = 256;
 
 Context * create_context(Model * model, ErrorSink sink);
 void destroy_context(Context * ctx);

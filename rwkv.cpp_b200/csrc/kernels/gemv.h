@@ -66,6 +66,11 @@ cudaError_t gemv_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t 
 cudaError_t gemv_tma_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream);      // cudaErrorNotSupported if a shape does not fit
 cudaError_t gemv_generic_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream);
 
+// Tensor-core (tcgen05) path for chunks of >= 32 tokens (gemm_tc.cu). act16_scratch: device scratch for the fp16 copies of the
+// input matrices (sum over distinct inputs of round16(T) * K halves).
+bool gemm_tc_supported(const GemvProblem & p, int T);
+cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream, void * act16_scratch, size_t scratch_bytes);
+
 // Programmatic dependent launch for every kernel of the eval path (RWKV_B200_NO_PDL=1 turns it off).
 extern bool g_use_pdl;
 

@@ -106,6 +106,8 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_trace_read.restype = ctypes.c_int
         lib.rwkv_b200_set_graphs.argtypes = [vp, ctypes.c_bool]
         lib.rwkv_b200_set_graphs.restype = None
+        lib.rwkv_b200_set_tensor_cores.argtypes = [vp, ctypes.c_bool]
+        lib.rwkv_b200_set_tensor_cores.restype = None
         lib.rwkv_b200_matvec.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, P_FLOAT, P_FLOAT, ctypes.c_int]
         lib.rwkv_b200_matvec.restype = ctypes.c_bool
 

@@ -87,3 +87,33 @@ def test_gemv_zero_and_extreme_activations(lib):
         got = run(lib, tid, K, M, 1, raw, x)
         want = ro.Mat(gf.Tensor("w", tid, (K, M), raw)).mul(x)
         assert np.abs(got - want).max() / np.abs(want).max() < 2e-5
+
+
+@pytest.mark.parametrize("fmt", ["FP16", "Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q8_0"])
+@pytest.mark.parametrize("shape,T", [((128, 64), 32), ((256, 128), 48), ((160, 4096), 128), ((4096, 256), 64), ((512, 14336), 128), ((130, 192), 33), ((128, 64), 256)])
+def test_tensor_core_gemm_matches_fp16_reference(lib, fmt, shape, T):
+    """tcgen05 prefill kernel (csrc/kernels/gemm_tc.cu), used for passes of >= 32 tokens: weights exactly as stored,
+    activations rounded to fp16, fp32 accumulation -- compared with that computation done in float64."""
+    M, K = shape
+    rng = np.random.default_rng(M + K + T)
+    tid, raw = make_weights(fmt, M, K, rng)
+    x = rng.standard_normal((K, T)).astype(np.float32)
+    got = run(lib, tid, K, M, T, raw, x)
+    w = ro.Mat(gf.Tensor("w", tid, (K, M), raw)).dense().astype(np.float64)
+    if fmt != "FP16":   # the kernel rounds dequantised weights to fp16 once
+        w = w.astype(np.float16).astype(np.float64)
+    want = w @ x.astype(np.float16).astype(np.float64)
+    scale = np.abs(want).max() + 1e-6
+    assert np.abs(got - want).max() / scale < 2e-5, (fmt, shape, T, np.abs(got - want).max() / scale)
+
+
+def test_tensor_core_gemm_epilogue_and_tracks_decode_path(lib):
+    """Same matrix through the tensor-core path (T = 64) and the batch-invariant GEMV (T = 1 columns): they differ only by
+    the activation rounding (fp16 vs Q8 blocks), i.e. by the reference's own quantisation noise."""
+    M, K, T = 256, 512, 64
+    rng = np.random.default_rng(9)
+    tid, raw = make_weights("Q5_1", M, K, rng)
+    x = rng.standard_normal((K, T)).astype(np.float32)
+    tc = run(lib, tid, K, M, T, raw, x, epi=4)
+    cols = np.concatenate([run(lib, tid, K, M, 1, raw, x[:, t:t + 1], epi=4) for t in range(T)], axis=1)
+    assert np.abs(tc - cols).max() / (np.abs(cols).max() + 1e-6) < 3e-2
