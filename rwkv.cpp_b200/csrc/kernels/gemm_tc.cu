@@ -31,7 +31,7 @@ namespace tc {
 constexpr int TILE_M = 128;
 constexpr int KSTEP = 64;                 // K elements per shared-memory stage = 4 MMAs of K = 16
 constexpr int THREADS = 256;
-constexpr int STAGES = 2;
+constexpr int STAGES = 4;                // shared-memory ring; global loads run 2 K-steps ahead of the MMAs
 constexpr int MAX_N = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -138,55 +138,59 @@ template <int TYPE> __device__ __forceinline__ void load_block(const uint8_t * r
         const uint4 * p = reinterpret_cast<const uint4 *>(row + (size_t) blk * 64);
 #pragma unroll
         for (int i = 0; i < 4; i++) { const uint4 v = __ldg(p + i); r.w[4 * i] = v.x; r.w[4 * i + 1] = v.y; r.w[4 * i + 2] = v.z; r.w[4 * i + 3] = v.w; }
-    } else {
-        // blocks are 2-byte aligned in general: fetch 16-bit pieces and pack (18 / 20 / 22 / 24 / 34 bytes)
-        constexpr int BB = QTraits<TYPE>::BLOCK_BYTES;
-        const uint16_t * p = reinterpret_cast<const uint16_t *>(row + (size_t) blk * BB);
+    } else if constexpr (TYPE == DT_Q5_1) {          // 24-byte blocks on an 8-byte grid
+        const uint2 * p = reinterpret_cast<const uint2 *>(row + (size_t) blk * 24);
 #pragma unroll
-        for (int i = 0; i < (BB + 3) / 4; i++) {
-            const uint32_t lo = __ldg(p + 2 * i);
-            const uint32_t hi = (2 * i + 1 < BB / 2) ? __ldg(p + 2 * i + 1) : 0u;
-            r.w[i] = lo | (hi << 16);
+        for (int i = 0; i < 3; i++) { const uint2 v = __ldg(p + i); r.w[2 * i] = v.x; r.w[2 * i + 1] = v.y; }
+    } else if constexpr (TYPE == DT_Q4_1) {          // 20-byte blocks on a 4-byte grid
+        const uint32_t * p = reinterpret_cast<const uint32_t *>(row + (size_t) blk * 20);
+#pragma unroll
+        for (int i = 0; i < 5; i++) r.w[i] = __ldg(p + i);
+    } else {
+        // 18 / 22 / 34-byte blocks start on a 2-byte grid: read whole words from the aligned-down address and realign
+        constexpr int BB = QTraits<TYPE>::BLOCK_BYTES;
+        constexpr int NW = BB / 4 + 1;
+        const size_t start = (size_t) blk * BB;
+        const uint32_t * p = reinterpret_cast<const uint32_t *>(row + (start & ~(size_t) 3));
+        uint32_t t[NW];
+#pragma unroll
+        for (int i = 0; i < NW; i++) t[i] = __ldg(p + i);
+        if (start & 2) {
+#pragma unroll
+            for (int i = 0; i < NW - 1; i++) r.w[i] = funnel16(t[i], t[i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NW - 1; i++) r.w[i] = t[i];
         }
+        if (NW - 1 < (int) (sizeof(r.w) / 4)) r.w[NW - 1] = (start & 2) ? (t[NW - 1] >> 16) : t[NW - 1];
     }
 }
 
-// Dequantise to 32 fp32 values in element order (dequantize_row_q*, ggml-quants.c:255-363).
+// Dequantise one block to 32 fp16 values in element order with packed-half arithmetic: the stored integer goes into
+// the mantissa of 1024.0h (0x6400 | q == 1024 + q exactly), one HSUB2 removes 1024 (+ the -8 / -16 offset of the
+// symmetric formats, + 128 for the sign-flipped bytes of Q8_0), one HFMA2 applies w = q * d + m with a single rounding
+// (dequantize_row_q*, ggml-quants.c:255-363, rounded to fp16). ~70 instructions per block instead of ~300 in fp32.
 template <int TYPE> __device__ __forceinline__ void block_to_half(const BlockRegs<TYPE> & r, uint4 out[4]) {
     if constexpr (TYPE == DT_F16) {
 #pragma unroll
         for (int i = 0; i < 4; i++) out[i] = make_uint4(r.w[4 * i], r.w[4 * i + 1], r.w[4 * i + 2], r.w[4 * i + 3]);
     } else {
-        // bytes of the block, little endian, inside r.w[]
-        auto byte_at = [&](int b) -> uint32_t { return (r.w[b >> 2] >> (8 * (b & 3))) & 0xFFu; };
-        const float d = half_bits_to_float(r.w[0] & 0xFFFFu);
-        float m = 0.f;
-        uint32_t qh = 0;
-        int qs_off = 2, off = 0;
-        if (TYPE == DT_Q4_0) { off = 8; }
-        if (TYPE == DT_Q4_1) { m = half_bits_to_float(r.w[0] >> 16); qs_off = 4; }
-        if (TYPE == DT_Q5_0) { off = 16; qh = (r.w[0] >> 16) | (r.w[1] << 16); qs_off = 6; }
-        if (TYPE == DT_Q5_1) { m = half_bits_to_float(r.w[0] >> 16); qh = r.w[1]; qs_off = 8; }
-        float v[32];
-        if (TYPE == DT_Q8_0) {
+        BlockQ bq;
+        decode_block<TYPE>(r.w, 0, bq);          // q[0..3]: elements 0..15, q[4..7]: elements 16..31, 4 per word
+        const __half2 d2 = __float2half2_rn(bq.d), m2 = __float2half2_rn(bq.m);
+        const float bias = 1024.0f + (float) QTraits<TYPE>::OFFSET + (TYPE == DT_Q8_0 ? 128.0f : 0.0f);
+        const __half2 bias2 = __float2half2_rn(bias);
+        uint32_t * o = reinterpret_cast<uint32_t *>(out);
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = (float) (int) (int8_t) byte_at(2 + j) * d;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const uint32_t b = byte_at(qs_off + j);
-                int q0 = (int) (b & 0x0Fu), q1 = (int) (b >> 4);
-                if (TYPE == DT_Q5_0 || TYPE == DT_Q5_1) { q0 |= (int) ((qh >> j) & 1u) << 4; q1 |= (int) ((qh >> (j + 16)) & 1u) << 4; }
-                v[j] = (float) (q0 - off) * d + m;
-                v[j + 16] = (float) (q1 - off) * d + m;
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            __half2 h0 = __floats2half2_rn(v[8 * c + 0], v[8 * c + 1]), h1 = __floats2half2_rn(v[8 * c + 2], v[8 * c + 3]);
-            __half2 h2 = __floats2half2_rn(v[8 * c + 4], v[8 * c + 5]), h3 = __floats2half2_rn(v[8 * c + 6], v[8 * c + 7]);
-            out[c] = make_uint4(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1), *reinterpret_cast<uint32_t *>(&h2),
-                                *reinterpret_cast<uint32_t *>(&h3));
+        for (int i = 0; i < 8; i++) {
+            uint32_t q = (uint32_t) bq.q[i];
+            if (TYPE == DT_Q8_0) q ^= 0x80808080u;                 // signed byte -> byte + 128
+            const uint32_t p0 = __byte_perm(q, 0x64646464u, 0x5140);   // [b0, 0x64, b1, 0x64] = halves (1024 + b0, 1024 + b1)
+            const uint32_t p1 = __byte_perm(q, 0x64646464u, 0x7362);   // [b2, 0x64, b3, 0x64]
+            __half2 h0 = __hfma2(__hsub2(*reinterpret_cast<const __half2 *>(&p0), bias2), d2, m2);
+            __half2 h1 = __hfma2(__hsub2(*reinterpret_cast<const __half2 *>(&p1), bias2), d2, m2);
+            o[2 * i] = *reinterpret_cast<uint32_t *>(&h0);
+            o[2 * i + 1] = *reinterpret_cast<uint32_t *>(&h1);
         }
     }
 }
@@ -199,6 +203,24 @@ struct TcBatch {
     TraceRec * trace;
 };
 
+__device__ __forceinline__ void cp_async16(void * smem_dst, const void * gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// B tile of K-step `ks` (NPAD x 64 halves of fp16 activations) -> stage, asynchronously. 16 lanes cover 16 tokens, lane / 16
+// picks one of two adjacent 8-element chunks, so a warp reads 32-byte runs and writes conflict-free 128-byte runs.
+__device__ __forceinline__ void copy_b_async(uint8_t * b_stage, const __half * act16, int K, int NPAD, int k0) {
+    const int NG = NPAD / 8;
+    for (int i = threadIdx.x; i < NPAD * 8; i += THREADS) {
+        const int pair = i / 32, lane = i % 32;
+        const int tg = pair / 4, cp = pair % 4;
+        const int n = tg * 16 + (lane % 16), kc = cp * 2 + lane / 16;
+        cp_async16(b_stage + (uint32_t) (kc * NG + n / 8) * 128 + (n % 8) * 16, act16 + (size_t) n * K + k0 + kc * 8);
+    }
+}
+
 template <int TYPE>
 __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, const __half * act16, int tile) {
     const GemvProblem & P = sh.P;
@@ -206,8 +228,8 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
     const int K = P.K, NPAD = batch.npad, NG = NPAD / 8;
     const int row0 = tile * TILE_M;
     const uint32_t a_bytes = TILE_M * KSTEP * 2, b_bytes = (uint32_t) NPAD * KSTEP * 2;
-    uint8_t * a_stage[STAGES] = {smem, smem + a_bytes};
-    uint8_t * b_stage[STAGES] = {smem + 2 * a_bytes, smem + 2 * a_bytes + b_bytes};
+    uint8_t * const a_base = smem;
+    uint8_t * const b_base = smem + STAGES * a_bytes;
 
     // my weight block of every K-step: row (tid / 2), block (tid % 2) of the step
     const int my_row = min(row0 + tid / 2, P.M - 1);
@@ -218,35 +240,43 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
 
     const uint32_t idesc = make_idesc(TILE_M, NPAD);
     const int nsteps = K / KSTEP;
-    BlockRegs<TYPE> cur, nxt;
-    load_block<TYPE>(wrow, blk_in_step, cur);
-    for (int ks = 0; ks < nsteps; ks++) {
-        const int s = ks & 1;
-        if (ks + 1 < nsteps) load_block<TYPE>(wrow, (ks + 1) * 2 + blk_in_step, nxt);
-        // the MMAs that read this stage two steps ago must have retired before we overwrite it
-        if (ks >= STAGES) mbar_wait(&sh.mma_done[s], (uint32_t) (((ks / STAGES) - 1) & 1));
-        // A: dequantise my block -> 4 chunks of 8 halves
+    // software pipeline, distance 2: weights of step ks+2 travel to registers and activations of step ks+2 to shared
+    // memory (cp.async) while step ks is dequantised and multiplied
+    // One K-step. `cur` holds this step's weight block, `fut` receives the block of step ks+2. The three register sets
+    // rotate by NAME (the loop below is unrolled by 3): a `w0 = w1` style rotation would read the in-flight load at the end
+    // of the very iteration that issued it and turn the distance-2 prefetch into distance 0.
+    // phase accounting of CTA 0 / thread 0 (cycles), reported through the trace marks
+    const bool acct = batch.trace != nullptr && blockIdx.x == 0 && tid == 0;
+    long long acc_wait = 0, acc_deq = 0, acc_cp = 0, acc_sync = 0, tq = 0;
+    auto tick = [&](long long & a) { if (acct) { const long long c = clock64(); a += c - tq; tq = c; } };
+    auto step = [&](int ks, const BlockRegs<TYPE> & cur, BlockRegs<TYPE> & fut) {
+        const int s = ks % STAGES;
+        if (acct) tq = clock64();
+        if (ks + 2 < nsteps) {
+            const int s2 = (ks + 2) % STAGES;
+            // stage s2 was last read by the MMAs of step ks-2
+            if (ks >= 2) mbar_wait(&sh.mma_done[s2], (uint32_t) ((((ks - 2) / STAGES)) & 1));
+            tick(acc_wait);
+            load_block<TYPE>(wrow, (ks + 2) * 2 + blk_in_step, fut);
+            copy_b_async(b_base + (size_t) s2 * b_bytes, act16, K, NPAD, (ks + 2) * KSTEP);
+        }
+        cp_async_commit();
+        // A: dequantise my block of step ks -> 4 chunks of 8 halves. Stage s was last read at step ks-4, whose commit was
+        // awaited at step ks-2.
         uint4 h[4];
         block_to_half<TYPE>(cur, h);
+        uint8_t * a_stage = a_base + (size_t) s * a_bytes;
 #pragma unroll
-        for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(a_stage[s] + a_dst0 + (uint32_t) c * 16 * 128) = h[c];
-        // B: NPAD x 64 halves of fp16 activations -> canonical layout. 16 lanes cover 16 tokens, lane / 16 picks one of
-        // two adjacent 8-element chunks, so a warp reads 32-byte runs and writes 128-byte runs.
-        const int k0 = ks * KSTEP;
-        for (int i = tid; i < NPAD * 8; i += THREADS) {
-            const int pair = i / 32, lane = i % 32;           // pair: (token group of 16, chunk pair)
-            const int tg = pair / 4, cp = pair % 4;
-            const int n = tg * 16 + (lane % 16), kc = cp * 2 + lane / 16;
-            if (n < NPAD) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(act16 + (size_t) n * K + k0 + kc * 8);
-                *reinterpret_cast<uint4 *>(b_stage[s] + (uint32_t) (kc * NG + n / 8) * 128 + (n % 8) * 16) = v;
-            }
-        }
+        for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(a_stage + a_dst0 + (uint32_t) c * 16 * 128) = h[c];
+        tick(acc_deq);
+        cp_async_wait<2>();
+        tick(acc_cp);          // the activations of step ks have landed (groups ks+1, ks+2 may still fly)
         fence_async_smem();          // generic-proxy writes -> visible to the tensor core's async proxy
         __syncthreads();
+        tick(acc_sync);
         if (tid == 0) {
             tc_fence_after_sync();
-            const uint32_t a_addr = smem_u32(a_stage[s]), b_addr = smem_u32(b_stage[s]);
+            const uint32_t a_addr = smem_u32(a_stage), b_addr = smem_u32(b_base + (size_t) s * b_bytes);
 #pragma unroll
             for (int j = 0; j < KSTEP / 16; j++) {
                 const uint64_t adesc = make_desc(a_addr + (uint32_t) (2 * j) * 16 * 128, 16 * 128, 128);
@@ -255,12 +285,31 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
             }
             umma_commit(&sh.mma_done[s]);
         }
-        cur = nxt;
+    };
+    BlockRegs<TYPE> w0, w1, w2;
+    load_block<TYPE>(wrow, blk_in_step, w0);
+    copy_b_async(b_base, act16, K, NPAD, 0);
+    cp_async_commit();
+    if (nsteps > 1) { load_block<TYPE>(wrow, 2 + blk_in_step, w1); copy_b_async(b_base + b_bytes, act16, K, NPAD, KSTEP); }
+    cp_async_commit();
+    for (int ks = 0; ks < nsteps; ks += 3) {
+        step(ks, w0, w2);
+        if (ks + 1 < nsteps) step(ks + 1, w1, w0);
+        if (ks + 2 < nsteps) step(ks + 2, w2, w1);
     }
-    // wait for the last commit of each stage (the final one covers every MMA of the tile)
+    if (acct && tile == (int) 0) {
+        // marks = kernel start + cycles spent in: waiting for the MMA barrier | issue loads + dequantise (= waiting for the
+        // weight block) | cp.async wait | __syncthreads
+        TraceRec * t = batch.trace;
+        t->mark[0] = t->start + (unsigned long long) acc_wait;
+        t->mark[1] = t->start + (unsigned long long) acc_deq;
+        t->mark[2] = t->start + (unsigned long long) acc_cp;
+        t->mark[3] = t->start + (unsigned long long) acc_sync;
+    }
+    // the last commit covers every MMA of the tile
     {
         const int last = nsteps - 1;
-        mbar_wait(&sh.mma_done[last & 1], (uint32_t) ((last / STAGES) & 1));
+        mbar_wait(&sh.mma_done[last % STAGES], (uint32_t) ((last / STAGES) & 1));
         tc_fence_after_sync();
     }
     // epilogue: warps 0..3 own TMEM lanes 32w .. 32w+31 = rows row0 + 32w + lane
@@ -282,7 +331,7 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const TcBatch batch) {
+__global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ TcShared sh;
     trace_begin(batch.trace);
@@ -370,10 +419,10 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
         next += p.n_cta;
         tb.p[i] = p;
     }
-    const size_t smem = (size_t) 2 * tc::TILE_M * tc::KSTEP * 2 + (size_t) 2 * tb.npad * tc::KSTEP * 2;
+    const size_t smem = (size_t) tc::STAGES * tc::TILE_M * tc::KSTEP * 2 + (size_t) tc::STAGES * tb.npad * tc::KSTEP * 2;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * tc::TILE_M * tc::KSTEP * 2 + 2 * tc::MAX_N * tc::KSTEP * 2);
+        cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::STAGES * tc::TILE_M * tc::KSTEP * 2 + tc::STAGES * tc::MAX_N * tc::KSTEP * 2);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }

@@ -63,48 +63,133 @@ __device__ __forceinline__ float head_norm(float y, float eps, float * red) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// v5 / v6: ggml_compute_forward_rwkv_wkv6_f32 (ggml-cpu.c:11870-11905). Thread j owns state column
-// S[.][j]; per token  kv = v_j*k_i;  y_j += (kv*tf_i + S_ij) * r_i;  S_ij = S_ij*td_i + kv
-// with the same FMA grouping as the reference's vector path.
+// v5 / v6: ggml_compute_forward_rwkv_wkv6_f32 (ggml-cpu.c:11870-11905). Four threads share state column S[.][j]
+// (thread 4j+q owns key rows i in [q*S/4, (q+1)*S/4)), so the per-token loop is S/4 long and the head's S outputs are
+// combined with two shuffles;  kv = v_j*k_i;  y_j += (kv*tf_i + S_ij) * r_i;  S_ij = S_ij*td_i + kv  with the same FMA
+// grouping as the reference's vector path. Per-head norm statistics (ggml_norm, double sums) by warp shuffles.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double wkv_warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void wkv_cp16(void * smem_dst, const void * gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t) __cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void wkv_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void wkv_cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+constexpr int WKV6_TB = 8;   // tokens per staged chunk
+template <int S> struct __align__(16) Wkv6Chunk { float k[WKV6_TB][S], r[WKV6_TB][S], d[WKV6_TB][S], v[WKV6_TB][S], g[WKV6_TB][S]; };
+
 template <int S>
-__global__ void __launch_bounds__(S) wkv6_kernel(const Wkv6Params p) {
-    __shared__ float sk[S], sr[S], sd[S], sf[S], red[S];
+__global__ void __launch_bounds__(4 * S) wkv6_kernel(const Wkv6Params p) {
+    constexpr int Q = S / 4, TB = WKV6_TB, NT = 4 * S;
+    __shared__ Wkv6Chunk<S> buf[2];
+    __shared__ __align__(16) float sf[S], sdc[S];
+    __shared__ float red[2][S];
     trace_begin(p.trace);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int h = blockIdx.x, j = threadIdx.x, C = p.H * S;
+    const int h = blockIdx.x, tid = threadIdx.x, j = tid >> 2, q = tid & 3, C = p.H * S;
     // the recurrent state (written by the previous token's pass) and the parameters do not depend on the previous
     // kernel: pull them in before the programmatic-dependency wait
-    float st[S];
+    float st[Q];
 #pragma unroll
-    for (int i = 0; i < S; i++) st[i] = p.state_in[((size_t) h * S + i) * S + j];
-    sf[j] = p.per_head_scalars ? p.tf[h] : p.tf[h * S + j];
-    if (!p.td_per_token) sd[j] = p.per_head_scalars ? p.td[h] : p.td[h * S + j];
+    for (int ii = 0; ii < Q; ii++) st[ii] = p.state_in[((size_t) h * S + q * Q + ii) * S + j];
+    if (tid < S) {
+        sf[tid] = p.per_head_scalars ? p.tf[h] : p.tf[h * S + tid];
+        sdc[tid] = p.td_per_token ? 0.f : (p.per_head_scalars ? p.td[h] : p.td[h * S + tid]);
+    }
     const float lw = p.lnx_w[h * S + j], lb = p.lnx_b[h * S + j];
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int t = 0; t < p.T; t++) {
-        const size_t o = (size_t) t * C + h * S + j;
-        __syncthreads();
-        sk[j] = p.k[o];
-        sr[j] = p.r[o];
-        if (p.td_per_token) sd[j] = p.td[o];
-        __syncthreads();
-        const float vj = p.v[o];
-        float y = 0.f;
-#pragma unroll
-        for (int i = 0; i < S; i++) {
-            const float kv = __fmul_rn(vj, sk[i]);
-            const float temp = __fmaf_rn(kv, sf[i], st[i]);
-            y = __fmaf_rn(temp, sr[i], y);
-            st[i] = __fmaf_rn(st[i], sd[i], kv);
+
+    // chunks of TB tokens of (k, r, decay, v, gate) rows of this head travel to shared memory by cp.async, one chunk
+    // ahead of the recurrence: the serial token loop never waits on a global load
+    const int nchunks = (p.T + TB - 1) / TB;
+    auto stage = [&](int c) {
+        Wkv6Chunk<S> & B = buf[c & 1];
+        const int t0 = c * TB, nt = min(TB, p.T - t0);
+        constexpr int PER_ROW = S / 4;
+        for (int idx = tid; idx < nt * PER_ROW; idx += NT) {
+            const int tt = idx / PER_ROW, f = (idx % PER_ROW) * 4;
+            const size_t o = (size_t) (t0 + tt) * C + h * S + f;
+            wkv_cp16(&B.k[tt][f], p.k + o);
+            wkv_cp16(&B.r[tt][f], p.r + o);
+            wkv_cp16(&B.v[tt][f], p.v + o);
+            if (p.td_per_token) wkv_cp16(&B.d[tt][f], p.td + o);
+            if (p.g) wkv_cp16(&B.g[tt][f], p.g + o);
         }
-        float n = head_norm<S>(y, p.eps, red);
-        n = __fadd_rn(__fmul_rn(n, lw), lb);
-        if (p.g) n = __fmul_rn(n, p.g[o]);
-        p.y[o] = n;
+    };
+    stage(0);
+    wkv_cp_commit();
+    for (int c = 0; c < nchunks; c++) {
+        if (c + 1 < nchunks) stage(c + 1);
+        wkv_cp_commit();
+        wkv_cp_wait<1>();
+        __syncthreads();
+        const Wkv6Chunk<S> & B = buf[c & 1];
+        const int t0 = c * TB, nt = min(TB, p.T - t0);
+        for (int tt = 0; tt < nt; tt++) {
+            const float * dd = p.td_per_token ? B.d[tt] : sdc;
+            const float vj = B.v[tt][j];
+            float y = 0.f;
+            if constexpr (Q % 4 == 0) {
+#pragma unroll
+                for (int i4 = 0; i4 < Q / 4; i4++) {
+                    const int i = q * Q + i4 * 4;
+                    const float4 k4 = *reinterpret_cast<const float4 *>(&B.k[tt][i]);
+                    const float4 r4 = *reinterpret_cast<const float4 *>(&B.r[tt][i]);
+                    const float4 d4 = *reinterpret_cast<const float4 *>(&dd[i]);
+                    const float4 f4 = *reinterpret_cast<const float4 *>(&sf[i]);
+                    const float kk[4] = {k4.x, k4.y, k4.z, k4.w}, rr[4] = {r4.x, r4.y, r4.z, r4.w};
+                    const float d_[4] = {d4.x, d4.y, d4.z, d4.w}, ff[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        float & sv = st[i4 * 4 + e];
+                        const float kv = __fmul_rn(vj, kk[e]);
+                        const float temp = __fmaf_rn(kv, ff[e], sv);
+                        y = __fmaf_rn(temp, rr[e], y);
+                        sv = __fmaf_rn(sv, d_[e], kv);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int ii = 0; ii < Q; ii++) {
+                    const int i = q * Q + ii;
+                    const float kv = __fmul_rn(vj, B.k[tt][i]);
+                    const float temp = __fmaf_rn(kv, sf[i], st[ii]);
+                    y = __fmaf_rn(temp, B.r[tt][i], y);
+                    st[ii] = __fmaf_rn(st[ii], dd[i], kv);
+                }
+            }
+            y += __shfl_xor_sync(0xffffffffu, y, 1);
+            y += __shfl_xor_sync(0xffffffffu, y, 2);
+            // per-head norm (ggml_norm over the head, ggml-cpu.c:6906-6925): sum and sum of squares in double
+            float * rd = red[tt & 1];
+            if (q == 0) rd[j] = y;
+            __syncthreads();
+            double s1 = 0, s2 = 0;
+            {
+                const int lane = tid & 31;
+#pragma unroll
+                for (int i = lane; i < S; i += 32) { const double e = (double) rd[i]; s1 += e; s2 += e * e; }
+                s1 = wkv_warp_sum_d(s1);
+                s2 = wkv_warp_sum_d(s2);
+            }
+            const double mean_d = s1 / S;
+            const float mean = (float) mean_d;
+            const float var = (float) fmax(s2 / S - mean_d * mean_d, 0.0);
+            float n = (y - mean) * (1.0f / sqrtf(var + p.eps));
+            n = __fadd_rn(__fmul_rn(n, lw), lb);
+            if (q == 0) {
+                if (p.g) n = __fmul_rn(n, B.g[tt][j]);
+                p.y[(size_t) (t0 + tt) * C + h * S + j] = n;
+            }
+        }
+        __syncthreads();     // the chunk buffer is refilled two iterations later, red[] parity restarts
     }
 #pragma unroll
-    for (int i = 0; i < S; i++) p.state_out[((size_t) h * S + i) * S + j] = st[i];
+    for (int ii = 0; ii < Q; ii++) p.state_out[((size_t) h * S + q * Q + ii) * S + j] = st[ii];
     trace_end(p.trace);
 }
 
@@ -197,7 +282,14 @@ cudaError_t launch_wkv6(const Wkv6Params & p_in, cudaStream_t s) {
     Wkv6Params p = p_in;
     p.trace = trace_slot("wkv6");
     g_kernel_launches++;
-    RWKV_DISPATCH_HEAD_SIZE(p.S, wkv6_kernel, p, s)
+    switch (p.S) {
+        case 8: return launch_pdl(wkv6_kernel<8>, dim3(p.H), dim3(32), 0, s, p);
+        case 16: return launch_pdl(wkv6_kernel<16>, dim3(p.H), dim3(64), 0, s, p);
+        case 32: return launch_pdl(wkv6_kernel<32>, dim3(p.H), dim3(128), 0, s, p);
+        case 64: return launch_pdl(wkv6_kernel<64>, dim3(p.H), dim3(256), 0, s, p);
+        case 128: return launch_pdl(wkv6_kernel<128>, dim3(p.H), dim3(512), 0, s, p);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_wkv7(const Wkv7Params & p_in, cudaStream_t s) {

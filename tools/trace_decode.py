@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import __graft_entry__, bench
 import synthetic_model as sm
-ap = argparse.ArgumentParser(); ap.add_argument("workload"); ap.add_argument("--out", default=None); ap.add_argument("--show", type=int, default=40)
+ap = argparse.ArgumentParser(); ap.add_argument("workload"); ap.add_argument("--out", default=None); ap.add_argument("--show", type=int, default=40); ap.add_argument("--prefill", type=int, default=0)
 a = ap.parse_args()
 pkg = __graft_entry__.load_package(); lib = pkg.load_rwkv_shared_library(); L = lib.library
 path, preset = bench.workload_file(a.workload)
@@ -19,9 +19,15 @@ st = (ctypes.c_double * N)(); en = (ctypes.c_double * N)(); names = ctypes.creat
 marks = (ctypes.c_double * (4 * N))()
 L.rwkv_b200_trace_set_marks_buffer.argtypes = [ctypes.POINTER(ctypes.c_double)]
 L.rwkv_b200_trace_set_marks_buffer(marks)
-for i in range(8):   # eager, eager, capture, replay...
-    L.rwkv_b200_eval_resident(ctx.ptr, ctypes.cast(ctypes.byref(arr, 4 * i), PU), 1, True, None)
-    n = L.rwkv_b200_trace_read(ctx.ptr, st, en, ctypes.cast(names, ctypes.c_void_p), N)
+if a.prefill:
+    toks = sm.synthetic_tokens(a.prefill, preset["V"]); arr = (ctypes.c_uint32 * a.prefill)(*toks)
+    for i in range(3):
+        L.rwkv_b200_eval_resident(ctx.ptr, arr, a.prefill, True, None)
+        n = L.rwkv_b200_trace_read(ctx.ptr, st, en, ctypes.cast(names, ctypes.c_void_p), N)
+else:
+    for i in range(8):   # eager, eager, capture, replay...
+        L.rwkv_b200_eval_resident(ctx.ptr, ctypes.cast(ctypes.byref(arr, 4 * i), PU), 1, True, None)
+        n = L.rwkv_b200_trace_read(ctx.ptr, st, en, ctypes.cast(names, ctypes.c_void_p), N)
 rows = [(names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode(), st[i], en[i]) for i in range(n)]
 total = max(r[2] for r in rows)
 print("records", n, "step span %.1f us" % total)
