@@ -332,13 +332,18 @@ bool rwkv_b200_matvec(int data_type, int K, int M, int T, const void * weights, 
         GemvProblem & p = b.p[0];
         p.W = dW; p.pitch = (long long) pitch; p.type = data_type; p.K = K; p.M = M;
         p.x = dx; p.ldx = K; p.y = dy; p.ldy = M; p.epi = epilogue; p.pro = PRO_NONE;
-        void * act16 = nullptr;
+        void * act16 = nullptr, * tiled = nullptr;
         const size_t act16_bytes = (size_t) ((T + 15) / 16 * 16) * K * 2 + 256;
-        const bool use_tc = gemm_tc_supported(p, T) && !getenv("RWKV_B200_NO_TC");
+        // passes of >= 32 tokens go through the tensor-core kernel, which streams the tile-major copy of the matrix
+        if (T >= 32 && gemm_tc_eligible(data_type, K) && !getenv("RWKV_B200_NO_TC")) {
+            ok = cudaMalloc(&tiled, gemm_tc_tiled_bytes(data_type, M, K)) == cudaSuccess && gemm_tc_repack(dW, (long long) pitch, data_type, M, K, tiled, 0) == cudaSuccess;
+            p.Wt = tiled;
+        }
+        const bool use_tc = ok && gemm_tc_supported(p, T);
         if (use_tc) ok = cudaMalloc(&act16, act16_bytes) == cudaSuccess && gemm_tc_launch(b, di, 0, act16, act16_bytes) == cudaSuccess;
         else ok = gemv_launch(b, di, 0) == cudaSuccess;
         ok = ok && cudaDeviceSynchronize() == cudaSuccess && cudaMemcpy(y, dy, sizeof(float) * M * T, cudaMemcpyDeviceToHost) == cudaSuccess;
-        cudaFree(act16);
+        cudaFree(act16); cudaFree(tiled);
     }
     cudaError_t e = cudaGetLastError();
     cudaFree(dW); cudaFree(dx); cudaFree(dy);

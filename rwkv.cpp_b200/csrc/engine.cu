@@ -63,7 +63,7 @@ struct Batch {
     explicit Batch(int T) { memset(&b, 0, sizeof(b)); b.T = T; }
     GemvProblem & add(const DevMatrix & W, const float * x, float * y, int epi = EPI_NONE) {
         GemvProblem & p = b.p[b.n++];
-        p.W = W.data; p.pitch = W.pitch; p.type = W.type; p.K = W.K; p.M = W.M;
+        p.W = W.data; p.Wt = W.tiled; p.pitch = W.pitch; p.type = W.type; p.K = W.K; p.M = W.M;
         p.x = x; p.ldx = W.K;
         p.y = y; p.ldy = W.M;
         p.epi = epi; p.pro = PRO_NONE;

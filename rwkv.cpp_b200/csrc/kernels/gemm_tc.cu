@@ -1,18 +1,27 @@
 // Chunked-prefill contraction on the 5th-generation tensor cores:  Y[M, T] = epilogue(W[M, K] . X[K, T])  for T >= 32.
 //
 // This is the one place of the eval path where the chunk x embedding contraction is dense enough for tensor cores
-// (~325 FLOP/B at T = 128). Per CTA: one 128-row tile of W against all T (<= 256) tokens.
+// (~325 FLOP/B at T = 128). Per CTA: one 128-row tile of W against all T (<= 256) tokens, warp-specialised:
 //
-//   A operand  the CTA's 256 threads read their own ggml block (or 32 f16 weights) of the tile from global memory
-//              each K-step of 64, dequantise it to fp16 in registers ((q - offset) * d + m, rounded once) and store it
-//              into shared memory in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices)
-//   B operand  fp16 activations [T][K] (converted once per launch by convert_f16_kernel), copied per K-step into the same
-//              canonical layout
-//   MMA        one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = T padded to 16, K = 16) four
-//              times per K-step; the fp32 accumulator lives in TMEM (N columns x 128 lanes); tcgen05.commit signals an
-//              mbarrier per shared-memory stage, so dequantisation of step k+1 overlaps the MMAs of step k
-//   epilogue   warps 0-3 pull the accumulator with tcgen05.ld (32x32b), apply the same fused epilogues as the GEMV
-//              (activation, bias, residual, gate) and store column-major.
+//   warp 8   raw producer   one contiguous bulk copy (cp.async.bulk, 50 KB) per K-chunk (8 K-steps: 128 rows x 16 ggml blocks,
+//                           still quantised) out of the TILE-MAJOR prefill copy of the matrix (tc_repack_kernel) into a
+//                           2-deep shared-memory ring; weights do not depend on the previous kernel, so this starts
+//                           before the programmatic-dependency wait. (A 2-D TMA box over the row-major matrix needed
+//                           ~58 cycles per 416-byte row: 3.7 us per chunk, which capped the K loop at ~1000 cycles per step.)
+//   warp 9   B producer     fp16 activations, stored by convert_f16_kernel directly in the UMMA canonical layout, one
+//                           contiguous bulk copy (16-32 KB) per K-step of 64
+//   warps 0-7 transform     each thread owns (row, block) of the K-step: read the raw block from shared memory, dequantise
+//                           to fp16 in packed-half arithmetic ((q - offset) * d + m, rounded once), store into the A stage
+//                           in the canonical K-major no-swizzle layout (8-row x 16-byte core matrices), proxy fence,
+//                           arrive. These threads never have a global load in flight, so the fence costs nothing (it is a
+//                           MEMBAR.ALL.CTA in SASS: with in-flight LDGs it serialised every K-step at HBM latency)
+//   warp 10  MMA issuer     one thread issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = T padded to 16, K = 16) four
+//                           times per K-step; the fp32 accumulator lives in TMEM (N columns x 128 lanes); tcgen05.commit
+//                           frees the A/B stage through an mbarrier
+//   epilogue warps 0-3 pull the accumulator with tcgen05.ld (32x32b), apply the same fused epilogues as the GEMV
+//                           (activation, bias, residual, gate) and store column-major.
+//
+// There is no __syncthreads in the K loop: every hand-off is an mbarrier (raw_full/raw_empty, a_full/b_full/ab_empty).
 //
 // Numerics: weights exactly as the file stores them, activations rounded to fp16, fp32 accumulate -- what the reference
 // does for F16 weights (ggml-cpu.c:259-264, 1463); for quantised weights the reference rounds activations to int8
@@ -23,16 +32,44 @@
 #include "quant_decode.cuh"
 
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <cstring>
 
 namespace rwkv {
 namespace tc {
 
 constexpr int TILE_M = 128;
-constexpr int KSTEP = 64;                 // K elements per shared-memory stage = 4 MMAs of K = 16
-constexpr int THREADS = 256;
-constexpr int STAGES = 4;                // shared-memory ring; global loads run 2 K-steps ahead of the MMAs
+constexpr int KSTEP = 64;                 // K elements per A/B stage = 4 MMAs of K = 16
+constexpr int XFORM_WARPS = 8;
+constexpr int WARP_RAW = 8, WARP_B = 9, WARP_MMA = 10;
+constexpr int THREADS = 352;
+constexpr int MAX_STAGES = 8;             // A/B ring depth (runtime: as many B stages as fit shared memory, <= 8). A stage = 32 columns of
+                                          // TENSOR MEMORY (dequantised weights) + NPAD x 64 halves of shared memory (activations)
+constexpr int MAX_RAW_STAGES = 2;         // raw (quantised) ring, in K-chunks
 constexpr int MAX_N = 256;
+// Tile-major prefill copy of a matrix: [tile of 128 rows][K-chunk][row][ROW_STRIDE bytes]; ROW_STRIDE = chunk bytes + a
+// pad that puts the 32 rows a warp reads on distinct shared-memory banks (64-bit loads for Q5_1, 128-bit for F16, 32-bit
+// for the rest), so one chunk of one tile is ONE contiguous, bank-conflict-free bulk copy.
+constexpr int QUANT_CHUNK_STEPS = 8;       // K-steps per raw chunk of the block formats
+template <int TYPE> struct RawTraits {
+    static constexpr int BLOCK_BYTES = QTraits<TYPE>::BLOCK_BYTES;
+    static constexpr int CHUNK_STEPS = QUANT_CHUNK_STEPS;
+    static constexpr int CHUNK_BYTES = CHUNK_STEPS * 2 * BLOCK_BYTES;
+    static constexpr int ROW_STRIDE = CHUNK_BYTES + (TYPE == DT_Q5_1 ? 8 : 4);
+};
+template <> struct RawTraits<DT_F16> {
+    static constexpr int BLOCK_BYTES = 64, CHUNK_STEPS = 2, CHUNK_BYTES = 256, ROW_STRIDE = CHUNK_BYTES + 16;
+};
+constexpr int MAX_RAW_STAGE_BYTES = TILE_M * (QUANT_CHUNK_STEPS * 2 * 34 + 4);
+struct RawGeom { int block_bytes, chunk_steps, chunk_bytes, row_stride; };
+inline RawGeom raw_geom(int type) {
+    RawGeom g;
+    g.block_bytes = type == DT_F16 ? 64 : dtype_block_bytes(type);
+    g.chunk_steps = type == DT_F16 ? 2 : QUANT_CHUNK_STEPS;
+    g.chunk_bytes = g.chunk_steps * 2 * g.block_bytes;
+    g.row_stride = g.chunk_bytes + (type == DT_F16 ? 16 : type == DT_Q5_1 ? 8 : 4);
+    return g;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t * bar, uint32_t count) {
@@ -48,8 +85,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity) {
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (spins > 32) __nanosleep(64);          // a waiting role must not steal issue slots from a co-resident kernel
         if (spins > (1u << 24)) __trap();
     }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void * dst, const void * src, uint32_t bytes, uint64_t * bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // ---- tcgen05 wrappers (PTX ISA 8.6+, sm_100a) ----------------------------------------------------------------------
@@ -71,6 +129,28 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// A operand from tensor memory (128 lanes x 8 columns of packed fp16 per K = 16), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes (this warp's quarter of TMEM) x 32 consecutive columns <- registers; r[j] goes to column j of the lane's row
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t * r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t * bar) {   // arrives on `bar` when every MMA issued so far has completed
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -105,56 +185,113 @@ __host__ __device__ inline uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
 }
 
-// Tile bookkeeping: [A stage0][A stage1][B stage0][B stage1]
-//   A stage: TILE_M x KSTEP halves = 16 KB : chunk (kc, g) at (kc * 16 + g) * 128 bytes   (kc = k / 8, g = row / 8)
-//   B stage: NPAD   x KSTEP halves         : chunk (kc, g) at (kc * NG + g) * 128 bytes   (NG = NPAD / 8)
+// Dynamic shared memory: [B stages][raw stages]
+//   B stage: NPAD x KSTEP halves : chunk (kc, g) at (kc * NG + g) * 128 bytes   (kc = k / 8, g = token / 8)
+//   raw stage: TILE_M rows x ROW_STRIDE bytes of quantised blocks, exactly as the tile-major copy stores them
+// Tensor memory: columns [0, NPAD) fp32 accumulator, then up to MAX_STAGES x 32 columns of A: lane = tile row, column j of a stage =
+//   fp16 pair (k = 2j, 2j + 1) of the K-step. The tensor core reads A from there (tcgen05.mma with a TMEM A operand), so
+//   the dequantised weights never touch shared memory: its bandwidth (128 B/clk) is left to the B operand and the TMA
+//   writes -- with A in shared memory the MMAs, the transform stores and the TMA traffic together needed ~600 cycles of
+//   shared-memory time per K-step against 262 cycles of tensor-core math.
 struct TcShared {
-    uint64_t mma_done[STAGES];
+    uint64_t raw_full[MAX_RAW_STAGES], raw_empty[MAX_RAW_STAGES];
+    uint64_t a_full[MAX_STAGES], b_full[MAX_STAGES], ab_empty[MAX_STAGES];
+    uint64_t acc_done;
     uint32_t tmem_base;
+    long long t0;            // clock64 at kernel start (trace marks)
     GemvProblem P;
 };
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
-__device__ __forceinline__ float tc_epilogue(const GemvProblem & P, int row, int col, float v) {
-    switch (P.epi) {
-        case EPI_SIGMOID: return sigmoidf_(v);
-        case EPI_SILU: return v / (1.0f + expf(-v));
-        case EPI_TANH: return tanhf(v);
-        case EPI_RELU_SQR: { float r = fmaxf(v, 0.0f); return r * r; }
-        case EPI_ADD: return P.res[(long long) col * P.ldres + row] + v;
-        case EPI_MUL_ADD: return P.res[(long long) col * P.ldres + row] + P.gate[(long long) col * P.ldgate + row] * v;
-        case EPI_BIAS_EXPNEGEXP: return expf(-expf(v + P.bias[row]));
-        case EPI_BIAS_SIGMOID: return sigmoidf_(v + P.bias[row]);
-        case EPI_BIAS_W7: return expf(sigmoidf_(v + P.bias[row]) * -0.606531f);
-        default: return v;
+
+// 32 accumulator columns of one row -> fused epilogue -> column-major store. Everything the loop needs sits in registers
+// (the problem record lives in shared memory: re-reading it per element made the unrolled body 250 instructions long).
+struct EpiRow { float * y; long long ldy; const float * res; long long ldres; const float * gate; long long ldgate; float bias; };
+template <int EPI> __device__ __forceinline__ void store_cols(const EpiRow & e, const uint32_t (&acc)[32], int c0, int T) {
+    // the residual / gate inputs of all 32 columns are requested before the first store: the output may alias the residual
+    // (x += ...), so a load placed after a store would have to wait for it, one L2 round trip per column
+    float rv[32], gv[32];
+    if constexpr (EPI == EPI_ADD || EPI == EPI_MUL_ADD) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) rv[j] = c0 + j < T ? e.res[(long long) (c0 + j) * e.ldres] : 0.f;
+    }
+    if constexpr (EPI == EPI_MUL_ADD) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) gv[j] = c0 + j < T ? e.gate[(long long) (c0 + j) * e.ldgate] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const int col = c0 + j;
+        if (col >= T) break;
+        float v = __uint_as_float(acc[j]);
+        if constexpr (EPI == EPI_SIGMOID) v = sigmoidf_(v);
+        else if constexpr (EPI == EPI_SILU) v = v / (1.0f + expf(-v));
+        else if constexpr (EPI == EPI_TANH) v = tanhf(v);
+        else if constexpr (EPI == EPI_RELU_SQR) { const float r = fmaxf(v, 0.0f); v = r * r; }
+        else if constexpr (EPI == EPI_ADD) v = rv[j] + v;
+        else if constexpr (EPI == EPI_MUL_ADD) v = rv[j] + gv[j] * v;
+        else if constexpr (EPI == EPI_BIAS_EXPNEGEXP) v = expf(-expf(v + e.bias));
+        else if constexpr (EPI == EPI_BIAS_SIGMOID) v = sigmoidf_(v + e.bias);
+        else if constexpr (EPI == EPI_BIAS_W7) v = expf(sigmoidf_(v + e.bias) * -0.606531f);
+        e.y[(long long) col * e.ldy] = v;
+    }
+}
+// warp w owns TMEM lanes 32 (w % 4) .. + 31 = rows row0 + 32 (w % 4) + lane; warps 0-3 take the even 32-column groups of the
+// accumulator, warps 4-7 the odd ones
+__device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, uint32_t tmem_base, int row0, int npad, int T) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3;
+    const int row = row0 + q * 32 + lane;
+    const bool live = row < Psh.M;
+    const int epi = Psh.epi;
+    EpiRow e;
+    e.y = Psh.y + row; e.ldy = Psh.ldy;
+    e.res = Psh.res ? Psh.res + row : nullptr; e.ldres = Psh.ldres;
+    e.gate = Psh.gate ? Psh.gate + row : nullptr; e.ldgate = Psh.ldgate;
+    e.bias = (live && Psh.bias) ? Psh.bias[row] : 0.f;
+#pragma unroll 1
+    for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += 64) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) c0, acc);
+        if (!live) continue;
+        switch (epi) {
+            case EPI_SIGMOID: store_cols<EPI_SIGMOID>(e, acc, c0, T); break;
+            case EPI_SILU: store_cols<EPI_SILU>(e, acc, c0, T); break;
+            case EPI_TANH: store_cols<EPI_TANH>(e, acc, c0, T); break;
+            case EPI_RELU_SQR: store_cols<EPI_RELU_SQR>(e, acc, c0, T); break;
+            case EPI_ADD: store_cols<EPI_ADD>(e, acc, c0, T); break;
+            case EPI_MUL_ADD: store_cols<EPI_MUL_ADD>(e, acc, c0, T); break;
+            case EPI_BIAS_EXPNEGEXP: store_cols<EPI_BIAS_EXPNEGEXP>(e, acc, c0, T); break;
+            case EPI_BIAS_SIGMOID: store_cols<EPI_BIAS_SIGMOID>(e, acc, c0, T); break;
+            case EPI_BIAS_W7: store_cols<EPI_BIAS_W7>(e, acc, c0, T); break;
+            default: store_cols<EPI_NONE>(e, acc, c0, T); break;
+        }
     }
 }
 
 // 32 weights of one ggml block (or 32 f16 values) -> 4 x 16 bytes of fp16, element order 0..31
 template <int TYPE> struct BlockRegs { uint32_t w[TYPE == DT_F16 ? 16 : (TYPE == DT_Q8_0 ? 9 : 6)]; };
 
-template <int TYPE> __device__ __forceinline__ void load_block(const uint8_t * row, int blk, BlockRegs<TYPE> & r) {
+// block `blk` of a raw row in shared memory (32-bit shared address) -> registers
+template <int TYPE> __device__ __forceinline__ void read_block(uint32_t row, int blk, BlockRegs<TYPE> & r) {
     if constexpr (TYPE == DT_F16) {
-        const uint4 * p = reinterpret_cast<const uint4 *>(row + (size_t) blk * 64);
 #pragma unroll
-        for (int i = 0; i < 4; i++) { const uint4 v = __ldg(p + i); r.w[4 * i] = v.x; r.w[4 * i + 1] = v.y; r.w[4 * i + 2] = v.z; r.w[4 * i + 3] = v.w; }
+        for (int i = 0; i < 4; i++) { const uint4 v = lds128(row + blk * 64 + i * 16); r.w[4 * i] = v.x; r.w[4 * i + 1] = v.y; r.w[4 * i + 2] = v.z; r.w[4 * i + 3] = v.w; }
     } else if constexpr (TYPE == DT_Q5_1) {          // 24-byte blocks on an 8-byte grid
-        const uint2 * p = reinterpret_cast<const uint2 *>(row + (size_t) blk * 24);
 #pragma unroll
-        for (int i = 0; i < 3; i++) { const uint2 v = __ldg(p + i); r.w[2 * i] = v.x; r.w[2 * i + 1] = v.y; }
+        for (int i = 0; i < 3; i++) { const uint2 v = lds64(row + blk * 24 + i * 8); r.w[2 * i] = v.x; r.w[2 * i + 1] = v.y; }
     } else if constexpr (TYPE == DT_Q4_1) {          // 20-byte blocks on a 4-byte grid
-        const uint32_t * p = reinterpret_cast<const uint32_t *>(row + (size_t) blk * 20);
 #pragma unroll
-        for (int i = 0; i < 5; i++) r.w[i] = __ldg(p + i);
+        for (int i = 0; i < 5; i++) r.w[i] = lds32(row + blk * 20 + i * 4);
     } else {
         // 18 / 22 / 34-byte blocks start on a 2-byte grid: read whole words from the aligned-down address and realign
         constexpr int BB = QTraits<TYPE>::BLOCK_BYTES;
         constexpr int NW = BB / 4 + 1;
-        const size_t start = (size_t) blk * BB;
-        const uint32_t * p = reinterpret_cast<const uint32_t *>(row + (start & ~(size_t) 3));
+        const uint32_t start = (uint32_t) blk * BB;
+        const uint32_t base = row + (start & ~3u);
         uint32_t t[NW];
 #pragma unroll
-        for (int i = 0; i < NW; i++) t[i] = __ldg(p + i);
+        for (int i = 0; i < NW; i++) t[i] = lds32(base + i * 4);
         if (start & 2) {
 #pragma unroll
             for (int i = 0; i < NW - 1; i++) r.w[i] = funnel16(t[i], t[i + 1]);
@@ -198,133 +335,150 @@ template <int TYPE> __device__ __forceinline__ void block_to_half(const BlockReg
 struct TcBatch {
     int n, T, npad;                  // problems, tokens, tokens padded to a multiple of 16
     int tmem_cols;                   // power of two >= 32
-    const __half * act16[GEMV_MAX_PROBLEMS];   // [npad][K] fp16 per problem
+    int raw_stages;                  // 2 or 3
+    int b_stages;                    // A/B ring depth, 2 .. MAX_STAGES
+    int experiment;                  // timing experiments (RWKV_B200_TC_EXPERIMENT): 1 = B copied only for the first ring pass, 2 = same for raw
+    const __half * act16[GEMV_MAX_PROBLEMS];   // canonical-layout fp16 activations per problem (convert_f16_kernel)
     GemvProblem p[GEMV_MAX_PROBLEMS];          // first_cta / n_cta = tiles of 128 rows
     TraceRec * trace;
 };
 
-__device__ __forceinline__ void cp_async16(void * smem_dst, const void * gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// B tile of K-step `ks` (NPAD x 64 halves of fp16 activations) -> stage, asynchronously. 16 lanes cover 16 tokens, lane / 16
-// picks one of two adjacent 8-element chunks, so a warp reads 32-byte runs and writes conflict-free 128-byte runs.
-__device__ __forceinline__ void copy_b_async(uint8_t * b_stage, const __half * act16, int K, int NPAD, int k0) {
-    const int NG = NPAD / 8;
-    for (int i = threadIdx.x; i < NPAD * 8; i += THREADS) {
-        const int pair = i / 32, lane = i % 32;
-        const int tg = pair / 4, cp = pair % 4;
-        const int n = tg * 16 + (lane % 16), kc = cp * 2 + lane / 16;
-        cp_async16(b_stage + (uint32_t) (kc * NG + n / 8) * 128 + (n % 8) * 16, act16 + (size_t) n * K + k0 + kc * 8);
-    }
-}
-
 template <int TYPE>
 __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, const __half * act16, int tile) {
+    using RT = RawTraits<TYPE>;
     const GemvProblem & P = sh.P;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = P.K, NPAD = batch.npad, NG = NPAD / 8;
     const int row0 = tile * TILE_M;
-    const uint32_t a_bytes = TILE_M * KSTEP * 2, b_bytes = (uint32_t) NPAD * KSTEP * 2;
-    uint8_t * const a_base = smem;
-    uint8_t * const b_base = smem + STAGES * a_bytes;
-
-    // my weight block of every K-step: row (tid / 2), block (tid % 2) of the step
-    const int my_row = min(row0 + tid / 2, P.M - 1);
-    const uint8_t * wrow = reinterpret_cast<const uint8_t *>(P.W) + (size_t) my_row * (size_t) P.pitch;
-    const int blk_in_step = tid & 1;
-    const int r_local = tid / 2;
-    const uint32_t a_dst0 = (uint32_t) ((blk_in_step * 4) * 16 + r_local / 8) * 128 + (r_local % 8) * 16;   // + c * 16 * 128 for chunk c
-
-    const uint32_t idesc = make_idesc(TILE_M, NPAD);
+    const uint32_t b_bytes = (uint32_t) NPAD * KSTEP * 2;
+    constexpr uint32_t raw_bytes = (uint32_t) TILE_M * RT::ROW_STRIDE;
+    uint8_t * const b_base = smem;
+    const uint32_t tmem_a0 = sh.tmem_base + (uint32_t) NPAD;      // + stage * 32 columns
+    const int nb = batch.b_stages;
+    uint8_t * const raw_base = b_base + (size_t) nb * b_bytes;
     const int nsteps = K / KSTEP;
-    // software pipeline, distance 2: weights of step ks+2 travel to registers and activations of step ks+2 to shared
-    // memory (cp.async) while step ks is dequantised and multiplied
-    // One K-step. `cur` holds this step's weight block, `fut` receives the block of step ks+2. The three register sets
-    // rotate by NAME (the loop below is unrolled by 3): a `w0 = w1` style rotation would read the in-flight load at the end
-    // of the very iteration that issued it and turn the distance-2 prefetch into distance 0.
-    // phase accounting of CTA 0 / thread 0 (cycles), reported through the trace marks
-    const bool acct = batch.trace != nullptr && blockIdx.x == 0 && tid == 0;
-    long long acc_wait = 0, acc_deq = 0, acc_cp = 0, acc_sync = 0, tq = 0;
-    auto tick = [&](long long & a) { if (acct) { const long long c = clock64(); a += c - tq; tq = c; } };
-    auto step = [&](int ks, const BlockRegs<TYPE> & cur, BlockRegs<TYPE> & fut) {
-        const int s = ks % STAGES;
-        if (acct) tq = clock64();
-        if (ks + 2 < nsteps) {
-            const int s2 = (ks + 2) % STAGES;
-            // stage s2 was last read by the MMAs of step ks-2
-            if (ks >= 2) mbar_wait(&sh.mma_done[s2], (uint32_t) ((((ks - 2) / STAGES)) & 1));
-            tick(acc_wait);
-            load_block<TYPE>(wrow, (ks + 2) * 2 + blk_in_step, fut);
-            copy_b_async(b_base + (size_t) s2 * b_bytes, act16, K, NPAD, (ks + 2) * KSTEP);
-        }
-        cp_async_commit();
-        // A: dequantise my block of step ks -> 4 chunks of 8 halves. Stage s was last read at step ks-4, whose commit was
-        // awaited at step ks-2.
-        uint4 h[4];
-        block_to_half<TYPE>(cur, h);
-        uint8_t * a_stage = a_base + (size_t) s * a_bytes;
-#pragma unroll
-        for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(a_stage + a_dst0 + (uint32_t) c * 16 * 128) = h[c];
-        tick(acc_deq);
-        cp_async_wait<2>();
-        tick(acc_cp);          // the activations of step ks have landed (groups ks+1, ks+2 may still fly)
-        fence_async_smem();          // generic-proxy writes -> visible to the tensor core's async proxy
-        __syncthreads();
-        tick(acc_sync);
-        if (tid == 0) {
-            tc_fence_after_sync();
-            const uint32_t a_addr = smem_u32(a_stage), b_addr = smem_u32(b_base + (size_t) s * b_bytes);
-#pragma unroll
-            for (int j = 0; j < KSTEP / 16; j++) {
-                const uint64_t adesc = make_desc(a_addr + (uint32_t) (2 * j) * 16 * 128, 16 * 128, 128);
-                const uint64_t bdesc = make_desc(b_addr + (uint32_t) (2 * j) * NG * 128, (uint32_t) NG * 128, 128);
-                umma_f16(sh.tmem_base, adesc, bdesc, idesc, (ks > 0 || j > 0) ? 1u : 0u);
-            }
-            umma_commit(&sh.mma_done[s]);
-        }
-    };
-    BlockRegs<TYPE> w0, w1, w2;
-    load_block<TYPE>(wrow, blk_in_step, w0);
-    copy_b_async(b_base, act16, K, NPAD, 0);
-    cp_async_commit();
-    if (nsteps > 1) { load_block<TYPE>(wrow, 2 + blk_in_step, w1); copy_b_async(b_base + b_bytes, act16, K, NPAD, KSTEP); }
-    cp_async_commit();
-    for (int ks = 0; ks < nsteps; ks += 3) {
-        step(ks, w0, w2);
-        if (ks + 1 < nsteps) step(ks + 1, w1, w0);
-        if (ks + 2 < nsteps) step(ks + 2, w2, w1);
-    }
-    if (acct && tile == (int) 0) {
-        // marks = kernel start + cycles spent in: waiting for the MMA barrier | issue loads + dequantise (= waiting for the
-        // weight block) | cp.async wait | __syncthreads
-        TraceRec * t = batch.trace;
-        t->mark[0] = t->start + (unsigned long long) acc_wait;
-        t->mark[1] = t->start + (unsigned long long) acc_deq;
-        t->mark[2] = t->start + (unsigned long long) acc_cp;
-        t->mark[3] = t->start + (unsigned long long) acc_sync;
-    }
-    // the last commit covers every MMA of the tile
-    {
-        const int last = nsteps - 1;
-        mbar_wait(&sh.mma_done[last % STAGES], (uint32_t) ((last / STAGES) & 1));
-        tc_fence_after_sync();
-    }
-    // epilogue: warps 0..3 own TMEM lanes 32w .. 32w+31 = rows row0 + 32w + lane
-    if (warp < 4) {
-        const int row = row0 + warp * 32 + (tid & 31);
-        for (int c0 = 0; c0 < NPAD; c0 += 32) {
-            uint32_t acc[32];
-            tmem_ld32(sh.tmem_base + ((uint32_t) (warp * 32) << 16) + (uint32_t) c0, acc);
-            if (row < P.M) {
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int col = c0 + j;
-                    if (col < batch.T) P.y[(long long) col * P.ldy + row] = tc_epilogue(P, row, col, __uint_as_float(acc[j]));
+    const int nraw = batch.raw_stages;
+
+    if (warp == WARP_RAW) {
+        if (lane == 0) {
+            const int nchunks = (nsteps + RT::CHUNK_STEPS - 1) / RT::CHUNK_STEPS;
+            const uint8_t * wt = reinterpret_cast<const uint8_t *>(P.Wt);
+            int rs = 0; uint32_t ph = 0;
+            for (int c = 0; c < nchunks; c++) {
+                mbar_wait(&sh.raw_empty[rs], ph ^ 1);
+                if ((batch.experiment & 2) && c >= nraw) { mbar_arrive(&sh.raw_full[rs]); }
+                else {
+                    mbar_expect_tx(&sh.raw_full[rs], raw_bytes);
+                    bulk_load(raw_base + (size_t) rs * raw_bytes, wt + ((size_t) tile * nchunks + c) * raw_bytes, raw_bytes, &sh.raw_full[rs]);
                 }
+                if (++rs == nraw) { rs = 0; ph ^= 1; }
             }
+        }
+    } else if (warp == WARP_B) {
+        if (lane == 0) {
+            pdl_prologue();     // the activations come from the previous kernels
+            int s = 0; uint32_t ph = 0;
+            for (int ks = 0; ks < nsteps; ks++) {
+                mbar_wait(&sh.ab_empty[s], ph ^ 1);
+                if ((batch.experiment & 1) && ks >= nb) { mbar_arrive(&sh.b_full[s]); }
+                else {
+                    mbar_expect_tx(&sh.b_full[s], b_bytes);
+                    bulk_load(b_base + (size_t) s * b_bytes, act16 + (size_t) ks * KSTEP * NPAD, b_bytes, &sh.b_full[s]);
+                }
+                if (++s == nb) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == WARP_MMA) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(TILE_M, NPAD);
+            // everything the issue loop needs sits in registers: TMEM addresses, the constant descriptor half and the 14-bit
+            // start-address field of each B stage; per K-step the thread does two waits, 4 MMAs and ONE commit
+            const uint32_t tmem_d = sh.tmem_base;
+            const uint64_t desc_fixed = make_desc(0, (uint32_t) NG * 128, 128);
+            const uint32_t b_addr0 = smem_u32(b_base) >> 4, b_stage16 = b_bytes >> 4, b_k16 = (uint32_t) (2 * NG * 128) >> 4;
+            int s = 0; uint32_t ph = 0;
+            for (int ks = 0; ks < nsteps; ks++) {
+                const uint32_t a_col = tmem_a0 + (uint32_t) (s * 32);
+                const uint64_t d0 = desc_fixed | (uint64_t) ((b_addr0 + (uint32_t) s * b_stage16) & 0x3FFFu);
+                const uint64_t d1 = desc_fixed | (uint64_t) ((b_addr0 + (uint32_t) s * b_stage16 + b_k16) & 0x3FFFu);
+                const uint64_t d2 = desc_fixed | (uint64_t) ((b_addr0 + (uint32_t) s * b_stage16 + 2 * b_k16) & 0x3FFFu);
+                const uint64_t d3 = desc_fixed | (uint64_t) ((b_addr0 + (uint32_t) s * b_stage16 + 3 * b_k16) & 0x3FFFu);
+                mbar_wait(&sh.b_full[s], ph);
+                mbar_wait(&sh.a_full[s], ph);
+                tc_fence_after_sync();
+                umma_f16_ts(tmem_d, a_col, d0, idesc, ks > 0 ? 1u : 0u);
+                umma_f16_ts(tmem_d, a_col + 8, d1, idesc, 1u);
+                umma_f16_ts(tmem_d, a_col + 16, d2, idesc, 1u);
+                umma_f16_ts(tmem_d, a_col + 24, d3, idesc, 1u);
+                umma_commit(&sh.ab_empty[s]);          // the A and B stage are free once these MMAs have read them
+                if (++s == nb) { s = 0; ph ^= 1; }
+            }
+            umma_commit(&sh.acc_done);                 // ... and the accumulator is final
+        }
+    } else {
+        // transform: thread = row r of the tile, BOTH blocks of a K-step (two independent dequantisation chains in
+        // flight, one wait / store / arrive per 64 k); warps 0-3 take the even K-steps, warps 4-7 the odd ones, so two
+        // A stages are being filled at any time. Warp w owns TMEM lanes 32 * (w % 4) .. + 31 = its 32 rows.
+        const int r = tid & (TILE_M - 1), grp = tid >> 7;
+        const uint32_t raw_row0 = smem_u32(raw_base) + (uint32_t) r * RT::ROW_STRIDE;
+        const uint32_t tmem_a_mine = tmem_a0 + ((uint32_t) ((warp & 3) * 32) << 16);
+        // trace marks of CTA 0 (cycles, stored as start + cycles): [0] transform waited for raw chunks, [1] for a free A
+        // stage, [2] the MMA issuer waited for operands, [3] the whole K loop
+        // trace marks of CTA 0, thread 0 (cycles, stored as start + cycles): [0] waiting for raw chunks, [1] reading + dequantising
+        // two blocks, [2] waiting for a free A stage, [3] tcgen05.st + fences + arrive
+        const bool acct = batch.trace != nullptr && blockIdx.x == 0 && tid == 0;
+        long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, tq = acct ? clock64() : 0;
+        auto tick = [&](long long & a) { if (acct) { const long long now = clock64(); a += now - tq; tq = now; } };
+        int s = grp, rs = 0, cur_chunk = -1; uint32_t ph = 0, rph = 0;
+        for (int ks = grp; ks < nsteps; ks += 2) {
+            const int c = ks / RT::CHUNK_STEPS, sc = ks % RT::CHUNK_STEPS;
+            if (c != cur_chunk) {
+                if (cur_chunk >= 0 && ++rs == nraw) { rs = 0; rph ^= 1; }
+                cur_chunk = c;
+                mbar_wait(&sh.raw_full[rs], rph);
+            }
+            tick(c0);
+            BlockRegs<TYPE> regs0, regs1;
+            read_block<TYPE>(raw_row0 + (uint32_t) rs * raw_bytes, sc * 2, regs0);
+            read_block<TYPE>(raw_row0 + (uint32_t) rs * raw_bytes, sc * 2 + 1, regs1);
+            // last step of this warp inside the chunk: the raw rows are in registers, hand the slot back
+            const bool last_in_chunk = sc + 2 >= RT::CHUNK_STEPS || ks + 2 >= nsteps;
+            uint4 h0[4], h1[4];
+            block_to_half<TYPE>(regs0, h0);
+            block_to_half<TYPE>(regs1, h1);
+            if (last_in_chunk) { __syncwarp(); if (lane == 0) mbar_arrive(&sh.raw_empty[rs]); }
+            tick(c1);
+            mbar_wait(&sh.ab_empty[s], ph ^ 1);
+            tick(c2);
+            tc_fence_after_sync();
+            {
+                uint32_t w32[32];
+#pragma unroll
+                for (int cc = 0; cc < 4; cc++) {
+                    w32[4 * cc] = h0[cc].x; w32[4 * cc + 1] = h0[cc].y; w32[4 * cc + 2] = h0[cc].z; w32[4 * cc + 3] = h0[cc].w;
+                    w32[16 + 4 * cc] = h1[cc].x; w32[16 + 4 * cc + 1] = h1[cc].y; w32[16 + 4 * cc + 2] = h1[cc].z; w32[16 + 4 * cc + 3] = h1[cc].w;
+                }
+                tmem_st32(tmem_a_mine + (uint32_t) (s * 32), w32);
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.a_full[s]);
+            tick(c3);
+            s += 2;
+            if (s >= nb) { s -= nb; ph ^= 1; }
+        }
+        if (acct) {
+            TraceRec * t = batch.trace;
+            t->mark[0] = t->start + (unsigned long long) c0; t->mark[1] = t->start + (unsigned long long) c1;
+            t->mark[2] = t->start + (unsigned long long) c2; t->mark[3] = t->start + (unsigned long long) c3;
+        }
+        {
+            pdl_prologue();     // residual / gate inputs come from the previous kernels
+            mbar_wait(&sh.acc_done, 0);
+            const bool acct_e = batch.trace != nullptr && blockIdx.x == 0 && tid == 0;
+            tc_fence_after_sync();
+            tc_epilogue_rows(P, sh.tmem_base, row0, NPAD, batch.T);
+            (void) acct_e;
         }
     }
     tc_fence_before_sync();
@@ -335,18 +489,21 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ TcShared sh;
     trace_begin(batch.trace);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     int pi = 0;
     for (int i = 1; i < batch.n; i++) if ((int) blockIdx.x >= batch.p[i].first_cta) pi = i;
     if (threadIdx.x == 0) {
+        sh.t0 = clock64();
         sh.P = batch.p[pi];
-        for (int s = 0; s < STAGES; s++) mbar_init(&sh.mma_done[s], 1);
+        for (int s = 0; s < MAX_RAW_STAGES; s++) { mbar_init(&sh.raw_full[s], 1); mbar_init(&sh.raw_empty[s], XFORM_WARPS); }
+        for (int s = 0; s < MAX_STAGES; s++) { mbar_init(&sh.a_full[s], XFORM_WARPS / 2); mbar_init(&sh.b_full[s], 1); mbar_init(&sh.ab_empty[s], 1); }
+        mbar_init(&sh.acc_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 32) tmem_alloc(&sh.tmem_base, (uint32_t) batch.tmem_cols);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    pdl_prologue();     // activations (act16, residuals) come from the previous kernels
     const int tile = (int) blockIdx.x - sh.P.first_cta;
     const __half * act16 = batch.act16[pi];
     switch (sh.P.type) {
@@ -361,27 +518,78 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
     trace_end(batch.trace);
 }
 
-// x fp32 [K, T] column-major (column t contiguous) -> fp16 [npad][K], rows >= T zero-filled
+// x fp32 [K, T] column-major (column t contiguous) -> fp16 in the UMMA canonical layout, one contiguous B stage per
+// K-step:  [K / 64][kc = 8][g = npad / 8][8 tokens][8 k]  (tokens >= T zero-filled). One thread = one 16-byte chunk.
 __global__ void convert_f16_kernel(const float * x, long long ldx, int K, int T, int npad, __half * out, TraceRec * trace) {
     trace_begin(trace);
     pdl_prologue();
-    const long long n4 = (long long) npad * K / 4;
-    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long) gridDim.x * blockDim.x) {
-        const long long e = i * 4;
-        const int t = (int) (e / K), k = (int) (e % K);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t < T) v = *reinterpret_cast<const float4 *>(x + (long long) t * ldx + k);
-        __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
-        *reinterpret_cast<uint2 *>(out + e) = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+    const int NG = npad / 8;
+    const long long nchunks = (long long) npad * K / 8;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < nchunks; i += (long long) gridDim.x * blockDim.x) {
+        const int t8 = (int) (i & 7);
+        const long long j = i >> 3;
+        const int g = (int) (j % NG);
+        const long long j2 = j / NG;
+        const int kc = (int) (j2 & 7), ks = (int) (j2 >> 3);
+        const int t = g * 8 + t8, k = ks * KSTEP + kc * 8;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (t < T) {
+            const float4 v0 = *reinterpret_cast<const float4 *>(x + (long long) t * ldx + k);
+            const float4 v1 = *reinterpret_cast<const float4 *>(x + (long long) t * ldx + k + 4);
+            __half2 a = __floats2half2_rn(v0.x, v0.y), b = __floats2half2_rn(v0.z, v0.w);
+            __half2 c = __floats2half2_rn(v1.x, v1.y), d = __floats2half2_rn(v1.z, v1.w);
+            o = make_uint4(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b), *reinterpret_cast<uint32_t *>(&c), *reinterpret_cast<uint32_t *>(&d));
+        }
+        *reinterpret_cast<uint4 *>(out + i * 8) = o;
     }
     trace_end(trace);
 }
 
+// Row-major matrix (rows of `pitch` bytes) -> tile-major prefill copy. One thread per 4-byte word of the destination.
+__global__ void tc_repack_kernel(const uint8_t * src, long long pitch, int M, int nchunks, int chunk_bytes, int row_stride, uint8_t * dst) {
+    const int words_per_row = row_stride / 4;
+    const long long stage_words = (long long) TILE_M * words_per_row;
+    const long long total = (long long) gridDim.y * nchunks * stage_words;      // gridDim.y = tiles
+    for (long long w = (long long) blockIdx.x * blockDim.x + threadIdx.x + (long long) blockIdx.y * nchunks * stage_words;
+         w < ((long long) blockIdx.y + 1) * nchunks * stage_words && w < total; w += (long long) gridDim.x * blockDim.x) {
+        const long long in_tile = w - (long long) blockIdx.y * nchunks * stage_words;
+        const int c = (int) (in_tile / stage_words);
+        const int rem = (int) (in_tile % stage_words);
+        const int r = rem / words_per_row, off = (rem % words_per_row) * 4;
+        const int row = blockIdx.y * TILE_M + r;
+        const long long col = (long long) c * chunk_bytes + off;
+        uint32_t v = 0;
+        if (row < M && off < chunk_bytes && col + 4 <= pitch) v = *reinterpret_cast<const uint32_t *>(src + (long long) row * pitch + col);
+        reinterpret_cast<uint32_t *>(dst)[w] = v;
+    }
+}
+
 }  // namespace tc
 
+bool gemm_tc_eligible(int type, int K) { return type != DT_F32 && K % tc::KSTEP == 0 && K >= tc::KSTEP; }
+
+size_t gemm_tc_tiled_bytes(int type, int M, int K) {
+    if (!gemm_tc_eligible(type, K)) return 0;
+    const tc::RawGeom g = tc::raw_geom(type);
+    const size_t nsteps = (size_t) K / tc::KSTEP, nchunks = (nsteps + g.chunk_steps - 1) / g.chunk_steps, ntiles = ((size_t) M + tc::TILE_M - 1) / tc::TILE_M;
+    return ntiles * nchunks * tc::TILE_M * (size_t) g.row_stride;
+}
+
+cudaError_t gemm_tc_repack(const void * W, long long pitch, int type, int M, int K, void * dst, cudaStream_t stream) {
+    if (!gemm_tc_eligible(type, K)) return cudaErrorInvalidValue;
+    const tc::RawGeom g = tc::raw_geom(type);
+    const int nsteps = K / tc::KSTEP, nchunks = (nsteps + g.chunk_steps - 1) / g.chunk_steps, ntiles = (M + tc::TILE_M - 1) / tc::TILE_M;
+    const long long words_per_tile = (long long) nchunks * tc::TILE_M * (g.row_stride / 4);
+    int bx = (int) ((words_per_tile + 255) / 256);
+    if (bx > 64) bx = 64;
+    tc::tc_repack_kernel<<<dim3(bx, ntiles), 256, 0, stream>>>(reinterpret_cast<const uint8_t *>(W), pitch, M, nchunks, g.chunk_bytes, g.row_stride,
+                                                               reinterpret_cast<uint8_t *>(dst));
+    return cudaGetLastError();
+}
+
 bool gemm_tc_supported(const GemvProblem & p, int T) {
-    return T >= 32 && T <= tc::MAX_N && p.type != DT_F32 && p.K % tc::KSTEP == 0 && p.K >= tc::KSTEP && (p.ldx % 4) == 0 &&
-           (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
+    return T >= 32 && T <= tc::MAX_N && p.Wt != nullptr && gemm_tc_eligible(p.type, p.K) && (p.ldx % 4) == 0 &&
+           (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.Wt) & 15) == 0;
 }
 
 // act16_scratch: device buffer of at least sum over problems of npad * K halves.
@@ -392,7 +600,9 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
     tb.n = batch.n; tb.T = batch.T;
     tb.npad = (batch.T + 15) / 16 * 16;
     tb.tmem_cols = 32;
-    while (tb.tmem_cols < tb.npad) tb.tmem_cols *= 2;
+    while (tb.tmem_cols < tb.npad + tc::MAX_STAGES * 32) tb.tmem_cols *= 2;      // accumulator + A stages
+    tb.raw_stages = 2;
+    { static const int ex = getenv("RWKV_B200_TC_EXPERIMENT") ? atoi(getenv("RWKV_B200_TC_EXPERIMENT")) : 0; tb.experiment = ex; }
     __half * scratch = reinterpret_cast<__half *>(act16_scratch);
     size_t used = 0;
     int next = 0;
@@ -405,8 +615,8 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
         if (!shared) {
             if (used + need > scratch_bytes) return cudaErrorMemoryAllocation;
             __half * dst = scratch + used / sizeof(__half);
-            const long long n4 = (long long) tb.npad * p.K / 4;
-            const int blocks = (int) ((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184);
+            const long long n8 = (long long) tb.npad * p.K / 8;
+            const int blocks = (int) ((n8 + 255) / 256 < 1184 ? (n8 + 255) / 256 : 1184);
             g_kernel_launches++;
             cudaError_t e = launch_pdl(tc::convert_f16_kernel, dim3(blocks), dim3(256), 0, stream, p.x, p.ldx, p.K, batch.T, tb.npad, dst, trace_slot("convert_f16"));
             if (e != cudaSuccess) return e;
@@ -419,10 +629,19 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
         next += p.n_cta;
         tb.p[i] = p;
     }
-    const size_t smem = (size_t) tc::STAGES * tc::TILE_M * tc::KSTEP * 2 + (size_t) tc::STAGES * tb.npad * tc::KSTEP * 2;
+    // shared memory: 2 raw chunks and as many B stages as fit (a bulk copy needs ~1500 cycles to land, a
+    // K-step takes ~400: the B ring has to run several steps ahead)
+    constexpr size_t smem_budget = 227 * 1024 - 2048;
+    constexpr size_t fixed = 2 * (((size_t) tc::MAX_RAW_STAGE_BYTES + 127) & ~(size_t) 127);
+    const size_t b_bytes = (size_t) tb.npad * tc::KSTEP * 2;
+    int nb = (int) ((smem_budget - fixed) / b_bytes);
+    if (nb > tc::MAX_STAGES) nb = tc::MAX_STAGES;
+    if (nb < 2) return cudaErrorInvalidValue;
+    tb.b_stages = nb;
+    const size_t smem = fixed + (size_t) nb * b_bytes;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::STAGES * tc::TILE_M * tc::KSTEP * 2 + tc::STAGES * tc::MAX_N * tc::KSTEP * 2);
+        cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_budget);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }

@@ -24,6 +24,7 @@ enum GemvPrologue : int { PRO_NONE = 0, PRO_LAYERNORM = 1 };   // LN(x; ln_w, ln
 
 struct GemvProblem {
     const void * W;          // device, rows of quant blocks / f16 / f32, `pitch` bytes apart (16-B multiple)
+    const void * Wt;         // device, tile-major prefill copy of W (gemm_tc_repack) or NULL: no tensor-core path
     long long pitch;
     int type, K, M;
     const float * x;  long long ldx;      // input  column t at x + t*ldx
@@ -69,6 +70,10 @@ cudaError_t gemv_generic_launch(GemvBatch & batch, const DeviceInfo & dev, cudaS
 // Tensor-core (tcgen05) path for chunks of >= 32 tokens (gemm_tc.cu). act16_scratch: device scratch for the fp16 copies of the
 // input matrices (sum over distinct inputs of round16(T) * K halves).
 bool gemm_tc_supported(const GemvProblem & p, int T);
+// The tile-major prefill copy of a matrix the tensor-core path streams (0 bytes = the matrix cannot take that path).
+bool gemm_tc_eligible(int type, int K);
+size_t gemm_tc_tiled_bytes(int type, int M, int K);
+cudaError_t gemm_tc_repack(const void * W, long long pitch, int type, int M, int K, void * dst, cudaStream_t stream);
 cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream, void * act16_scratch, size_t scratch_bytes);
 
 // Programmatic dependent launch for every kernel of the eval path (RWKV_B200_NO_PDL=1 turns it off).

@@ -152,85 +152,73 @@ __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const LnMixParams p)
     trace_end(p.trace);
 }
 
-// 8 lanes per channel, 32 channels x `tile_tokens` tokens per CTA: each (j, channel) row of W2 is `mix` contiguous floats.
-// The W2 rows (5.2 MB per layer at 7B, straight from HBM) are pulled into registers before the programmatic-dependency
-// wait and reused for every token of the tile; z, sx, xx of the tile are staged in shared memory and the five outputs
-// leave through shared memory as 128-byte rows.
-constexpr int LERP_MAX_F4 = 4;   // float4 per lane per j held in registers: mix <= 128
-constexpr int LERP_TILE_TOKENS = 16;
-__global__ void __launch_bounds__(GLUE_THREADS) v6_lerp_kernel(const V6LerpParams p, const int tile_tokens) {
-    extern __shared__ __align__(16) float lerp_smem[];
+// One thread per channel, 128 channels x LERP_TILE_TOKENS tokens per CTA. For each of the five mixes the thread holds
+// its W2 row (`mix` contiguous floats, 5.2 MB per layer at 7B) in registers and walks the tile's tokens; z[:, t] of the
+// tile sits in shared memory and is read as broadcasts. The first W2 row is pulled before the programmatic-dependency wait.
+constexpr int LERP_THREADS = 128;
+constexpr int LERP_TILE_TOKENS = 8;
+constexpr int LERP_MAX_F4 = 16;   // W2 row in registers: mix <= 64
+__global__ void __launch_bounds__(LERP_THREADS) v6_lerp_kernel(const V6LerpParams p) {
+    extern __shared__ __align__(16) float lerp_zs[];        // [tile][5 * mix]
     trace_begin(p.trace);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int mix = p.mix, C = p.C, tid = threadIdx.x;
-    const int grp = tid >> 3, sub = tid & 7;
-    const int c0 = blockIdx.x * 32, c = c0 + grp;
+    const int c = blockIdx.x * LERP_THREADS + tid;
     const bool live = c < C;
-    const bool vec = (mix & 3) == 0 && mix / 4 <= 8 * LERP_MAX_F4;
-    const int t0 = blockIdx.y * tile_tokens, nt = min(tile_tokens, p.T - t0);
-    float * zs = lerp_smem;                            // [tile][5*mix]
-    float * sxs = zs + (size_t) tile_tokens * 5 * mix; // [tile][32]
-    float * xxs = sxs + tile_tokens * 32;              // [tile][32]
-    float * outs = xxs + tile_tokens * 32;             // [5][tile][32]
-    float4 wreg[5][LERP_MAX_F4];
-    float maa[5];
+    const int cc = live ? c : 0;
+    const int m4 = mix / 4;
+    const bool vec = (mix & 3) == 0 && m4 <= LERP_MAX_F4;
+    const int t0 = blockIdx.y * LERP_TILE_TOKENS, nt = min(LERP_TILE_TOKENS, p.T - t0);
+    float4 w[LERP_MAX_F4];
+    auto load_w = [&](int j) {
+        const float4 * wrow = reinterpret_cast<const float4 *>(p.w2 + ((size_t) j * C + cc) * mix);
 #pragma unroll
-    for (int j = 0; j < 5; j++) {
-        const float4 * wrow = reinterpret_cast<const float4 *>(p.w2 + ((size_t) j * C + (live ? c : 0)) * mix);
-#pragma unroll
-        for (int q = 0; q < LERP_MAX_F4; q++) {
-            const int i4 = sub + 8 * q;
-            wreg[j][q] = (vec && live && i4 < mix / 4) ? __ldg(wrow + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        maa[j] = live ? p.maa[j][c] : 0.f;
-    }
+        for (int i = 0; i < LERP_MAX_F4; i++) w[i] = (vec && i < m4) ? __ldg(wrow + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    load_w(0);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     {
         const float * zsrc = p.z + (size_t) t0 * 5 * mix;          // the tile's z columns are contiguous
         const int nz = nt * 5 * mix;
         if ((mix & 3) == 0) {
-            for (int i = tid; i < nz / 4; i += GLUE_THREADS) reinterpret_cast<float4 *>(zs)[i] = __ldg(reinterpret_cast<const float4 *>(zsrc) + i);
+            for (int i = tid; i < nz / 4; i += LERP_THREADS) reinterpret_cast<float4 *>(lerp_zs)[i] = __ldg(reinterpret_cast<const float4 *>(zsrc) + i);
         } else {
-            for (int i = tid; i < nz; i += GLUE_THREADS) zs[i] = zsrc[i];
-        }
-        for (int i = tid; i < nt * 32; i += GLUE_THREADS) {
-            const int tt = i >> 5, cc = c0 + (i & 31);
-            const size_t o = (size_t) (t0 + tt) * C + cc;
-            sxs[i] = cc < C ? p.sx[o] : 0.f;
-            xxs[i] = cc < C ? p.xx[o] : 0.f;
+            for (int i = tid; i < nz; i += LERP_THREADS) lerp_zs[i] = zsrc[i];
         }
     }
+    float sx[LERP_TILE_TOKENS], xx[LERP_TILE_TOKENS];
+#pragma unroll
+    for (int tt = 0; tt < LERP_TILE_TOKENS; tt++) {
+        const size_t o = (size_t) (t0 + (tt < nt ? tt : 0)) * C + cc;
+        sx[tt] = __ldg(p.sx + o);
+        xx[tt] = __ldg(p.xx + o);
+    }
     __syncthreads();
-    for (int tt = 0; tt < nt; tt++) {
-        const float * zt = zs + (size_t) tt * 5 * mix;
+#pragma unroll 1
+    for (int j = 0; j < 5; j++) {
+        if (j > 0) load_w(j);
+        const float maa = p.maa[j][cc];
 #pragma unroll
-        for (int j = 0; j < 5; j++) {
-            float acc = 0.f;
-            const float * zj = zt + j * mix;
-            if (vec) {
+        for (int tt = 0; tt < LERP_TILE_TOKENS; tt++) {
+            if (tt < nt) {
+                const float * zj = lerp_zs + (size_t) tt * 5 * mix + j * mix;
+                float acc = 0.f;
+                if (vec) {
 #pragma unroll
-                for (int q = 0; q < LERP_MAX_F4; q++) {
-                    const int i4 = sub + 8 * q;
-                    if (i4 < mix / 4) {
-                        const float4 w = wreg[j][q], z = reinterpret_cast<const float4 *>(zj)[i4];
-                        acc = __fmaf_rn(w.x, z.x, acc); acc = __fmaf_rn(w.y, z.y, acc);
-                        acc = __fmaf_rn(w.z, z.z, acc); acc = __fmaf_rn(w.w, z.w, acc);
+                    for (int i = 0; i < LERP_MAX_F4; i++) {
+                        if (i < m4) {
+                            const float4 z = reinterpret_cast<const float4 *>(zj)[i];
+                            acc = __fmaf_rn(w[i].x, z.x, acc); acc = __fmaf_rn(w[i].y, z.y, acc);
+                            acc = __fmaf_rn(w[i].z, z.z, acc); acc = __fmaf_rn(w[i].w, z.w, acc);
+                        }
                     }
+                } else {
+                    const float * wrow = p.w2 + ((size_t) j * C + cc) * mix;
+                    for (int i = 0; i < mix; i++) acc = __fmaf_rn(__ldg(wrow + i), zj[i], acc);
                 }
-            } else if (live) {
-                const float * wrow = p.w2 + ((size_t) j * C + c) * mix;
-                for (int i = sub; i < mix; i += 8) acc = __fmaf_rn(__ldg(wrow + i), zj[i], acc);
+                if (live) p.out[j][(size_t) (t0 + tt) * C + c] = __fadd_rn(__fmul_rn(__fadd_rn(acc, maa), sx[tt]), xx[tt]);
             }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            if (sub == 0) outs[(j * tile_tokens + tt) * 32 + grp] = __fadd_rn(__fmul_rn(__fadd_rn(acc, maa[j]), sxs[tt * 32 + grp]), xxs[tt * 32 + grp]);
         }
-    }
-    __syncthreads();
-    for (int i = tid; i < 5 * nt * 32; i += GLUE_THREADS) {
-        const int j = i / (nt * 32), r = i % (nt * 32), tt = r >> 5, cc = c0 + (r & 31);
-        if (cc < C) p.out[j][(size_t) (t0 + tt) * C + cc] = outs[(j * tile_tokens + tt) * 32 + (r & 31)];
     }
     trace_end(p.trace);
 }
@@ -259,15 +247,11 @@ cudaError_t launch_ln_mix(const LnMixParams & p_in, cudaStream_t s) {
 cudaError_t launch_v6_lerp(const V6LerpParams & p_in, cudaStream_t s) {
     V6LerpParams p = p_in;
     p.trace = trace_slot("v6_lerp");
-    // tile of tokens per CTA: as many as fit 40 KB of shared memory, at most LERP_TILE_TOKENS
-    const int per_token = (5 * p.mix + 64 + 160) * (int) sizeof(float);
-    int tile = LERP_TILE_TOKENS;
-    while (tile > 1 && tile * per_token > 40 * 1024) tile >>= 1;
-    if (tile > p.T) tile = p.T;
-    if (tile * per_token > 48 * 1024) return cudaErrorInvalidValue;
-    dim3 grid((p.C + 31) / 32, (p.T + tile - 1) / tile);
+    const size_t smem = (size_t) LERP_TILE_TOKENS * 5 * p.mix * sizeof(float);
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    dim3 grid((p.C + LERP_THREADS - 1) / LERP_THREADS, (p.T + LERP_TILE_TOKENS - 1) / LERP_TILE_TOKENS);
     g_kernel_launches++;
-    return launch_pdl(v6_lerp_kernel, grid, dim3(GLUE_THREADS), (size_t) tile * per_token, s, p, tile);
+    return launch_pdl(v6_lerp_kernel, grid, dim3(LERP_THREADS), smem, s, p);
 }
 
 }  // namespace rwkv

@@ -4,6 +4,7 @@
 // payloads to the device.
 #define _FILE_OFFSET_BITS 64
 #include "model.h"
+#include "kernels/gemv.h"   // gemm_tc_tiled_bytes / gemm_tc_repack
 
 #include <cinttypes>
 #include <cstdlib>
@@ -30,6 +31,7 @@ struct Request {
     uint64_t expect_n = 0;                 // vectors:  0 = unchecked
     const TensorInfo * info = nullptr;
     size_t arena_offset = 0;
+    size_t tiled_offset = 0, tiled_bytes = 0;   // matrices that get a tile-major prefill copy
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -41,7 +43,8 @@ inline long long matrix_pitch(int type, uint64_t K) {
         uint64_t nblk = K / 32;
         bytes = (size_t) ((nblk + 1) / 2 * 2) * dtype_block_bytes(type);
     }
-    return (long long) align_up(bytes, 16);
+    static const long long extra = getenv("RWKV_B200_PITCH_PAD") ? atoll(getenv("RWKV_B200_PITCH_PAD")) : 0;   // experiment knob
+    return (long long) align_up(bytes, 16) + extra;
 }
 
 // Host dequantisation of a whole tensor to fp32 (only for element-wise parameters that someone
@@ -235,6 +238,7 @@ Model * load_model(const char * path, int device, int layer_begin, int layer_end
     }
 
     // ---- resolve + validate + lay out the arena ----
+    const bool tc_copies = getenv("RWKV_B200_NO_TC") == nullptr;
     size_t arena_bytes = 0, staging_bytes = 0;
     for (Request & r : reqs) {
         r.info = mf.find(r.name);
@@ -255,6 +259,13 @@ Model * load_model(const char * path, int device, int layer_begin, int layer_end
             const long long pitch = matrix_pitch((int) t.data_type, K);
             r.arena_offset = arena_bytes;
             arena_bytes += align_up((size_t) M * (size_t) pitch + 256, 256);
+            // every per-layer matrix also gets the tile-major copy the tensor-core prefill kernel streams (gemm_tc.cu); the
+            // embedding is a gather and the head only ever sees the last token of a pass
+            if (tc_copies && r.name != "emb.weight" && r.name != "head.weight") {
+                r.tiled_bytes = gemm_tc_tiled_bytes((int) t.data_type, (int) M, (int) K);
+                r.tiled_offset = arena_bytes;
+                arena_bytes += align_up(r.tiled_bytes, 256);
+            }
         } else {
             RWKV_CHECK(sink, RWKV_ERROR_MODEL_PARAMS | RWKV_ERROR_SHAPE, nullptr, (r.expect_n == 0 || n == r.expect_n) && n > 0,
                        "Unexpected element count %" PRIu64 " of parameter %s", n, r.name.c_str());
@@ -311,6 +322,13 @@ Model * load_model(const char * path, int device, int layer_begin, int layer_end
             } else {
                 ce = cudaMemset(dst, 0, (size_t) d.M * (size_t) d.pitch);
                 if (ce == cudaSuccess) ce = cudaMemcpy2D(dst, (size_t) d.pitch, staging.get(), row_bytes, row_bytes, (size_t) d.M, cudaMemcpyHostToDevice);
+            }
+            if (ce == cudaSuccess && r.tiled_bytes) {
+                uint8_t * td = m.arena + r.tiled_offset;
+                ce = gemm_tc_repack(dst, d.pitch, d.type, d.M, d.K, td, 0);
+                if (ce == cudaSuccess) ce = cudaStreamSynchronize(0);     // the staging buffer is reused by the next tensor
+                d.tiled = td;
+                m.tiled_bytes += r.tiled_bytes;
             }
             const size_t bytes = t.nbytes;
             if (r.name == "emb.weight") m.weight_bytes_per_token += row_bytes;

@@ -16,6 +16,7 @@ namespace rwkv {
 
 struct DevMatrix {          // y = W x : K = ne0 (input), M = ne1*ne2 (output rows)
     const uint8_t * data = nullptr;
+    const uint8_t * tiled = nullptr;   // tile-major prefill copy (gemm_tc_repack) or NULL
     int type = 0, K = 0, M = 0;
     long long pitch = 0;
     explicit operator bool() const { return data != nullptr; }
@@ -62,6 +63,7 @@ struct Model {
     DeviceInfo dev{};
     uint8_t * arena = nullptr;
     size_t arena_bytes = 0;
+    size_t tiled_bytes = 0;              // of which: tile-major prefill copies of the layer matrices
     size_t weight_bytes_per_token = 0;   // byte model of SURVEY.md 8(d), resident layers, with head
     size_t head_bytes = 0;
     std::atomic<int> refcount{0};

@@ -90,7 +90,7 @@ def test_gemv_zero_and_extreme_activations(lib):
 
 
 @pytest.mark.parametrize("fmt", ["FP16", "Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q8_0"])
-@pytest.mark.parametrize("shape,T", [((128, 64), 32), ((256, 128), 48), ((160, 4096), 128), ((4096, 256), 64), ((512, 14336), 128), ((130, 192), 33), ((128, 64), 256)])
+@pytest.mark.parametrize("shape,T", [((128, 64), 32), ((256, 128), 48), ((160, 4096), 128), ((4096, 256), 64), ((512, 14336), 128), ((130, 192), 33), ((128, 64), 256), ((300, 2688), 100), ((140, 320), 250)])
 def test_tensor_core_gemm_matches_fp16_reference(lib, fmt, shape, T):
     """tcgen05 prefill kernel (csrc/kernels/gemm_tc.cu), used for passes of >= 32 tokens: weights exactly as stored,
     activations rounded to fp16, fp32 accumulation -- compared with that computation done in float64."""

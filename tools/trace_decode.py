@@ -44,6 +44,32 @@ print("...")
 for l in lines[-6:]: print(l)
 for nm, (c, d, g) in sorted(agg.items(), key=lambda x: -x[1][1]):
     print("%-18s n=%4d busy %8.1f us  (avg %6.2f)  gaps-before %7.1f us" % (nm, c, d, d / c, g))
+# critical-path attribution: each kernel is charged the time by which it pushed the end of the timeline out
+att = {}; pe = None
+for nm, s_, e_ in rows:
+    if pe is None: pe = s_
+    att.setdefault(nm, [0, 0.0]); att[nm][0] += 1
+    if e_ > pe: att[nm][1] += e_ - pe; pe = e_
+print("critical-path attribution:")
+for nm, (c, d) in sorted(att.items(), key=lambda x: -x[1][1]): print("  %-16s n=%4d  %9.1f us  (avg %7.2f)" % (nm, c, d, d / c))
+# one layer from the middle, with the in-kernel cycle counters of the kernels that report them
+mid = [i for i, r in enumerate(rows) if r[0].startswith("wkv")]
+if mid:
+    k = mid[len(mid) // 2]; pe = None
+    for i in range(max(0, k - 14), min(len(rows), k + 8)):
+        nm, s_, e_ = rows[i]
+        cyc = [int(round((marks[4 * i + q] - s_) * 1000)) for q in range(4)] if marks[4 * i] >= 0 else ""
+        print("  %-12s start %9.1f dur %7.1f crit %7.1f %s" % (nm, s_, e_ - s_, e_ - (pe if pe is not None else s_), cyc))
+        pe = max(pe or 0, e_)
+try:
+    import pynvml
+    pynvml.nvmlInit(); h = pynvml.nvmlDeviceGetHandleByIndex(0); clk = []
+    for i in range(10):
+        L.rwkv_b200_eval_resident(ctx.ptr, arr, a.prefill or 1, True, None)
+        clk.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+    print("sm clock MHz under load:", clk)
+except Exception as ex:
+    print("clock sample failed:", ex)
 if a.out:
     with open(a.out, "w") as f:
         f.write("idx,name,start_us,end_us,m0_after_wait,m1_after_stage,m2_after_tile0,m3_after_tile2\n")
