@@ -116,6 +116,23 @@ def host_buffers(n_state, n_logits):
     return s, l, s.ctypes.data, l.ctypes.data, "pageable"
 
 
+def prefill_matmul_flops(preset, n_tokens):
+    """FLOPs of the weight contractions of one chunk (2 * weights * tokens), per-layer matrices only; None for shapes not modelled."""
+    if preset.get("arch", (0, 0))[0] != 6:
+        return None
+    C, F, Lr, mix, dec = preset["C"], preset["F"], preset["L"], preset["mix"], preset["decay"]
+    per_layer = 5 * C * C + C * 5 * mix + 5 * mix * C + 2 * C * dec + 2 * C * F + C * C
+    return 2.0 * per_layer * Lr * n_tokens
+
+
+def measured_tensor_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        return 1500.0, "fallback (B200_PROFILING.md)"
+
+
 def measured_peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -359,7 +376,12 @@ def run_ours(args, rank, world, dist):
                     "host_buffers": kind, "ms_per_step": e2e_s / K * 1e3},
             "gpu_launches": int(launches),
             "prefill": {"tokens_per_s": world * P * PREFILL_TOKENS / (pms / 1e3), "ms_per_chunk": pms / P, "chunk": PREFILL_TOKENS, "steps": P,
-                        "e2e_tokens_per_s": world * PREFILL_TOKENS / pe2e_s},
+                        "e2e_tokens_per_s": world * PREFILL_TOKENS / pe2e_s,
+                        "kernel": "gemm_tc_kernel (tcgen05, TMEM accumulators + TMEM A operand) for every layer matrix; wkv6 / lerp / LN on CUDA cores",
+                        "tensor": (lambda fl, pk: None if fl is None else {"bound": "tensor", "achieved": fl / (pms / P * 1e-3) / 1e12, "peak": pk[0], "unit": "TFLOP/s",
+                                                                            "frac": fl / (pms / P * 1e-3) / 1e12 / pk[0], "peak_source": pk[1],
+                                                                            "note": "whole chunk (GEMMs + recurrence + glue) against the dense bf16 peak"})(
+                            prefill_matmul_flops(preset, PREFILL_TOKENS), measured_tensor_peak())},
             "roofline": {"bound": "hbm", "kernel": "gemv_kernel (fused dequantize-GEMV, all launches of one decode step)",
                          "achieved": gemv_bytes / (gemv_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": gemv_bytes / (gemv_ms * 1e-3) / 1e9 / peak,
                          "peak_source": peak_src, "traffic": None, "bytes_per_step": gemv_bytes, "ms_per_step": gemv_ms,
@@ -382,6 +404,117 @@ def run_ours(args, rank, world, dist):
         print(json.dumps(line), flush=True)
 
 
+def run_pipeline(args, rank, world, dist):
+    """N > 1: layer pipeline (rwkv.cpp_b200/pipeline.py). Rank g holds layers [g*L/N, (g+1)*L/N) and their slice of
+    the recurrent state; `world` sequences are in flight, one per stage; x f32[C x T] crosses each stage boundary by NCCL
+    send/recv on the stream the stage kernels run on. One step = one token of every in-flight sequence (`world` tokens)."""
+    import torch
+    import __graft_entry__
+    import synthetic_model as sm
+    pkg = __graft_entry__.load_package()
+    pipeline = pkg.pipeline
+    lib = pkg.load_rwkv_shared_library()
+    L = lib.library
+    path, preset = workload_file(args.workload, rank, world, lambda: dist.barrier())
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    begin, end = pipeline.stage_layers(preset["L"], world, rank)
+    t0 = time.time()
+    ctxs = [lib.rwkv_b200_init_from_file_ex(path, local, begin, end)]
+    for _ in range(world - 1):
+        ctxs.append(lib.rwkv_clone_context(ctxs[0], 1))          # one context = one in-flight sequence's state slice
+    load_s = time.time() - t0
+    log("rank %d: layers [%d, %d) loaded in %.1fs" % (rank, begin, end, load_s))
+    n_vocab = lib.rwkv_get_logits_len(ctxs[0])
+    for c in ctxs:
+        L.rwkv_b200_state_load(c.ptr, None)
+        L.rwkv_b200_synchronize(c.ptr)
+    K, W, P = args.steps, args.warmup, args.prefill_steps
+    first, last = rank == 0, rank == world - 1
+    stream = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    transport = pipeline.Transport(dist, rank, world)
+    sampler = ClockSampler(local)
+    sampler.start()
+    windows = []
+    logits_host = torch.zeros(n_vocab, dtype=torch.float32).pin_memory()
+    bytes_tok = int(L.rwkv_b200_bytes_per_token(ctxs[0].ptr, True))   # this stage's share of the byte model
+
+    def leg(T, steps, warm, read_logits):
+        """`steps` timed steps of `world` work items each (one per in-flight sequence), after `warm` untimed ones."""
+        toks = sm.synthetic_tokens((steps + warm) * world * T + T, n_vocab)
+        arr = (ctypes.c_uint32 * len(toks))(*toks)
+        n_hidden = L.rwkv_b200_stage_hidden_len(ctxs[0].ptr, T)
+        recv = torch.empty(n_hidden, dtype=torch.float32, device=f"cuda:{local}")
+        send = torch.empty(n_hidden, dtype=torch.float32, device=f"cuda:{local}")
+        state = {"u": 0}
+
+        def stage(seq, step, hin, hout):
+            u = state["u"]; state["u"] += 1
+            ok = L.rwkv_b200_stage_eval(ctxs[seq].ptr, ctypes.cast(ctypes.byref(arr, 4 * u * T), PU), T,
+                                        ctypes.c_void_p(hin.data_ptr()) if hin is not None else None,
+                                        ctypes.c_void_p(hout.data_ptr()) if hout is not None else None, True, sp)
+            assert ok, "stage_eval failed"
+            if read_logits and last:
+                assert L.rwkv_b200_stage_logits(ctxs[seq].ptr, ctypes.cast(logits_host.data_ptr(), PF), sp)
+
+        pipeline.run_ticks(transport, pipeline.schedule(world, world, warm * world, rank), stage, recv, send)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = L.rwkv_b200_kernel_launch_count()
+        w0 = time.time(); t0 = time.perf_counter()
+        e0.record(stream)
+        pipeline.run_ticks(transport, pipeline.schedule(world, world, steps * world, rank), stage, recv, send)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dist.barrier()
+        windows.append((w0, time.time()))
+        t = torch.tensor([e0.elapsed_time(e1), wall * 1e3, float(L.rwkv_b200_kernel_launch_count() - launches0)], device=f"cuda:{local}")
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm_ = t.clone(); dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
+        return float(mx[0]), float(mx[1]), float(sm_[2])
+
+    dev_ms, _, launches = leg(1, K, max(W, 3), False)                      # decode, logits stay on the last stage's GPU
+    log("pipeline decode: %.3f ms per step of %d tokens" % (dev_ms / K, world))
+    _, e2e_ms, _ = leg(1, K, max(W, 3), True)                              # + token H2D on stage 0, logits D2H on the last stage, per token
+    pdev_ms, _, _ = leg(PREFILL_TOKENS, P, 2, False)
+    _, pe2e_ms, _ = leg(PREFILL_TOKENS, P, 1, True)
+    sampler.stop()
+    clocks = sampler.summary(windows)
+    stage_bytes = torch.tensor([float(bytes_tok)], device=f"cuda:{local}")
+    dist.all_reduce(stage_bytes, op=dist.ReduceOp.MAX)
+    for c in ctxs[1:]:
+        lib.rwkv_free(c)
+    lib.rwkv_free(ctxs[0])
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        tick_ms = dev_ms / (K * world)                                      # one token leaves the pipeline per tick
+        gbs = float(stage_bytes.item()) / (tick_ms * 1e-3) / 1e9
+        line = {
+            "metric": "decode_tokens_per_sec", "value": world * K / (dev_ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "q5_1 weights x q8_1 activations (int8 dp4a, fp32 accumulate); fp16 head" if "Q5_1" in args.workload else args.workload.split(":")[1],
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload} single-token eval with logits ({preset['L']} layers, n_embed {preset['C']}, ffn {preset['F']}, vocab {preset['V']})",
+                       "parallelism": f"pp{world}: {preset['L'] // world} layers + their state slice per GPU, {world} sequences in flight (one per stage), "
+                                      f"x f32[{preset['C']}] per token over NCCL send/recv; one step = {world} tokens",
+                       "l2": "each stage streams its share of 6.1 GB of weights per token >> 126 MB L2, no flush needed", "load_s": round(load_s, 2), "cuda_graph": True},
+            "clocks": clocks,
+            "e2e": {"value": world * K / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": 4 * world, "d2h_bytes_per_step": 4 * n_vocab * world,
+                    "host_buffers": "pinned", "ms_per_step": e2e_ms / K,
+                    "note": "token ids enter on stage 0, logits leave from the last stage; the recurrent state stays resident on its stage"},
+            "gpu_launches": int(launches),
+            "prefill": {"tokens_per_s": world * P * PREFILL_TOKENS / (pdev_ms / 1e3), "ms_per_chunk": pdev_ms / (P * world), "chunk": PREFILL_TOKENS, "steps": P,
+                        "e2e_tokens_per_s": world * P * PREFILL_TOKENS / (pe2e_ms / 1e3)},
+            "roofline": {"bound": "hbm", "kernel": "whole pipeline tick of the slowest stage (fused dequant-GEMV launches + glue)",
+                         "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": peak_src, "traffic": None,
+                         "bytes_per_step": float(stage_bytes.item()), "ms_per_step": tick_ms,
+                         "note": "per GPU: the largest stage's bytes per token / time per pipeline tick; per-launch figures are in the N=1 line"},
+            "cpu_baseline": {"value": None, "unit": "tokens/s", "cores": 0, "kind": "reference", "sample": "reported by the N=1 run and by --impl reference"},
+        }
+        print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -396,7 +529,10 @@ def main():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
         dist_mod.init_process_group("nccl")
         dist = dist_mod
-    run_ours(args, rank, world, dist)
+    if world > 1:
+        run_pipeline(args, rank, world, dist)
+    else:
+        run_ours(args, rank, world, dist)
     if dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -38,6 +38,21 @@ RWKV_API bool rwkv_b200_state_store(struct rwkv_context * ctx, float * state_out
 /* Blocks until everything enqueued on the context's stream has finished. */
 RWKV_API bool rwkv_b200_synchronize(struct rwkv_context * ctx);
 
+/* Layer pipeline across GPUs (the reference has no equivalent: ggml offloads layers of ONE context,
+ * rwkv.cpp:97-116). A context created with rwkv_b200_init_from_file_ex(path, device, begin, end) is one stage; its slice
+ * of the recurrent state stays resident on that device. Per pass of n_tokens (<= 256):
+ *   first stage : embeds `tokens`, writes its output activations to hidden_out
+ *   inner stage : reads hidden_in, writes hidden_out
+ *   last stage  : reads hidden_in, computes the logits when want_logits (fetch them with rwkv_b200_stage_logits)
+ * hidden_in / hidden_out are DEVICE pointers to rwkv_b200_stage_hidden_len(ctx, n_tokens) floats: x f32[n_embed x n_tokens]
+ * followed, for RWKV v7, by v_first f32[n_embed x n_tokens]; the caller moves them between GPUs (NCCL send/recv or a peer
+ * copy). cuda_stream (a cudaStream_t, NULL = the context's own stream) is where the pass is enqueued, so it can be ordered
+ * against the transfers without host synchronisation. A single-stage context (all layers) accepts the call too. */
+RWKV_API size_t rwkv_b200_stage_hidden_len(const struct rwkv_context * ctx, size_t n_tokens);
+RWKV_API bool rwkv_b200_stage_eval(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, const float * hidden_in, float * hidden_out,
+                                   bool want_logits, void * cuda_stream);
+RWKV_API bool rwkv_b200_stage_logits(struct rwkv_context * ctx, float * logits_out, void * cuda_stream);
+
 /* Measurement hooks. */
 RWKV_API float rwkv_b200_last_device_ms(const struct rwkv_context * ctx);     /* CUDA-event time of the last pass */
 RWKV_API uint64_t rwkv_b200_kernel_launch_count(void);                         /* kernels enqueued by this process */

@@ -8,5 +8,6 @@ python/rwkv_cpp/ (rwkv_cpp_shared_library.py, rwkv_cpp_model.py):
 """
 from .shared_library import RWKVSharedLibrary, RWKVContext, load_rwkv_shared_library, library_path
 from .model import RWKVModel
+from . import pipeline
 
-__all__ = ["RWKVSharedLibrary", "RWKVContext", "load_rwkv_shared_library", "library_path", "RWKVModel"]
+__all__ = ["RWKVSharedLibrary", "RWKVContext", "load_rwkv_shared_library", "library_path", "RWKVModel", "pipeline"]

@@ -205,6 +205,35 @@ bool rwkv_b200_eval_resident(struct rwkv_context * ctx, const uint32_t * tokens,
     return true;
 }
 
+size_t rwkv_b200_stage_hidden_len(const struct rwkv_context * ctx, size_t n_tokens) { return stage_hidden_len(*C(ctx)->model, n_tokens); }
+
+bool rwkv_b200_stage_eval(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, const float * hidden_in, float * hidden_out, bool want_logits,
+                          void * cuda_stream) {
+    Context * c = C(ctx);
+    c->last_error = RWKV_ERROR_NONE;
+    const Model & m = *c->model;
+    const bool first = m.layer_begin == 0, last = m.layer_end == m.n_layer;
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, n_tokens > 0 && n_tokens <= (size_t) MAX_TOKENS_PER_PASS, "A stage pass takes 1 .. %d tokens", MAX_TOKENS_PER_PASS);
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, first ? tokens != nullptr : hidden_in != nullptr, "Stage [%d, %d) needs %s", m.layer_begin, m.layer_end,
+               first ? "tokens" : "the previous stage's activations");
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, last || hidden_out != nullptr, "Stage [%d, %d) needs an output buffer for its activations", m.layer_begin, m.layer_end);
+    if (first)
+        for (size_t i = 0; i < n_tokens; i++)
+            RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, tokens[i] < (uint32_t) m.n_vocab, "Token at index %zu (%" PRIu32 ") is out of range (0 .. %d)", i, tokens[i], m.n_vocab - 1);
+    return stage_forward(c, tokens, n_tokens, hidden_in, hidden_out, want_logits && last, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+bool rwkv_b200_stage_logits(struct rwkv_context * ctx, float * logits_out, void * cuda_stream) {
+    Context * c = C(ctx);
+    c->last_error = RWKV_ERROR_NONE;
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, logits_out && c->model->layer_end == c->model->n_layer, "Only the last stage holds logits");
+    cudaStream_t s = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->stream;
+    cudaError_t e = cudaMemcpyAsync(logits_out, c->logits, (size_t) c->model->n_vocab * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, e == cudaSuccess, "Reading the logits failed: %s", cudaGetErrorString(e));
+    return true;
+}
+
 float rwkv_b200_last_device_ms(const struct rwkv_context * ctx) {
     float ms = -1.f;
     const Context * c = C(ctx);

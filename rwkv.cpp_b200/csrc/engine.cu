@@ -340,8 +340,10 @@ bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase) {
     g_trace_next = 0;
     const int C = m.n_embed;
     const Scratch s = carve(m, ctx->scratch, T);
-    CUDA_OK(ctx, cudaMemcpyAsync(ctx->tokens, ctx->tokens_host[phase], (size_t) T * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_OK(ctx, launch_embed_ln0(m.emb.data, m.emb.type, m.emb.pitch, ctx->tokens, T, C, m.ln0_w.data, m.ln0_b.data, s.x, ctx->stream));
+    if (m.layer_begin == 0) {
+        CUDA_OK(ctx, cudaMemcpyAsync(ctx->tokens, ctx->tokens_host[phase], (size_t) T * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_OK(ctx, launch_embed_ln0(m.emb.data, m.emb.type, m.emb.pitch, ctx->tokens, T, C, m.ln0_w.data, m.ln0_b.data, s.x, ctx->stream));
+    }   // a later pipeline stage finds x (and v_first) already in place: forward_pass copied the hand-off in
     const size_t per_layer = m.state_floats_per_layer();
     for (int i = m.layer_begin; i < m.layer_end; i++) {
         const Layer & L = m.layers[i];
@@ -356,7 +358,7 @@ bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase) {
         }
         if (!ok || !ffn(ctx, L, s, T, st_in, st_out)) return false;
     }
-    if (want_logits) {   // :705-708 / :851-854  head . LN(x_last; ln_out)
+    if (want_logits && m.layer_end == m.n_layer) {   // :705-708 / :851-854  head . LN(x_last; ln_out)
         Batch b(1);
         GemvProblem & p = b.add(m.head, s.x + (size_t) (T - 1) * C, ctx->logits);
         p.pro = PRO_LAYERNORM; p.ln_w = m.ln_out_w.data; p.ln_b = m.ln_out_b.data;
@@ -372,8 +374,15 @@ bool forward_pass(Context * ctx, const uint32_t * tokens, int T, bool want_logit
     if (!ensure_capacity(ctx, T)) return false;
     const int phase = ctx->phase;
     if (ctx->slot_used[phase]) CUDA_OK(ctx, cudaEventSynchronize(ctx->slot_free[phase]));   // pass n-2 has consumed this slot
-    for (int t = 0; t < T; t++) ctx->tokens_host[phase][t] = (int) tokens[t];
+    const Model & m = *ctx->model;
+    if (m.layer_begin == 0) for (int t = 0; t < T; t++) ctx->tokens_host[phase][t] = (int) tokens[t];
+    const Scratch hs = carve(m, ctx->scratch, T);
+    const size_t ct = (size_t) m.n_embed * (size_t) T * sizeof(float);
     CUDA_OK(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    if (ctx->hidden_in) {    // outside the captured graph: the caller's pointers may change from call to call
+        CUDA_OK(ctx, cudaMemcpyAsync(hs.x, ctx->hidden_in, ct, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (m.arch_major == 7) CUDA_OK(ctx, cudaMemcpyAsync(hs.v_first, ctx->hidden_in + (size_t) m.n_embed * T, ct, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     Context::GraphSlot * g = (T == 1 && ctx->use_graphs && !ctx->profiling) ? &ctx->graphs[want_logits ? 1 : 0][phase] : nullptr;
     if (g && g->exec) {
         CUDA_OK(ctx, cudaGraphLaunch(g->exec, ctx->stream));
@@ -394,6 +403,10 @@ bool forward_pass(Context * ctx, const uint32_t * tokens, int T, bool want_logit
     } else {
         if (g) g->uses++;
         if (!enqueue_pass(ctx, T, want_logits, phase)) return false;
+    }
+    if (ctx->hidden_out) {
+        CUDA_OK(ctx, cudaMemcpyAsync(ctx->hidden_out, hs.x, ct, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (m.arch_major == 7) CUDA_OK(ctx, cudaMemcpyAsync(ctx->hidden_out + (size_t) m.n_embed * T, hs.v_first, ct, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     CUDA_OK(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
     CUDA_OK(ctx, cudaEventRecord(ctx->slot_free[phase], ctx->stream));
@@ -487,6 +500,21 @@ bool forward(Context * ctx, const uint32_t * tokens, size_t T, bool want_logits)
         done += n;
     }
     return true;
+}
+
+size_t stage_hidden_len(const Model & m, size_t T) { return (size_t) (m.arch_major == 7 ? 2 : 1) * (size_t) m.n_embed * T; }
+
+bool stage_forward(Context * ctx, const uint32_t * tokens, size_t T, const float * hidden_in, float * hidden_out, bool want_logits, cudaStream_t stream) {
+    const Model & m = *ctx->model;
+    CUDA_OK(ctx, cudaSetDevice(m.dev.device));
+    cudaStream_t own = ctx->stream;
+    if (stream) ctx->stream = stream;
+    ctx->hidden_in = m.layer_begin == 0 ? nullptr : hidden_in;
+    ctx->hidden_out = m.layer_end == m.n_layer ? nullptr : hidden_out;
+    const bool ok = forward_pass(ctx, tokens, (int) T, want_logits);
+    ctx->hidden_in = nullptr; ctx->hidden_out = nullptr;
+    ctx->stream = own;
+    return ok;
 }
 
 }  // namespace rwkv

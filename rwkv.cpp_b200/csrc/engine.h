@@ -46,6 +46,11 @@ struct Context {
     TraceRec * trace_buf = nullptr;  // in-kernel timeline records (rwkv_b200_trace_*), 1024 slots
     int trace_count = 0;             // slots used by the last enqueued / captured pass
 
+    // Pipeline-stage hand-off: device pointers of the caller for the pass being enqueued, or NULL.
+    // Layout: x f32[C x T], then (v7 only) v_first f32[C x T].
+    const float * hidden_in = nullptr;
+    float * hidden_out = nullptr;
+
     float last_device_ms = 0.f;      // CUDA-event time of the last forward (kernels only)
     int last_error = 0;              // rwkv_error_flags
     bool print_errors = true;
@@ -73,5 +78,13 @@ bool download_outputs(Context * ctx, float * state_out, float * logits_out);
 // state_a (buffers are swapped internally), and, if want_logits, ln_out + head of the last token
 // into ctx->logits. Asynchronous except for the token upload.
 bool forward(Context * ctx, const uint32_t * tokens, size_t T, bool want_logits);
+
+// One pipeline stage: the resident layers [layer_begin, layer_end) for T <= MAX_TOKENS_PER_PASS tokens. The first stage
+// embeds `tokens`, the others start from `hidden_in`; every stage but the last leaves its result in `hidden_out`
+// (device pointers, stage_hidden_len(T) floats); the last one computes the logits when asked. `stream` (may be NULL = the
+// context's own) is the CUDA stream everything is enqueued on, so the hand-off can be ordered against NCCL sends and
+// receives without host synchronisation.
+size_t stage_hidden_len(const Model & m, size_t T);
+bool stage_forward(Context * ctx, const uint32_t * tokens, size_t T, const float * hidden_in, float * hidden_out, bool want_logits, cudaStream_t stream);
 
 }  // namespace rwkv

@@ -90,6 +90,12 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_synchronize.restype = ctypes.c_bool
         lib.rwkv_b200_eval_resident.argtypes = [vp, P_U32, ctypes.c_size_t, ctypes.c_bool, P_FLOAT]
         lib.rwkv_b200_eval_resident.restype = ctypes.c_bool
+        lib.rwkv_b200_stage_hidden_len.argtypes = [vp, ctypes.c_size_t]
+        lib.rwkv_b200_stage_hidden_len.restype = ctypes.c_size_t
+        lib.rwkv_b200_stage_eval.argtypes = [vp, P_U32, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_bool, ctypes.c_void_p]
+        lib.rwkv_b200_stage_eval.restype = ctypes.c_bool
+        lib.rwkv_b200_stage_logits.argtypes = [vp, P_FLOAT, ctypes.c_void_p]
+        lib.rwkv_b200_stage_logits.restype = ctypes.c_bool
         lib.rwkv_b200_last_device_ms.argtypes = [vp]
         lib.rwkv_b200_last_device_ms.restype = ctypes.c_float
         lib.rwkv_b200_kernel_launch_count.argtypes = []
