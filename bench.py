@@ -133,6 +133,20 @@ def measured_tensor_peak():
         return 1500.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(preset):
+    """DRAM bytes of the dominant kernel's largest per-layer launch from the committed ncu capture (tools/ncu_summary.py --traffic),
+    next to that launch's algorithmic bytes (ffn key + receptance batch: (F + C) rows of C/32 Q5_1 blocks)."""
+    try:
+        import glob
+        f = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_traffic.json")))[-1]
+        t = json.load(open(f))
+        algo = (preset["F"] + preset["C"]) * (preset["C"] // 32) * 24
+        return t["dram_bytes"], {"source": os.path.relpath(f, ROOT), "kernel": t["kernel"], "launch": "ffn key + receptance (one launch, 296 CTAs)",
+                                 "algorithmic_bytes": algo, "dram_over_algorithmic": t["dram_bytes"] / algo}
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -384,7 +398,9 @@ def run_ours(args, rank, world, dist):
                             prefill_matmul_flops(preset, PREFILL_TOKENS), measured_tensor_peak())},
             "roofline": {"bound": "hbm", "kernel": "gemv_kernel (fused dequantize-GEMV, all launches of one decode step)",
                          "achieved": gemv_bytes / (gemv_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": gemv_bytes / (gemv_ms * 1e-3) / 1e9 / peak,
-                         "peak_source": peak_src, "traffic": None, "bytes_per_step": gemv_bytes, "ms_per_step": gemv_ms,
+                         "peak_source": peak_src, "traffic": ncu_traffic(preset)[0] if "rwkv6-7b:Q5_1" == args.workload else None,
+                         "traffic_launch": ncu_traffic(preset)[1] if "rwkv6-7b:Q5_1" == args.workload else None,
+                         "bytes_per_step": gemv_bytes, "ms_per_step": gemv_ms,
                          "launches_per_step": int(profs[0][3]), "share_of_step": gemv_ms / pass_ms,
                          "largest_launch": {"bytes": top[6], "ms": top[5], "gbs": top[6] / (top[5] * 1e-3) / 1e9},
                          "whole_step": {"bytes": bytes_tok, "ms": step_ms, "gbs": bytes_tok / (step_ms * 1e-3) / 1e9, "frac": bytes_tok / (step_ms * 1e-3) / 1e9 / peak}},

@@ -45,12 +45,12 @@ constexpr int WARP_RAW = 8, WARP_B = 9, WARP_MMA = 10;
 constexpr int THREADS = 352;
 constexpr int MAX_STAGES = 8;             // A/B ring depth (runtime: as many B stages as fit shared memory, <= 8). A stage = 32 columns of
                                           // TENSOR MEMORY (dequantised weights) + NPAD x 64 halves of shared memory (activations)
-constexpr int MAX_RAW_STAGES = 2;         // raw (quantised) ring, in K-chunks
+constexpr int MAX_RAW_STAGES = 3;         // raw (quantised) ring, in K-chunks
 constexpr int MAX_N = 256;
 // Tile-major prefill copy of a matrix: [tile of 128 rows][K-chunk][row][ROW_STRIDE bytes]; ROW_STRIDE = chunk bytes + a
 // pad that puts the 32 rows a warp reads on distinct shared-memory banks (64-bit loads for Q5_1, 128-bit for F16, 32-bit
 // for the rest), so one chunk of one tile is ONE contiguous, bank-conflict-free bulk copy.
-constexpr int QUANT_CHUNK_STEPS = 8;       // K-steps per raw chunk of the block formats
+constexpr int QUANT_CHUNK_STEPS = 4;       // K-steps per raw chunk of the block formats (18-35 KB per bulk copy)
 template <int TYPE> struct RawTraits {
     static constexpr int BLOCK_BYTES = QTraits<TYPE>::BLOCK_BYTES;
     static constexpr int CHUNK_STEPS = QUANT_CHUNK_STEPS;
@@ -60,7 +60,6 @@ template <int TYPE> struct RawTraits {
 template <> struct RawTraits<DT_F16> {
     static constexpr int BLOCK_BYTES = 64, CHUNK_STEPS = 2, CHUNK_BYTES = 256, ROW_STRIDE = CHUNK_BYTES + 16;
 };
-constexpr int MAX_RAW_STAGE_BYTES = TILE_M * (QUANT_CHUNK_STEPS * 2 * 34 + 4);
 struct RawGeom { int block_bytes, chunk_steps, chunk_bytes, row_stride; };
 inline RawGeom raw_geom(int type) {
     RawGeom g;
@@ -85,7 +84,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity) {
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (spins > 32) __nanosleep(64);          // a waiting role must not steal issue slots from a co-resident kernel
+        if (spins > 256) __nanosleep(32);          // a waiting role must not steal issue slots from a co-resident kernel
         if (spins > (1u << 24)) __trap();
     }
 }
@@ -336,8 +335,8 @@ struct TcBatch {
     int n, T, npad;                  // problems, tokens, tokens padded to a multiple of 16
     int tmem_cols;                   // power of two >= 32
     int raw_stages;                  // 2 or 3
+    int raw_stage_bytes;             // ring slot size: the largest 128-row chunk of the batch's formats, 128-byte multiple
     int b_stages;                    // A/B ring depth, 2 .. MAX_STAGES
-    int experiment;                  // timing experiments (RWKV_B200_TC_EXPERIMENT): 1 = B copied only for the first ring pass, 2 = same for raw
     const __half * act16[GEMV_MAX_PROBLEMS];   // canonical-layout fp16 activations per problem (convert_f16_kernel)
     GemvProblem p[GEMV_MAX_PROBLEMS];          // first_cta / n_cta = tiles of 128 rows
     TraceRec * trace;
@@ -356,6 +355,7 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
     const uint32_t tmem_a0 = sh.tmem_base + (uint32_t) NPAD;      // + stage * 32 columns
     const int nb = batch.b_stages;
     uint8_t * const raw_base = b_base + (size_t) nb * b_bytes;
+    const uint32_t raw_slot = (uint32_t) batch.raw_stage_bytes;
     const int nsteps = K / KSTEP;
     const int nraw = batch.raw_stages;
 
@@ -366,11 +366,8 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
             int rs = 0; uint32_t ph = 0;
             for (int c = 0; c < nchunks; c++) {
                 mbar_wait(&sh.raw_empty[rs], ph ^ 1);
-                if ((batch.experiment & 2) && c >= nraw) { mbar_arrive(&sh.raw_full[rs]); }
-                else {
-                    mbar_expect_tx(&sh.raw_full[rs], raw_bytes);
-                    bulk_load(raw_base + (size_t) rs * raw_bytes, wt + ((size_t) tile * nchunks + c) * raw_bytes, raw_bytes, &sh.raw_full[rs]);
-                }
+                mbar_expect_tx(&sh.raw_full[rs], raw_bytes);
+                bulk_load(raw_base + (size_t) rs * raw_slot, wt + ((size_t) tile * nchunks + c) * raw_bytes, raw_bytes, &sh.raw_full[rs]);
                 if (++rs == nraw) { rs = 0; ph ^= 1; }
             }
         }
@@ -380,11 +377,8 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
             int s = 0; uint32_t ph = 0;
             for (int ks = 0; ks < nsteps; ks++) {
                 mbar_wait(&sh.ab_empty[s], ph ^ 1);
-                if ((batch.experiment & 1) && ks >= nb) { mbar_arrive(&sh.b_full[s]); }
-                else {
-                    mbar_expect_tx(&sh.b_full[s], b_bytes);
-                    bulk_load(b_base + (size_t) s * b_bytes, act16 + (size_t) ks * KSTEP * NPAD, b_bytes, &sh.b_full[s]);
-                }
+                mbar_expect_tx(&sh.b_full[s], b_bytes);
+                bulk_load(b_base + (size_t) s * b_bytes, act16 + (size_t) ks * KSTEP * NPAD, b_bytes, &sh.b_full[s]);
                 if (++s == nb) { s = 0; ph ^= 1; }
             }
         }
@@ -439,8 +433,8 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
             }
             tick(c0);
             BlockRegs<TYPE> regs0, regs1;
-            read_block<TYPE>(raw_row0 + (uint32_t) rs * raw_bytes, sc * 2, regs0);
-            read_block<TYPE>(raw_row0 + (uint32_t) rs * raw_bytes, sc * 2 + 1, regs1);
+            read_block<TYPE>(raw_row0 + (uint32_t) rs * raw_slot, sc * 2, regs0);
+            read_block<TYPE>(raw_row0 + (uint32_t) rs * raw_slot, sc * 2 + 1, regs1);
             // last step of this warp inside the chunk: the raw rows are in registers, hand the slot back
             const bool last_in_chunk = sc + 2 >= RT::CHUNK_STEPS || ks + 2 >= nsteps;
             uint4 h0[4], h1[4];
@@ -601,8 +595,7 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
     tb.npad = (batch.T + 15) / 16 * 16;
     tb.tmem_cols = 32;
     while (tb.tmem_cols < tb.npad + tc::MAX_STAGES * 32) tb.tmem_cols *= 2;      // accumulator + A stages
-    tb.raw_stages = 2;
-    { static const int ex = getenv("RWKV_B200_TC_EXPERIMENT") ? atoi(getenv("RWKV_B200_TC_EXPERIMENT")) : 0; tb.experiment = ex; }
+
     __half * scratch = reinterpret_cast<__half *>(act16_scratch);
     size_t used = 0;
     int next = 0;
@@ -629,10 +622,19 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
         next += p.n_cta;
         tb.p[i] = p;
     }
-    // shared memory: 2 raw chunks and as many B stages as fit (a bulk copy needs ~1500 cycles to land, a
-    // K-step takes ~400: the B ring has to run several steps ahead)
+    // shared memory: 3 raw chunks (sized for the widest format of this batch) and as many B stages as fit, at most 8. The ring has
+    // to be deep: a stage comes back only after store -> arrive -> MMA issue -> MMA -> commit -> wake-up, and each of the two
+    // transform groups owns every other stage
     constexpr size_t smem_budget = 227 * 1024 - 2048;
-    constexpr size_t fixed = 2 * (((size_t) tc::MAX_RAW_STAGE_BYTES + 127) & ~(size_t) 127);
+    size_t raw_slot = 0;
+    for (int i = 0; i < batch.n; i++) {
+        const size_t b = (size_t) tc::TILE_M * tc::raw_geom(batch.p[i].type).row_stride;
+        if (b > raw_slot) raw_slot = b;
+    }
+    raw_slot = (raw_slot + 127) & ~(size_t) 127;
+    tb.raw_stages = tc::MAX_RAW_STAGES;
+    tb.raw_stage_bytes = (int) raw_slot;
+    const size_t fixed = (size_t) tb.raw_stages * raw_slot;
     const size_t b_bytes = (size_t) tb.npad * tc::KSTEP * 2;
     int nb = (int) ((smem_budget - fixed) / b_bytes);
     if (nb > tc::MAX_STAGES) nb = tc::MAX_STAGES;

@@ -152,7 +152,73 @@ __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const LnMixParams p)
     trace_end(p.trace);
 }
 
-// One thread per channel, 128 channels x LERP_TILE_TOKENS tokens per CTA. For each of the five mixes the thread holds
+// Passes of fewer than LERP_TILE_TOKENS tokens (decode): 8 lanes per channel, 32 channels per CTA, one CTA row per token: each (j, channel) row of W2 is `mix` contiguous floats. The W2 rows
+// (5.2 MB per layer at 7B, straight from HBM) are pulled into registers before the programmatic-dependency wait.
+constexpr int LERP1_MAX_F4 = 4;   // float4 per lane per j held in registers: mix <= 128
+__global__ void __launch_bounds__(GLUE_THREADS) v6_lerp_decode_kernel(const V6LerpParams p) {
+    extern __shared__ float zs[];   // [5*mix]
+    trace_begin(p.trace);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int t = blockIdx.y, mix = p.mix, C = p.C;
+    const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    const int c = blockIdx.x * 32 + grp;
+    const bool live = c < C;
+    const bool vec = (mix & 3) == 0 && mix / 4 <= 8 * LERP1_MAX_F4;
+    float4 wreg[5][LERP1_MAX_F4];
+    float maa[5];
+    if (vec) {
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            const float4 * wrow = reinterpret_cast<const float4 *>(p.w2 + ((size_t) j * C + (live ? c : 0)) * mix);
+#pragma unroll
+            for (int q = 0; q < LERP1_MAX_F4; q++) {
+                const int i4 = sub + 8 * q;
+                wreg[j][q] = (live && i4 < mix / 4) ? __ldg(wrow + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            maa[j] = live ? p.maa[j][c] : 0.f;
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int i = threadIdx.x; i < 5 * mix; i += GLUE_THREADS) zs[i] = p.z[(size_t) t * 5 * mix + i];
+    const size_t o = (size_t) t * C + (live ? c : 0);
+    const float sx = live ? p.sx[o] : 0.f, xx = live ? p.xx[o] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        float acc = 0.f;
+        const float * zj = zs + j * mix;
+        if (vec) {
+#pragma unroll
+            for (int q = 0; q < LERP1_MAX_F4; q++) {
+                const int i4 = sub + 8 * q;
+                if (i4 < mix / 4) {
+                    const float4 w = wreg[j][q], z = reinterpret_cast<const float4 *>(zj)[i4];
+                    acc = __fmaf_rn(w.x, z.x, acc); acc = __fmaf_rn(w.y, z.y, acc);
+                    acc = __fmaf_rn(w.z, z.z, acc); acc = __fmaf_rn(w.w, z.w, acc);
+                }
+            }
+        } else if (live) {
+            const float * wrow = p.w2 + ((size_t) j * C + c) * mix;
+            if ((mix & 3) == 0) {
+                for (int i4 = sub; i4 < mix / 4; i4 += 8) {
+                    const float4 w = __ldg(reinterpret_cast<const float4 *>(wrow) + i4), z = reinterpret_cast<const float4 *>(zj)[i4];
+                    acc = __fmaf_rn(w.x, z.x, acc); acc = __fmaf_rn(w.y, z.y, acc);
+                    acc = __fmaf_rn(w.z, z.z, acc); acc = __fmaf_rn(w.w, z.w, acc);
+                }
+            } else {
+                for (int i = sub; i < mix; i += 8) acc = __fmaf_rn(wrow[i], zj[i], acc);
+            }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (live && sub == 0) p.out[j][o] = __fadd_rn(__fmul_rn(__fadd_rn(acc, vec ? maa[j] : p.maa[j][c]), sx), xx);
+    }
+    trace_end(p.trace);
+}
+
+
+// Passes of >= LERP_TILE_TOKENS tokens: one thread per channel, 128 channels x LERP_TILE_TOKENS tokens per CTA. For each of the five mixes the thread holds
 // its W2 row (`mix` contiguous floats, 5.2 MB per layer at 7B) in registers and walks the tile's tokens; z[:, t] of the
 // tile sits in shared memory and is read as broadcasts. The first W2 row is pulled before the programmatic-dependency wait.
 constexpr int LERP_THREADS = 128;
@@ -202,20 +268,40 @@ __global__ void __launch_bounds__(LERP_THREADS) v6_lerp_kernel(const V6LerpParam
         for (int tt = 0; tt < LERP_TILE_TOKENS; tt++) {
             if (tt < nt) {
                 const float * zj = lerp_zs + (size_t) tt * 5 * mix + j * mix;
-                float acc = 0.f;
+                // the same eight partial sums and the same combination tree as the decode kernel's 8 lanes + shuffles: a chunked
+                // evaluation stays bit-identical to the serial one (tests/test_eval_sequence_in_chunks.c memcmp's them)
+                float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (vec) {
 #pragma unroll
                     for (int i = 0; i < LERP_MAX_F4; i++) {
                         if (i < m4) {
                             const float4 z = reinterpret_cast<const float4 *>(zj)[i];
-                            acc = __fmaf_rn(w[i].x, z.x, acc); acc = __fmaf_rn(w[i].y, z.y, acc);
-                            acc = __fmaf_rn(w[i].z, z.z, acc); acc = __fmaf_rn(w[i].w, z.w, acc);
+                            float & s8 = a[i & 7];
+                            s8 = __fmaf_rn(w[i].x, z.x, s8); s8 = __fmaf_rn(w[i].y, z.y, s8);
+                            s8 = __fmaf_rn(w[i].z, z.z, s8); s8 = __fmaf_rn(w[i].w, z.w, s8);
+                        }
+                    }
+                } else if ((mix & 3) == 0) {
+                    const float4 * wrow = reinterpret_cast<const float4 *>(p.w2 + ((size_t) j * C + cc) * mix);
+                    for (int i0 = 0; i0 < m4; i0 += 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            if (i0 + u < m4) {
+                                const float4 wv = __ldg(wrow + i0 + u), z = reinterpret_cast<const float4 *>(zj)[i0 + u];
+                                a[u] = __fmaf_rn(wv.x, z.x, a[u]); a[u] = __fmaf_rn(wv.y, z.y, a[u]);
+                                a[u] = __fmaf_rn(wv.z, z.z, a[u]); a[u] = __fmaf_rn(wv.w, z.w, a[u]);
+                            }
                         }
                     }
                 } else {
                     const float * wrow = p.w2 + ((size_t) j * C + cc) * mix;
-                    for (int i = 0; i < mix; i++) acc = __fmaf_rn(__ldg(wrow + i), zj[i], acc);
+                    for (int i0 = 0; i0 < mix; i0 += 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++)
+                            if (i0 + u < mix) a[u] = __fmaf_rn(__ldg(wrow + i0 + u), zj[i0 + u], a[u]);
+                    }
                 }
+                const float acc = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[4]), __fadd_rn(a[2], a[6])), __fadd_rn(__fadd_rn(a[1], a[5]), __fadd_rn(a[3], a[7])));
                 if (live) p.out[j][(size_t) (t0 + tt) * C + c] = __fadd_rn(__fmul_rn(__fadd_rn(acc, maa), sx[tt]), xx[tt]);
             }
         }
@@ -247,6 +333,11 @@ cudaError_t launch_ln_mix(const LnMixParams & p_in, cudaStream_t s) {
 cudaError_t launch_v6_lerp(const V6LerpParams & p_in, cudaStream_t s) {
     V6LerpParams p = p_in;
     p.trace = trace_slot("v6_lerp");
+    if (p.T < LERP_TILE_TOKENS) {
+        dim3 grid((p.C + 31) / 32, p.T);
+        g_kernel_launches++;
+        return launch_pdl(v6_lerp_decode_kernel, grid, dim3(GLUE_THREADS), (size_t) 5 * p.mix * sizeof(float), s, p);
+    }
     const size_t smem = (size_t) LERP_TILE_TOKENS * 5 * p.mix * sizeof(float);
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
     dim3 grid((p.C + LERP_THREADS - 1) / LERP_THREADS, (p.T + LERP_TILE_TOKENS - 1) / LERP_TILE_TOKENS);

@@ -43,8 +43,7 @@ inline long long matrix_pitch(int type, uint64_t K) {
         uint64_t nblk = K / 32;
         bytes = (size_t) ((nblk + 1) / 2 * 2) * dtype_block_bytes(type);
     }
-    static const long long extra = getenv("RWKV_B200_PITCH_PAD") ? atoll(getenv("RWKV_B200_PITCH_PAD")) : 0;   // experiment knob
-    return (long long) align_up(bytes, 16) + extra;
+    return (long long) align_up(bytes, 16);
 }
 
 // Host dequantisation of a whole tensor to fp32 (only for element-wise parameters that someone
