@@ -446,8 +446,12 @@ def run_pipeline(args, rank, world, dist):
         L.rwkv_b200_synchronize(c.ptr)
     K, W, P = args.steps, args.warmup, args.prefill_steps
     first, last = rank == 0, rank == world - 1
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: torch's NCCL send / recv and the stage kernels are all ordered on it. (The legacy default
+    # stream has handle 0, which rwkv_b200_stage_eval reads as "use the context's own stream".)
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
     sp = ctypes.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
     transport = pipeline.Transport(dist, rank, world)
     sampler = ClockSampler(local)
     sampler.start()

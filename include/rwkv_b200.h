@@ -47,7 +47,8 @@ RWKV_API bool rwkv_b200_synchronize(struct rwkv_context * ctx);
  * hidden_in / hidden_out are DEVICE pointers to rwkv_b200_stage_hidden_len(ctx, n_tokens) floats: x f32[n_embed x n_tokens]
  * followed, for RWKV v7, by v_first f32[n_embed x n_tokens]; the caller moves them between GPUs (NCCL send/recv or a peer
  * copy). cuda_stream (a cudaStream_t, NULL = the context's own stream) is where the pass is enqueued, so it can be ordered
- * against the transfers without host synchronisation. A single-stage context (all layers) accepts the call too. */
+ * against the transfers without host synchronisation (note that the legacy default stream's handle IS NULL: create a stream).
+ * A single-stage context (all layers) accepts the call too. */
 RWKV_API size_t rwkv_b200_stage_hidden_len(const struct rwkv_context * ctx, size_t n_tokens);
 RWKV_API bool rwkv_b200_stage_eval(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, const float * hidden_in, float * hidden_out,
                                    bool want_logits, void * cuda_stream);
