@@ -269,7 +269,7 @@ def run_reference(args, rank, world):
         "prefill": {"tokens_per_s": r.get("prefill_tokens_per_s"), "chunk": PREFILL_TOKENS},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, rank, world, dist):
@@ -417,7 +417,7 @@ def run_ours(args, rank, world, dist):
                 line["cpu_baseline"] = dict(ref_line["cpu_baseline"], prefill_tokens_per_s=ref_line["prefill"]["tokens_per_s"], cpu=ref_line["config"]["cpu"])
             except Exception as e:   # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def run_pipeline(args, rank, world, dist):
@@ -532,10 +532,23 @@ def run_pipeline(args, rank, world, dist):
                          "note": "per GPU: the largest stage's bytes per token / time per pipeline tick; per-launch figures are in the N=1 line"},
             "cpu_baseline": {"value": None, "unit": "tokens/s", "cores": 0, "kind": "reference", "sample": "reported by the N=1 run and by --impl reference"},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything libraries print (NCCL's version banner ...) goes to stderr."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
