@@ -513,10 +513,23 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
 }
 
 // x fp32 [K, T] column-major (column t contiguous) -> fp16 in the UMMA canonical layout, one contiguous B stage per
-// K-step:  [K / 64][kc = 8][g = npad / 8][8 tokens][8 k]  (tokens >= T zero-filled). One thread = one 16-byte chunk.
-__global__ void convert_f16_kernel(const float * x, long long ldx, int K, int T, int npad, __half * out, TraceRec * trace) {
-    trace_begin(trace);
+// K-step:  [K / 64][kc = 8][g = npad / 8][8 tokens][8 k]  (tokens >= T zero-filled). One thread = one 16-byte chunk; all
+// distinct inputs of a GEMM batch (up to 8: x_r, x_k, x_v, x_g, x_w of the time mix) go through ONE launch, blockIdx.y = input.
+struct ConvertBatch {
+    int n, T, npad;
+    const float * x[GEMV_MAX_PROBLEMS];
+    long long ldx[GEMV_MAX_PROBLEMS];
+    int K[GEMV_MAX_PROBLEMS];
+    __half * out[GEMV_MAX_PROBLEMS];
+    TraceRec * trace;
+};
+__global__ void convert_f16_kernel(const ConvertBatch cb) {
+    trace_begin(cb.trace);
     pdl_prologue();
+    const int q = blockIdx.y, T = cb.T, npad = cb.npad, K = cb.K[q];
+    const float * x = cb.x[q];
+    const long long ldx = cb.ldx[q];
+    __half * out = cb.out[q];
     const int NG = npad / 8;
     const long long nchunks = (long long) npad * K / 8;
     for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < nchunks; i += (long long) gridDim.x * blockDim.x) {
@@ -536,7 +549,7 @@ __global__ void convert_f16_kernel(const float * x, long long ldx, int K, int T,
         }
         *reinterpret_cast<uint4 *>(out + i * 8) = o;
     }
-    trace_end(trace);
+    trace_end(cb.trace);
 }
 
 // Row-major matrix (rows of `pitch` bytes) -> tile-major prefill copy. One thread per 4-byte word of the destination.
@@ -599,6 +612,10 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
     __half * scratch = reinterpret_cast<__half *>(act16_scratch);
     size_t used = 0;
     int next = 0;
+    tc::ConvertBatch cvt;
+    memset(&cvt, 0, sizeof(cvt));
+    cvt.T = batch.T; cvt.npad = tb.npad;
+    int cvt_kmax = 0;
     for (int i = 0; i < batch.n; i++) {
         GemvProblem & p = batch.p[i];
         const size_t need = (size_t) tb.npad * p.K * sizeof(__half);
@@ -608,11 +625,9 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
         if (!shared) {
             if (used + need > scratch_bytes) return cudaErrorMemoryAllocation;
             __half * dst = scratch + used / sizeof(__half);
-            const long long n8 = (long long) tb.npad * p.K / 8;
-            const int blocks = (int) ((n8 + 255) / 256 < 1184 ? (n8 + 255) / 256 : 1184);
-            g_kernel_launches++;
-            cudaError_t e = launch_pdl(tc::convert_f16_kernel, dim3(blocks), dim3(256), 0, stream, p.x, p.ldx, p.K, batch.T, tb.npad, dst, trace_slot("convert_f16"));
-            if (e != cudaSuccess) return e;
+            cvt.x[cvt.n] = p.x; cvt.ldx[cvt.n] = p.ldx; cvt.K[cvt.n] = p.K; cvt.out[cvt.n] = dst;
+            cvt.n++;
+            if (p.K > cvt_kmax) cvt_kmax = p.K;
             shared = dst;
             used += (need + 255) & ~(size_t) 255;
         }
@@ -621,6 +636,14 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
         p.n_cta = (p.M + tc::TILE_M - 1) / tc::TILE_M;
         next += p.n_cta;
         tb.p[i] = p;
+    }
+    {   // every distinct input of the batch -> fp16 canonical layout, one launch
+        const long long n8 = (long long) tb.npad * cvt_kmax / 8;
+        const int blocks = (int) ((n8 + 255) / 256 < 592 ? (n8 + 255) / 256 : 592);
+        cvt.trace = trace_slot("convert_f16");
+        g_kernel_launches++;
+        cudaError_t e = launch_pdl(tc::convert_f16_kernel, dim3(blocks, cvt.n), dim3(256), 0, stream, cvt);
+        if (e != cudaSuccess) return e;
     }
     // shared memory: 3 raw chunks (sized for the widest format of this batch) and as many B stages as fit, at most 8. The ring has
     // to be deep: a stage comes back only after store -> arrive -> MMA issue -> MMA -> commit -> wake-up, and each of the two
@@ -641,11 +664,13 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
     if (nb < 2) return cudaErrorInvalidValue;
     tb.b_stages = nb;
     const size_t smem = fixed + (size_t) nb * b_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};           // the opt-in is per device
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (cur_dev < 0 || cur_dev >= 64 || !attr_set[cur_dev]) {
         cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_budget);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (cur_dev >= 0 && cur_dev < 64) attr_set[cur_dev] = true;
     }
     tb.trace = trace_slot("gemm_tc");
     g_kernel_launches++;

@@ -290,7 +290,11 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvBatch batc
 
 template <int NC>
 cudaError_t launch_nc(const GemvBatch & batch, int grid, size_t smem, int max_optin, cudaStream_t stream) {
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};       // the shared-memory opt-in is per device
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    cur_dev = (cur_dev < 0 || cur_dev >= 64) ? 0 : cur_dev;
+    bool & attr_set = attr_set_dev[cur_dev];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemv_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
         if (e != cudaSuccess) return e;

@@ -620,7 +620,11 @@ bool plan_wk(GemvProblem & p) {
 
 template <int NC>
 cudaError_t launch_tma_nc(const GemvBatch & batch, int grid, size_t smem, cudaStream_t stream) {
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};       // the shared-memory opt-in is per device
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    cur_dev = (cur_dev < 0 || cur_dev >= 64) ? 0 : cur_dev;
+    bool & attr_set = attr_set_dev[cur_dev];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tma::gemv_tma_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::CTA_SMEM_BUDGET);
         if (e != cudaSuccess) return e;
