@@ -85,6 +85,24 @@ RWKV_API void rwkv_b200_set_graphs(struct rwkv_context * ctx, bool enabled);
 /* Enables / disables the tcgen05 tensor-core kernel for passes of >= 32 tokens (on by default; off = batch-invariant SIMT path). */
 RWKV_API void rwkv_b200_set_tensor_cores(struct rwkv_context * ctx, bool enabled);
 
+/* Single-token passes as ONE persistent kernel (csrc/kernels/decode_persistent.h): every CTA walks the layer program, the
+ * launch boundaries of the per-launch path become grid barriers and the weight stream continues across them. Results are
+ * bit-identical to the per-launch path. RWKV v5 / v6 with n_embed <= 4096 and head size <= 64 fit it; everything else keeps
+ * using the per-launch path. The environment variable RWKV_B200_PERSISTENT=0/1 sets the default of new contexts.
+ * rwkv_b200_persistent_state: 1 = in use, 0 = not tried yet, -1 = this model / device does not fit it. */
+RWKV_API void rwkv_b200_set_persistent(struct rwkv_context * ctx, bool enabled);
+RWKV_API int rwkv_b200_persistent_state(const struct rwkv_context * ctx);
+/* Phase timeline of the persistent kernel: the first call arms a device buffer (returns 0); after the next single-token pass a
+ * second call returns n_phases + 1 boundaries (microseconds since the kernel's first phase began, %globaltimer of CTA 0). */
+RWKV_API int rwkv_b200_phase_trace(struct rwkv_context * ctx, double * boundaries_us, int max_records);
+
+/* Host-only self-test of the persistent kernel's planner (no GPU, no file): plans the single-token program of a fake RWKV v5 /
+ * v6 model of the given shape for a device with num_sms SMs and replays every CTA's tile walk. 1 = planned and consistent,
+ * 0 = the shape does not fit the kernel, -1 = bad arguments. info (optional, 4 ints) = ring stage bytes, activation region
+ * bytes, number of phases, dynamic shared memory per CTA. */
+RWKV_API int rwkv_b200_plan_selftest(int arch_major, int arch_minor, int data_type, int n_embed, int ffn, int n_vocab, int head_size, int mix, int decay,
+                                     int n_layer, int num_sms, int * info);
+
 /* Test hook: one fused dequantize-GEMV on host buffers, y[M,T] = W[M,K] . x[K,T] (column-major activations),
  * through exactly the kernel the eval path uses (csrc/kernels/gemv.cu). `weights` holds M rows in the file
  * layout of `data_type` (rwkv_file_format.inc:5-24 ids; ggml quant blocks / f16 / f32, unpadded).

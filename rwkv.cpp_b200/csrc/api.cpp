@@ -294,6 +294,40 @@ bool rwkv_b200_profile_pass(struct rwkv_context * ctx, const uint32_t * tokens, 
 
 void rwkv_b200_set_graphs(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_graphs = enabled; }
 void rwkv_b200_set_tensor_cores(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_tensor_cores = enabled; }
+void rwkv_b200_set_persistent(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_persistent = enabled; }
+int rwkv_b200_persistent_state(const struct rwkv_context * ctx) {
+    const Context * c = C(ctx);
+    int best = 0;
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) {
+        if (c->persistent_state[a][b] > 0) return 1;
+        if (c->persistent_state[a][b] < 0) best = -1;
+    }
+    return best;
+}
+
+int rwkv_b200_plan_selftest(int arch_major, int arch_minor, int data_type, int n_embed, int ffn, int n_vocab, int head_size, int mix, int decay, int n_layer, int num_sms, int * info) {
+    return plan_selftest(arch_major, arch_minor, data_type, n_embed, ffn, n_vocab, head_size, mix, decay, n_layer, num_sms, info);
+}
+
+int rwkv_b200_phase_trace(struct rwkv_context * ctx, double * boundaries_us, int max_records) {
+    Context * c = C(ctx);
+    if (cudaSetDevice(c->model->dev.device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    const int cap = 4096;
+    if (!c->phase_trace) {      // first call arms the buffer; the next single-token pass fills it
+        if (cudaMalloc((void **) &c->phase_trace, (size_t) cap * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cudaMemset(c->phase_trace, 0, (size_t) cap * sizeof(unsigned long long));
+        c->phase_trace_len = cap;
+        return 0;
+    }
+    int n = 0;
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) if (c->programs[a][b].supported && c->programs[a][b].n_phases + 1 > n) n = c->programs[a][b].n_phases + 1;
+    if (n > max_records) n = max_records;
+    if (n <= 0 || !boundaries_us) return 0;
+    std::vector<unsigned long long> raw((size_t) n);
+    if (cudaMemcpy(raw.data(), c->phase_trace, (size_t) n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (int i = 0; i < n; i++) boundaries_us[i] = raw[i] >= raw[0] && raw[i] ? (double) (raw[i] - raw[0]) * 1e-3 : -1.0;
+    return n;
+}
 
 static bool trace_rearm(Context * c) {
     std::vector<TraceRec> init(1024);

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "model.h"
+#include "kernels/decode_persistent.h"
 
 namespace rwkv {
 
@@ -37,6 +38,16 @@ struct Context {
     struct GraphSlot { cudaGraphExec_t exec = nullptr; int uses = 0; unsigned long long launches = 0; };
     GraphSlot graphs[2][2];
     bool use_graphs = true;
+
+    // Persistent single-token kernel (kernels/decode_persistent.h): one program per [want_logits][phase], built on first use.
+    // `persistent_state`: 0 = not tried yet, 1 = in use, -1 = this model / device does not fit it (per-launch path is used).
+    DecodeProgram programs[2][2];
+    int persistent_state[2][2] = {{0, 0}, {0, 0}};
+    bool use_persistent = false;
+    unsigned long long * grid_barrier = nullptr;     // device counter of the kernel's grid barrier
+    unsigned long long grid_barrier_value = 0;       // its value once everything enqueued so far has run
+    unsigned long long * phase_trace = nullptr;      // optional device buffer: %globaltimer of CTA 0 at every phase boundary
+    int phase_trace_len = 0;
 
     // Profiling mode (bench.py roofline leg): CUDA events around every GEMV launch, graphs off.
     bool profiling = false;
@@ -85,6 +96,10 @@ bool forward(Context * ctx, const uint32_t * tokens, size_t T, bool want_logits)
 // context's own) is the CUDA stream everything is enqueued on, so the hand-off can be ordered against NCCL sends and
 // receives without host synchronisation.
 size_t stage_hidden_len(const Model & m, size_t T);
+
+// Host-only self-test of the persistent-kernel planner on a fake model of the given shape: 1 = a program was planned and passed
+// its tile-walk check, 0 = the shape does not fit the kernel, -1 = bad arguments. info[4] = stage bytes, region bytes, phases, smem.
+int plan_selftest(int arch_major, int arch_minor, int type, int C, int F, int V, int S, int mix, int decay, int n_layer, int num_sms, int * info);
 bool stage_forward(Context * ctx, const uint32_t * tokens, size_t T, const float * hidden_in, float * hidden_out, bool want_logits, cudaStream_t stream);
 
 }  // namespace rwkv

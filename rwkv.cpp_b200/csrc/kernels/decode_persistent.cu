@@ -1,0 +1,570 @@
+// Persistent single-token kernel: see decode_persistent.h for the design. Device code below reuses the ring, the
+// activation staging and the consumers of gemv_tma_device.cuh unchanged; the stages folded in between (LayerNorm + mix,
+// v6 lerp, WKV5/6 step) restate glue.cu / wkv.cu for T = 1 with the same per-element operations and reduction trees.
+#include "decode_persistent.h"
+#include "gemv_tma_device.cuh"
+
+#include <cstdio>
+#include <cstring>
+
+namespace rwkv {
+namespace dp {
+
+using namespace tma;
+
+constexpr int LN_MAXCH = 16;               // channels per consumer thread in the LayerNorm stage: n_embed <= 4096
+constexpr int LERP_MAXF4 = 2;              // float4 per lane per mix kept in registers across the barrier: mix <= 64
+constexpr size_t DYN_SMEM_BUDGET = 110 * 1024;   // + ~2 KB static: two CTAs per SM
+constexpr size_t RED_BYTES = (size_t) 2 * MAX_TILE_ROWS * CONSUMER_WARPS * sizeof(float);
+
+struct Args {
+    const DecodePhase * phases;
+    int n_phases;
+    unsigned long long * bar;
+    unsigned long long bar_base;
+    uint32_t stage_bytes, tmp_offset, region_bytes;
+    unsigned long long * trace;
+};
+
+struct WkvStep {             // Wkv6Params without its default member initialisers (lives in shared memory)
+    const float * r, * k, * v, * td, * tf, * state_in, * lnx_w, * lnx_b, * g;
+    float * state_out, * y;
+    float eps;
+    int td_per_token, per_head_scalars, H, S;
+};
+struct PhaseLocal {          // published by thread 0 while the CTA waits in the grid barrier
+    int op[2];               // op of phase ph at [ph & 1]
+    int active, local, my_tiles, head;
+    DecodeLnMix ln;          // coef[0] = the mixing vector of this CTA's problem
+    WkvStep wkv;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long * p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer() {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    return g;
+}
+__device__ __forceinline__ int tiles_of(const GemvProblem & P, int local) {
+    const int n_tiles = (P.M + P.tile_rows - 1) / P.tile_rows;
+    return (local < P.n_cta && local < n_tiles) ? (n_tiles - local + P.n_cta - 1) / P.n_cta : 0;
+}
+
+// ---- LayerNorm + token shift + mixing for T = 1, by the 256 consumer threads, bit-identical to ln_mix_kernel<PER> (glue.cu):
+// that kernel runs 1024 threads, thread v summing channels v, v + 1024, ... in double, then a warp xor-tree, 32 slots and a second
+// xor-tree over the slots. Consumer thread t plays the four virtual threads v = t + 256 q: virtual warp (t >> 5) + 8 q, same lane.
+__device__ __forceinline__ double warp_tree_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ void ln_mix_stage(const DecodeLnMix & L, float * tmp, double (* slots)[32], bool writer) {
+    const int C = L.C, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int PER = (C + 1023) / 1024;
+    float xa[LN_MAXCH];                   // channel t + 256 m, m = q + 4 i  (virtual thread q, its i-th channel)
+    double sa[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int m = q + 4 * i, c = t + 256 * m;
+            const bool live = i < PER && c < C;
+            xa[m] = live ? L.x[c] : 0.f;
+            sa[q] += (double) xa[m];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const double r = warp_tree_d(sa[q]);
+        if (lane == 0) slots[0][warp + 8 * q] = r;
+    }
+    consumer_barrier();
+    const float mean_a = (float) (warp_tree_d(slots[0][lane]) / C);
+    double va[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int m = q + 4 * i, c = t + 256 * m;
+            const bool live = i < PER && c < C;
+            xa[m] = live ? xa[m] - mean_a : 0.f;
+            va[q] += (double) (xa[m] * xa[m]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const double r = warp_tree_d(va[q]);
+        if (lane == 0) slots[1][warp + 8 * q] = r;
+    }
+    consumer_barrier();
+    const float scale_a = 1.0f / sqrtf((float) (warp_tree_d(slots[1][lane]) / C) + 1e-5f);
+    const float * coef = L.coef[0];
+#pragma unroll
+    for (int m = 0; m < LN_MAXCH; m++) {
+        const int c = t + 256 * m;
+        if (c < C) {
+            const float a = __fadd_rn(__fmul_rn(__fmul_rn(xa[m], scale_a), L.ln_w[c]), L.ln_b[c]);     // LN(x)
+            const float b = L.state_in[c];                                                               // LN(x) of the previous token
+            const float mc = coef[c];
+            tmp[c] = (L.formula == 0) ? __fadd_rn(__fmul_rn(a, mc), __fsub_rn(b, __fmul_rn(b, mc)))
+                                      : __fadd_rn(__fmul_rn(__fsub_rn(b, a), mc), a);
+            if (writer) {
+                L.state_out[c] = a;
+                if (L.out_sx) L.out_sx[c] = __fsub_rn(b, a);
+                if (L.out_xx) L.out_xx[c] = a;
+            }
+        }
+    }
+}
+
+// ---- v6 data-dependent lerp for T = 1 (v6_lerp_decode_kernel, glue.cu): 8 lanes per channel, the same eight partial sums and
+// xor-tree. The W2 rows (immutable) are pulled into registers between arriving at the grid barrier and waiting on it.
+struct LerpRegs { float4 w[5][LERP_MAXF4]; float maa[5]; int c; bool live; };
+__device__ __forceinline__ void lerp_prefetch(const V6LerpParams & p, LerpRegs & r) {
+    const int C = p.C, mix = p.mix;
+    const int cpc = (C + (int) gridDim.x - 1) / (int) gridDim.x;
+    const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    r.c = (int) blockIdx.x * cpc + grp;
+    r.live = grp < cpc && r.c < C;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const float4 * wrow = reinterpret_cast<const float4 *>(p.w2 + ((size_t) j * C + (r.live ? r.c : 0)) * mix);
+#pragma unroll
+        for (int q = 0; q < LERP_MAXF4; q++) {
+            const int i4 = sub + 8 * q;
+            r.w[j][q] = (r.live && i4 < mix / 4) ? __ldg(wrow + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        r.maa[j] = r.live ? p.maa[j][r.c] : 0.f;
+    }
+}
+__device__ __forceinline__ void lerp_run(const V6LerpParams & p, const LerpRegs & r, float * zs) {
+    const int mix = p.mix, sub = threadIdx.x & 7;
+    for (int i = threadIdx.x; i < 5 * mix; i += CONSUMER_THREADS) zs[i] = p.z[i];
+    const float sx = r.live ? p.sx[r.c] : 0.f, xx = r.live ? p.xx[r.c] : 0.f;
+    consumer_barrier();
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        float acc = 0.f;
+        const float * zj = zs + j * mix;
+#pragma unroll
+        for (int q = 0; q < LERP_MAXF4; q++) {
+            const int i4 = sub + 8 * q;
+            if (i4 < mix / 4) {
+                const float4 w = r.w[j][q], z = reinterpret_cast<const float4 *>(zj)[i4];
+                acc = __fmaf_rn(w.x, z.x, acc); acc = __fmaf_rn(w.y, z.y, acc);
+                acc = __fmaf_rn(w.z, z.z, acc); acc = __fmaf_rn(w.w, z.w, acc);
+            }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (r.live && sub == 0) p.out[j][r.c] = __fadd_rn(__fmul_rn(__fadd_rn(acc, r.maa[j]), sx), xx);
+    }
+}
+
+// ---- one WKV5/6 step of head h + per-head norm + ln_x + gate (wkv6_kernel<S>, wkv.cu, for T = 1): thread (oct, jg) owns the
+// 8 x 4 state patch, partial outputs meet over the octants by the same xor-shuffles, warp 0 normalises the head.
+template <int S>
+__device__ void wkv6_step(const WkvStep & p, int h, float * ybuf) {
+    constexpr int NOCT = S / 8, NJG = S / 4, NT = NOCT * NJG, NW = (NT + 31) / 32, CPL = (S + 31) / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp < NW) {
+        const bool worker = tid < NT;
+        const int oct = worker ? tid % NOCT : 0, jg = worker ? tid / NOCT : 0;
+        const int i0 = oct * 8, j0 = jg * 4;
+        const size_t hb = (size_t) h * S;
+        float st[8][4], kk[8], rr[8], dv[8], tfr[8], vv[4];
+#pragma unroll
+        for (int ii = 0; ii < 8; ii++) {
+            const float4 v = *reinterpret_cast<const float4 *>(p.state_in + (hb + i0 + ii) * S + j0);
+            st[ii][0] = v.x; st[ii][1] = v.y; st[ii][2] = v.z; st[ii][3] = v.w;
+            tfr[ii] = p.per_head_scalars ? p.tf[h] : p.tf[hb + i0 + ii];
+            kk[ii] = p.k[hb + i0 + ii];
+            rr[ii] = p.r[hb + i0 + ii];
+            dv[ii] = p.td_per_token ? p.td[hb + i0 + ii] : (p.per_head_scalars ? p.td[h] : p.td[hb + i0 + ii]);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) vv[jj] = p.v[hb + j0 + jj];
+        float y[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ii = 0; ii < 8; ii++) {
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const float kv = __fmul_rn(vv[jj], kk[ii]);
+                const float temp = __fmaf_rn(kv, tfr[ii], st[ii][jj]);
+                y[jj] = __fmaf_rn(temp, rr[ii], y[jj]);
+                st[ii][jj] = __fmaf_rn(st[ii][jj], dv[ii], kv);
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < NOCT; o <<= 1) {
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) y[jj] += __shfl_xor_sync(0xffffffffu, y[jj], o);
+        }
+        if (worker && oct == 0) *reinterpret_cast<float4 *>(&ybuf[j0]) = make_float4(y[0], y[1], y[2], y[3]);
+        if (worker) {
+#pragma unroll
+            for (int ii = 0; ii < 8; ii++)
+                *reinterpret_cast<float4 *>(p.state_out + (hb + i0 + ii) * S + j0) = make_float4(st[ii][0], st[ii][1], st[ii][2], st[ii][3]);
+        }
+    }
+    consumer_barrier();
+    if (warp == 0) {
+        float yv[CPL];
+        double s1 = 0, s2 = 0;
+#pragma unroll
+        for (int i = 0; i < CPL; i++) {
+            const int col = lane + 32 * i;
+            yv[i] = col < S ? ybuf[col] : 0.f;
+            s1 += (double) yv[i];
+            s2 += (double) yv[i] * (double) yv[i];
+        }
+        s1 = warp_tree_d(s1);
+        s2 = warp_tree_d(s2);
+        const double mean_d = s1 / S;
+        const float mean = (float) mean_d;
+        const float var = (float) fmax(s2 / S - mean_d * mean_d, 0.0);
+        const float rstd = 1.0f / sqrtf(var + p.eps);
+        const size_t o = (size_t) h * S;
+#pragma unroll
+        for (int i = 0; i < CPL; i++) {
+            const int col = lane + 32 * i;
+            if (col < S) {
+                float n = (yv[i] - mean) * rstd;
+                n = __fadd_rn(__fmul_rn(n, p.lnx_w[o + col]), p.lnx_b[o + col]);
+                if (p.g) n = __fmul_rn(n, p.g[o + col]);
+                p.y[o + col] = n;
+            }
+        }
+    }
+}
+
+// ---- the GEMV of a phase on this CTA's tiles: stage the (single) activation column, then the unchanged consumers
+__device__ void run_gemv(Shared & sh, uint8_t * ring, uint32_t stage_bytes, uint8_t * act, float * red, int it0, int local, int my_tiles) {
+    const GemvProblem & P = sh.P;
+    stage_column(P, 0, act, sh.red_d);
+    consumer_barrier();
+    const size_t colb = act_bytes_per_column(P.type, P.K);
+#define RWKV_DP_REGS(T_) consume_quant_regs<T_, true>(sh, ring, stage_bytes, act, 0, red, it0, my_tiles, local, P.n_cta)
+#define RWKV_DP_SMEM(T_) consume_smem<T_, 1, true>(sh, ring, stage_bytes, act, colb, 0, 1, red, it0, my_tiles, local, P.n_cta)
+    switch (P.type) {
+        case DT_Q4_0: RWKV_DP_REGS(DT_Q4_0); break;
+        case DT_Q4_1: RWKV_DP_REGS(DT_Q4_1); break;
+        case DT_Q5_0: RWKV_DP_REGS(DT_Q5_0); break;
+        case DT_Q5_1: RWKV_DP_REGS(DT_Q5_1); break;
+        case DT_Q8_0: RWKV_DP_REGS(DT_Q8_0); break;
+        case DT_F16: RWKV_DP_SMEM(DT_F16); break;
+        default: RWKV_DP_SMEM(DT_F32); break;
+    }
+#undef RWKV_DP_REGS
+#undef RWKV_DP_SMEM
+}
+
+__global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Args a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ Shared sh;
+    __shared__ PhaseLocal pl;
+    __shared__ double slots[2][32];
+
+    if (threadIdx.x == 0) {
+        sh.trace = nullptr;
+        for (int s = 0; s < NSTAGES; s++) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], CONSUMER_WARPS); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const uint32_t stage_bytes = a.stage_bytes;
+    uint8_t * ring = smem;
+    uint8_t * act = smem + (size_t) NSTAGES * stage_bytes;
+    float * tmp = reinterpret_cast<float *>(act + a.tmp_offset);
+    const int n = a.n_phases;
+
+    if (threadIdx.x >= CONSUMER_THREADS) {
+        // ===== producer: one thread walks the whole program and streams this CTA's weight tiles of every phase through the
+        // ring, as far ahead of the consumers as the ring allows (across phase boundaries: weights are immutable) =====
+        if (threadIdx.x == CONSUMER_THREADS) {
+            const uint64_t policy = policy_evict_first();
+            int it = 0;
+            for (int ph = 0; ph < n; ph++) {
+                const GemvBatch & B = a.phases[ph].batch;
+                const int nb = B.n;
+                if (nb == 0) continue;
+                int pi = 0;
+                for (int i = 1; i < nb; i++) if ((int) blockIdx.x >= B.p[i].first_cta) pi = i;
+                const GemvProblem & P = B.p[pi];
+                const int local = (int) blockIdx.x - P.first_cta;
+                const int my_tiles = tiles_of(P, local);
+                const uint8_t * Wb = reinterpret_cast<const uint8_t *>(P.W);
+                const int tile_rows = P.tile_rows, n_cta = P.n_cta, M = P.M;
+                const size_t pitch = (size_t) P.pitch;
+                for (int i = 0; i < my_tiles; i++, it++) {
+                    const int row0 = (local + i * n_cta) * tile_rows;
+                    const int rows = min(tile_rows, M - row0);
+                    const int s = it % NSTAGES;
+                    if (it >= NSTAGES) mbar_wait_t<true>(&sh.empty[s], (uint32_t) (((it / NSTAGES) - 1) & 1));
+                    const uint32_t bytes = (uint32_t) ((size_t) rows * pitch);
+                    mbar_expect_tx(&sh.full[s], bytes);
+                    bulk_copy_g2s(ring + (size_t) s * stage_bytes, Wb + (size_t) row0 * pitch, bytes, &sh.full[s], policy);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    float * red = reinterpret_cast<float *>(act + a.region_bytes);
+    const int tid = threadIdx.x;
+    int it = 0;
+    for (int ph = 0; ph < n; ph++) {
+        const DecodePhase & D = a.phases[ph];
+        // (1) the previous phase is complete on this CTA; arrive at the grid barrier
+        if (ph > 0) {
+            consumer_barrier();
+            if (tid == 0) { __threadfence(); atomicAdd(a.bar, 1ull); }
+        }
+        // (2) work that needs nothing from the previous phase
+        const int op = (ph == 0) ? D.op : pl.op[ph & 1];
+        LerpRegs lr;
+        if (op == DOP_LERP) lerp_prefetch(D.lerp, lr);
+        // (3) thread 0 reads this CTA's part of the phase descriptor, then waits for everyone
+        if (tid == 0) {
+            const GemvBatch & B = D.batch;
+            const int nb = B.n;
+            int active = 0, local = (int) blockIdx.x, my_tiles = 0;
+            if (nb > 0) {
+                int pi = 0;
+                for (int i = 1; i < nb; i++) if ((int) blockIdx.x >= B.p[i].first_cta) pi = i;
+                sh.P = B.p[pi];
+                local = (int) blockIdx.x - sh.P.first_cta;
+                my_tiles = tiles_of(sh.P, local);
+                active = my_tiles > 0;
+                if (op == DOP_LNMIX_GEMV) {
+                    pl.ln = D.ln;
+                    pl.ln.coef[0] = D.ln.coef[pi];
+                    sh.P.x = tmp; sh.P.ldx = 0;
+                }
+            }
+            int head = -1;
+            if (op == DOP_GEMV_WKV) {
+                const Wkv6Params & w = D.wkv;
+                pl.wkv.r = w.r; pl.wkv.k = w.k; pl.wkv.v = w.v; pl.wkv.td = w.td; pl.wkv.tf = w.tf; pl.wkv.state_in = w.state_in;
+                pl.wkv.lnx_w = w.lnx_w; pl.wkv.lnx_b = w.lnx_b; pl.wkv.g = w.g; pl.wkv.state_out = w.state_out; pl.wkv.y = w.y;
+                pl.wkv.eps = w.eps; pl.wkv.td_per_token = w.td_per_token; pl.wkv.per_head_scalars = w.per_head_scalars; pl.wkv.H = w.H; pl.wkv.S = w.S;
+                head = (nb > 0) ? (active ? local : -1) : ((int) blockIdx.x < D.wkv.H ? (int) blockIdx.x : -1);
+            }
+            pl.active = active; pl.local = local; pl.my_tiles = my_tiles; pl.head = head;
+            pl.op[(ph + 1) & 1] = (ph + 1 < n) ? a.phases[ph + 1].op : 0;
+            if (ph > 0) {
+                const unsigned long long target = a.bar_base + (unsigned long long) ph * gridDim.x;
+                const long long t0 = clock64();
+                unsigned spins = 0;
+                while (ld_acquire_u64(a.bar) < target) {
+                    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > GUARD_CYCLES) __trap();
+                }
+                __threadfence();
+            }
+            if (a.trace && blockIdx.x == 0) a.trace[ph] = global_timer();
+        }
+        consumer_barrier();
+        // (4) the phase
+        const int active = pl.active, local = pl.local, my_tiles = pl.my_tiles;
+        switch (op) {
+            case DOP_LNMIX_GEMV:
+                if (active) {
+                    ln_mix_stage(pl.ln, tmp, slots, blockIdx.x == 0);
+                    consumer_barrier();
+                    run_gemv(sh, ring, stage_bytes, act, red, it, local, my_tiles);
+                }
+                break;
+            case DOP_LERP:
+                lerp_run(D.lerp, lr, tmp);
+                break;
+            case DOP_GEMV_WKV: {
+                if (active) run_gemv(sh, ring, stage_bytes, act, red, it, local, my_tiles);
+                const int h = pl.head;
+                if (h >= 0) {
+                    consumer_barrier();     // the head's decay values just stored by this CTA are visible to all its threads
+                    switch (pl.wkv.S) {
+                        case 8: wkv6_step<8>(pl.wkv, h, tmp); break;
+                        case 16: wkv6_step<16>(pl.wkv, h, tmp); break;
+                        case 32: wkv6_step<32>(pl.wkv, h, tmp); break;
+                        default: wkv6_step<64>(pl.wkv, h, tmp); break;
+                    }
+                }
+                break;
+            }
+            default:
+                if (active) run_gemv(sh, ring, stage_bytes, act, red, it, local, my_tiles);
+                break;
+        }
+        it += my_tiles;
+    }
+    if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[n] = global_timer();
+}
+
+}  // namespace dp
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+bool gemv_tma_plan(GemvBatch & batch, int total_ctas, long long stage_bytes, size_t * max_col_bytes);   // gemv_tma.cu
+
+void decode_program_free(DecodeProgram & program) {
+    if (program.phases) cudaFree(program.phases);
+    program = DecodeProgram();
+}
+
+// Replays the tile walk of every CTA exactly as the kernel's producer and consumers compute it and checks that each tile of
+// each matrix is taken exactly once, fits a ring stage, and that a WKV phase maps one tile to one head. A program that fails
+// this is never launched (the kernel has no way to recover from a tile-count mismatch between producer and consumers).
+static bool program_selfcheck(const std::vector<DecodePhase> & phases, const DecodeProgram & program) {
+    std::vector<int> taken;
+    for (size_t ph = 0; ph < phases.size(); ph++) {
+        const DecodePhase & D = phases[ph];
+        const GemvBatch & B = D.batch;
+        if (B.n < 0 || B.n > GEMV_MAX_PROBLEMS) return false;
+        for (int i = 0; i < B.n; i++) {
+            const GemvProblem & P = B.p[i];
+            if (P.tile_rows <= 0 || P.n_cta <= 0 || P.first_cta < 0 || P.first_cta + P.n_cta > program.grid) return false;
+            if (i > 0 && P.first_cta != B.p[i - 1].first_cta + B.p[i - 1].n_cta) return false;
+            if (i == 0 && P.first_cta != 0) return false;
+            if ((long long) P.tile_rows * P.pitch > (long long) program.stage_bytes) return false;
+            if (P.tile_rows > tma::MAX_TILE_ROWS || P.tile_rows % (tma::CONSUMER_WARPS / P.wk) != 0) return false;
+            if (tma::act_bytes_per_column(P.type, P.K) > program.region_bytes) return false;
+            const int n_tiles = (P.M + P.tile_rows - 1) / P.tile_rows;
+            taken.assign((size_t) n_tiles, 0);
+            for (int cta = 0; cta < program.grid; cta++) {
+                int pi = 0;                                   // the kernel's problem lookup
+                for (int j = 1; j < B.n; j++) if (cta >= B.p[j].first_cta) pi = j;
+                if (pi != i) continue;
+                const int local = cta - P.first_cta;
+                const int my = (local < P.n_cta && local < n_tiles) ? (n_tiles - local + P.n_cta - 1) / P.n_cta : 0;
+                for (int t = 0; t < my; t++) {
+                    const int tile = local + t * P.n_cta;
+                    if (tile < 0 || tile >= n_tiles) return false;
+                    taken[(size_t) tile]++;
+                }
+            }
+            for (int t = 0; t < n_tiles; t++) if (taken[(size_t) t] != 1) return false;
+        }
+        if (D.op == DOP_GEMV_WKV && B.n == 1) {
+            const GemvProblem & P = B.p[0];
+            if (P.tile_rows != D.wkv.S || P.n_cta != D.wkv.H || P.M != D.wkv.H * D.wkv.S) return false;
+        }
+        if (D.op == DOP_LNMIX_GEMV && (size_t) program.tmp_offset + (size_t) D.ln.C * 4 > program.region_bytes) return false;
+        if (D.op == DOP_LERP && (size_t) program.tmp_offset + (size_t) 5 * D.lerp.mix * 4 > program.region_bytes) return false;
+    }
+    return (size_t) tma::NSTAGES * program.stage_bytes + program.region_bytes + dp::RED_BYTES == program.smem_bytes && program.smem_bytes <= dp::DYN_SMEM_BUDGET;
+}
+
+// Host-only part of decode_program_build: shapes -> shared-memory layout -> tiles and CTA shares.
+bool decode_program_plan(std::vector<DecodePhase> & phases, int num_sms, DecodeProgram & program) {
+    using namespace dp;
+    program = DecodeProgram();
+    const int total_ctas = 2 * num_sms;
+    if (phases.empty() || num_sms <= 0) return false;
+    // pass 1: shapes -> shared-memory layout
+    size_t max_col = 0, tmp_off = 0, tmp_need = 0;
+    for (DecodePhase & D : phases) {
+        size_t col = 0;
+        if (D.batch.n > 0) {
+            D.batch.T = 1;
+            if (!gemv_tma_plan(D.batch, total_ctas, tma::NOMINAL_STAGE_BYTES, &col)) return false;
+            if (col > max_col) max_col = col;
+        }
+        if (D.op == DOP_LNMIX_GEMV) {
+            if (D.batch.n == 0 || D.ln.C > 256 * LN_MAXCH) return false;
+            if (col > tmp_off) tmp_off = col;
+            if ((size_t) D.ln.C * 4 > tmp_need) tmp_need = (size_t) D.ln.C * 4;
+        } else if (D.op == DOP_LERP) {
+            const V6LerpParams & p = D.lerp;
+            const int cpc = (p.C + total_ctas - 1) / total_ctas;
+            if (D.batch.n != 0 || (p.mix & 3) || p.mix / 4 > 8 * LERP_MAXF4 || cpc > 32 || p.T != 1) return false;
+            if ((size_t) 5 * p.mix * 4 > tmp_need) tmp_need = (size_t) 5 * p.mix * 4;
+        } else if (D.op == DOP_GEMV_WKV) {
+            const Wkv6Params & p = D.wkv;
+            if (!(p.S == 8 || p.S == 16 || p.S == 32 || p.S == 64) || p.H > total_ctas || p.T != 1 || D.batch.n > 1) return false;
+            if (col > tmp_off) tmp_off = col;
+            if ((size_t) p.S * 4 > tmp_need) tmp_need = (size_t) p.S * 4;
+        } else if (D.op != DOP_GEMV || D.batch.n == 0) {
+            return false;
+        }
+    }
+    tmp_off = (tmp_off + 15) & ~(size_t) 15;
+    size_t region = tmp_off + tmp_need;
+    if (max_col > region) region = max_col;
+    region = (region + 127) & ~(size_t) 127;
+    if (region + RED_BYTES + 3 * 16 * 1024 > DYN_SMEM_BUDGET) return false;
+    const long long stage_bytes = (long long) ((DYN_SMEM_BUDGET - region - RED_BYTES) / tma::NSTAGES / 1024 * 1024);
+    // pass 2: tiles and CTA shares for the real stage size
+    for (DecodePhase & D : phases) {
+        if (D.batch.n == 0) continue;
+        if (!gemv_tma_plan(D.batch, total_ctas, stage_bytes, nullptr)) return false;
+        D.batch.stage_bytes = stage_bytes;
+        D.batch.trace = nullptr;
+        if (D.op == DOP_GEMV_WKV) {     // one tile = one head, CTA h owns head h
+            GemvProblem & p = D.batch.p[0];
+            const int S = D.wkv.S, wr = tma::CONSUMER_WARPS / p.wk;
+            if (p.M != D.wkv.H * S || S % wr != 0 || S > tma::MAX_TILE_ROWS || (long long) S * p.pitch > stage_bytes) return false;
+            p.tile_rows = S; p.n_cta = D.wkv.H; p.first_cta = 0;
+        }
+    }
+    program.grid = total_ctas;
+    program.stage_bytes = (uint32_t) stage_bytes;
+    program.tmp_offset = (uint32_t) tmp_off;
+    program.region_bytes = (uint32_t) region;
+    program.smem_bytes = (size_t) tma::NSTAGES * (size_t) stage_bytes + region + RED_BYTES;
+    program.n_phases = (int) phases.size();
+    if (!program_selfcheck(phases, program)) {
+        fprintf(stderr, "rwkv_b200: the persistent decode program failed its self-check; using the per-launch path\n");
+        return false;
+    }
+    return true;
+}
+
+bool decode_program_build(std::vector<DecodePhase> & phases, const DeviceInfo & dev, DecodeProgram & program) {
+    using namespace dp;
+    if (!decode_program_plan(phases, dev.num_sms, program)) { program = DecodeProgram(); return false; }
+    static bool attr_set_dev[64] = {};
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    cur_dev = (cur_dev < 0 || cur_dev >= 64) ? 0 : cur_dev;
+    if (!attr_set_dev[cur_dev]) {
+        if (cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) DYN_SMEM_BUDGET) != cudaSuccess) { cudaGetLastError(); return false; }
+        attr_set_dev[cur_dev] = true;
+    }
+    int per_sm = 0, coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cur_dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persistent_kernel, tma::THREADS, program.smem_bytes) != cudaSuccess || per_sm < 2 || !coop) {
+        cudaGetLastError();
+        fprintf(stderr, "rwkv_b200: the persistent decode kernel cannot keep 2 CTAs per SM resident (%d, cooperative launch %d); using the per-launch path\n", per_sm, coop);
+        program = DecodeProgram();
+        return false;
+    }
+    if (cudaMalloc(reinterpret_cast<void **>(&program.phases), phases.size() * sizeof(DecodePhase)) != cudaSuccess) { cudaGetLastError(); program = DecodeProgram(); return false; }
+    if (cudaMemcpy(program.phases, phases.data(), phases.size() * sizeof(DecodePhase), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        decode_program_free(program);
+        return false;
+    }
+    program.supported = true;
+    return true;
+}
+
+cudaError_t decode_program_launch(const DecodeProgram & program, unsigned long long * barrier_counter, unsigned long long barrier_base,
+                                  unsigned long long * trace, cudaStream_t stream) {
+    if (!program.supported) return cudaErrorNotSupported;
+    dp::Args a;
+    a.phases = program.phases; a.n_phases = program.n_phases;
+    a.bar = barrier_counter; a.bar_base = barrier_base;
+    a.stage_bytes = program.stage_bytes; a.tmp_offset = program.tmp_offset; a.region_bytes = program.region_bytes;
+    a.trace = trace;
+    void * args[] = {&a};
+    g_kernel_launches++;
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(dp::decode_persistent_kernel), dim3((unsigned) program.grid), dim3(tma::THREADS), args,
+                                       program.smem_bytes, stream);
+}
+
+}  // namespace rwkv

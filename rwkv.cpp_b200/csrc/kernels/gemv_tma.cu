@@ -173,29 +173,12 @@ cudaError_t launch_tma_nc(const GemvBatch & batch, int grid, size_t smem, cudaSt
 
 }  // namespace
 
-// Returns cudaErrorNotSupported when some problem of the batch does not fit the streaming kernel
-// (the caller then uses the generic kernel for the whole batch).
-cudaError_t gemv_tma_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream) {
+// Tile height and CTA share of every problem for ring stages of `stage_bytes`: CTAs are split over the problems by weight
+// bytes (largest remainders get the leftovers). Returns the number of CTAs used (<= total_ctas).
+static int assign_tiles_and_ctas(GemvBatch & batch, int total_ctas, long long stage_bytes) {
     using namespace tma;
     double total_bytes = 0;
-    size_t max_col = 0;
-    for (int i = 0; i < batch.n; i++) {
-        GemvProblem & p = batch.p[i];
-        if (!plan_wk(p)) return cudaErrorNotSupported;
-        total_bytes += (double) p.M * (double) p.pitch;
-        const size_t cb = act_bytes_per_column(p.type, p.K);
-        if (cb > max_col) max_col = cb;
-    }
-    // columns staged together, and the ring stage size that leaves
-    auto stage_for = [&](int nc) -> long long {
-        const long long rest = (long long) nc * (long long) max_col + (long long) 2 * MAX_TILE_ROWS * CONSUMER_WARPS * nc * (long long) sizeof(float);
-        return ((long long) CTA_SMEM_BUDGET - rest) / NSTAGES / 1024 * 1024;
-    };
-    int nc = 1;
-    if (batch.T >= 4 && stage_for(4) >= NOMINAL_STAGE_BYTES) nc = 4;
-    else if (batch.T >= 2 && stage_for(2) >= NOMINAL_STAGE_BYTES) nc = 2;
-    const long long stage_bytes = stage_for(nc);
-    if (stage_bytes < NOMINAL_STAGE_BYTES) return cudaErrorNotSupported;
+    for (int i = 0; i < batch.n; i++) total_bytes += (double) batch.p[i].M * (double) batch.p[i].pitch;
     for (int i = 0; i < batch.n; i++) {
         GemvProblem & p = batch.p[i];
         const int wr = CONSUMER_WARPS / p.wk;
@@ -204,8 +187,6 @@ cudaError_t gemv_tma_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStrea
         if (rows > MAX_TILE_ROWS) rows = MAX_TILE_ROWS;
         p.tile_rows = rows;
     }
-    // two CTAs per SM, split over the problems by weight bytes (largest remainders get the leftovers)
-    const int total_ctas = 2 * dev.num_sms;
     int assigned = 0, cap[GEMV_MAX_PROBLEMS];
     double frac[GEMV_MAX_PROBLEMS];
     for (int i = 0; i < batch.n; i++) {
@@ -227,6 +208,48 @@ cudaError_t gemv_tma_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStrea
     }
     int next = 0;
     for (int i = 0; i < batch.n; i++) { batch.p[i].first_cta = next; next += batch.p[i].n_cta; }
+    return next;
+}
+
+bool gemv_tma_plan(GemvBatch & batch, int total_ctas, long long stage_bytes, size_t * max_col_bytes) {
+    using namespace tma;
+    size_t max_col = 0;
+    for (int i = 0; i < batch.n; i++) {
+        GemvProblem & p = batch.p[i];
+        if (!plan_wk(p)) return false;
+        if ((long long) (CONSUMER_WARPS / p.wk) * p.pitch > stage_bytes) return false;   // not even one row per warp row-slot fits a stage
+        const size_t cb = act_bytes_per_column(p.type, p.K);
+        if (cb > max_col) max_col = cb;
+    }
+    if (batch.n > total_ctas) return false;
+    assign_tiles_and_ctas(batch, total_ctas, stage_bytes);
+    if (max_col_bytes) *max_col_bytes = max_col;
+    return true;
+}
+
+// Returns cudaErrorNotSupported when some problem of the batch does not fit the streaming kernel
+// (the caller then uses the generic kernel for the whole batch).
+cudaError_t gemv_tma_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream) {
+    using namespace tma;
+    size_t max_col = 0;
+    for (int i = 0; i < batch.n; i++) {
+        GemvProblem & p = batch.p[i];
+        if (!plan_wk(p)) return cudaErrorNotSupported;
+        const size_t cb = act_bytes_per_column(p.type, p.K);
+        if (cb > max_col) max_col = cb;
+    }
+    // columns staged together, and the ring stage size that leaves
+    auto stage_for = [&](int nc) -> long long {
+        const long long rest = (long long) nc * (long long) max_col + (long long) 2 * MAX_TILE_ROWS * CONSUMER_WARPS * nc * (long long) sizeof(float);
+        return ((long long) CTA_SMEM_BUDGET - rest) / NSTAGES / 1024 * 1024;
+    };
+    int nc = 1;
+    if (batch.T >= 4 && stage_for(4) >= NOMINAL_STAGE_BYTES) nc = 4;
+    else if (batch.T >= 2 && stage_for(2) >= NOMINAL_STAGE_BYTES) nc = 2;
+    const long long stage_bytes = stage_for(nc);
+    if (stage_bytes < NOMINAL_STAGE_BYTES) return cudaErrorNotSupported;
+    // two CTAs per SM
+    const int next = assign_tiles_and_ctas(batch, 2 * dev.num_sms, stage_bytes);
     batch.max_col_bytes = (long long) max_col;
     batch.stage_bytes = stage_bytes;
     batch.trace = trace_slot(batch.n > 1 ? "gemv_tma(batch)" : "gemv_tma");

@@ -55,7 +55,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t * bar, uint32_t parity) {
         "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-__device__ __noinline__ void mbar_wait_slow(uint64_t * bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint64_t * bar, uint32_t parity) {
     const long long t0 = clock64();
     unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -180,7 +180,7 @@ template <int TYPE> __device__ __forceinline__ void load_unit(const uint8_t * ro
 // would multiply with (ggml-cpu.c:253-311 `vec_dot_type`): Q8_0 / Q8_1 blocks for quantised weights (x86 flavour of
 // quantize_row_q8_0 / q8_1, ggml-cpu-quants.c:781-846, 1085-1160; one thread per 32-element block), fp16 for F16
 // weights, fp32 for F32 weights. PRO_LAYERNORM applies rwkv_layer_norm (rwkv_operators.inc:93-97) on the fly.
-__device__ void stage_column(const GemvProblem & P, int col_index, uint8_t * col, double * red_d) {
+static __device__ void stage_column(const GemvProblem & P, int col_index, uint8_t * col, double * red_d) {
     const int K = P.K, tid = threadIdx.x;
     const float * x = P.x + (long long) col_index * P.ldx;
     float mean = 0.f, rstd = 1.f;

@@ -114,6 +114,14 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_set_graphs.restype = None
         lib.rwkv_b200_set_tensor_cores.argtypes = [vp, ctypes.c_bool]
         lib.rwkv_b200_set_tensor_cores.restype = None
+        lib.rwkv_b200_set_persistent.argtypes = [vp, ctypes.c_bool]
+        lib.rwkv_b200_set_persistent.restype = None
+        lib.rwkv_b200_persistent_state.argtypes = [vp]
+        lib.rwkv_b200_persistent_state.restype = ctypes.c_int
+        lib.rwkv_b200_phase_trace.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_int]
+        lib.rwkv_b200_phase_trace.restype = ctypes.c_int
+        lib.rwkv_b200_plan_selftest.argtypes = [ctypes.c_int] * 11 + [ctypes.POINTER(ctypes.c_int)]
+        lib.rwkv_b200_plan_selftest.restype = ctypes.c_int
         lib.rwkv_b200_matvec.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, P_FLOAT, P_FLOAT, ctypes.c_int]
         lib.rwkv_b200_matvec.restype = ctypes.c_bool
 

@@ -31,6 +31,8 @@ PRESETS = {
     "rwkv5.1-small": dict(arch=(5, 1), C=256, F=896, L=3, V=1000, S=64),
     "rwkv5-small": dict(arch=(5, 2), C=256, F=896, L=3, V=1000, S=64),
     "rwkv6-small": dict(arch=(6, 0), C=512, F=1792, L=4, V=2000, S=64, mix=32, decay=64),
+    "rwkv6-mid": dict(arch=(6, 0), C=2048, F=7168, L=2, V=4000, S=64, mix=32, decay=64),      # ffn rows split over 2 warps
+    "rwkv6-wide": dict(arch=(6, 0), C=4096, F=14336, L=1, V=2000, S=64, mix=64, decay=128),   # one layer of the 7B shape
     "rwkv7-small": dict(arch=(7, 0), C=512, F=2048, L=4, V=2000, S=64, lora_w=64, lora_a=64, lora_v=32, lora_g=128),
 }
 
