@@ -1,0 +1,104 @@
+"""Diagnoses the persistent single-token kernel against the per-launch path on one model file.
+
+    python tools/persistent_probe.py <model.bin> [--tokens 6] [--trace]
+
+Prints, per layer, whether the slots of the recurrent state written by each phase agree bit for bit (the state holds
+LN1(x) = att_xx, the WKV state and LN2(x) = ffn_xx of every layer, so the first differing slot names the first phase that
+went wrong), the logits difference, timings of both paths and (--trace) the persistent kernel's phase timeline.
+"""
+import argparse
+import ctypes
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("model")
+    ap.add_argument("--tokens", type=int, default=6)
+    ap.add_argument("--trace", action="store_true")
+    ap.add_argument("--time", type=int, default=0, help="time this many resident decode steps on both paths")
+    args = ap.parse_args()
+    pkg = __graft_entry__.load_package()
+    lib = pkg.load_rwkv_shared_library()
+    L = lib.library
+    ctx = lib.rwkv_init_from_file(args.model, 1, 0)
+    n_state, n_logits = lib.rwkv_get_state_buffer_element_count(ctx), lib.rwkv_get_logits_buffer_element_count(ctx)
+    n_layer, C = L.rwkv_get_n_layer(ctx.ptr), L.rwkv_get_n_embed(ctx.ptr)
+    per_layer = n_state // n_layer
+    P_F = ctypes.POINTER(ctypes.c_float)
+    toks = [(7919 * i + 3) % n_logits for i in range(args.tokens)]
+
+    def run(persistent):
+        L.rwkv_b200_set_persistent(ctx.ptr, persistent)
+        state = np.zeros(n_state, dtype=np.float32)
+        logits = np.zeros(n_logits, dtype=np.float32)
+        states = []
+        for i, t in enumerate(toks):
+            ok = L.rwkv_eval(ctx.ptr, t, None if i == 0 else state.ctypes.data_as(P_F), state.ctypes.data_as(P_F), logits.ctypes.data_as(P_F))
+            if not ok:
+                print(f"rwkv_eval failed at token {i} (persistent={persistent}), flags 0x{lib.rwkv_get_last_error(ctx):x}")
+                sys.exit(2)
+            states.append(state.copy())
+        return logits.copy(), states
+
+    want_logits, want_states = run(False)
+    got_logits, got_states = run(True)
+    print("persistent_state:", L.rwkv_b200_persistent_state(ctx.ptr))
+    bad = False
+    for i, (ws, gs) in enumerate(zip(want_states, got_states)):
+        if ws.tobytes() == gs.tobytes():
+            continue
+        bad = True
+        print(f"token {i}: state differs")
+        for l in range(n_layer):
+            w, g = ws[l * per_layer:(l + 1) * per_layer], gs[l * per_layer:(l + 1) * per_layer]
+            slots = (("ffn_xx", 0, C), ("att_xx", C, 2 * C), ("wkv", 2 * C, per_layer))
+            msg = []
+            for name, a, b in slots:
+                d = np.abs(w[a:b] - g[a:b])
+                nbad = int((w[a:b].view(np.uint32) != g[a:b].view(np.uint32)).sum())
+                if nbad:
+                    msg.append(f"{name}: {nbad}/{b - a} differ, max {d.max():.3e}, first at {int(np.argmax(w[a:b].view(np.uint32) != g[a:b].view(np.uint32)))}")
+            if msg:
+                print(f"  layer {l}: " + "; ".join(msg))
+        break
+    dl = np.abs(want_logits - got_logits)
+    print(f"logits: max |diff| {dl.max():.3e}, bitwise equal {want_logits.tobytes() == got_logits.tobytes()}, finite {bool(np.isfinite(got_logits).all())}")
+    print("RESULT", "MISMATCH" if bad or want_logits.tobytes() != got_logits.tobytes() else "BIT-EXACT")
+
+    if args.time:
+        arr = (ctypes.c_uint32 * (args.time + 8))(*[(7919 * i) % n_logits for i in range(args.time + 8)])
+        for persistent in (False, True):
+            L.rwkv_b200_set_persistent(ctx.ptr, persistent)
+            L.rwkv_b200_state_load(ctx.ptr, None)
+            ms = L.rwkv_b200_time_resident(ctx.ptr, arr, 1, args.time, 8, True)
+            print(f"resident decode, persistent={persistent}: {ms / args.time:.4f} ms/token")
+    if args.trace:
+        L.rwkv_b200_set_persistent(ctx.ptr, True)
+        buf = (ctypes.c_double * 4096)()
+        L.rwkv_b200_phase_trace(ctx.ptr, buf, 4096)      # arm
+        one = (ctypes.c_uint32 * 1)(toks[0])
+        for _ in range(3):
+            L.rwkv_b200_eval_resident(ctx.ptr, one, 1, True, None)
+        n = L.rwkv_b200_phase_trace(ctx.ptr, buf, 4096)
+        b = [buf[i] for i in range(max(n, 0))]
+        print(f"phase trace: {n} boundaries, total {b[-1] if b else -1:.1f} us")
+        if n > 8:
+            dur = np.diff(np.array(b))
+            per = 7 if (n - 2) % 7 == 0 else 5
+            body = dur[:(len(dur) - 1) // per * per].reshape(-1, per)
+            print("per-layer phase durations (us), median over layers:", np.round(np.median(body, axis=0), 2).tolist(), "layer total", round(float(np.median(body.sum(axis=1))), 2))
+            print("first layer:", np.round(body[0], 2).tolist(), " head:", round(float(dur[-1]), 2))
+    lib.rwkv_free(ctx)
+
+
+if __name__ == "__main__":
+    main()
