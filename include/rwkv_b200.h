@@ -38,6 +38,16 @@ RWKV_API bool rwkv_b200_state_store(struct rwkv_context * ctx, float * state_out
 /* Blocks until everything enqueued on the context's stream has finished. */
 RWKV_API bool rwkv_b200_synchronize(struct rwkv_context * ctx);
 
+/* On-device sampling: the next token is drawn on the GPU from the logits of the most recent evaluation that
+ * computed them, following the reference's python/sampling.py:10-52 (softmax, optional logit bias, temperature 0 = argmax, top-p
+ * cutoff, power by 1/temperature, renormalise, inverse-CDF draw); only the 4-byte token id crosses PCIe instead of n_vocab floats.
+ * `u` is a uniform number in [0, 1) from the caller's generator -- with u = numpy's RandomState.random_sample() the result is the
+ * token numpy.random.choice would return in the reference. temperature >= 0, 0 <= top_p <= 1 (0 means 1), n_vocab <= 65536.
+ * rwkv_b200_eval_sample = rwkv_b200_eval_resident(token, with logits) + rwkv_b200_sample without bias. */
+RWKV_API bool rwkv_b200_sample(struct rwkv_context * ctx, float temperature, float top_p, double u, const uint32_t * bias_ids, const float * bias_values,
+                               size_t n_bias, uint32_t * token_out);
+RWKV_API bool rwkv_b200_eval_sample(struct rwkv_context * ctx, uint32_t token, float temperature, float top_p, double u, uint32_t * next_token_out);
+
 /* Layer pipeline across GPUs (the reference has no equivalent: ggml offloads layers of ONE context,
  * rwkv.cpp:97-116). A context created with rwkv_b200_init_from_file_ex(path, device, begin, end) is one stage; its slice
  * of the recurrent state stays resident on that device. Per pass of n_tokens (<= 256):

@@ -205,6 +205,18 @@ bool rwkv_b200_eval_resident(struct rwkv_context * ctx, const uint32_t * tokens,
     return true;
 }
 
+bool rwkv_b200_sample(struct rwkv_context * ctx, float temperature, float top_p, double u, const uint32_t * bias_ids, const float * bias_values, size_t n_bias,
+                      uint32_t * token_out) {
+    Context * c = C(ctx);
+    c->last_error = RWKV_ERROR_NONE;
+    return sample_token(c, temperature, top_p, u, bias_ids, bias_values, n_bias, token_out);
+}
+
+bool rwkv_b200_eval_sample(struct rwkv_context * ctx, uint32_t token, float temperature, float top_p, double u, uint32_t * next_token_out) {
+    if (!rwkv_b200_eval_resident(ctx, &token, 1, true, nullptr)) return false;
+    return sample_token(C(ctx), temperature, top_p, u, nullptr, nullptr, 0, next_token_out);
+}
+
 size_t rwkv_b200_stage_hidden_len(const struct rwkv_context * ctx, size_t n_tokens) { return stage_hidden_len(*C(ctx)->model, n_tokens); }
 
 bool rwkv_b200_stage_eval(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, const float * hidden_in, float * hidden_out, bool want_logits,

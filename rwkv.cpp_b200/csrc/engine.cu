@@ -606,6 +606,7 @@ bool forward_pass(Context * ctx, const uint32_t * tokens, int T, bool want_logit
     ctx->slot_used[phase] = true;
     float * tmp = ctx->state_a; ctx->state_a = ctx->state_b; ctx->state_b = tmp;
     ctx->phase ^= 1;
+    ctx->logits_valid = want_logits && m.layer_end == m.n_layer;
     return true;
 }
 
@@ -664,6 +665,8 @@ void destroy_context(Context * ctx) {
     for (auto & row : ctx->graphs) for (auto & g : row) if (g.exec) cudaGraphExecDestroy(g.exec);
     drop_programs(ctx);
     cudaFree(ctx->grid_barrier); cudaFree(ctx->phase_trace);
+    cudaFree(ctx->sample_token); cudaFree(ctx->sample_scratch); cudaFree(ctx->bias_ids); cudaFree(ctx->bias_values);
+    if (ctx->sample_token_host) cudaFreeHost(ctx->sample_token_host);
     for (auto & r : ctx->prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
@@ -757,9 +760,49 @@ int plan_selftest(int arch_major, int arch_minor, int type, int C, int F, int V,
         phase_gemv(prog, b);
     }
     DecodeProgram program;
-    const bool ok = decode_program_plan(prog, num_sms, program);
+    const bool ok = decode_program_plan_check_records(prog, num_sms, program);
     if (info) { info[0] = (int) program.stage_bytes; info[1] = (int) program.region_bytes; info[2] = program.n_phases; info[3] = (int) program.smem_bytes; }
     return ok ? 1 : 0;
+}
+
+bool sample_token(Context * ctx, float temperature, float top_p, double u, const uint32_t * bias_ids, const float * bias_values, size_t n_bias, uint32_t * token_out) {
+    const Model & m = *ctx->model;
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, token_out != nullptr, "token_out is NULL");
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, temperature >= 0.0f, "temperature must be >= 0");            // sampling.py:20-21
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, top_p >= 0.0f && top_p <= 1.0f, "top_p must be in [0, 1]");    // sampling.py:22-23
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, u >= 0.0 && u < 1.0, "u must be in [0, 1)");
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, n_bias == 0 || (bias_ids && bias_values), "logit bias arrays are NULL");
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, ctx->logits_valid, "No logits to sample from: the last evaluation skipped the head");
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, m.n_vocab <= 65536, "On-device sampling supports n_vocab <= 65536");
+    CUDA_OK(ctx, cudaSetDevice(m.dev.device));
+    if (!ctx->sample_token) {
+        CUDA_OK(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->sample_token), 2 * sizeof(uint32_t)));
+        CUDA_OK(ctx, cudaMallocHost(reinterpret_cast<void **>(&ctx->sample_token_host), 2 * sizeof(uint32_t)));
+    }
+    for (size_t i = 0; i < n_bias; i++)
+        RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, bias_ids[i] < (uint32_t) m.n_vocab, "logit bias id %u is out of range", bias_ids[i]);
+    if (n_bias > 0) {
+        if (!ctx->sample_scratch) CUDA_OK(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->sample_scratch), (size_t) m.n_vocab * sizeof(float)));
+        if (n_bias > ctx->bias_capacity) {
+            CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->bias_ids); cudaFree(ctx->bias_values);
+            ctx->bias_ids = nullptr; ctx->bias_values = nullptr; ctx->bias_capacity = 0;
+            CUDA_OK(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->bias_ids), n_bias * sizeof(uint32_t)));
+            CUDA_OK(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->bias_values), n_bias * sizeof(float)));
+            ctx->bias_capacity = n_bias;
+        }
+        CUDA_OK(ctx, cudaMemcpyAsync(ctx->bias_ids, bias_ids, n_bias * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_OK(ctx, cudaMemcpyAsync(ctx->bias_values, bias_values, n_bias * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    SampleParams sp{};
+    sp.logits = ctx->logits; sp.n_vocab = m.n_vocab; sp.temperature = temperature; sp.top_p = top_p; sp.u = u;
+    sp.bias_ids = ctx->bias_ids; sp.bias_values = ctx->bias_values; sp.n_bias = (int) n_bias;
+    sp.scratch = ctx->sample_scratch; sp.token_out = ctx->sample_token; sp.prob_out = nullptr;
+    CUDA_OK(ctx, launch_sample(sp, ctx->stream));
+    CUDA_OK(ctx, cudaMemcpyAsync(ctx->sample_token_host, ctx->sample_token, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    *token_out = ctx->sample_token_host[0];
+    return true;
 }
 
 size_t stage_hidden_len(const Model & m, size_t T) { return (size_t) (m.arch_major == 7 ? 2 : 1) * (size_t) m.n_embed * T; }

@@ -62,6 +62,13 @@ struct Context {
     const float * hidden_in = nullptr;
     float * hidden_out = nullptr;
 
+    // On-device sampling (kernels/sampling.cu): result word, scratch for biased logits, device copy of the caller's logit bias.
+    bool logits_valid = false;       // ctx->logits holds the head output of the most recent pass
+    uint32_t * sample_token = nullptr;   // device
+    uint32_t * sample_token_host = nullptr;   // pinned
+    float * sample_scratch = nullptr;    // [n_vocab] device
+    uint32_t * bias_ids = nullptr; float * bias_values = nullptr; size_t bias_capacity = 0;   // device
+
     float last_device_ms = 0.f;      // CUDA-event time of the last forward (kernels only)
     int last_error = 0;              // rwkv_error_flags
     bool print_errors = true;
@@ -95,6 +102,10 @@ bool forward(Context * ctx, const uint32_t * tokens, size_t T, bool want_logits)
 // (device pointers, stage_hidden_len(T) floats); the last one computes the logits when asked. `stream` (may be NULL = the
 // context's own) is the CUDA stream everything is enqueued on, so the hand-off can be ordered against NCCL sends and
 // receives without host synchronisation.
+// Samples the next token from ctx->logits on the device (reference python/sampling.py:10-52 with the caller's uniform number u in
+// [0, 1) in place of numpy's RandomState draw); only the token id is copied back. Requires a preceding pass that computed logits.
+bool sample_token(Context * ctx, float temperature, float top_p, double u, const uint32_t * bias_ids, const float * bias_values, size_t n_bias, uint32_t * token_out);
+
 size_t stage_hidden_len(const Model & m, size_t T);
 
 // Host-only self-test of the persistent-kernel planner on a fake model of the given shape: 1 = a program was planned and passed

@@ -17,26 +17,41 @@ constexpr int LERP_MAXF4 = 2;              // float4 per lane per mix kept in re
 constexpr size_t DYN_SMEM_BUDGET = 110 * 1024;   // + ~2 KB static: two CTAs per SM
 constexpr size_t RED_BYTES = (size_t) 2 * MAX_TILE_ROWS * CONSUMER_WARPS * sizeof(float);
 
-struct Args {
-    const DecodePhase * phases;
-    int n_phases;
-    unsigned long long * bar;
-    unsigned long long bar_base;
-    uint32_t stage_bytes, tmp_offset, region_bytes;
-    unsigned long long * trace;
+// ---- the program as the kernel reads it: one fully resolved record per (CTA, phase), CTA-major, so that a CTA's next record is
+// ONE contiguous block it can pull into shared memory with cp.async a whole phase ahead (the descriptor chain "which problem is
+// mine -> its GemvProblem -> the stage parameters" cost ~2 us of dependent L2 round trips per phase when read on demand).
+struct LnLocal {
+    const float * x, * ln_w, * ln_b, * state_in, * coef;
+    float * state_out, * out_xx, * out_sx;
+    int formula, C;
 };
-
-struct WkvStep {             // Wkv6Params without its default member initialisers (lives in shared memory)
+struct WkvStep {
     const float * r, * k, * v, * td, * tf, * state_in, * lnx_w, * lnx_b, * g;
     float * state_out, * y;
     float eps;
     int td_per_token, per_head_scalars, H, S;
 };
-struct PhaseLocal {          // published by thread 0 while the CTA waits in the grid barrier
-    int op[2];               // op of phase ph at [ph & 1]
-    int active, local, my_tiles, head;
-    DecodeLnMix ln;          // coef[0] = the mixing vector of this CTA's problem
-    WkvStep wkv;
+struct LerpLocal {
+    const float * w2, * z, * xx, * sx;
+    const float * maa[5];
+    float * out[5];
+    int C, mix, c0, n;        // this CTA's channels [c0, c0 + n), n <= 32
+};
+struct alignas(16) CtaPhase {
+    int op, active, local, my_tiles, head, pad_[3];
+    GemvProblem P;
+    union { LnLocal ln; WkvStep wkv; LerpLocal lerp; } u;
+};
+static_assert(sizeof(CtaPhase) % 16 == 0 && sizeof(CtaPhase) <= 512, "CtaPhase must be a whole number of 16-byte cp.async granules");
+constexpr int REC_GRANULES = (int) (sizeof(CtaPhase) / 16);
+
+struct Args {
+    const CtaPhase * records;        // [grid][n_phases]
+    int n_phases;
+    unsigned long long * bar;
+    unsigned long long bar_base;
+    uint32_t stage_bytes, tmp_offset, region_bytes;
+    unsigned long long * trace;
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long * p) {
@@ -49,22 +64,64 @@ __device__ __forceinline__ unsigned long long global_timer() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
     return g;
 }
-__device__ __forceinline__ int tiles_of(const GemvProblem & P, int local) {
+__device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__host__ __device__ __forceinline__ int tiles_of(const GemvProblem & P, int local) {
     const int n_tiles = (P.M + P.tile_rows - 1) / P.tile_rows;
-    return (local < P.n_cta && local < n_tiles) ? (n_tiles - local + P.n_cta - 1) / P.n_cta : 0;
+    return (local >= 0 && local < P.n_cta && local < n_tiles) ? (n_tiles - local + P.n_cta - 1) / P.n_cta : 0;
 }
 
 // ---- LayerNorm + token shift + mixing for T = 1, by the 256 consumer threads, bit-identical to ln_mix_kernel<PER> (glue.cu):
 // that kernel runs 1024 threads, thread v summing channels v, v + 1024, ... in double, then a warp xor-tree, 32 slots and a second
 // xor-tree over the slots. Consumer thread t plays the four virtual threads v = t + 256 q: virtual warp (t >> 5) + 8 q, same lane.
+// The per-channel parameters (LayerNorm weight and bias, the previous token's LN(x), the mixing vector) never change during the
+// launch: the first eight channels' worth is requested before the x loads and the reductions (LnRegs), the rest before the first
+// output is stored, so none of these loads is serialised behind a store it might alias.
 __device__ __forceinline__ double warp_tree_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ void ln_mix_stage(const DecodeLnMix & L, float * tmp, double (* slots)[32], bool writer) {
+struct LnRegs { float w[8], b[8], pv[8], cf[8]; };
+__device__ __forceinline__ void ln_prefetch(const LnLocal & L, LnRegs & r, int m0) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        const int c = t + 256 * (m0 + m);
+        const bool live = c < L.C;
+        r.w[m] = live ? L.ln_w[c] : 0.f;
+        r.b[m] = live ? L.ln_b[c] : 0.f;
+        r.pv[m] = live ? L.state_in[c] : 0.f;
+        r.cf[m] = live ? L.coef[c] : 0.f;
+    }
+}
+__device__ __forceinline__ void ln_emit(const LnLocal & L, const LnRegs & r, const float * xa, float scale_a, int m0, float * tmp, bool writer) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        const int c = t + 256 * (m0 + m);
+        if (c < L.C) {
+            const float a = __fadd_rn(__fmul_rn(__fmul_rn(xa[m0 + m], scale_a), r.w[m]), r.b[m]);     // LN(x)
+            const float b = r.pv[m];                                                                  // LN(x) of the previous token
+            const float mc = r.cf[m];
+            tmp[c] = (L.formula == 0) ? __fadd_rn(__fmul_rn(a, mc), __fsub_rn(b, __fmul_rn(b, mc)))
+                                      : __fadd_rn(__fmul_rn(__fsub_rn(b, a), mc), a);
+            if (writer) {
+                L.state_out[c] = a;
+                if (L.out_sx) L.out_sx[c] = __fsub_rn(b, a);
+                if (L.out_xx) L.out_xx[c] = a;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void ln_mix_stage(const LnLocal & L, float * tmp, double (* slots)[32], bool writer) {
     const int C = L.C, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int PER = (C + 1023) / 1024;
+    LnRegs first;
+    ln_prefetch(L, first, 0);            // in flight during the x loads and the two reductions
     float xa[LN_MAXCH];                   // channel t + 256 m, m = q + 4 i  (virtual thread q, its i-th channel)
     double sa[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -72,8 +129,7 @@ __device__ void ln_mix_stage(const DecodeLnMix & L, float * tmp, double (* slots
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int m = q + 4 * i, c = t + 256 * m;
-            const bool live = i < PER && c < C;
-            xa[m] = live ? L.x[c] : 0.f;
+            xa[m] = (c < C) ? L.x[c] : 0.f;
             sa[q] += (double) xa[m];
         }
     }
@@ -90,8 +146,7 @@ __device__ void ln_mix_stage(const DecodeLnMix & L, float * tmp, double (* slots
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int m = q + 4 * i, c = t + 256 * m;
-            const bool live = i < PER && c < C;
-            xa[m] = live ? xa[m] - mean_a : 0.f;
+            xa[m] = (c < C) ? xa[m] - mean_a : 0.f;
             va[q] += (double) (xa[m] * xa[m]);
         }
     }
@@ -102,34 +157,24 @@ __device__ void ln_mix_stage(const DecodeLnMix & L, float * tmp, double (* slots
     }
     consumer_barrier();
     const float scale_a = 1.0f / sqrtf((float) (warp_tree_d(slots[1][lane]) / C) + 1e-5f);
-    const float * coef = L.coef[0];
-#pragma unroll
-    for (int m = 0; m < LN_MAXCH; m++) {
-        const int c = t + 256 * m;
-        if (c < C) {
-            const float a = __fadd_rn(__fmul_rn(__fmul_rn(xa[m], scale_a), L.ln_w[c]), L.ln_b[c]);     // LN(x)
-            const float b = L.state_in[c];                                                               // LN(x) of the previous token
-            const float mc = coef[c];
-            tmp[c] = (L.formula == 0) ? __fadd_rn(__fmul_rn(a, mc), __fsub_rn(b, __fmul_rn(b, mc)))
-                                      : __fadd_rn(__fmul_rn(__fsub_rn(b, a), mc), a);
-            if (writer) {
-                L.state_out[c] = a;
-                if (L.out_sx) L.out_sx[c] = __fsub_rn(b, a);
-                if (L.out_xx) L.out_xx[c] = a;
-            }
-        }
+    if (C > 2048) {       // CTA-uniform
+        LnRegs second;
+        ln_prefetch(L, second, 8);
+        ln_emit(L, first, xa, scale_a, 0, tmp, writer);
+        ln_emit(L, second, xa, scale_a, 8, tmp, writer);
+    } else {
+        ln_emit(L, first, xa, scale_a, 0, tmp, writer);
     }
 }
 
 // ---- v6 data-dependent lerp for T = 1 (v6_lerp_decode_kernel, glue.cu): 8 lanes per channel, the same eight partial sums and
 // xor-tree. The W2 rows (immutable) are pulled into registers between arriving at the grid barrier and waiting on it.
 struct LerpRegs { float4 w[5][LERP_MAXF4]; float maa[5]; int c; bool live; };
-__device__ __forceinline__ void lerp_prefetch(const V6LerpParams & p, LerpRegs & r) {
+__device__ __forceinline__ void lerp_prefetch(const LerpLocal & p, LerpRegs & r) {
     const int C = p.C, mix = p.mix;
-    const int cpc = (C + (int) gridDim.x - 1) / (int) gridDim.x;
     const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
-    r.c = (int) blockIdx.x * cpc + grp;
-    r.live = grp < cpc && r.c < C;
+    r.c = p.c0 + grp;
+    r.live = grp < p.n && r.c < C;
 #pragma unroll
     for (int j = 0; j < 5; j++) {
         const float4 * wrow = reinterpret_cast<const float4 *>(p.w2 + ((size_t) j * C + (r.live ? r.c : 0)) * mix);
@@ -141,9 +186,9 @@ __device__ __forceinline__ void lerp_prefetch(const V6LerpParams & p, LerpRegs &
         r.maa[j] = r.live ? p.maa[j][r.c] : 0.f;
     }
 }
-__device__ __forceinline__ void lerp_run(const V6LerpParams & p, const LerpRegs & r, float * zs) {
+__device__ __forceinline__ void lerp_run(const LerpLocal & p, const LerpRegs & r, float * zs) {
     const int mix = p.mix, sub = threadIdx.x & 7;
-    for (int i = threadIdx.x; i < 5 * mix; i += CONSUMER_THREADS) zs[i] = p.z[i];
+    if (p.n > 0) for (int i = threadIdx.x; i < 5 * mix; i += CONSUMER_THREADS) zs[i] = p.z[i];
     const float sx = r.live ? p.sx[r.c] : 0.f, xx = r.live ? p.xx[r.c] : 0.f;
     consumer_barrier();
 #pragma unroll
@@ -168,27 +213,49 @@ __device__ __forceinline__ void lerp_run(const V6LerpParams & p, const LerpRegs 
 
 // ---- one WKV5/6 step of head h + per-head norm + ln_x + gate (wkv6_kernel<S>, wkv.cu, for T = 1): thread (oct, jg) owns the
 // 8 x 4 state patch, partial outputs meet over the octants by the same xor-shuffles, warp 0 normalises the head.
+__device__ __forceinline__ void load8(const float * p, float (&o)[8]) {
+    const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
 template <int S>
 __device__ void wkv6_step(const WkvStep & p, int h, float * ybuf) {
     constexpr int NOCT = S / 8, NJG = S / 4, NT = NOCT * NJG, NW = (NT + 31) / 32, CPL = (S + 31) / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t hb = (size_t) h * S;
+    float lw[CPL], lb[CPL], gg[CPL];
+    if (warp == 0) {      // parameters of the normalisation, requested before the recurrence
+#pragma unroll
+        for (int i = 0; i < CPL; i++) {
+            const int col = lane + 32 * i;
+            lw[i] = col < S ? p.lnx_w[hb + col] : 0.f;
+            lb[i] = col < S ? p.lnx_b[hb + col] : 0.f;
+            gg[i] = (col < S && p.g) ? p.g[hb + col] : 0.f;
+        }
+    }
     if (warp < NW) {
         const bool worker = tid < NT;
         const int oct = worker ? tid % NOCT : 0, jg = worker ? tid / NOCT : 0;
         const int i0 = oct * 8, j0 = jg * 4;
-        const size_t hb = (size_t) h * S;
         float st[8][4], kk[8], rr[8], dv[8], tfr[8], vv[4];
 #pragma unroll
         for (int ii = 0; ii < 8; ii++) {
             const float4 v = *reinterpret_cast<const float4 *>(p.state_in + (hb + i0 + ii) * S + j0);
             st[ii][0] = v.x; st[ii][1] = v.y; st[ii][2] = v.z; st[ii][3] = v.w;
-            tfr[ii] = p.per_head_scalars ? p.tf[h] : p.tf[hb + i0 + ii];
-            kk[ii] = p.k[hb + i0 + ii];
-            rr[ii] = p.r[hb + i0 + ii];
-            dv[ii] = p.td_per_token ? p.td[hb + i0 + ii] : (p.per_head_scalars ? p.td[h] : p.td[hb + i0 + ii]);
         }
+        load8(p.k + hb + i0, kk);
+        load8(p.r + hb + i0, rr);
+        if (p.per_head_scalars) {
+            const float tf = p.tf[h], td = p.td[h];
 #pragma unroll
-        for (int jj = 0; jj < 4; jj++) vv[jj] = p.v[hb + j0 + jj];
+            for (int ii = 0; ii < 8; ii++) { tfr[ii] = tf; dv[ii] = td; }
+        } else {
+            load8(p.tf + hb + i0, tfr);
+            load8(p.td + hb + i0, dv);      // per token (v6) or per channel (v5.2): the same index for T = 1
+        }
+        {
+            const float4 g4 = *reinterpret_cast<const float4 *>(p.v + hb + j0);
+            vv[0] = g4.x; vv[1] = g4.y; vv[2] = g4.z; vv[3] = g4.w;
+        }
         float y[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ii = 0; ii < 8; ii++) {
@@ -229,15 +296,14 @@ __device__ void wkv6_step(const WkvStep & p, int h, float * ybuf) {
         const float mean = (float) mean_d;
         const float var = (float) fmax(s2 / S - mean_d * mean_d, 0.0);
         const float rstd = 1.0f / sqrtf(var + p.eps);
-        const size_t o = (size_t) h * S;
 #pragma unroll
         for (int i = 0; i < CPL; i++) {
             const int col = lane + 32 * i;
             if (col < S) {
                 float n = (yv[i] - mean) * rstd;
-                n = __fadd_rn(__fmul_rn(n, p.lnx_w[o + col]), p.lnx_b[o + col]);
-                if (p.g) n = __fmul_rn(n, p.g[o + col]);
-                p.y[o + col] = n;
+                n = __fadd_rn(__fmul_rn(n, lw[i]), lb[i]);
+                if (p.g) n = __fmul_rn(n, gg[i]);
+                p.y[hb + col] = n;
             }
         }
     }
@@ -246,7 +312,7 @@ __device__ void wkv6_step(const WkvStep & p, int h, float * ybuf) {
 // ---- the GEMV of a phase on this CTA's tiles: stage the (single) activation column, then the unchanged consumers
 __device__ void run_gemv(Shared & sh, uint8_t * ring, uint32_t stage_bytes, uint8_t * act, float * red, int it0, int local, int my_tiles) {
     const GemvProblem & P = sh.P;
-    stage_column(P, 0, act, sh.red_d);
+    stage_column<8>(P, 0, act, sh.red_d);
     consumer_barrier();
     const size_t colb = act_bytes_per_column(P.type, P.K);
 #define RWKV_DP_REGS(T_) consume_quant_regs<T_, true>(sh, ring, stage_bytes, act, 0, red, it0, my_tiles, local, P.n_cta)
@@ -267,7 +333,7 @@ __device__ void run_gemv(Shared & sh, uint8_t * ring, uint32_t stage_bytes, uint
 __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Args a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ Shared sh;
-    __shared__ PhaseLocal pl;
+    __shared__ __align__(16) CtaPhase rec[2];
     __shared__ double slots[2][32];
 
     if (threadIdx.x == 0) {
@@ -282,25 +348,21 @@ __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Arg
     uint8_t * act = smem + (size_t) NSTAGES * stage_bytes;
     float * tmp = reinterpret_cast<float *>(act + a.tmp_offset);
     const int n = a.n_phases;
+    const CtaPhase * mine = a.records + (size_t) blockIdx.x * (size_t) n;
 
     if (threadIdx.x >= CONSUMER_THREADS) {
-        // ===== producer: one thread walks the whole program and streams this CTA's weight tiles of every phase through the
-        // ring, as far ahead of the consumers as the ring allows (across phase boundaries: weights are immutable) =====
+        // ===== producer: one thread walks this CTA's records and streams its weight tiles of every phase through the ring, as
+        // far ahead of the consumers as the ring allows (across phase boundaries: weights are immutable) =====
         if (threadIdx.x == CONSUMER_THREADS) {
             const uint64_t policy = policy_evict_first();
             int it = 0;
             for (int ph = 0; ph < n; ph++) {
-                const GemvBatch & B = a.phases[ph].batch;
-                const int nb = B.n;
-                if (nb == 0) continue;
-                int pi = 0;
-                for (int i = 1; i < nb; i++) if ((int) blockIdx.x >= B.p[i].first_cta) pi = i;
-                const GemvProblem & P = B.p[pi];
-                const int local = (int) blockIdx.x - P.first_cta;
-                const int my_tiles = tiles_of(P, local);
-                const uint8_t * Wb = reinterpret_cast<const uint8_t *>(P.W);
-                const int tile_rows = P.tile_rows, n_cta = P.n_cta, M = P.M;
-                const size_t pitch = (size_t) P.pitch;
+                const CtaPhase & R = mine[ph];
+                const int my_tiles = R.my_tiles;
+                if (my_tiles == 0) continue;
+                const int local = R.local, tile_rows = R.P.tile_rows, n_cta = R.P.n_cta, M = R.P.M;
+                const uint8_t * Wb = reinterpret_cast<const uint8_t *>(R.P.W);
+                const size_t pitch = (size_t) R.P.pitch;
                 for (int i = 0; i < my_tiles; i++, it++) {
                     const int row0 = (local + i * n_cta) * tile_rows;
                     const int rows = min(tile_rows, M - row0);
@@ -318,46 +380,28 @@ __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Arg
     // ===== consumers =====
     float * red = reinterpret_cast<float *>(act + a.region_bytes);
     const int tid = threadIdx.x;
+    if (tid < REC_GRANULES) cp_async16(reinterpret_cast<uint8_t *>(&rec[0]) + tid * 16, reinterpret_cast<const uint8_t *>(mine) + tid * 16);
+    cp_async_commit();
     int it = 0;
     for (int ph = 0; ph < n; ph++) {
-        const DecodePhase & D = a.phases[ph];
-        // (1) the previous phase is complete on this CTA; arrive at the grid barrier
-        if (ph > 0) {
-            consumer_barrier();
-            if (tid == 0) { __threadfence(); atomicAdd(a.bar, 1ull); }
-        }
-        // (2) work that needs nothing from the previous phase
-        const int op = (ph == 0) ? D.op : pl.op[ph & 1];
+        // (1) this phase's record has landed; the previous phase is complete on this CTA: arrive at the grid barrier
+        cp_async_wait_all();
+        consumer_barrier();
+        if (ph > 0 && tid == 0) { __threadfence(); atomicAdd(a.bar, 1ull); }
+        const CtaPhase & R = rec[ph & 1];
+        const int op = R.op, active = R.active, local = R.local, my_tiles = R.my_tiles;
+        // (2) work that needs nothing from the previous phase: the next record, immutable operands of this phase's stage
+        if (ph + 1 < n && tid < REC_GRANULES)
+            cp_async16(reinterpret_cast<uint8_t *>(&rec[(ph + 1) & 1]) + tid * 16, reinterpret_cast<const uint8_t *>(mine + ph + 1) + tid * 16);
+        cp_async_commit();
         LerpRegs lr;
-        if (op == DOP_LERP) lerp_prefetch(D.lerp, lr);
-        // (3) thread 0 reads this CTA's part of the phase descriptor, then waits for everyone
+        if (op == DOP_LERP) lerp_prefetch(R.u.lerp, lr);
+        // (3) wait for every CTA
         if (tid == 0) {
-            const GemvBatch & B = D.batch;
-            const int nb = B.n;
-            int active = 0, local = (int) blockIdx.x, my_tiles = 0;
-            if (nb > 0) {
-                int pi = 0;
-                for (int i = 1; i < nb; i++) if ((int) blockIdx.x >= B.p[i].first_cta) pi = i;
-                sh.P = B.p[pi];
-                local = (int) blockIdx.x - sh.P.first_cta;
-                my_tiles = tiles_of(sh.P, local);
-                active = my_tiles > 0;
-                if (op == DOP_LNMIX_GEMV) {
-                    pl.ln = D.ln;
-                    pl.ln.coef[0] = D.ln.coef[pi];
-                    sh.P.x = tmp; sh.P.ldx = 0;
-                }
+            if (active) {
+                sh.P = R.P;
+                if (op == DOP_LNMIX_GEMV) { sh.P.x = tmp; sh.P.ldx = 0; }
             }
-            int head = -1;
-            if (op == DOP_GEMV_WKV) {
-                const Wkv6Params & w = D.wkv;
-                pl.wkv.r = w.r; pl.wkv.k = w.k; pl.wkv.v = w.v; pl.wkv.td = w.td; pl.wkv.tf = w.tf; pl.wkv.state_in = w.state_in;
-                pl.wkv.lnx_w = w.lnx_w; pl.wkv.lnx_b = w.lnx_b; pl.wkv.g = w.g; pl.wkv.state_out = w.state_out; pl.wkv.y = w.y;
-                pl.wkv.eps = w.eps; pl.wkv.td_per_token = w.td_per_token; pl.wkv.per_head_scalars = w.per_head_scalars; pl.wkv.H = w.H; pl.wkv.S = w.S;
-                head = (nb > 0) ? (active ? local : -1) : ((int) blockIdx.x < D.wkv.H ? (int) blockIdx.x : -1);
-            }
-            pl.active = active; pl.local = local; pl.my_tiles = my_tiles; pl.head = head;
-            pl.op[(ph + 1) & 1] = (ph + 1 < n) ? a.phases[ph + 1].op : 0;
             if (ph > 0) {
                 const unsigned long long target = a.bar_base + (unsigned long long) ph * gridDim.x;
                 const long long t0 = clock64();
@@ -371,28 +415,27 @@ __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Arg
         }
         consumer_barrier();
         // (4) the phase
-        const int active = pl.active, local = pl.local, my_tiles = pl.my_tiles;
         switch (op) {
             case DOP_LNMIX_GEMV:
                 if (active) {
-                    ln_mix_stage(pl.ln, tmp, slots, blockIdx.x == 0);
+                    ln_mix_stage(R.u.ln, tmp, slots, blockIdx.x == 0);
                     consumer_barrier();
                     run_gemv(sh, ring, stage_bytes, act, red, it, local, my_tiles);
                 }
                 break;
             case DOP_LERP:
-                lerp_run(D.lerp, lr, tmp);
+                lerp_run(R.u.lerp, lr, tmp);
                 break;
             case DOP_GEMV_WKV: {
                 if (active) run_gemv(sh, ring, stage_bytes, act, red, it, local, my_tiles);
-                const int h = pl.head;
+                const int h = R.head;
                 if (h >= 0) {
                     consumer_barrier();     // the head's decay values just stored by this CTA are visible to all its threads
-                    switch (pl.wkv.S) {
-                        case 8: wkv6_step<8>(pl.wkv, h, tmp); break;
-                        case 16: wkv6_step<16>(pl.wkv, h, tmp); break;
-                        case 32: wkv6_step<32>(pl.wkv, h, tmp); break;
-                        default: wkv6_step<64>(pl.wkv, h, tmp); break;
+                    switch (R.u.wkv.S) {
+                        case 8: wkv6_step<8>(R.u.wkv, h, tmp); break;
+                        case 16: wkv6_step<16>(R.u.wkv, h, tmp); break;
+                        case 32: wkv6_step<32>(R.u.wkv, h, tmp); break;
+                        default: wkv6_step<64>(R.u.wkv, h, tmp); break;
                     }
                 }
                 break;
@@ -412,7 +455,7 @@ __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Arg
 bool gemv_tma_plan(GemvBatch & batch, int total_ctas, long long stage_bytes, size_t * max_col_bytes);   // gemv_tma.cu
 
 void decode_program_free(DecodeProgram & program) {
-    if (program.phases) cudaFree(program.phases);
+    if (program.records) cudaFree(program.records);
     program = DecodeProgram();
 }
 
@@ -458,6 +501,9 @@ static bool program_selfcheck(const std::vector<DecodePhase> & phases, const Dec
     }
     return (size_t) tma::NSTAGES * program.stage_bytes + program.region_bytes + dp::RED_BYTES == program.smem_bytes && program.smem_bytes <= dp::DYN_SMEM_BUDGET;
 }
+
+static std::vector<dp::CtaPhase> flatten_program(const std::vector<DecodePhase> & phases, const DecodeProgram & program);
+static bool records_selfcheck(const std::vector<dp::CtaPhase> & rec, const std::vector<DecodePhase> & phases, const DecodeProgram & program);
 
 // Host-only part of decode_program_build: shapes -> shared-memory layout -> tiles and CTA shares.
 bool decode_program_plan(std::vector<DecodePhase> & phases, int num_sms, DecodeProgram & program) {
@@ -524,6 +570,111 @@ bool decode_program_plan(std::vector<DecodePhase> & phases, int num_sms, DecodeP
     return true;
 }
 
+bool decode_program_plan_check_records(std::vector<DecodePhase> & phases, int num_sms, DecodeProgram & program) {
+    if (!decode_program_plan(phases, num_sms, program)) return false;
+    return records_selfcheck(flatten_program(phases, program), phases, program);
+}
+
+// The planned phase list resolved per CTA (see CtaPhase): what each CTA does in each phase, with the same problem lookup and
+// tile arithmetic the self-check replayed.
+static std::vector<dp::CtaPhase> flatten_program(const std::vector<DecodePhase> & phases, const DecodeProgram & program) {
+    using namespace dp;
+    const int grid = program.grid, n = (int) phases.size();
+    std::vector<CtaPhase> rec((size_t) grid * (size_t) n);
+    memset(rec.data(), 0, rec.size() * sizeof(CtaPhase));
+    int prev_active = 0;      // CTAs [0, prev_active) had tiles in the previous phase
+    for (int ph = 0; ph < n; ph++) {
+        const DecodePhase & D = phases[(size_t) ph];
+        const GemvBatch & B = D.batch;
+        int used = 0;
+        for (int i = 0; i < B.n; i++) used = B.p[i].first_cta + B.p[i].n_cta;
+        // lerp channels go to the CTAs that sat idle in the previous phase when those alone can take them (<= 32 channels each)
+        int lerp_first = 0, lerp_ctas = grid, lerp_cpc = 0;
+        if (D.op == DOP_LERP) {
+            if (prev_active < grid && (long long) (grid - prev_active) * 32 >= D.lerp.C) { lerp_first = prev_active; lerp_ctas = grid - prev_active; }
+            lerp_cpc = (D.lerp.C + lerp_ctas - 1) / lerp_ctas;
+        }
+        for (int cta = 0; cta < grid; cta++) {
+            CtaPhase & R = rec[(size_t) cta * (size_t) n + (size_t) ph];
+            R.op = D.op; R.head = -1; R.local = cta;
+            if (B.n > 0) {
+                int pi = 0;
+                for (int j = 1; j < B.n; j++) if (cta >= B.p[j].first_cta) pi = j;
+                const GemvProblem & P = B.p[pi];
+                R.local = cta - P.first_cta;
+                R.my_tiles = tiles_of(P, R.local);
+                R.active = R.my_tiles > 0;
+                if (R.active) R.P = P; else R.local = cta;
+                if (D.op == DOP_LNMIX_GEMV && R.active) {
+                    LnLocal & l = R.u.ln;
+                    l.x = D.ln.x; l.ln_w = D.ln.ln_w; l.ln_b = D.ln.ln_b; l.state_in = D.ln.state_in; l.coef = D.ln.coef[pi];
+                    l.state_out = D.ln.state_out; l.out_xx = D.ln.out_xx; l.out_sx = D.ln.out_sx; l.formula = D.ln.formula; l.C = D.ln.C;
+                }
+            }
+            if (D.op == DOP_GEMV_WKV) {
+                const Wkv6Params & w = D.wkv;
+                R.head = (B.n > 0) ? (R.active ? R.local : -1) : (cta < w.H ? cta : -1);
+                WkvStep & k = R.u.wkv;
+                k.r = w.r; k.k = w.k; k.v = w.v; k.td = w.td; k.tf = w.tf; k.state_in = w.state_in; k.lnx_w = w.lnx_w; k.lnx_b = w.lnx_b; k.g = w.g;
+                k.state_out = w.state_out; k.y = w.y; k.eps = w.eps; k.td_per_token = w.td_per_token; k.per_head_scalars = w.per_head_scalars;
+                k.H = w.H; k.S = w.S;
+            } else if (D.op == DOP_LERP) {
+                const V6LerpParams & v = D.lerp;
+                LerpLocal & l = R.u.lerp;
+                l.w2 = v.w2; l.z = v.z; l.xx = v.xx; l.sx = v.sx; l.C = v.C; l.mix = v.mix;
+                for (int j = 0; j < 5; j++) { l.maa[j] = v.maa[j]; l.out[j] = v.out[j]; }
+                const int idx = cta - lerp_first;
+                l.c0 = (idx >= 0) ? idx * lerp_cpc : v.C;
+                l.n = (idx >= 0 && l.c0 < v.C) ? (v.C - l.c0 < lerp_cpc ? v.C - l.c0 : lerp_cpc) : 0;
+                if (l.n == 0) l.c0 = 0;
+            }
+        }
+        prev_active = used;
+    }
+    return rec;
+}
+
+// Host check of the flattened records: every tile of every phase exactly once (again, now from what the kernel will actually
+// read), every lerp channel exactly once, at most 32 lerp channels per CTA.
+static bool records_selfcheck(const std::vector<dp::CtaPhase> & rec, const std::vector<DecodePhase> & phases, const DecodeProgram & program) {
+    using namespace dp;
+    const int grid = program.grid, n = (int) phases.size();
+    std::vector<int> seen;
+    for (int ph = 0; ph < n; ph++) {
+        const DecodePhase & D = phases[(size_t) ph];
+        for (int i = 0; i < D.batch.n; i++) {
+            const GemvProblem & P = D.batch.p[i];
+            const int n_tiles = (P.M + P.tile_rows - 1) / P.tile_rows;
+            seen.assign((size_t) n_tiles, 0);
+            for (int cta = 0; cta < grid; cta++) {
+                const CtaPhase & R = rec[(size_t) cta * n + ph];
+                if (!R.active || R.P.W != P.W) continue;
+                for (int t = 0; t < R.my_tiles; t++) {
+                    const int tile = R.local + t * R.P.n_cta;
+                    if (tile < 0 || tile >= n_tiles) return false;
+                    seen[(size_t) tile]++;
+                }
+            }
+            for (int t = 0; t < n_tiles; t++) if (seen[(size_t) t] != 1) return false;
+        }
+        if (D.op == DOP_LERP) {
+            seen.assign((size_t) D.lerp.C, 0);
+            for (int cta = 0; cta < grid; cta++) {
+                const LerpLocal & l = rec[(size_t) cta * n + ph].u.lerp;
+                if (l.n < 0 || l.n > 32 || l.c0 < 0 || l.c0 + l.n > D.lerp.C) return false;
+                for (int c = l.c0; c < l.c0 + l.n; c++) seen[(size_t) c]++;
+            }
+            for (int c = 0; c < D.lerp.C; c++) if (seen[(size_t) c] != 1) return false;
+        }
+        if (D.op == DOP_GEMV_WKV) {
+            seen.assign((size_t) D.wkv.H, 0);
+            for (int cta = 0; cta < grid; cta++) { const int h = rec[(size_t) cta * n + ph].head; if (h >= D.wkv.H) return false; if (h >= 0) seen[(size_t) h]++; }
+            for (int h = 0; h < D.wkv.H; h++) if (seen[(size_t) h] != 1) return false;
+        }
+    }
+    return true;
+}
+
 bool decode_program_build(std::vector<DecodePhase> & phases, const DeviceInfo & dev, DecodeProgram & program) {
     using namespace dp;
     if (!decode_program_plan(phases, dev.num_sms, program)) { program = DecodeProgram(); return false; }
@@ -543,12 +694,19 @@ bool decode_program_build(std::vector<DecodePhase> & phases, const DeviceInfo & 
         program = DecodeProgram();
         return false;
     }
-    if (cudaMalloc(reinterpret_cast<void **>(&program.phases), phases.size() * sizeof(DecodePhase)) != cudaSuccess) { cudaGetLastError(); program = DecodeProgram(); return false; }
-    if (cudaMemcpy(program.phases, phases.data(), phases.size() * sizeof(DecodePhase), cudaMemcpyHostToDevice) != cudaSuccess) {
+    const std::vector<CtaPhase> rec = flatten_program(phases, program);
+    if (!records_selfcheck(rec, phases, program)) {
+        fprintf(stderr, "rwkv_b200: the persistent decode program's per-CTA records failed their self-check; using the per-launch path\n");
+        program = DecodeProgram();
+        return false;
+    }
+    if (cudaMalloc(&program.records, rec.size() * sizeof(CtaPhase)) != cudaSuccess) { cudaGetLastError(); program = DecodeProgram(); return false; }
+    if (cudaMemcpy(program.records, rec.data(), rec.size() * sizeof(CtaPhase), cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaGetLastError();
         decode_program_free(program);
         return false;
     }
+    program.record_bytes = rec.size() * sizeof(CtaPhase);
     program.supported = true;
     return true;
 }
@@ -557,7 +715,7 @@ cudaError_t decode_program_launch(const DecodeProgram & program, unsigned long l
                                   unsigned long long * trace, cudaStream_t stream) {
     if (!program.supported) return cudaErrorNotSupported;
     dp::Args a;
-    a.phases = program.phases; a.n_phases = program.n_phases;
+    a.records = reinterpret_cast<const dp::CtaPhase *>(program.records); a.n_phases = program.n_phases;
     a.bar = barrier_counter; a.bar_base = barrier_base;
     a.stage_bytes = program.stage_bytes; a.tmp_offset = program.tmp_offset; a.region_bytes = program.region_bytes;
     a.trace = trace;

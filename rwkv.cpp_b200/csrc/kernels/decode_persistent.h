@@ -44,7 +44,8 @@ struct DecodePhase {
 };
 
 struct DecodeProgram {      // device-resident, immutable once built
-    DecodePhase * phases = nullptr;     // device
+    void * records = nullptr;           // device: one resolved record per (CTA, phase), CTA-major (decode_persistent.cu: CtaPhase)
+    size_t record_bytes = 0;
     int n_phases = 0;
     int grid = 0;
     uint32_t stage_bytes = 0, tmp_offset = 0, region_bytes = 0;
@@ -58,6 +59,8 @@ struct DecodeProgram {      // device-resident, immutable once built
 bool decode_program_build(std::vector<DecodePhase> & phases, const DeviceInfo & dev, DecodeProgram & program);
 // The host-only part of the above (no CUDA calls): planning, layout and the tile-walk self-check.
 bool decode_program_plan(std::vector<DecodePhase> & phases, int num_sms, DecodeProgram & program);
+// decode_program_plan + the per-CTA flattening and its self-check (still host only).
+bool decode_program_plan_check_records(std::vector<DecodePhase> & phases, int num_sms, DecodeProgram & program);
 void decode_program_free(DecodeProgram & program);
 
 // Enqueues one token. `barrier_counter` is a device u64 that only this kernel touches; `barrier_base` its value before the

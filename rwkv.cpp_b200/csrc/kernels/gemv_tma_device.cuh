@@ -180,6 +180,7 @@ template <int TYPE> __device__ __forceinline__ void load_unit(const uint8_t * ro
 // would multiply with (ggml-cpu.c:253-311 `vec_dot_type`): Q8_0 / Q8_1 blocks for quantised weights (x86 flavour of
 // quantize_row_q8_0 / q8_1, ggml-cpu-quants.c:781-846, 1085-1160; one thread per 32-element block), fp16 for F16
 // weights, fp32 for F32 weights. PRO_LAYERNORM applies rwkv_layer_norm (rwkv_operators.inc:93-97) on the fly.
+template <int UNR = 4>     // float4 loads a thread keeps in flight per round of the quantising loop
 static __device__ void stage_column(const GemvProblem & P, int col_index, uint8_t * col, double * red_d) {
     const int K = P.K, tid = threadIdx.x;
     const float * x = P.x + (long long) col_index * P.ldx;
@@ -220,7 +221,7 @@ static __device__ void stage_column(const GemvProblem & P, int col_index, uint8_
         const int UB = has_min ? 1 : 2;
         const int nblk = K / 32, nunits = (nblk + UB - 1) / UB;
         const int sub = tid & 7;
-        constexpr int UNR = 4;   // loads of UNR iterations are issued together: the loop is L2-latency bound, not math bound
+        // loads of UNR iterations are issued together: the loop is L2-latency bound, not math bound
         const int kpad = (K + 127) & ~127;
         for (int base0 = tid * 4; base0 < kpad; base0 += CONSUMER_THREADS * 4 * UNR) {
             float4 tv[UNR];

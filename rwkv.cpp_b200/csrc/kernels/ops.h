@@ -93,4 +93,19 @@ struct Wkv7Params {
 };
 cudaError_t launch_wkv7(const Wkv7Params & p, cudaStream_t s);
 
+// On-device sampling from the logits of the last evaluated token (reference python/sampling.py:10-52); see sampling.cu.
+struct SampleParams {
+    const float * logits;             // [n_vocab] device
+    int n_vocab;
+    float temperature, top_p;
+    double u;                         // uniform number in [0, 1) drawn by the caller
+    const uint32_t * bias_ids;        // device, n_bias entries (logit_bias of the reference), or NULL
+    const float * bias_values;
+    int n_bias;
+    float * scratch;                  // [n_vocab] device, used only when n_bias > 0
+    uint32_t * token_out;             // device
+    float * prob_out;                 // optional device: probability the chosen token had
+};
+cudaError_t launch_sample(const SampleParams & p, cudaStream_t s);
+
 }  // namespace rwkv

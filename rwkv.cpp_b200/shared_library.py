@@ -122,6 +122,10 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_phase_trace.restype = ctypes.c_int
         lib.rwkv_b200_plan_selftest.argtypes = [ctypes.c_int] * 11 + [ctypes.POINTER(ctypes.c_int)]
         lib.rwkv_b200_plan_selftest.restype = ctypes.c_int
+        lib.rwkv_b200_sample.argtypes = [vp, ctypes.c_float, ctypes.c_float, ctypes.c_double, P_U32, P_FLOAT, ctypes.c_size_t, P_U32]
+        lib.rwkv_b200_sample.restype = ctypes.c_bool
+        lib.rwkv_b200_eval_sample.argtypes = [vp, ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_double, P_U32]
+        lib.rwkv_b200_eval_sample.restype = ctypes.c_bool
         lib.rwkv_b200_matvec.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, P_FLOAT, P_FLOAT, ctypes.c_int]
         lib.rwkv_b200_matvec.restype = ctypes.c_bool
 
