@@ -48,6 +48,11 @@ RWKV_API bool rwkv_b200_sample(struct rwkv_context * ctx, float temperature, flo
                                size_t n_bias, uint32_t * token_out);
 RWKV_API bool rwkv_b200_eval_sample(struct rwkv_context * ctx, uint32_t token, float temperature, float top_p, double u, uint32_t * next_token_out);
 
+/* Test hook: the same sampling kernel on caller-provided host logits (any n_vocab <= 65536), no model needed.
+ * prob_out (optional) receives the probability the chosen token had after top-p / temperature. */
+RWKV_API bool rwkv_b200_sample_logits(const float * logits, size_t n_vocab, float temperature, float top_p, double u, const uint32_t * bias_ids,
+                                      const float * bias_values, size_t n_bias, uint32_t * token_out, float * prob_out);
+
 /* Layer pipeline across GPUs (the reference has no equivalent: ggml offloads layers of ONE context,
  * rwkv.cpp:97-116). A context created with rwkv_b200_init_from_file_ex(path, device, begin, end) is one stage; its slice
  * of the recurrent state stays resident on that device. Per pass of n_tokens (<= 256):
@@ -102,6 +107,12 @@ RWKV_API void rwkv_b200_set_tensor_cores(struct rwkv_context * ctx, bool enabled
  * rwkv_b200_persistent_state: 1 = in use, 0 = not tried yet, -1 = this model / device does not fit it. */
 RWKV_API void rwkv_b200_set_persistent(struct rwkv_context * ctx, bool enabled);
 RWKV_API int rwkv_b200_persistent_state(const struct rwkv_context * ctx);
+/* rwkv_eval / rwkv_eval_sequence with caller-owned HOST state: copy the state per layer group (n_layer / 4 groups, at most 8) on
+ * dedicated copy streams so that the host-to-device copy of group g+1 and the device-to-host copy of group g-1 overlap the kernels
+ * of group g (the ABI state layout is layer-major, so a group is one contiguous slice). Results are bit-identical to the plain
+ * upload - evaluate - download order. RWKV_B200_OVERLAP=0/1 sets the default of new contexts. */
+RWKV_API void rwkv_b200_set_overlap(struct rwkv_context * ctx, bool enabled);
+
 /* Phase timeline of the persistent kernel: the first call arms a device buffer (returns 0); after the next single-token pass a
  * second call returns n_phases + 1 boundaries (microseconds since the kernel's first phase began, %globaltimer of CTA 0). */
 RWKV_API int rwkv_b200_phase_trace(struct rwkv_context * ctx, double * boundaries_us, int max_records);

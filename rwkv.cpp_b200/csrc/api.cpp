@@ -12,6 +12,7 @@
 #include "../../include/rwkv.h"
 #include "../../include/rwkv_b200.h"
 #include "engine.h"
+#include "kernels/ops.h"
 #include "quantizer.h"
 
 using namespace rwkv;
@@ -66,7 +67,7 @@ bool rwkv_eval(struct rwkv_context * ctx, const uint32_t token, const float * st
     RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, token < n_vocab, "Token (%" PRIu32 ") is out of range (0 .. %zu)", token, n_vocab - 1);
     RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer,
                "This context holds only a pipeline stage; use the rwkv_b200 stage API");
-    return upload_state(c, state_in) && forward(c, &token, 1, logits_out != nullptr) && download_outputs(c, state_out, logits_out);
+    return eval_host(c, &token, 1, state_in, state_out, logits_out);
 }
 
 bool rwkv_eval_sequence(struct rwkv_context * ctx, const uint32_t * sequence, const size_t sequence_len, const float * state_in, float * state_out, float * logits_out) {
@@ -79,7 +80,7 @@ bool rwkv_eval_sequence(struct rwkv_context * ctx, const uint32_t * sequence, co
         RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, sequence[i] < n_vocab, "Token at index %zu (%" PRIu32 ") is out of range (0 .. %zu)", i, sequence[i], n_vocab - 1);
     RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer,
                "This context holds only a pipeline stage; use the rwkv_b200 stage API");
-    return upload_state(c, state_in) && forward(c, sequence, sequence_len, logits_out != nullptr) && download_outputs(c, state_out, logits_out);
+    return eval_host(c, sequence, sequence_len, state_in, state_out, logits_out);
 }
 
 bool rwkv_eval_sequence_in_chunks(struct rwkv_context * ctx, const uint32_t * tokens, const size_t sequence_len, const size_t chunk_size,
@@ -212,6 +213,35 @@ bool rwkv_b200_sample(struct rwkv_context * ctx, float temperature, float top_p,
     return sample_token(c, temperature, top_p, u, bias_ids, bias_values, n_bias, token_out);
 }
 
+bool rwkv_b200_sample_logits(const float * logits, size_t n_vocab, float temperature, float top_p, double u, const uint32_t * bias_ids, const float * bias_values,
+                             size_t n_bias, uint32_t * token_out, float * prob_out) {
+    g_last_error = RWKV_ERROR_NONE;
+    ErrorSink sink = global_sink();
+    RWKV_CHECK(sink, RWKV_ERROR_ARGS, false, logits && token_out && n_vocab > 0 && n_vocab <= 65536 && temperature >= 0.0f && top_p >= 0.0f && top_p <= 1.0f &&
+               u >= 0.0 && u < 1.0 && (n_bias == 0 || (bias_ids && bias_values)), "Invalid sampling arguments");
+    int dev = default_device(), n_dev = 0;
+    RWKV_CHECK(sink, RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, cudaGetDeviceCount(&n_dev) == cudaSuccess && dev < n_dev && cudaSetDevice(dev) == cudaSuccess,
+               "No usable CUDA device; this engine has no CPU execution path");
+    float * d_logits = nullptr, * d_scratch = nullptr, * d_bv = nullptr, * d_prob = nullptr;
+    uint32_t * d_bi = nullptr, * d_tok = nullptr;
+    bool ok = cudaMalloc((void **) &d_logits, n_vocab * 4) == cudaSuccess && cudaMalloc((void **) &d_scratch, n_vocab * 4) == cudaSuccess &&
+              cudaMalloc((void **) &d_tok, 4) == cudaSuccess && cudaMalloc((void **) &d_prob, 4) == cudaSuccess &&
+              cudaMemcpy(d_logits, logits, n_vocab * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok && n_bias) ok = cudaMalloc((void **) &d_bi, n_bias * 4) == cudaSuccess && cudaMalloc((void **) &d_bv, n_bias * 4) == cudaSuccess &&
+                           cudaMemcpy(d_bi, bias_ids, n_bias * 4, cudaMemcpyHostToDevice) == cudaSuccess && cudaMemcpy(d_bv, bias_values, n_bias * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok) {
+        SampleParams sp{};
+        sp.logits = d_logits; sp.n_vocab = (int) n_vocab; sp.temperature = temperature; sp.top_p = top_p; sp.u = u;
+        sp.bias_ids = d_bi; sp.bias_values = d_bv; sp.n_bias = (int) n_bias; sp.scratch = d_scratch; sp.token_out = d_tok; sp.prob_out = d_prob;
+        ok = launch_sample(sp, 0) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess && cudaMemcpy(token_out, d_tok, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (ok && prob_out) ok = cudaMemcpy(prob_out, d_prob, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaFree(d_logits); cudaFree(d_scratch); cudaFree(d_tok); cudaFree(d_prob); cudaFree(d_bi); cudaFree(d_bv);
+    RWKV_CHECK(sink, RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, ok, "sampling failed on the device: %s", cudaGetErrorString(e));
+    return true;
+}
+
 bool rwkv_b200_eval_sample(struct rwkv_context * ctx, uint32_t token, float temperature, float top_p, double u, uint32_t * next_token_out) {
     if (!rwkv_b200_eval_resident(ctx, &token, 1, true, nullptr)) return false;
     return sample_token(C(ctx), temperature, top_p, u, nullptr, nullptr, 0, next_token_out);
@@ -307,12 +337,13 @@ bool rwkv_b200_profile_pass(struct rwkv_context * ctx, const uint32_t * tokens, 
 void rwkv_b200_set_graphs(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_graphs = enabled; }
 void rwkv_b200_set_tensor_cores(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_tensor_cores = enabled; }
 void rwkv_b200_set_persistent(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_persistent = enabled; }
+void rwkv_b200_set_overlap(struct rwkv_context * ctx, bool enabled) { C(ctx)->overlap_copies = enabled; }
 int rwkv_b200_persistent_state(const struct rwkv_context * ctx) {
     const Context * c = C(ctx);
     int best = 0;
-    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) {
-        if (c->persistent_state[a][b] > 0) return 1;
-        if (c->persistent_state[a][b] < 0) best = -1;
+    for (int i = 0; i < Context::N_SLOTS; i++) {
+        if (c->persistent_state[i] > 0) return 1;
+        if (c->persistent_state[i] < 0) best = -1;
     }
     return best;
 }
@@ -332,7 +363,7 @@ int rwkv_b200_phase_trace(struct rwkv_context * ctx, double * boundaries_us, int
         return 0;
     }
     int n = 0;
-    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) if (c->programs[a][b].supported && c->programs[a][b].n_phases + 1 > n) n = c->programs[a][b].n_phases + 1;
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) { const DecodeProgram & pr = c->programs[Context::slot_index(a != 0, b, 0)]; if (pr.supported && pr.n_phases + 1 > n) n = pr.n_phases + 1; }
     if (n > max_records) n = max_records;
     if (n <= 0 || !boundaries_us) return 0;
     std::vector<unsigned long long> raw((size_t) n);
@@ -352,7 +383,7 @@ bool rwkv_b200_trace_enable(struct rwkv_context * ctx) {
     if (cudaSetDevice(c->model->dev.device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
     if (!c->trace_buf && cudaMalloc((void **) &c->trace_buf, 1024 * sizeof(TraceRec)) != cudaSuccess) return false;
     // graphs captured so far carry no trace slots: drop them so they are re-captured
-    for (auto & row : c->graphs) for (auto & g : row) { if (g.exec) cudaGraphExecDestroy(g.exec); g = Context::GraphSlot(); }
+    for (auto & g : c->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g = Context::GraphSlot(); }
     return trace_rearm(c);
 }
 

@@ -19,6 +19,8 @@ namespace {
 
 // Single-token passes as one persistent kernel by default? (RWKV_B200_PERSISTENT=0/1 overrides, rwkv_b200_set_persistent per context)
 constexpr bool PERSISTENT_DEFAULT = false;
+// rwkv_eval with host state buffers: pipeline the state copies against layer groups? (RWKV_B200_OVERLAP=0/1, rwkv_b200_set_overlap)
+constexpr bool OVERLAP_DEFAULT = false;
 
 struct Scratch {      // carve-up of ctx->scratch for T tokens
     float * x, * xx, * sx;
@@ -40,6 +42,16 @@ Dims model_dims(const Model & m) {
     }
     if (d.R == 0) d.R = 1;
     return d;
+}
+
+// Layers [l0, l1) of segment `seg` (0 = every resident layer).
+void segment_range(const Context * ctx, int seg, int & l0, int & l1) {
+    const Model & m = *ctx->model;
+    l0 = m.layer_begin; l1 = m.layer_end;
+    if (seg <= 0) return;
+    const int n = m.layer_end - m.layer_begin, G = ctx->n_segments;
+    l0 = m.layer_begin + (int) ((long long) n * (seg - 1) / G);
+    l1 = m.layer_begin + (int) ((long long) n * seg / G);
 }
 
 size_t scratch_floats_for(const Model & m, int T) {
@@ -431,16 +443,19 @@ void program_att_v6(const Model & m, const Layer & L, const Scratch & s, const f
 }
 
 // Builds (once) the program of a single-token pass for this [want_logits][phase]; false = use the per-launch path.
-bool ensure_program(Context * ctx, bool want_logits, int phase) {
-    int & state = ctx->persistent_state[want_logits ? 1 : 0][phase];
+bool ensure_program(Context * ctx, bool want_logits, int phase, int seg) {
+    const int slot = Context::slot_index(want_logits, phase, seg);
+    int & state = ctx->persistent_state[slot];
     if (state != 0) return state > 0;
     state = -1;
     const Model & m = *ctx->model;
     if (m.arch_major != 5 && m.arch_major != 6) return false;
+    int l0, l1;
+    segment_range(ctx, seg, l0, l1);
     const Scratch s = carve(m, ctx->scratch, 1);
     const size_t per_layer = m.state_floats_per_layer();
     std::vector<DecodePhase> prog;
-    for (int i = m.layer_begin; i < m.layer_end; i++) {
+    for (int i = l0; i < l1; i++) {
         const Layer & L = m.layers[i];
         const float * st_in = ctx->state_a + (size_t) i * per_layer;
         float * st_out = ctx->state_b + (size_t) i * per_layer;
@@ -448,7 +463,7 @@ bool ensure_program(Context * ctx, bool want_logits, int phase) {
         else program_att_v5(m, L, s, st_in, st_out, prog);
         program_ffn(m, L, s, st_in, st_out, prog);
     }
-    if (want_logits && m.layer_end == m.n_layer) {
+    if (want_logits && l1 == m.n_layer) {
         Batch b(1);
         GemvProblem & p = b.add(m.head, s.x, ctx->logits);
         p.pro = PRO_LAYERNORM; p.ln_w = m.ln_out_w.data; p.ln_b = m.ln_out_b.data;
@@ -459,13 +474,13 @@ bool ensure_program(Context * ctx, bool want_logits, int phase) {
             cudaMemset(ctx->grid_barrier, 0, sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return false; }
         ctx->grid_barrier_value = 0;
     }
-    if (!decode_program_build(prog, m.dev, ctx->programs[want_logits ? 1 : 0][phase])) return false;
+    if (!decode_program_build(prog, m.dev, ctx->programs[slot])) return false;
     state = 1;
     return true;
 }
 
 void drop_programs(Context * ctx) {
-    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) { decode_program_free(ctx->programs[a][b]); ctx->persistent_state[a][b] = 0; }
+    for (int i = 0; i < Context::N_SLOTS; i++) { decode_program_free(ctx->programs[i]); ctx->persistent_state[i] = 0; }
 }
 
 bool ensure_capacity(Context * ctx, int T) {
@@ -482,7 +497,7 @@ bool ensure_capacity(Context * ctx, int T) {
         if (ctx->tokens_host[i]) { cudaFreeHost(ctx->tokens_host[i]); ctx->tokens_host[i] = nullptr; }
         ctx->slot_used[i] = false;
     }
-    for (auto & row : ctx->graphs) for (auto & g : row) { if (g.exec) cudaGraphExecDestroy(g.exec); g = Context::GraphSlot(); }
+    for (auto & g : ctx->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g = Context::GraphSlot(); }
     drop_programs(ctx);
     ctx->capacity_T = 0;
     const size_t n = scratch_floats_for(m, cap);
@@ -507,18 +522,20 @@ bool ensure_capacity(Context * ctx, int T) {
 }
 
 // Enqueues one pass (token upload + every kernel) on ctx->stream; pure stream work, so it can be captured.
-bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase) {
+bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase, int seg) {
     const Model & m = *ctx->model;
+    int l0, l1;
+    segment_range(ctx, seg, l0, l1);
     g_trace_base = ctx->trace_buf;
     g_trace_next = 0;
     const int C = m.n_embed;
     const Scratch s = carve(m, ctx->scratch, T);
-    if (m.layer_begin == 0) {
+    if (l0 == 0) {
         CUDA_OK(ctx, cudaMemcpyAsync(ctx->tokens, ctx->tokens_host[phase], (size_t) T * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         CUDA_OK(ctx, launch_embed_ln0(m.emb.data, m.emb.type, m.emb.pitch, ctx->tokens, T, C, m.ln0_w.data, m.ln0_b.data, s.x, ctx->stream));
-    }   // a later pipeline stage finds x (and v_first) already in place: forward_pass copied the hand-off in
+    }   // a later pipeline stage / layer group finds x (and v_first) already in place
     const size_t per_layer = m.state_floats_per_layer();
-    for (int i = m.layer_begin; i < m.layer_end; i++) {
+    for (int i = l0; i < l1; i++) {
         const Layer & L = m.layers[i];
         const float * st_in = ctx->state_a + (size_t) i * per_layer;
         float * st_out = ctx->state_b + (size_t) i * per_layer;
@@ -531,7 +548,7 @@ bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase) {
         }
         if (!ok || !ffn(ctx, L, s, T, st_in, st_out)) return false;
     }
-    if (want_logits && m.layer_end == m.n_layer) {   // :705-708 / :851-854  head . LN(x_last; ln_out)
+    if (want_logits && l1 == m.n_layer) {   // :705-708 / :851-854  head . LN(x_last; ln_out)
         Batch b(1);
         GemvProblem & p = b.add(m.head, s.x + (size_t) (T - 1) * C, ctx->logits);
         p.pro = PRO_LAYERNORM; p.ln_w = m.ln_out_w.data; p.ln_b = m.ln_out_b.data;
@@ -542,8 +559,9 @@ bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase) {
     return true;
 }
 
-// One pass of at most MAX_TOKENS_PER_PASS tokens: state_a -> state_b, then swap.
-bool forward_pass(Context * ctx, const uint32_t * tokens, int T, bool want_logits) {
+// One pass of at most MAX_TOKENS_PER_PASS tokens (state_a -> state_b, then swap) in three steps, so that the overlapped path can
+// put copies between the layer groups: begin_pass (capacity, token staging, hand-off in), run_layers per segment, end_pass.
+bool begin_pass(Context * ctx, const uint32_t * tokens, int T) {
     if (!ensure_capacity(ctx, T)) return false;
     const int phase = ctx->phase;
     if (ctx->slot_used[phase]) CUDA_OK(ctx, cudaEventSynchronize(ctx->slot_free[phase]));   // pass n-2 has consumed this slot
@@ -556,15 +574,27 @@ bool forward_pass(Context * ctx, const uint32_t * tokens, int T, bool want_logit
         CUDA_OK(ctx, cudaMemcpyAsync(hs.x, ctx->hidden_in, ct, cudaMemcpyDeviceToDevice, ctx->stream));
         if (m.arch_major == 7) CUDA_OK(ctx, cudaMemcpyAsync(hs.v_first, ctx->hidden_in + (size_t) m.n_embed * T, ct, cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    return true;
+}
+
+// The kernels of segment `seg` (0 = all resident layers) for the pass begun by begin_pass.
+bool run_layers(Context * ctx, int T, bool want_logits, int seg) {
+    const Model & m = *ctx->model;
+    const int phase = ctx->phase;
+    int l0, l1;
+    segment_range(ctx, seg, l0, l1);
+    want_logits = want_logits && l1 == m.n_layer;        // only the group that ends the model can run the head
+    const int slot = Context::slot_index(want_logits, phase, seg);
     // Single-token passes: one persistent kernel per token when enabled and the model fits it (kernels/decode_persistent.h)
     bool done = false;
-    if (T == 1 && ctx->use_persistent && !ctx->profiling && !ctx->trace_buf && ensure_program(ctx, want_logits, phase)) {
-        const DecodeProgram & prog = ctx->programs[want_logits ? 1 : 0][phase];
-        if (m.layer_begin == 0) {
+    if (T == 1 && ctx->use_persistent && !ctx->profiling && !ctx->trace_buf && ensure_program(ctx, want_logits, phase, seg)) {
+        const DecodeProgram & prog = ctx->programs[slot];
+        if (l0 == 0) {
+            const Scratch hs = carve(m, ctx->scratch, 1);
             CUDA_OK(ctx, cudaMemcpyAsync(ctx->tokens, ctx->tokens_host[phase], sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
             CUDA_OK(ctx, launch_embed_ln0(m.emb.data, m.emb.type, m.emb.pitch, ctx->tokens, 1, m.n_embed, m.ln0_w.data, m.ln0_b.data, hs.x, ctx->stream));
         }
-        unsigned long long * tr = (ctx->phase_trace && ctx->phase_trace_len > prog.n_phases) ? ctx->phase_trace : nullptr;
+        unsigned long long * tr = (seg == 0 && ctx->phase_trace && ctx->phase_trace_len > prog.n_phases) ? ctx->phase_trace : nullptr;
         const cudaError_t e = decode_program_launch(prog, ctx->grid_barrier, ctx->grid_barrier_value, tr, ctx->stream);
         if (e == cudaSuccess) {
             ctx->grid_barrier_value += decode_program_barrier_arrivals(prog);
@@ -572,19 +602,19 @@ bool forward_pass(Context * ctx, const uint32_t * tokens, int T, bool want_logit
         } else {
             cudaGetLastError();
             fprintf(stderr, "rwkv_b200: persistent decode kernel launch failed (%s); falling back to the per-launch path\n", cudaGetErrorString(e));
-            ctx->persistent_state[want_logits ? 1 : 0][phase] = -1;
+            ctx->persistent_state[slot] = -1;
         }
     }
-    Context::GraphSlot * g = (!done && T == 1 && ctx->use_graphs && !ctx->profiling) ? &ctx->graphs[want_logits ? 1 : 0][phase] : nullptr;
+    Context::GraphSlot * g = (!done && T == 1 && ctx->use_graphs && !ctx->profiling) ? &ctx->graphs[slot] : nullptr;
     if (done) {
     } else if (g && g->exec) {
         CUDA_OK(ctx, cudaGraphLaunch(g->exec, ctx->stream));
         g_kernel_launches += g->launches;
     } else if (g && g->uses >= 1) {
-        // second use of this (logits, phase) combination: capture the launch sequence once, replay from now on
+        // second use of this slot: capture the launch sequence once, replay from now on
         const unsigned long long before = g_kernel_launches;
         CUDA_OK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        const bool ok = enqueue_pass(ctx, T, want_logits, phase);
+        const bool ok = enqueue_pass(ctx, T, want_logits, phase, seg);
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
         RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, ok && e == cudaSuccess && graph, "CUDA graph capture failed: %s", cudaGetErrorString(e));
@@ -595,9 +625,17 @@ bool forward_pass(Context * ctx, const uint32_t * tokens, int T, bool want_logit
         CUDA_OK(ctx, cudaGraphLaunch(g->exec, ctx->stream));
     } else {
         if (g) g->uses++;
-        if (!enqueue_pass(ctx, T, want_logits, phase)) return false;
+        if (!enqueue_pass(ctx, T, want_logits, phase, seg)) return false;
     }
+    return true;
+}
+
+bool end_pass(Context * ctx, int T, bool want_logits) {
+    const Model & m = *ctx->model;
+    const int phase = ctx->phase;
     if (ctx->hidden_out) {
+        const Scratch hs = carve(m, ctx->scratch, T);
+        const size_t ct = (size_t) m.n_embed * (size_t) T * sizeof(float);
         CUDA_OK(ctx, cudaMemcpyAsync(ctx->hidden_out, hs.x, ct, cudaMemcpyDeviceToDevice, ctx->stream));
         if (m.arch_major == 7) CUDA_OK(ctx, cudaMemcpyAsync(ctx->hidden_out + (size_t) m.n_embed * T, hs.v_first, ct, cudaMemcpyDeviceToDevice, ctx->stream));
     }
@@ -607,6 +645,22 @@ bool forward_pass(Context * ctx, const uint32_t * tokens, int T, bool want_logit
     float * tmp = ctx->state_a; ctx->state_a = ctx->state_b; ctx->state_b = tmp;
     ctx->phase ^= 1;
     ctx->logits_valid = want_logits && m.layer_end == m.n_layer;
+    return true;
+}
+
+bool forward_pass(Context * ctx, const uint32_t * tokens, int T, bool want_logits) {
+    return begin_pass(ctx, tokens, T) && run_layers(ctx, T, want_logits, 0) && end_pass(ctx, T, want_logits);
+}
+
+bool ensure_copy_streams(Context * ctx) {
+    if (ctx->copy_in) return true;
+    CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->pass_begin, cudaEventDisableTiming));
+    for (int i = 0; i < Context::MAX_SEGMENTS; i++) {
+        CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->seg_in[i], cudaEventDisableTiming));
+        CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->seg_out[i], cudaEventDisableTiming));
+    }
     return true;
 }
 
@@ -628,6 +682,13 @@ Context * create_context(Model * model, ErrorSink sink) {
     model->refcount.fetch_add(1);
     ctx->print_errors = *sink.print;
     { const char * e = getenv("RWKV_B200_PERSISTENT"); ctx->use_persistent = e ? atoi(e) != 0 : PERSISTENT_DEFAULT; }
+    { const char * e = getenv("RWKV_B200_OVERLAP"); ctx->overlap_copies = e ? atoi(e) != 0 : OVERLAP_DEFAULT; }
+    {   // layer groups of the overlapped host-state path: at least 4 layers each, at most MAX_SEGMENTS groups
+        const int n = model->layer_end - model->layer_begin;
+        int g = n / 4;
+        if (const char * e = getenv("RWKV_B200_SEGMENTS")) g = atoi(e);
+        ctx->n_segments = g < 1 ? 1 : (g > Context::MAX_SEGMENTS ? Context::MAX_SEGMENTS : (g > n ? n : g));
+    }
     const size_t n = model->state_len();
     bool ok = cudaSetDevice(model->dev.device) == cudaSuccess
         && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess
@@ -662,9 +723,13 @@ void destroy_context(Context * ctx) {
         if (ctx->tokens_host[i]) cudaFreeHost(ctx->tokens_host[i]);
         if (ctx->slot_free[i]) cudaEventDestroy(ctx->slot_free[i]);
     }
-    for (auto & row : ctx->graphs) for (auto & g : row) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto & g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     drop_programs(ctx);
     cudaFree(ctx->grid_barrier); cudaFree(ctx->phase_trace);
+    if (ctx->copy_in) { cudaStreamSynchronize(ctx->copy_in); cudaStreamDestroy(ctx->copy_in); }
+    if (ctx->copy_out) { cudaStreamSynchronize(ctx->copy_out); cudaStreamDestroy(ctx->copy_out); }
+    if (ctx->pass_begin) cudaEventDestroy(ctx->pass_begin);
+    for (int i = 0; i < Context::MAX_SEGMENTS; i++) { if (ctx->seg_in[i]) cudaEventDestroy(ctx->seg_in[i]); if (ctx->seg_out[i]) cudaEventDestroy(ctx->seg_out[i]); }
     cudaFree(ctx->sample_token); cudaFree(ctx->sample_scratch); cudaFree(ctx->bias_ids); cudaFree(ctx->bias_values);
     if (ctx->sample_token_host) cudaFreeHost(ctx->sample_token_host);
     for (auto & r : ctx->prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
@@ -677,16 +742,72 @@ void destroy_context(Context * ctx) {
 
 bool upload_state(Context * ctx, const float * state_in) {
     const size_t bytes = ctx->model->state_len() * sizeof(float);
-    if (state_in) CUDA_OK(ctx, cudaMemcpyAsync(ctx->state_a, state_in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // cudaMemcpyDefault: state_in / state_out / logits_out may be host memory (the rwkv.h contract) or device memory of this process
+    // (a CUDA tensor handed over by the Python wrapper): unified addressing tells them apart
+    if (state_in) CUDA_OK(ctx, cudaMemcpyAsync(ctx->state_a, state_in, bytes, cudaMemcpyDefault, ctx->stream));
     else CUDA_OK(ctx, cudaMemcpyAsync(ctx->state_a, ctx->state_init, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return true;
 }
 
 bool download_outputs(Context * ctx, float * state_out, float * logits_out) {
-    if (state_out) CUDA_OK(ctx, cudaMemcpyAsync(state_out, ctx->state_a, ctx->model->state_len() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    if (logits_out) CUDA_OK(ctx, cudaMemcpyAsync(logits_out, ctx->logits, (size_t) ctx->model->n_vocab * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (state_out) CUDA_OK(ctx, cudaMemcpyAsync(state_out, ctx->state_a, ctx->model->state_len() * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    if (logits_out) CUDA_OK(ctx, cudaMemcpyAsync(logits_out, ctx->logits, (size_t) ctx->model->n_vocab * sizeof(float), cudaMemcpyDefault, ctx->stream));
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     return true;
+}
+
+// One pass with the caller's host state pipelined against the layer groups: H2D of group g+1 and D2H of group g-1 run on their
+// own streams while group g computes (the state layout is layer-major, rwkv_graph.inc:545-606, so a group is one contiguous
+// slice). state_in == NULL starts from the init image (a device copy); state_out / logits_out may be NULL.
+static bool eval_host_overlapped(Context * ctx, const uint32_t * tokens, int T, const float * state_in, float * state_out, float * logits_out) {
+    const Model & m = *ctx->model;
+    const int G = ctx->n_segments;
+    if (!ensure_copy_streams(ctx)) return false;
+    const size_t per_layer = m.state_floats_per_layer();
+    // nothing of this pass may start before everything enqueued earlier on the context's stream has finished with the state
+    CUDA_OK(ctx, cudaEventRecord(ctx->pass_begin, ctx->stream));
+    CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->pass_begin, 0));
+    if (state_in) {
+        for (int g = 1; g <= G; g++) {
+            int l0, l1;
+            segment_range(ctx, g, l0, l1);
+            const size_t off = (size_t) l0 * per_layer, cnt = (size_t) (l1 - l0) * per_layer;
+            CUDA_OK(ctx, cudaMemcpyAsync(ctx->state_a + off, state_in + off, cnt * sizeof(float), cudaMemcpyDefault, ctx->copy_in));
+            CUDA_OK(ctx, cudaEventRecord(ctx->seg_in[g - 1], ctx->copy_in));
+        }
+    } else {
+        CUDA_OK(ctx, cudaMemcpyAsync(ctx->state_a, ctx->state_init, m.state_len() * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (!begin_pass(ctx, tokens, T)) return false;
+    const bool want_logits = logits_out != nullptr;
+    for (int g = 1; g <= G; g++) {
+        if (state_in) CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->seg_in[g - 1], 0));
+        if (!run_layers(ctx, T, want_logits, g)) return false;
+        CUDA_OK(ctx, cudaEventRecord(ctx->seg_out[g - 1], ctx->stream));
+    }
+    if (!end_pass(ctx, T, want_logits)) return false;      // the new state is ctx->state_a from here on
+    if (logits_out) CUDA_OK(ctx, cudaMemcpyAsync(logits_out, ctx->logits, (size_t) m.n_vocab * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    if (state_out) {
+        for (int g = 1; g <= G; g++) {
+            int l0, l1;
+            segment_range(ctx, g, l0, l1);
+            const size_t off = (size_t) l0 * per_layer, cnt = (size_t) (l1 - l0) * per_layer;
+            CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->seg_out[g - 1], 0));
+            CUDA_OK(ctx, cudaMemcpyAsync(state_out + off, ctx->state_a + off, cnt * sizeof(float), cudaMemcpyDefault, ctx->copy_out));
+        }
+    }
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (state_out) CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy_out));
+    return true;
+}
+
+bool eval_host(Context * ctx, const uint32_t * tokens, size_t T, const float * state_in, float * state_out, float * logits_out) {
+    const Model & m = *ctx->model;
+    CUDA_OK(ctx, cudaSetDevice(m.dev.device));
+    const bool whole_model = m.layer_begin == 0 && m.layer_end == m.n_layer;
+    if (ctx->overlap_copies && ctx->n_segments > 1 && whole_model && T <= (size_t) MAX_TOKENS_PER_PASS && !ctx->profiling && (state_in || state_out))
+        return eval_host_overlapped(ctx, tokens, (int) T, state_in, state_out, logits_out);
+    return upload_state(ctx, state_in) && forward(ctx, tokens, T, logits_out != nullptr) && download_outputs(ctx, state_out, logits_out);
 }
 
 bool forward(Context * ctx, const uint32_t * tokens, size_t T, bool want_logits) {

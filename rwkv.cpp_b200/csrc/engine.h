@@ -34,15 +34,27 @@ struct Context {
     bool slot_used[2] = {false, false};
     int phase = 0;                   // flips every pass together with the state_a/state_b swap
 
-    // CUDA graphs for single-token passes, keyed by [want_logits][phase]; captured on the second use.
+    // A single-token pass runs either over all resident layers at once (segment 0) or, when the caller's host state is copied in
+    // and out around it, as n_segments consecutive layer groups (segments 1..n_segments) so that the H2D copy of group g+1 and the
+    // D2H copy of group g-1 overlap the kernels of group g. Slots below are keyed by slot_index(want_logits, phase, segment).
+    static constexpr int MAX_SEGMENTS = 8;
+    static constexpr int N_SLOTS = 2 * 2 * (1 + MAX_SEGMENTS);
+    static int slot_index(bool want_logits, int phase, int segment) { return ((want_logits ? 1 : 0) * 2 + phase) * (1 + MAX_SEGMENTS) + segment; }
+    int n_segments = 1;              // layer groups of the overlapped path (1 = no overlap)
+    bool overlap_copies = false;     // rwkv_eval with host state: pipeline the state copies against the layer groups
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t seg_in[MAX_SEGMENTS] = {}, seg_out[MAX_SEGMENTS] = {};
+    cudaEvent_t pass_begin = nullptr;
+
+    // CUDA graphs for single-token passes; captured on the second use of a slot.
     struct GraphSlot { cudaGraphExec_t exec = nullptr; int uses = 0; unsigned long long launches = 0; };
-    GraphSlot graphs[2][2];
+    GraphSlot graphs[N_SLOTS];
     bool use_graphs = true;
 
-    // Persistent single-token kernel (kernels/decode_persistent.h): one program per [want_logits][phase], built on first use.
+    // Persistent single-token kernel (kernels/decode_persistent.h): one program per slot, built on first use.
     // `persistent_state`: 0 = not tried yet, 1 = in use, -1 = this model / device does not fit it (per-launch path is used).
-    DecodeProgram programs[2][2];
-    int persistent_state[2][2] = {{0, 0}, {0, 0}};
+    DecodeProgram programs[N_SLOTS];
+    int persistent_state[N_SLOTS] = {};
     bool use_persistent = false;
     unsigned long long * grid_barrier = nullptr;     // device counter of the kernel's grid barrier
     unsigned long long grid_barrier_value = 0;       // its value once everything enqueued so far has run
@@ -91,6 +103,11 @@ void fill_init_state(const Model & m, float * state);
 bool upload_state(Context * ctx, const float * state_in);
 // host <- state_a / logits; synchronises the stream.
 bool download_outputs(Context * ctx, float * state_out, float * logits_out);
+
+// rwkv_eval / rwkv_eval_sequence with caller-owned host buffers: state_in (NULL = fresh state) -> T tokens -> state_out / logits_out
+// (either may be NULL). With ctx->overlap_copies and a pass that fits one launch sequence the state travels per layer group,
+// overlapped with the kernels; otherwise upload_state + forward + download_outputs. Synchronises before returning.
+bool eval_host(Context * ctx, const uint32_t * tokens, size_t T, const float * state_in, float * state_out, float * logits_out);
 
 // Runs T tokens (host pointer) through all resident layers: reads state_a, leaves the new state in
 // state_a (buffers are swapped internally), and, if want_logits, ln_out + head of the last token

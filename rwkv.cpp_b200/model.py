@@ -54,10 +54,12 @@ class RWKVModel:
 
     # -- helpers ---------------------------------------------------------------------------------
     def _validate(self, buf, name: str, size: int) -> None:
-        """rwkv_cpp_model.py:330-351: CPU, float32, contiguous, exact shape."""
+        """rwkv_cpp_model.py:330-351: float32, contiguous, exact shape. Unlike the reference (which rejects non-CPU tensors,
+        :334) CUDA tensors are accepted: the library copies with cudaMemcpyDefault, so a state or logits tensor that already
+        lives on the GPU never crosses PCIe."""
         if _is_torch(buf):
-            if buf.device.type != "cpu":
-                raise ValueError(f"{name} is not on CPU")
+            if buf.device.type not in ("cpu", "cuda"):
+                raise ValueError(f"{name} is neither on CPU nor on a CUDA device")
             import torch
             if buf.dtype != torch.float32:
                 raise ValueError(f"{name} is not of type float32")
@@ -83,24 +85,27 @@ class RWKVModel:
         if not self._valid:
             raise ValueError("Model was freed")
         use_numpy = use_numpy or not any(_is_torch(b) for b in (state_in, state_out, logits_out))
+        if any(_is_torch(b) and b.device.type == "cuda" for b in (state_in, state_out, logits_out)):
+            import torch
+            torch.cuda.current_stream().synchronize()     # the library works on its own stream: the caller's writes must have landed
         if state_in is not None:
             self._validate(state_in, "state_in", self._state_buffer_element_count)
         if state_out is not None:
             self._validate(state_out, "state_out", self._state_buffer_element_count)
         else:
-            state_out = self._zeros(self._state_buffer_element_count, use_numpy)
+            state_out = self._zeros(self._state_buffer_element_count, use_numpy, state_in)     # outputs follow the input's device
         if logits_out is not None:
             self._validate(logits_out, "logits_out", self._logits_buffer_element_count)
         else:
-            logits_out = self._zeros(self._logits_buffer_element_count, use_numpy)
+            logits_out = self._zeros(self._logits_buffer_element_count, use_numpy, state_in)
         return state_out, logits_out
 
     @staticmethod
-    def _zeros(n: int, use_numpy: bool):
+    def _zeros(n: int, use_numpy: bool, like=None):
         if use_numpy:
             return np.zeros(n, dtype=np.float32)
         import torch
-        return torch.zeros(n, dtype=torch.float32, device="cpu")
+        return torch.zeros(n, dtype=torch.float32, device=like.device if like is not None and _is_torch(like) else "cpu")
 
     # -- evaluation (rwkv_cpp_model.py:85-298) -------------------------------------------------
     def eval(self, token: int, state_in, state_out=None, logits_out=None, use_numpy: bool = False) -> Tuple:

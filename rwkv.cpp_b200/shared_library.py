@@ -116,6 +116,8 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_set_tensor_cores.restype = None
         lib.rwkv_b200_set_persistent.argtypes = [vp, ctypes.c_bool]
         lib.rwkv_b200_set_persistent.restype = None
+        lib.rwkv_b200_set_overlap.argtypes = [vp, ctypes.c_bool]
+        lib.rwkv_b200_set_overlap.restype = None
         lib.rwkv_b200_persistent_state.argtypes = [vp]
         lib.rwkv_b200_persistent_state.restype = ctypes.c_int
         lib.rwkv_b200_phase_trace.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_int]
@@ -124,6 +126,8 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_plan_selftest.restype = ctypes.c_int
         lib.rwkv_b200_sample.argtypes = [vp, ctypes.c_float, ctypes.c_float, ctypes.c_double, P_U32, P_FLOAT, ctypes.c_size_t, P_U32]
         lib.rwkv_b200_sample.restype = ctypes.c_bool
+        lib.rwkv_b200_sample_logits.argtypes = [P_FLOAT, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_double, P_U32, P_FLOAT, ctypes.c_size_t, P_U32, P_FLOAT]
+        lib.rwkv_b200_sample_logits.restype = ctypes.c_bool
         lib.rwkv_b200_eval_sample.argtypes = [vp, ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_double, P_U32]
         lib.rwkv_b200_eval_sample.restype = ctypes.c_bool
         lib.rwkv_b200_matvec.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, P_FLOAT, P_FLOAT, ctypes.c_int]

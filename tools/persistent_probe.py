@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=6)
     ap.add_argument("--trace", action="store_true")
     ap.add_argument("--time", type=int, default=0, help="time this many resident decode steps on both paths")
+    ap.add_argument("--e2e", type=int, default=0, help="time this many rwkv_eval calls with pinned host state for persistent x overlap")
     args = ap.parse_args()
     pkg = __graft_entry__.load_package()
     lib = pkg.load_rwkv_shared_library()
@@ -81,6 +82,24 @@ def main():
             L.rwkv_b200_state_load(ctx.ptr, None)
             ms = L.rwkv_b200_time_resident(ctx.ptr, arr, 1, args.time, 8, True)
             print(f"resident decode, persistent={persistent}: {ms / args.time:.4f} ms/token")
+    if args.e2e:
+        import torch
+        st = torch.zeros(n_state, dtype=torch.float32).pin_memory()
+        lg = torch.zeros(n_logits, dtype=torch.float32).pin_memory()
+        sp, lp = ctypes.cast(st.data_ptr(), P_F), ctypes.cast(lg.data_ptr(), P_F)
+        for persistent in (False, True):
+            for overlap in (False, True):
+                L.rwkv_b200_set_persistent(ctx.ptr, persistent)
+                L.rwkv_b200_set_overlap(ctx.ptr, overlap)
+                lib.rwkv_init_state(ctx, st.data_ptr())
+                for i in range(6):
+                    L.rwkv_eval(ctx.ptr, (7919 * i) % n_logits, sp, sp, lp)
+                t0 = time.perf_counter()
+                for i in range(args.e2e):
+                    L.rwkv_eval(ctx.ptr, (7919 * (i + 6)) % n_logits, sp, sp, lp)
+                dt = (time.perf_counter() - t0) / args.e2e * 1e3
+                print(f"e2e rwkv_eval, pinned host state, persistent={persistent} overlap={overlap}: {dt:.4f} ms/token ({1e3 / dt:.1f} tok/s)  checksum {float(lg.sum()):.6f}")
+        L.rwkv_b200_set_overlap(ctx.ptr, False)
     if args.trace:
         L.rwkv_b200_set_persistent(ctx.ptr, True)
         buf = (ctypes.c_double * 4096)()
