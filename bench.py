@@ -317,6 +317,7 @@ def run_ours(args, rank, world, dist):
         ms_max = float(t.item())
     decode_tps = world * K / (ms_max / 1e3)
     persistent = int(L.rwkv_b200_persistent_state(ctx.ptr)) == 1
+    overlap_groups = int(L.rwkv_b200_overlap_groups(ctx.ptr))
     log("decode resident: %.3f ms/token (%s)" % (ms_max / K, "one persistent kernel per token" if persistent else "CUDA graph of per-launch kernels"))
 
     # ---- decode end to end through rwkv_eval with host buffers ------------------------------------------------
@@ -388,7 +389,8 @@ def run_ours(args, rank, world, dist):
                        "cuda_graph": not persistent, "persistent_kernel": persistent},
             "clocks": clocks,
             "e2e": {"value": e2e_tps, "unit": "tokens/s", "h2d_bytes_per_step": n_state * 4 + 4, "d2h_bytes_per_step": n_state * 4 + n_vocab * 4,
-                    "host_buffers": kind, "ms_per_step": e2e_s / K * 1e3},
+                    "host_buffers": kind, "ms_per_step": e2e_s / K * 1e3,
+                    "state_copies": ("pipelined against %d layer groups on copy streams" % overlap_groups) if overlap_groups else "one upload before, one download after the pass"},
             "gpu_launches": int(launches),
             "prefill": {"tokens_per_s": world * P * PREFILL_TOKENS / (pms / 1e3), "ms_per_chunk": pms / P, "chunk": PREFILL_TOKENS, "steps": P,
                         "e2e_tokens_per_s": world * PREFILL_TOKENS / pe2e_s,

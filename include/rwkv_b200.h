@@ -110,8 +110,11 @@ RWKV_API int rwkv_b200_persistent_state(const struct rwkv_context * ctx);
 /* rwkv_eval / rwkv_eval_sequence with caller-owned HOST state: copy the state per layer group (n_layer / 4 groups, at most 8) on
  * dedicated copy streams so that the host-to-device copy of group g+1 and the device-to-host copy of group g-1 overlap the kernels
  * of group g (the ABI state layout is layer-major, so a group is one contiguous slice). Results are bit-identical to the plain
- * upload - evaluate - download order. RWKV_B200_OVERLAP=0/1 sets the default of new contexts. */
+ * upload - evaluate - download order. On by default; RWKV_B200_OVERLAP=0/1 sets the default of new contexts. rwkv_eval_sequence_in_chunks
+ * pipelines the upload against its first chunk and the download against its last one. */
 RWKV_API void rwkv_b200_set_overlap(struct rwkv_context * ctx, bool enabled);
+/* Number of layer groups the overlapped path uses for this context (0 = overlap off or a single group). */
+RWKV_API int rwkv_b200_overlap_groups(const struct rwkv_context * ctx);
 
 /* Phase timeline of the persistent kernel: the first call arms a device buffer (returns 0); after the next single-token pass a
  * second call returns n_phases + 1 boundaries (microseconds since the kernel's first phase began, %globaltimer of CTA 0). */

@@ -95,17 +95,7 @@ bool rwkv_eval_sequence_in_chunks(struct rwkv_context * ctx, const uint32_t * to
         RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, tokens[i] < n_vocab, "Token at index %zu (%" PRIu32 ") is out of range (0 .. %zu)", i, tokens[i], n_vocab - 1);
     RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer,
                "This context holds only a pipeline stage; use the rwkv_b200 stage API");
-    // Same chunk boundaries as the reference loop (rwkv_eval.inc:179-218); the state never leaves HBM
-    // between chunks, logits are computed for the final chunk only.
-    if (!upload_state(c, state_in)) return false;
-    size_t off = 0;
-    while (off < sequence_len) {
-        const size_t n = sequence_len - off < chunk_size ? sequence_len - off : chunk_size;
-        const bool last = off + n == sequence_len;
-        if (!forward(c, tokens + off, n, last && logits_out != nullptr)) return false;
-        off += n;
-    }
-    return download_outputs(c, state_out, logits_out);
+    return eval_host_chunks(c, tokens, sequence_len, chunk_size, state_in, state_out, logits_out);
 }
 
 size_t rwkv_get_n_vocab(const struct rwkv_context * ctx) { return (size_t) C(ctx)->model->n_vocab; }
@@ -338,6 +328,7 @@ void rwkv_b200_set_graphs(struct rwkv_context * ctx, bool enabled) { C(ctx)->use
 void rwkv_b200_set_tensor_cores(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_tensor_cores = enabled; }
 void rwkv_b200_set_persistent(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_persistent = enabled; }
 void rwkv_b200_set_overlap(struct rwkv_context * ctx, bool enabled) { C(ctx)->overlap_copies = enabled; }
+int rwkv_b200_overlap_groups(const struct rwkv_context * ctx) { return C(ctx)->overlap_copies && C(ctx)->n_segments > 1 ? C(ctx)->n_segments : 0; }
 int rwkv_b200_persistent_state(const struct rwkv_context * ctx) {
     const Context * c = C(ctx);
     int best = 0;

@@ -20,7 +20,7 @@ namespace {
 // Single-token passes as one persistent kernel by default? (RWKV_B200_PERSISTENT=0/1 overrides, rwkv_b200_set_persistent per context)
 constexpr bool PERSISTENT_DEFAULT = false;
 // rwkv_eval with host state buffers: pipeline the state copies against layer groups? (RWKV_B200_OVERLAP=0/1, rwkv_b200_set_overlap)
-constexpr bool OVERLAP_DEFAULT = false;
+constexpr bool OVERLAP_DEFAULT = true;
 
 struct Scratch {      // carve-up of ctx->scratch for T tokens
     float * x, * xx, * sx;
@@ -759,7 +759,7 @@ bool download_outputs(Context * ctx, float * state_out, float * logits_out) {
 // One pass with the caller's host state pipelined against the layer groups: H2D of group g+1 and D2H of group g-1 run on their
 // own streams while group g computes (the state layout is layer-major, rwkv_graph.inc:545-606, so a group is one contiguous
 // slice). state_in == NULL starts from the init image (a device copy); state_out / logits_out may be NULL.
-static bool eval_host_overlapped(Context * ctx, const uint32_t * tokens, int T, const float * state_in, float * state_out, float * logits_out) {
+static bool eval_host_overlapped(Context * ctx, const uint32_t * tokens, int T, const float * state_in, bool resident_in, float * state_out, float * logits_out) {
     const Model & m = *ctx->model;
     const int G = ctx->n_segments;
     if (!ensure_copy_streams(ctx)) return false;
@@ -775,7 +775,7 @@ static bool eval_host_overlapped(Context * ctx, const uint32_t * tokens, int T, 
             CUDA_OK(ctx, cudaMemcpyAsync(ctx->state_a + off, state_in + off, cnt * sizeof(float), cudaMemcpyDefault, ctx->copy_in));
             CUDA_OK(ctx, cudaEventRecord(ctx->seg_in[g - 1], ctx->copy_in));
         }
-    } else {
+    } else if (!resident_in) {
         CUDA_OK(ctx, cudaMemcpyAsync(ctx->state_a, ctx->state_init, m.state_len() * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     }
     if (!begin_pass(ctx, tokens, T)) return false;
@@ -801,13 +801,37 @@ static bool eval_host_overlapped(Context * ctx, const uint32_t * tokens, int T, 
     return true;
 }
 
-bool eval_host(Context * ctx, const uint32_t * tokens, size_t T, const float * state_in, float * state_out, float * logits_out) {
+static bool can_overlap(const Context * ctx) {
     const Model & m = *ctx->model;
-    CUDA_OK(ctx, cudaSetDevice(m.dev.device));
-    const bool whole_model = m.layer_begin == 0 && m.layer_end == m.n_layer;
-    if (ctx->overlap_copies && ctx->n_segments > 1 && whole_model && T <= (size_t) MAX_TOKENS_PER_PASS && !ctx->profiling && (state_in || state_out))
-        return eval_host_overlapped(ctx, tokens, (int) T, state_in, state_out, logits_out);
+    return ctx->overlap_copies && ctx->n_segments > 1 && m.layer_begin == 0 && m.layer_end == m.n_layer && !ctx->profiling;
+}
+
+bool eval_host(Context * ctx, const uint32_t * tokens, size_t T, const float * state_in, float * state_out, float * logits_out) {
+    CUDA_OK(ctx, cudaSetDevice(ctx->model->dev.device));
+    if (can_overlap(ctx) && T <= (size_t) MAX_TOKENS_PER_PASS && (state_in || state_out))
+        return eval_host_overlapped(ctx, tokens, (int) T, state_in, false, state_out, logits_out);
     return upload_state(ctx, state_in) && forward(ctx, tokens, T, logits_out != nullptr) && download_outputs(ctx, state_out, logits_out);
+}
+
+bool eval_host_chunks(Context * ctx, const uint32_t * tokens, size_t T, size_t chunk, const float * state_in, float * state_out, float * logits_out) {
+    CUDA_OK(ctx, cudaSetDevice(ctx->model->dev.device));
+    const bool overlap = can_overlap(ctx) && chunk <= (size_t) MAX_TOKENS_PER_PASS && (state_in || state_out);
+    if (!overlap && !upload_state(ctx, state_in)) return false;
+    // Same chunk boundaries as the reference loop (rwkv_eval.inc:179-218); the state never leaves HBM between chunks, logits are
+    // computed for the final chunk only. With overlap the first chunk takes the caller's state group by group while it computes and
+    // the last one hands the new state back the same way.
+    size_t off = 0;
+    while (off < T) {
+        const size_t n = T - off < chunk ? T - off : chunk;
+        const bool first = off == 0, last = off + n == T;
+        if (overlap && (first || last)) {
+            if (!eval_host_overlapped(ctx, tokens + off, (int) n, first ? state_in : nullptr, !first, last ? state_out : nullptr, last ? logits_out : nullptr)) return false;
+        } else if (!forward(ctx, tokens + off, n, last && logits_out != nullptr)) {
+            return false;
+        }
+        off += n;
+    }
+    return overlap ? true : download_outputs(ctx, state_out, logits_out);
 }
 
 bool forward(Context * ctx, const uint32_t * tokens, size_t T, bool want_logits) {

@@ -109,6 +109,9 @@ bool download_outputs(Context * ctx, float * state_out, float * logits_out);
 // overlapped with the kernels; otherwise upload_state + forward + download_outputs. Synchronises before returning.
 bool eval_host(Context * ctx, const uint32_t * tokens, size_t T, const float * state_in, float * state_out, float * logits_out);
 
+// rwkv_eval_sequence_in_chunks: the reference's chunk loop (rwkv_eval.inc:158-222) with the state resident between chunks.
+bool eval_host_chunks(Context * ctx, const uint32_t * tokens, size_t T, size_t chunk, const float * state_in, float * state_out, float * logits_out);
+
 // Runs T tokens (host pointer) through all resident layers: reads state_a, leaves the new state in
 // state_a (buffers are swapped internally), and, if want_logits, ln_out + head of the last token
 // into ctx->logits. Asynchronous except for the token upload.

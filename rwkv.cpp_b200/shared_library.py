@@ -118,6 +118,8 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_set_persistent.restype = None
         lib.rwkv_b200_set_overlap.argtypes = [vp, ctypes.c_bool]
         lib.rwkv_b200_set_overlap.restype = None
+        lib.rwkv_b200_overlap_groups.argtypes = [vp]
+        lib.rwkv_b200_overlap_groups.restype = ctypes.c_int
         lib.rwkv_b200_persistent_state.argtypes = [vp]
         lib.rwkv_b200_persistent_state.restype = ctypes.c_int
         lib.rwkv_b200_phase_trace.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_int]
