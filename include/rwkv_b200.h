@@ -119,6 +119,9 @@ RWKV_API int rwkv_b200_overlap_groups(const struct rwkv_context * ctx);
 /* Phase timeline of the persistent kernel: the first call arms a device buffer (returns 0); after the next single-token pass a
  * second call returns n_phases + 1 boundaries (microseconds since the kernel's first phase began, %globaltimer of CTA 0). */
 RWKV_API int rwkv_b200_phase_trace(struct rwkv_context * ctx, double * boundaries_us, int max_records);
+/* Intra-phase marks of CTA 0 from the same traced pass: per phase [inputs ready (after LayerNorm), activation column staged,
+ * tiles consumed], microseconds on the time base of rwkv_b200_phase_trace, -1 where a phase has no such step. Returns the phase count. */
+RWKV_API int rwkv_b200_phase_marks(struct rwkv_context * ctx, double * marks_us, int max_phases);
 
 /* Host-only self-test of the persistent kernel's planner (no GPU, no file): plans the single-token program of a fake RWKV v5 /
  * v6 model of the given shape for a device with num_sms SMs and replays every CTA's tile walk. 1 = planned and consistent,

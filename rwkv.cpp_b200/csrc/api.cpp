@@ -339,6 +339,23 @@ int rwkv_b200_persistent_state(const struct rwkv_context * ctx) {
     return best;
 }
 
+int rwkv_b200_phase_marks(struct rwkv_context * ctx, double * marks_us, int max_phases) {
+    Context * c = C(ctx);
+    if (!c->phase_trace || !marks_us || cudaSetDevice(c->model->dev.device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    int n = 0;
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) { const DecodeProgram & pr = c->programs[Context::slot_index(a != 0, b, 0)]; if (pr.supported && pr.n_phases > n) n = pr.n_phases; }
+    if (n > max_phases) n = max_phases;
+    if (n > 700) n = 700;
+    if (n <= 0) return 0;
+    std::vector<unsigned long long> raw((size_t) 1024 + 4 * (size_t) n);
+    if (cudaMemcpy(raw.data(), c->phase_trace, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (int i = 0; i < n; i++) for (int k = 0; k < 3; k++) {
+        const unsigned long long v = raw[1024 + 4 * (size_t) i + k];
+        marks_us[3 * i + k] = (v && v >= raw[0]) ? (double) (v - raw[0]) * 1e-3 : -1.0;
+    }
+    return n;
+}
+
 int rwkv_b200_plan_selftest(int arch_major, int arch_minor, int data_type, int n_embed, int ffn, int n_vocab, int head_size, int mix, int decay, int n_layer, int num_sms, int * info) {
     return plan_selftest(arch_major, arch_minor, data_type, n_embed, ffn, n_vocab, head_size, mix, decay, n_layer, num_sms, info);
 }

@@ -15,6 +15,7 @@ using namespace tma;
 constexpr int LN_MAXCH = 16;               // channels per consumer thread in the LayerNorm stage: n_embed <= 4096
 constexpr int LERP_MAXF4 = 2;              // float4 per lane per mix kept in registers across the barrier: mix <= 64
 constexpr size_t DYN_SMEM_BUDGET = 110 * 1024;   // + ~2 KB static: two CTAs per SM
+constexpr int PHASE_MARK_BASE = 1024, PHASE_MARK_MAX = 700;     // layout of the optional trace buffer (4096 u64)
 constexpr size_t RED_BYTES = (size_t) 2 * MAX_TILE_ROWS * CONSUMER_WARPS * sizeof(float);
 
 // ---- the program as the kernel reads it: one fully resolved record per (CTA, phase), CTA-major, so that a CTA's next record is
@@ -310,10 +311,12 @@ __device__ void wkv6_step(const WkvStep & p, int h, float * ybuf) {
 }
 
 // ---- the GEMV of a phase on this CTA's tiles: stage the (single) activation column, then the unchanged consumers
-__device__ void run_gemv(Shared & sh, uint8_t * ring, uint32_t stage_bytes, uint8_t * act, float * red, int it0, int local, int my_tiles) {
+__device__ void run_gemv(Shared & sh, uint8_t * ring, uint32_t stage_bytes, uint8_t * act, float * red, int it0, int local, int my_tiles, unsigned long long * marks) {
     const GemvProblem & P = sh.P;
+    if (marks && threadIdx.x == 0) marks[0] = global_timer();      // stage inputs ready (LayerNorm / nothing done)
     stage_column<8>(P, 0, act, sh.red_d);
     consumer_barrier();
+    if (marks && threadIdx.x == 0) marks[1] = global_timer();      // activation column staged
     const size_t colb = act_bytes_per_column(P.type, P.K);
 #define RWKV_DP_REGS(T_) consume_quant_regs<T_, true>(sh, ring, stage_bytes, act, 0, red, it0, my_tiles, local, P.n_cta)
 #define RWKV_DP_SMEM(T_) consume_smem<T_, 1, true>(sh, ring, stage_bytes, act, colb, 0, 1, red, it0, my_tiles, local, P.n_cta)
@@ -328,6 +331,7 @@ __device__ void run_gemv(Shared & sh, uint8_t * ring, uint32_t stage_bytes, uint
     }
 #undef RWKV_DP_REGS
 #undef RWKV_DP_SMEM
+    if (marks && threadIdx.x == 0) marks[2] = global_timer();      // this CTA's tiles consumed
 }
 
 __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Args a) {
@@ -414,20 +418,21 @@ __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Arg
             if (a.trace && blockIdx.x == 0) a.trace[ph] = global_timer();
         }
         consumer_barrier();
-        // (4) the phase
+        // (4) the phase. CTA 0 leaves three intra-phase time marks per phase behind the boundary array when tracing is armed.
+        unsigned long long * marks = (a.trace && blockIdx.x == 0 && ph < PHASE_MARK_MAX) ? a.trace + PHASE_MARK_BASE + 4 * ph : nullptr;
         switch (op) {
             case DOP_LNMIX_GEMV:
                 if (active) {
                     ln_mix_stage(R.u.ln, tmp, slots, blockIdx.x == 0);
                     consumer_barrier();
-                    run_gemv(sh, ring, stage_bytes, act, red, it, local, my_tiles);
+                    run_gemv(sh, ring, stage_bytes, act, red, it, local, my_tiles, marks);
                 }
                 break;
             case DOP_LERP:
                 lerp_run(R.u.lerp, lr, tmp);
                 break;
             case DOP_GEMV_WKV: {
-                if (active) run_gemv(sh, ring, stage_bytes, act, red, it, local, my_tiles);
+                if (active) run_gemv(sh, ring, stage_bytes, act, red, it, local, my_tiles, marks);
                 const int h = R.head;
                 if (h >= 0) {
                     consumer_barrier();     // the head's decay values just stored by this CTA are visible to all its threads
@@ -441,7 +446,7 @@ __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Arg
                 break;
             }
             default:
-                if (active) run_gemv(sh, ring, stage_bytes, act, red, it, local, my_tiles);
+                if (active) run_gemv(sh, ring, stage_bytes, act, red, it, local, my_tiles, marks);
                 break;
         }
         it += my_tiles;

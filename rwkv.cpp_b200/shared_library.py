@@ -124,6 +124,8 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_persistent_state.restype = ctypes.c_int
         lib.rwkv_b200_phase_trace.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_int]
         lib.rwkv_b200_phase_trace.restype = ctypes.c_int
+        lib.rwkv_b200_phase_marks.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_int]
+        lib.rwkv_b200_phase_marks.restype = ctypes.c_int
         lib.rwkv_b200_plan_selftest.argtypes = [ctypes.c_int] * 11 + [ctypes.POINTER(ctypes.c_int)]
         lib.rwkv_b200_plan_selftest.restype = ctypes.c_int
         lib.rwkv_b200_sample.argtypes = [vp, ctypes.c_float, ctypes.c_float, ctypes.c_double, P_U32, P_FLOAT, ctypes.c_size_t, P_U32]

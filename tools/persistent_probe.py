@@ -116,6 +116,19 @@ def main():
             body = dur[:(len(dur) - 1) // per * per].reshape(-1, per)
             print("per-layer phase durations (us), median over layers:", np.round(np.median(body, axis=0), 2).tolist(), "layer total", round(float(np.median(body.sum(axis=1))), 2))
             print("first layer:", np.round(body[0], 2).tolist(), " head:", round(float(dur[-1]), 2))
+            mk = (ctypes.c_double * (3 * 700))()
+            nm = L.rwkv_b200_phase_marks(ctx.ptr, mk, 700)
+            if nm > 0:
+                marks = np.array([mk[i] for i in range(3 * nm)]).reshape(nm, 3)
+                starts = np.array(b[:nm])
+                rel = np.where(marks >= 0, marks - starts[:, None], np.nan)       # since the phase's barrier released
+                nl = (nm - 1) // per
+                relb = rel[:nl * per].reshape(nl, per, 3)
+                with np.errstate(all="ignore"):
+                    med = np.nanmedian(relb, axis=0)
+                print("CTA 0, us after the phase's barrier released [inputs ready, column staged, tiles consumed], median over layers:")
+                for i in range(per):
+                    print(f"  phase {i}: {np.round(med[i], 2).tolist()}  (phase length {np.round(np.median(body[:, i]), 2)})")
     lib.rwkv_free(ctx)
 
 
