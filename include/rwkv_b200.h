@@ -38,6 +38,23 @@ RWKV_API bool rwkv_b200_state_store(struct rwkv_context * ctx, float * state_out
 /* Blocks until everything enqueued on the context's stream has finished. */
 RWKV_API bool rwkv_b200_synchronize(struct rwkv_context * ctx);
 
+/* Batched multi-sequence decode (the reference has no equivalent -- it evaluates one context per call): a batch
+ * context holds the recurrent states of n_sequences independent sequences in HBM and evaluates ONE token of EACH per call, so every
+ * weight matrix is streamed once for n_sequences tokens (the fused dequantize-GEMV runs its multi-column path). Per sequence the
+ * result is bit-identical to evaluating that sequence alone with rwkv_eval (below 32 sequences; from 32 on the tensor-core path
+ * takes the layer matrices, with its own rounding of the activations). RWKV v4 / v5 / v6, n_embed <= 4096, head size <= 64.
+ *   rwkv_b200_batch_create    : from any context of the model (shares its weights); free with rwkv_free; NULL on failure
+ *   rwkv_b200_batch_set_state : state of one sequence <- state_in (host or device pointer, NULL = fresh state)
+ *   rwkv_b200_batch_eval      : tokens[n_sequences], one per sequence; want_logits = run the head for every sequence
+ *   rwkv_b200_batch_get_logits / rwkv_b200_batch_get_state : copy one sequence's logits / state out (host or device pointer)
+ * rwkv_eval* and the resident / stage entry points refuse a batch context. */
+RWKV_API struct rwkv_context * rwkv_b200_batch_create(struct rwkv_context * ctx, size_t n_sequences);
+RWKV_API bool rwkv_b200_batch_set_state(struct rwkv_context * batch, size_t sequence, const float * state_in);
+RWKV_API bool rwkv_b200_batch_get_state(struct rwkv_context * batch, size_t sequence, float * state_out);
+RWKV_API bool rwkv_b200_batch_eval(struct rwkv_context * batch, const uint32_t * tokens, bool want_logits);
+RWKV_API bool rwkv_b200_batch_get_logits(struct rwkv_context * batch, size_t sequence, float * logits_out);
+RWKV_API size_t rwkv_b200_batch_size(const struct rwkv_context * ctx);   /* 0 for an ordinary context */
+
 /* On-device sampling: the next token is drawn on the GPU from the logits of the most recent evaluation that
  * computed them, following the reference's python/sampling.py:10-52 (softmax, optional logit bias, temperature 0 = argmax, top-p
  * cutoff, power by 1/temperature, renormalise, inverse-CDF draw); only the 4-byte token id crosses PCIe instead of n_vocab floats.

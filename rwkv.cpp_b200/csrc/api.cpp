@@ -2,6 +2,7 @@
 // Argument checks, error categories and NULL conventions follow the reference entry points
 // (rwkv.cpp:71-258, rwkv_eval.inc:38-241) so its C tests run unchanged against this library.
 #include <cinttypes>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -65,8 +66,8 @@ bool rwkv_eval(struct rwkv_context * ctx, const uint32_t token, const float * st
     c->last_error = RWKV_ERROR_NONE;
     const size_t n_vocab = (size_t) c->model->n_vocab;
     RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, token < n_vocab, "Token (%" PRIu32 ") is out of range (0 .. %zu)", token, n_vocab - 1);
-    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer,
-               "This context holds only a pipeline stage; use the rwkv_b200 stage API");
+    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer && c->batch_n == 0,
+               "This context holds only a pipeline stage or is a batch context; use the rwkv_b200 stage / batch API");
     return eval_host(c, &token, 1, state_in, state_out, logits_out);
 }
 
@@ -78,8 +79,8 @@ bool rwkv_eval_sequence(struct rwkv_context * ctx, const uint32_t * sequence, co
     const size_t n_vocab = (size_t) c->model->n_vocab;
     for (size_t i = 0; i < sequence_len; i++)
         RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, sequence[i] < n_vocab, "Token at index %zu (%" PRIu32 ") is out of range (0 .. %zu)", i, sequence[i], n_vocab - 1);
-    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer,
-               "This context holds only a pipeline stage; use the rwkv_b200 stage API");
+    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer && c->batch_n == 0,
+               "This context holds only a pipeline stage or is a batch context; use the rwkv_b200 stage / batch API");
     return eval_host(c, sequence, sequence_len, state_in, state_out, logits_out);
 }
 
@@ -93,8 +94,8 @@ bool rwkv_eval_sequence_in_chunks(struct rwkv_context * ctx, const uint32_t * to
     const size_t n_vocab = (size_t) c->model->n_vocab;
     for (size_t i = 0; i < sequence_len; i++)
         RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, tokens[i] < n_vocab, "Token at index %zu (%" PRIu32 ") is out of range (0 .. %zu)", i, tokens[i], n_vocab - 1);
-    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer,
-               "This context holds only a pipeline stage; use the rwkv_b200 stage API");
+    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer && c->batch_n == 0,
+               "This context holds only a pipeline stage or is a batch context; use the rwkv_b200 stage / batch API");
     return eval_host_chunks(c, tokens, sequence_len, chunk_size, state_in, state_out, logits_out);
 }
 
@@ -180,14 +181,15 @@ bool rwkv_b200_inspect_file(const char * path, struct rwkv_b200_file_info * out)
     return true;
 }
 
-bool rwkv_b200_state_load(struct rwkv_context * ctx, const float * state_in) { C(ctx)->last_error = 0; return upload_state(C(ctx), state_in); }
-bool rwkv_b200_state_store(struct rwkv_context * ctx, float * state_out) { return download_outputs(C(ctx), state_out, nullptr); }
+bool rwkv_b200_state_load(struct rwkv_context * ctx, const float * state_in) { C(ctx)->last_error = 0; return C(ctx)->batch_n == 0 && upload_state(C(ctx), state_in); }
+bool rwkv_b200_state_store(struct rwkv_context * ctx, float * state_out) { return C(ctx)->batch_n == 0 && download_outputs(C(ctx), state_out, nullptr); }
 bool rwkv_b200_synchronize(struct rwkv_context * ctx) { return download_outputs(C(ctx), nullptr, nullptr); }
 
 bool rwkv_b200_eval_resident(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, bool want_logits, float * logits_out) {
     Context * c = C(ctx);
     c->last_error = RWKV_ERROR_NONE;
     RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, tokens && n_tokens > 0, "No tokens");
+    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->batch_n == 0, "This is a batch context; use rwkv_b200_batch_eval");
     const size_t n_vocab = (size_t) c->model->n_vocab;
     for (size_t i = 0; i < n_tokens; i++)
         RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, tokens[i] < n_vocab, "Token at index %zu (%" PRIu32 ") is out of range (0 .. %zu)", i, tokens[i], n_vocab - 1);
@@ -195,6 +197,49 @@ bool rwkv_b200_eval_resident(struct rwkv_context * ctx, const uint32_t * tokens,
     if (logits_out) return download_outputs(c, nullptr, logits_out);
     return true;
 }
+
+struct rwkv_context * rwkv_b200_batch_create(struct rwkv_context * ctx, size_t n_sequences) {
+    if (!ctx) return nullptr;
+    Context * c = C(ctx);
+    bool print = c->print_errors;
+    int flags = 0;
+    ErrorSink sink{&flags, &print};
+    const Model & m = *c->model;
+    Context * b = nullptr;
+    if (n_sequences == 0 || n_sequences > (size_t) MAX_TOKENS_PER_PASS) {
+        flags |= RWKV_ERROR_ARGS;
+        if (print) fprintf(stderr, "A batch holds 1 .. %d sequences\n", MAX_TOKENS_PER_PASS);
+    } else if (m.layer_begin != 0 || m.layer_end != m.n_layer || !batch_shape_supported(m.arch_major, m.n_embed, m.head_size)) {
+        flags |= RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED;
+        if (print) fprintf(stderr, "Batched decode supports whole RWKV v4 / v5 / v6 models with n_embed <= 4096 and head size <= 64\n");
+    } else {
+        b = create_context(c->model, sink, (int) n_sequences);
+    }
+    if (!b) { g_last_error |= flags; return nullptr; }
+    b->print_errors = c->print_errors;
+    return static_cast<struct rwkv_context *>(b);
+}
+bool rwkv_b200_batch_set_state(struct rwkv_context * batch, size_t sequence, const float * state_in) {
+    C(batch)->last_error = RWKV_ERROR_NONE;
+    return batch_set_state(C(batch), (int) sequence, state_in);
+}
+bool rwkv_b200_batch_get_state(struct rwkv_context * batch, size_t sequence, float * state_out) {
+    C(batch)->last_error = RWKV_ERROR_NONE;
+    return batch_get_state(C(batch), (int) sequence, state_out);
+}
+bool rwkv_b200_batch_eval(struct rwkv_context * batch, const uint32_t * tokens, bool want_logits) {
+    Context * c = C(batch);
+    c->last_error = RWKV_ERROR_NONE;
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, c->batch_n > 0 && tokens, "Not a batch context or NULL tokens");
+    for (int i = 0; i < c->batch_n; i++)
+        RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, tokens[i] < (uint32_t) c->model->n_vocab, "Token of sequence %d (%" PRIu32 ") is out of range (0 .. %d)", i, tokens[i], c->model->n_vocab - 1);
+    return batch_eval(c, tokens, want_logits);
+}
+bool rwkv_b200_batch_get_logits(struct rwkv_context * batch, size_t sequence, float * logits_out) {
+    C(batch)->last_error = RWKV_ERROR_NONE;
+    return batch_get_logits(C(batch), (int) sequence, logits_out);
+}
+size_t rwkv_b200_batch_size(const struct rwkv_context * ctx) { return (size_t) C(ctx)->batch_n; }
 
 bool rwkv_b200_sample(struct rwkv_context * ctx, float temperature, float top_p, double u, const uint32_t * bias_ids, const float * bias_values, size_t n_bias,
                       uint32_t * token_out) {

@@ -127,6 +127,18 @@ bool run_batch(Context * ctx, Batch & batch) {
     return true;
 }
 
+// The three stages that touch the recurrent state: a batch context (one token of each of batch_n sequences) uses the kernels of
+// batch.cu, where column t works on sequence t's state; everything else is identical for both kinds of context.
+cudaError_t do_ln_mix(Context * ctx, const LnMixParams & lp) {
+    return ctx->batch_stride ? launch_ln_mix_batch(lp, ctx->batch_stride, ctx->stream) : launch_ln_mix(lp, ctx->stream);
+}
+cudaError_t do_wkv6(Context * ctx, const Wkv6Params & wp) {
+    return ctx->batch_stride ? launch_wkv6_batch(wp, ctx->batch_stride, ctx->stream) : launch_wkv6(wp, ctx->stream);
+}
+cudaError_t do_wkv4(Context * ctx, const Wkv4Params & wp) {
+    return ctx->batch_stride ? launch_wkv4_batch(wp, ctx->batch_stride, ctx->stream) : launch_wkv4(wp, ctx->stream);
+}
+
 // Channel mixing, all versions (rwkv_ffn_v4_v5 :484-511, rwkv_ffn_v6 :513-531, rwkv_ffn_v7 :533-543).
 bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
     const Model & m = *ctx->model;
@@ -145,7 +157,7 @@ bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const float *
         lp.coef[0] = L.ffn_time_mix_k.data; lp.out[0] = s.mix[0];
         lp.coef[1] = L.ffn_time_mix_r.data; lp.out[1] = s.mix[1];
     }
-    CUDA_OK(ctx, launch_ln_mix(lp, ctx->stream));
+    CUDA_OK(ctx, do_ln_mix(ctx, lp));
     {
         Batch b(T);
         b.add(L.ffn_key, s.mix[0], s.ffn_k, EPI_RELU_SQR);
@@ -178,7 +190,7 @@ bool att_v4(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     lp.coef[0] = L.att_time_mix_k.data; lp.out[0] = s.mix[0];
     lp.coef[1] = L.att_time_mix_v.data; lp.out[1] = s.mix[1];
     lp.coef[2] = L.att_time_mix_r.data; lp.out[2] = s.mix[2];
-    CUDA_OK(ctx, launch_ln_mix(lp, ctx->stream));
+    CUDA_OK(ctx, do_ln_mix(ctx, lp));
     Batch b(T);
     b.add(L.att_receptance, s.mix[2], s.r, EPI_SIGMOID);
     b.add(L.att_key, s.mix[0], s.k);
@@ -190,7 +202,7 @@ bool att_v4(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     wp.aa_in = st_in + 2 * C; wp.bb_in = st_in + 3 * C; wp.pp_in = st_in + 4 * C;
     wp.aa_out = st_out + 2 * C; wp.bb_out = st_out + 3 * C; wp.pp_out = st_out + 4 * C;
     wp.y = s.y; wp.C = C; wp.T = T;
-    CUDA_OK(ctx, launch_wkv4(wp, ctx->stream));
+    CUDA_OK(ctx, do_wkv4(ctx, wp));
     return att_output(ctx, L, s, T);
 }
 
@@ -206,7 +218,7 @@ bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     lp.coef[1] = L.att_time_mix_v.data; lp.out[1] = s.mix[1];
     lp.coef[2] = L.att_time_mix_r.data; lp.out[2] = s.mix[2];
     if (v52) { lp.coef[3] = L.att_time_mix_g.data; lp.out[3] = s.mix[3]; }
-    CUDA_OK(ctx, launch_ln_mix(lp, ctx->stream));
+    CUDA_OK(ctx, do_ln_mix(ctx, lp));
     Batch b(T);
     b.add(L.att_receptance, s.mix[2], s.r);
     b.add(L.att_key, s.mix[0], s.k);
@@ -222,7 +234,7 @@ bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
     wp.g = v52 ? s.g : nullptr;
     wp.y = s.y; wp.eps = 1e-5f; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
-    CUDA_OK(ctx, launch_wkv6(wp, ctx->stream));
+    CUDA_OK(ctx, do_wkv6(ctx, wp));
     return att_output(ctx, L, s, T);
 }
 
@@ -234,7 +246,7 @@ bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     lp.state_in = st_in + C; lp.state_out = st_out + C; lp.C = C; lp.T = T;
     lp.formula = 1; lp.n_out = 1; lp.coef[0] = L.att_maa_x.data; lp.out[0] = s.mix[0];
     lp.out_xx = s.xx; lp.out_sx = s.sx;
-    CUDA_OK(ctx, launch_ln_mix(lp, ctx->stream));
+    CUDA_OK(ctx, do_ln_mix(ctx, lp));
     {   // :313-321  tanh(W1 . xxx)
         Batch b(T);
         b.add(L.att_maa_w1, s.mix[0], s.lora[0], EPI_TANH);
@@ -268,7 +280,7 @@ bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     wp.state_in = st_in + 2 * C; wp.state_out = st_out + 2 * C;
     wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
     wp.g = s.g; wp.y = s.y; wp.eps = 64e-5f; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
-    CUDA_OK(ctx, launch_wkv6(wp, ctx->stream));
+    CUDA_OK(ctx, do_wkv6(ctx, wp));
     return att_output(ctx, L, s, T);
 }
 
@@ -548,9 +560,9 @@ bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase, int seg) {
         }
         if (!ok || !ffn(ctx, L, s, T, st_in, st_out)) return false;
     }
-    if (want_logits && l1 == m.n_layer) {   // :705-708 / :851-854  head . LN(x_last; ln_out)
-        Batch b(1);
-        GemvProblem & p = b.add(m.head, s.x + (size_t) (T - 1) * C, ctx->logits);
+    if (want_logits && l1 == m.n_layer) {   // :705-708 / :851-854  head . LN(x_last; ln_out); a batch context wants every column
+        Batch b(ctx->batch_n ? T : 1);
+        GemvProblem & p = b.add(m.head, ctx->batch_n ? s.x : s.x + (size_t) (T - 1) * C, ctx->logits);
         p.pro = PRO_LAYERNORM; p.ln_w = m.ln_out_w.data; p.ln_b = m.ln_out_b.data;
         if (!run_batch(ctx, b)) return false;
     }
@@ -675,7 +687,7 @@ void fill_init_state(const Model & m, float * state) {
         for (size_t c = 0; c < C; c++) state[(size_t) l * 5 * C + 4 * C + c] = -1e30f;
 }
 
-Context * create_context(Model * model, ErrorSink sink) {
+Context * create_context(Model * model, ErrorSink sink, int batch_n) {
     Context * ctx = new (std::nothrow) Context();
     RWKV_CHECK(sink, RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, nullptr, ctx, "Failed to allocate rwkv_context");
     ctx->model = model;
@@ -690,19 +702,23 @@ Context * create_context(Model * model, ErrorSink sink) {
         ctx->n_segments = g < 1 ? 1 : (g > Context::MAX_SEGMENTS ? Context::MAX_SEGMENTS : (g > n ? n : g));
     }
     const size_t n = model->state_len();
+    const size_t seqs = batch_n > 0 ? (size_t) batch_n : 1;
+    if (batch_n > 0) { ctx->batch_n = batch_n; ctx->batch_stride = (long long) n; ctx->use_persistent = false; ctx->overlap_copies = false; }
     bool ok = cudaSetDevice(model->dev.device) == cudaSuccess
         && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess
         && cudaEventCreate(&ctx->ev_start) == cudaSuccess && cudaEventCreate(&ctx->ev_stop) == cudaSuccess
         && cudaEventCreateWithFlags(&ctx->slot_free[0], cudaEventDisableTiming) == cudaSuccess
         && cudaEventCreateWithFlags(&ctx->slot_free[1], cudaEventDisableTiming) == cudaSuccess
-        && cudaMalloc(reinterpret_cast<void **>(&ctx->state_a), n * sizeof(float)) == cudaSuccess
-        && cudaMalloc(reinterpret_cast<void **>(&ctx->state_b), n * sizeof(float)) == cudaSuccess
+        && cudaMalloc(reinterpret_cast<void **>(&ctx->state_a), seqs * n * sizeof(float)) == cudaSuccess
+        && cudaMalloc(reinterpret_cast<void **>(&ctx->state_b), seqs * n * sizeof(float)) == cudaSuccess
         && cudaMalloc(reinterpret_cast<void **>(&ctx->state_init), n * sizeof(float)) == cudaSuccess
-        && cudaMalloc(reinterpret_cast<void **>(&ctx->logits), (size_t) model->n_vocab * sizeof(float)) == cudaSuccess;
+        && cudaMalloc(reinterpret_cast<void **>(&ctx->logits), seqs * (size_t) model->n_vocab * sizeof(float)) == cudaSuccess;
     if (ok) {
         std::vector<float> init(n);
         fill_init_state(*model, init.data());
         ok = cudaMemcpy(ctx->state_init, init.data(), n * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+        for (size_t q = 0; ok && batch_n > 0 && q < seqs; q++)
+            ok = cudaMemcpy(ctx->state_a + q * n, ctx->state_init, n * sizeof(float), cudaMemcpyDeviceToDevice) == cudaSuccess;
     }
     if (!ok) {
         cudaError_t e = cudaGetLastError();
@@ -910,9 +926,45 @@ int plan_selftest(int arch_major, int arch_minor, int type, int C, int F, int V,
     return ok ? 1 : 0;
 }
 
+bool batch_set_state(Context * ctx, int seq, const float * state_in) {
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, ctx->batch_n > 0 && seq >= 0 && seq < ctx->batch_n, "Not a batch context or sequence index out of range");
+    CUDA_OK(ctx, cudaSetDevice(ctx->model->dev.device));
+    const size_t n = ctx->model->state_len();
+    float * dst = ctx->state_a + (size_t) seq * n;
+    if (state_in) CUDA_OK(ctx, cudaMemcpyAsync(dst, state_in, n * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    else CUDA_OK(ctx, cudaMemcpyAsync(dst, ctx->state_init, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    return true;
+}
+
+bool batch_get_state(Context * ctx, int seq, float * state_out) {
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, ctx->batch_n > 0 && seq >= 0 && seq < ctx->batch_n && state_out, "Not a batch context, sequence index out of range or NULL buffer");
+    CUDA_OK(ctx, cudaSetDevice(ctx->model->dev.device));
+    const size_t n = ctx->model->state_len();
+    CUDA_OK(ctx, cudaMemcpyAsync(state_out, ctx->state_a + (size_t) seq * n, n * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return true;
+}
+
+bool batch_eval(Context * ctx, const uint32_t * tokens, bool want_logits) {
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, ctx->batch_n > 0 && tokens, "Not a batch context or NULL tokens");
+    CUDA_OK(ctx, cudaSetDevice(ctx->model->dev.device));
+    return forward_pass(ctx, tokens, ctx->batch_n, want_logits);
+}
+
+bool batch_get_logits(Context * ctx, int seq, float * logits_out) {
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, ctx->batch_n > 0 && seq >= 0 && seq < ctx->batch_n && logits_out, "Not a batch context, sequence index out of range or NULL buffer");
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, ctx->logits_valid, "The last batch evaluation skipped the head");
+    CUDA_OK(ctx, cudaSetDevice(ctx->model->dev.device));
+    const size_t V = (size_t) ctx->model->n_vocab;
+    CUDA_OK(ctx, cudaMemcpyAsync(logits_out, ctx->logits + (size_t) seq * V, V * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return true;
+}
+
 bool sample_token(Context * ctx, float temperature, float top_p, double u, const uint32_t * bias_ids, const float * bias_values, size_t n_bias, uint32_t * token_out) {
     const Model & m = *ctx->model;
     RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, token_out != nullptr, "token_out is NULL");
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, ctx->batch_n == 0, "Sampling on a batch context is not supported");
     RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, temperature >= 0.0f, "temperature must be >= 0");            // sampling.py:20-21
     RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, top_p >= 0.0f && top_p <= 1.0f, "top_p must be in [0, 1]");    // sampling.py:22-23
     RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, u >= 0.0 && u < 1.0, "u must be in [0, 1)");

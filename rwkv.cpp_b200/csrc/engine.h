@@ -74,6 +74,12 @@ struct Context {
     const float * hidden_in = nullptr;
     float * hidden_out = nullptr;
 
+    // Batched multi-sequence decode (kernels/batch.cu, rwkv_b200_batch_*): batch_n > 0 makes this a batch context whose state
+    // buffers hold batch_n states back to back (batch_stride = state_len floats apart) and whose logits buffer holds batch_n columns;
+    // every pass evaluates exactly one token of each sequence.
+    int batch_n = 0;
+    long long batch_stride = 0;
+
     // On-device sampling (kernels/sampling.cu): result word, scratch for biased logits, device copy of the caller's logit bias.
     bool logits_valid = false;       // ctx->logits holds the head output of the most recent pass
     uint32_t * sample_token = nullptr;   // device
@@ -93,7 +99,7 @@ struct Context {
 // pieces of this size with the state staying on the device.
 constexpr int MAX_TOKENS_PER_PASS = 256;
 
-Context * create_context(Model * model, ErrorSink sink);
+Context * create_context(Model * model, ErrorSink sink, int batch_n = 0);   // batch_n > 0: a batch context for that many sequences
 void destroy_context(Context * ctx);
 
 // Host image of a fresh state (rwkv_init_state, rwkv_eval.inc:224-241).
@@ -122,6 +128,12 @@ bool forward(Context * ctx, const uint32_t * tokens, size_t T, bool want_logits)
 // (device pointers, stage_hidden_len(T) floats); the last one computes the logits when asked. `stream` (may be NULL = the
 // context's own) is the CUDA stream everything is enqueued on, so the hand-off can be ordered against NCCL sends and
 // receives without host synchronisation.
+// Batch contexts: state of sequence `seq` <- host state (NULL = fresh) / -> host; one token of every sequence; logits of `seq`.
+bool batch_set_state(Context * ctx, int seq, const float * state_in);
+bool batch_get_state(Context * ctx, int seq, float * state_out);
+bool batch_eval(Context * ctx, const uint32_t * tokens, bool want_logits);
+bool batch_get_logits(Context * ctx, int seq, float * logits_out);
+
 // Samples the next token from ctx->logits on the device (reference python/sampling.py:10-52 with the caller's uniform number u in
 // [0, 1) in place of numpy's RandomState draw); only the token id is copied back. Requires a preceding pass that computed logits.
 bool sample_token(Context * ctx, float temperature, float top_p, double u, const uint32_t * bias_ids, const float * bias_values, size_t n_bias, uint32_t * token_out);

@@ -3,6 +3,7 @@
 // v6 lerp, WKV5/6 step) restate glue.cu / wkv.cu for T = 1 with the same per-element operations and reduction trees.
 #include "decode_persistent.h"
 #include "gemv_tma_device.cuh"
+#include "decode_steps.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -11,8 +12,8 @@ namespace rwkv {
 namespace dp {
 
 using namespace tma;
+using namespace steps;
 
-constexpr int LN_MAXCH = 16;               // channels per consumer thread in the LayerNorm stage: n_embed <= 4096
 constexpr int LERP_MAXF4 = 2;              // float4 per lane per mix kept in registers across the barrier: mix <= 64
 constexpr size_t DYN_SMEM_BUDGET = 110 * 1024;   // + ~2 KB static: two CTAs per SM
 constexpr int PHASE_MARK_BASE = 1024, PHASE_MARK_MAX = 700;     // layout of the optional trace buffer (4096 u64)
@@ -25,12 +26,6 @@ struct LnLocal {
     const float * x, * ln_w, * ln_b, * state_in, * coef;
     float * state_out, * out_xx, * out_sx;
     int formula, C;
-};
-struct WkvStep {
-    const float * r, * k, * v, * td, * tf, * state_in, * lnx_w, * lnx_b, * g;
-    float * state_out, * y;
-    float eps;
-    int td_per_token, per_head_scalars, H, S;
 };
 struct LerpLocal {
     const float * w2, * z, * xx, * sx;
@@ -82,11 +77,6 @@ __host__ __device__ __forceinline__ int tiles_of(const GemvProblem & P, int loca
 // The per-channel parameters (LayerNorm weight and bias, the previous token's LN(x), the mixing vector) never change during the
 // launch: the first eight channels' worth is requested before the x loads and the reductions (LnRegs), the rest before the first
 // output is stored, so none of these loads is serialised behind a store it might alias.
-__device__ __forceinline__ double warp_tree_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 struct LnRegs { float w[8], b[8], pv[8], cf[8]; };
 __device__ __forceinline__ void ln_prefetch(const LnLocal & L, LnRegs & r, int m0) {
     const int t = threadIdx.x;
@@ -120,44 +110,12 @@ __device__ __forceinline__ void ln_emit(const LnLocal & L, const LnRegs & r, con
     }
 }
 __device__ __forceinline__ void ln_mix_stage(const LnLocal & L, float * tmp, double (* slots)[32], bool writer) {
-    const int C = L.C, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int C = L.C;
     LnRegs first;
     ln_prefetch(L, first, 0);            // in flight during the x loads and the two reductions
-    float xa[LN_MAXCH];                   // channel t + 256 m, m = q + 4 i  (virtual thread q, its i-th channel)
-    double sa[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int m = q + 4 * i, c = t + 256 * m;
-            xa[m] = (c < C) ? L.x[c] : 0.f;
-            sa[q] += (double) xa[m];
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const double r = warp_tree_d(sa[q]);
-        if (lane == 0) slots[0][warp + 8 * q] = r;
-    }
-    consumer_barrier();
-    const float mean_a = (float) (warp_tree_d(slots[0][lane]) / C);
-    double va[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int m = q + 4 * i, c = t + 256 * m;
-            xa[m] = (c < C) ? xa[m] - mean_a : 0.f;
-            va[q] += (double) (xa[m] * xa[m]);
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const double r = warp_tree_d(va[q]);
-        if (lane == 0) slots[1][warp + 8 * q] = r;
-    }
-    consumer_barrier();
-    const float scale_a = 1.0f / sqrtf((float) (warp_tree_d(slots[1][lane]) / C) + 1e-5f);
+    float xa[LN_MAXCH];                   // channel t + 256 m: centred x
+    float scale_a;
+    ln_center_scale_256(L.x, C, xa, scale_a, slots);
     if (C > 2048) {       // CTA-uniform
         LnRegs second;
         ln_prefetch(L, second, 8);
@@ -209,104 +167,6 @@ __device__ __forceinline__ void lerp_run(const LerpLocal & p, const LerpRegs & r
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         if (r.live && sub == 0) p.out[j][r.c] = __fadd_rn(__fmul_rn(__fadd_rn(acc, r.maa[j]), sx), xx);
-    }
-}
-
-// ---- one WKV5/6 step of head h + per-head norm + ln_x + gate (wkv6_kernel<S>, wkv.cu, for T = 1): thread (oct, jg) owns the
-// 8 x 4 state patch, partial outputs meet over the octants by the same xor-shuffles, warp 0 normalises the head.
-__device__ __forceinline__ void load8(const float * p, float (&o)[8]) {
-    const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
-    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
-}
-template <int S>
-__device__ void wkv6_step(const WkvStep & p, int h, float * ybuf) {
-    constexpr int NOCT = S / 8, NJG = S / 4, NT = NOCT * NJG, NW = (NT + 31) / 32, CPL = (S + 31) / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t hb = (size_t) h * S;
-    float lw[CPL], lb[CPL], gg[CPL];
-    if (warp == 0) {      // parameters of the normalisation, requested before the recurrence
-#pragma unroll
-        for (int i = 0; i < CPL; i++) {
-            const int col = lane + 32 * i;
-            lw[i] = col < S ? p.lnx_w[hb + col] : 0.f;
-            lb[i] = col < S ? p.lnx_b[hb + col] : 0.f;
-            gg[i] = (col < S && p.g) ? p.g[hb + col] : 0.f;
-        }
-    }
-    if (warp < NW) {
-        const bool worker = tid < NT;
-        const int oct = worker ? tid % NOCT : 0, jg = worker ? tid / NOCT : 0;
-        const int i0 = oct * 8, j0 = jg * 4;
-        float st[8][4], kk[8], rr[8], dv[8], tfr[8], vv[4];
-#pragma unroll
-        for (int ii = 0; ii < 8; ii++) {
-            const float4 v = *reinterpret_cast<const float4 *>(p.state_in + (hb + i0 + ii) * S + j0);
-            st[ii][0] = v.x; st[ii][1] = v.y; st[ii][2] = v.z; st[ii][3] = v.w;
-        }
-        load8(p.k + hb + i0, kk);
-        load8(p.r + hb + i0, rr);
-        if (p.per_head_scalars) {
-            const float tf = p.tf[h], td = p.td[h];
-#pragma unroll
-            for (int ii = 0; ii < 8; ii++) { tfr[ii] = tf; dv[ii] = td; }
-        } else {
-            load8(p.tf + hb + i0, tfr);
-            load8(p.td + hb + i0, dv);      // per token (v6) or per channel (v5.2): the same index for T = 1
-        }
-        {
-            const float4 g4 = *reinterpret_cast<const float4 *>(p.v + hb + j0);
-            vv[0] = g4.x; vv[1] = g4.y; vv[2] = g4.z; vv[3] = g4.w;
-        }
-        float y[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int ii = 0; ii < 8; ii++) {
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-                const float kv = __fmul_rn(vv[jj], kk[ii]);
-                const float temp = __fmaf_rn(kv, tfr[ii], st[ii][jj]);
-                y[jj] = __fmaf_rn(temp, rr[ii], y[jj]);
-                st[ii][jj] = __fmaf_rn(st[ii][jj], dv[ii], kv);
-            }
-        }
-#pragma unroll
-        for (int o = 1; o < NOCT; o <<= 1) {
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) y[jj] += __shfl_xor_sync(0xffffffffu, y[jj], o);
-        }
-        if (worker && oct == 0) *reinterpret_cast<float4 *>(&ybuf[j0]) = make_float4(y[0], y[1], y[2], y[3]);
-        if (worker) {
-#pragma unroll
-            for (int ii = 0; ii < 8; ii++)
-                *reinterpret_cast<float4 *>(p.state_out + (hb + i0 + ii) * S + j0) = make_float4(st[ii][0], st[ii][1], st[ii][2], st[ii][3]);
-        }
-    }
-    consumer_barrier();
-    if (warp == 0) {
-        float yv[CPL];
-        double s1 = 0, s2 = 0;
-#pragma unroll
-        for (int i = 0; i < CPL; i++) {
-            const int col = lane + 32 * i;
-            yv[i] = col < S ? ybuf[col] : 0.f;
-            s1 += (double) yv[i];
-            s2 += (double) yv[i] * (double) yv[i];
-        }
-        s1 = warp_tree_d(s1);
-        s2 = warp_tree_d(s2);
-        const double mean_d = s1 / S;
-        const float mean = (float) mean_d;
-        const float var = (float) fmax(s2 / S - mean_d * mean_d, 0.0);
-        const float rstd = 1.0f / sqrtf(var + p.eps);
-#pragma unroll
-        for (int i = 0; i < CPL; i++) {
-            const int col = lane + 32 * i;
-            if (col < S) {
-                float n = (yv[i] - mean) * rstd;
-                n = __fadd_rn(__fmul_rn(n, lw[i]), lb[i]);
-                if (p.g) n = __fmul_rn(n, gg[i]);
-                p.y[hb + col] = n;
-            }
-        }
     }
 }
 

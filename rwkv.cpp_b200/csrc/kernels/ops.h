@@ -93,6 +93,13 @@ struct Wkv7Params {
 };
 cudaError_t launch_wkv7(const Wkv7Params & p, cudaStream_t s);
 
+// Batched multi-sequence decode (batch.cu): the same stages with column t working on the recurrent state of sequence t, which
+// lives seq_stride floats after sequence t-1's (p.T = number of sequences; state pointers are sequence 0's).
+bool batch_shape_supported(int arch_major, int n_embed, int head_size);
+cudaError_t launch_ln_mix_batch(const LnMixParams & p, long long seq_stride, cudaStream_t s);
+cudaError_t launch_wkv6_batch(const Wkv6Params & p, long long seq_stride, cudaStream_t s);
+cudaError_t launch_wkv4_batch(const Wkv4Params & p, long long seq_stride, cudaStream_t s);
+
 // On-device sampling from the logits of the last evaluated token (reference python/sampling.py:10-52); see sampling.cu.
 struct SampleParams {
     const float * logits;             // [n_vocab] device

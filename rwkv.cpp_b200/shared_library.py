@@ -128,6 +128,18 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_phase_marks.restype = ctypes.c_int
         lib.rwkv_b200_plan_selftest.argtypes = [ctypes.c_int] * 11 + [ctypes.POINTER(ctypes.c_int)]
         lib.rwkv_b200_plan_selftest.restype = ctypes.c_int
+        lib.rwkv_b200_batch_create.argtypes = [vp, ctypes.c_size_t]
+        lib.rwkv_b200_batch_create.restype = vp
+        lib.rwkv_b200_batch_set_state.argtypes = [vp, ctypes.c_size_t, P_FLOAT]
+        lib.rwkv_b200_batch_set_state.restype = ctypes.c_bool
+        lib.rwkv_b200_batch_get_state.argtypes = [vp, ctypes.c_size_t, P_FLOAT]
+        lib.rwkv_b200_batch_get_state.restype = ctypes.c_bool
+        lib.rwkv_b200_batch_eval.argtypes = [vp, P_U32, ctypes.c_bool]
+        lib.rwkv_b200_batch_eval.restype = ctypes.c_bool
+        lib.rwkv_b200_batch_get_logits.argtypes = [vp, ctypes.c_size_t, P_FLOAT]
+        lib.rwkv_b200_batch_get_logits.restype = ctypes.c_bool
+        lib.rwkv_b200_batch_size.argtypes = [vp]
+        lib.rwkv_b200_batch_size.restype = ctypes.c_size_t
         lib.rwkv_b200_sample.argtypes = [vp, ctypes.c_float, ctypes.c_float, ctypes.c_double, P_U32, P_FLOAT, ctypes.c_size_t, P_U32]
         lib.rwkv_b200_sample.restype = ctypes.c_bool
         lib.rwkv_b200_sample_logits.argtypes = [P_FLOAT, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_double, P_U32, P_FLOAT, ctypes.c_size_t, P_U32, P_FLOAT]

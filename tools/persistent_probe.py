@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=6)
     ap.add_argument("--trace", action="store_true")
     ap.add_argument("--time", type=int, default=0, help="time this many resident decode steps on both paths")
+    ap.add_argument("--batch", type=int, default=0, help="time this many steps of batched multi-sequence decode for 2, 4, 8, 16 sequences")
     ap.add_argument("--e2e", type=int, default=0, help="time this many rwkv_eval calls with pinned host state for persistent x overlap")
     args = ap.parse_args()
     pkg = __graft_entry__.load_package()
@@ -100,6 +101,24 @@ def main():
                 dt = (time.perf_counter() - t0) / args.e2e * 1e3
                 print(f"e2e rwkv_eval, pinned host state, persistent={persistent} overlap={overlap}: {dt:.4f} ms/token ({1e3 / dt:.1f} tok/s)  checksum {float(lg.sum()):.6f}")
         L.rwkv_b200_set_overlap(ctx.ptr, False)
+    if args.batch:
+        for n_seq in (2, 4, 8, 16):
+            bptr = L.rwkv_b200_batch_create(ctx.ptr, n_seq)
+            if not bptr:
+                print(f"batch of {n_seq}: not supported for this model")
+                break
+            b = ctypes.c_void_p(bptr)
+            toks_b = (ctypes.c_uint32 * n_seq)(*[(7919 * i + 11) % n_logits for i in range(n_seq)])
+            for _ in range(3):
+                L.rwkv_b200_batch_eval(b, toks_b, True)
+            L.rwkv_b200_synchronize(b)
+            t0 = time.perf_counter()
+            for _ in range(args.batch):
+                L.rwkv_b200_batch_eval(b, toks_b, True)
+            L.rwkv_b200_synchronize(b)
+            dt = (time.perf_counter() - t0) / args.batch * 1e3
+            print(f"batched decode, {n_seq} sequences: {dt:.3f} ms/step, {n_seq / dt * 1e3:.0f} tok/s aggregate")
+            L.rwkv_free(b)
     if args.trace:
         L.rwkv_b200_set_persistent(ctx.ptr, True)
         buf = (ctypes.c_double * 4096)()
