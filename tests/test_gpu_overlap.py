@@ -41,7 +41,7 @@ def test_overlapped_copies_bitwise(lib, ver, fmt):
         n_state, n_logits = lib.rwkv_get_state_buffer_element_count(ctx), lib.rwkv_get_logits_buffer_element_count(ctx)
         toks = LONG_PROMPT[:20]
         want = run(lib, ctx, toks, False, False, n_state, n_logits)
-        for skip in (False, True):      # (the persistent kernel x overlap combination is checked out of process, test_gpu_persistent.py)
+        for skip in (False, True):      # (the persistent kernel x overlap combination is checked out of process, test_zz_gpu_persistent.py)
             got = run(lib, ctx, toks, True, False, n_state, n_logits, skip_logits=skip)
             assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes(), (ver, fmt, skip)
         want_seq = run(lib, ctx, toks, False, False, n_state, n_logits, seq=7)
