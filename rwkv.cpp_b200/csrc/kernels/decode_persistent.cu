@@ -6,6 +6,7 @@
 #include "decode_steps.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace rwkv {
@@ -171,10 +172,11 @@ __device__ __forceinline__ void lerp_run(const LerpLocal & p, const LerpRegs & r
 }
 
 // ---- the GEMV of a phase on this CTA's tiles: stage the (single) activation column, then the unchanged consumers
+template <bool STAGE_V2>
 __device__ void run_gemv(Shared & sh, uint8_t * ring, uint32_t stage_bytes, uint8_t * act, float * red, int it0, int local, int my_tiles, unsigned long long * marks) {
     const GemvProblem & P = sh.P;
     if (marks && threadIdx.x == 0) marks[0] = global_timer();      // stage inputs ready (LayerNorm / nothing done)
-    stage_column<8>(P, 0, act, sh.red_d);
+    stage_column<8, STAGE_V2>(P, 0, act, sh.red_d);
     consumer_barrier();
     if (marks && threadIdx.x == 0) marks[1] = global_timer();      // activation column staged
     const size_t colb = act_bytes_per_column(P.type, P.K);
@@ -194,6 +196,7 @@ __device__ void run_gemv(Shared & sh, uint8_t * ring, uint32_t stage_bytes, uint
     if (marks && threadIdx.x == 0) marks[2] = global_timer();      // this CTA's tiles consumed
 }
 
+template <bool STAGE_V2>       // experimental per-block activation staging (RWKV_B200_STAGE_V2=1), see gemv_tma_device.cuh
 __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Args a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ Shared sh;
@@ -285,14 +288,14 @@ __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Arg
                 if (active) {
                     ln_mix_stage(R.u.ln, tmp, slots, blockIdx.x == 0);
                     consumer_barrier();
-                    run_gemv(sh, ring, stage_bytes, act, red, it, local, my_tiles, marks);
+                    run_gemv<STAGE_V2>(sh, ring, stage_bytes, act, red, it, local, my_tiles, marks);
                 }
                 break;
             case DOP_LERP:
                 lerp_run(R.u.lerp, lr, tmp);
                 break;
             case DOP_GEMV_WKV: {
-                if (active) run_gemv(sh, ring, stage_bytes, act, red, it, local, my_tiles, marks);
+                if (active) run_gemv<STAGE_V2>(sh, ring, stage_bytes, act, red, it, local, my_tiles, marks);
                 const int h = R.head;
                 if (h >= 0) {
                     consumer_barrier();     // the head's decay values just stored by this CTA are visible to all its threads
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Arg
                 break;
             }
             default:
-                if (active) run_gemv(sh, ring, stage_bytes, act, red, it, local, my_tiles, marks);
+                if (active) run_gemv<STAGE_V2>(sh, ring, stage_bytes, act, red, it, local, my_tiles, marks);
                 break;
         }
         it += my_tiles;
@@ -318,6 +321,11 @@ __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Arg
 
 // ---- host side ----------------------------------------------------------------------------------------------------
 bool gemv_tma_plan(GemvBatch & batch, int total_ctas, long long stage_bytes, size_t * max_col_bytes);   // gemv_tma.cu
+
+static bool stage_v2_enabled() {
+    static const bool on = [] { const char * e = getenv("RWKV_B200_STAGE_V2"); return e && atoi(e) != 0; }();
+    return on;
+}
 
 void decode_program_free(DecodeProgram & program) {
     if (program.records) cudaFree(program.records);
@@ -548,12 +556,15 @@ bool decode_program_build(std::vector<DecodePhase> & phases, const DeviceInfo & 
     cudaGetDevice(&cur_dev);
     cur_dev = (cur_dev < 0 || cur_dev >= 64) ? 0 : cur_dev;
     if (!attr_set_dev[cur_dev]) {
-        if (cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) DYN_SMEM_BUDGET) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (cudaFuncSetAttribute(decode_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) DYN_SMEM_BUDGET) != cudaSuccess ||
+            cudaFuncSetAttribute(decode_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) DYN_SMEM_BUDGET) != cudaSuccess) { cudaGetLastError(); return false; }
         attr_set_dev[cur_dev] = true;
     }
-    int per_sm = 0, coop = 0;
+    int per_sm = 0, per_sm_v2 = 0, coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cur_dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persistent_kernel, tma::THREADS, program.smem_bytes) != cudaSuccess || per_sm < 2 || !coop) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_v2, decode_persistent_kernel<true>, tma::THREADS, program.smem_bytes) != cudaSuccess) per_sm_v2 = 0;
+    if (stage_v2_enabled() && per_sm_v2 < 2) { cudaGetLastError(); program = DecodeProgram(); return false; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persistent_kernel<false>, tma::THREADS, program.smem_bytes) != cudaSuccess || per_sm < 2 || !coop) {
         cudaGetLastError();
         fprintf(stderr, "rwkv_b200: the persistent decode kernel cannot keep 2 CTAs per SM resident (%d, cooperative launch %d); using the per-launch path\n", per_sm, coop);
         program = DecodeProgram();
@@ -586,8 +597,8 @@ cudaError_t decode_program_launch(const DecodeProgram & program, unsigned long l
     a.trace = trace;
     void * args[] = {&a};
     g_kernel_launches++;
-    return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(dp::decode_persistent_kernel), dim3((unsigned) program.grid), dim3(tma::THREADS), args,
-                                       program.smem_bytes, stream);
+    const void * kernel = stage_v2_enabled() ? reinterpret_cast<const void *>(dp::decode_persistent_kernel<true>) : reinterpret_cast<const void *>(dp::decode_persistent_kernel<false>);
+    return cudaLaunchCooperativeKernel(kernel, dim3((unsigned) program.grid), dim3(tma::THREADS), args, program.smem_bytes, stream);
 }
 
 }  // namespace rwkv

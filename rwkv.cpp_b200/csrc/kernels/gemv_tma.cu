@@ -20,10 +20,12 @@
 // evaluated alone and inside a chunk therefore produces identical bits (tests/test_eval_sequence_in_chunks.c:54).
 #include "gemv_tma_device.cuh"
 
+#include <cstdlib>
+
 namespace rwkv {
 namespace tma {
 
-template <int NC>
+template <int NC, bool STAGE_V2 = false>
 __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch batch) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ Shared sh;
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch ba
     for (int g = 0; g < n_groups; g++) {
         const int c0 = g * NC, nc = min(NC, batch.T - c0);
         if (g > 0) consumer_barrier();   // everyone finished reading the previous group's activations
-        for (int c = 0; c < nc; c++) stage_column(P, c0 + c, act + c * colb, sh.red_d);
+        for (int c = 0; c < nc; c++) stage_column<4, STAGE_V2>(P, c0 + c, act + c * colb, sh.red_d);
         consumer_barrier();
         trace_mark(batch.trace, 1);
         const int it0 = g * my_tiles;
@@ -145,15 +147,20 @@ bool plan_wk(GemvProblem & p) {
     return false;
 }
 
-template <int NC>
+template <int NC, bool STAGE_V2 = false>
 cudaError_t launch_tma_nc(const GemvBatch & batch, int grid, size_t smem, cudaStream_t stream) {
+    if constexpr (NC == 1 && !STAGE_V2) {
+        // experimental: single-column launches with the per-block activation staging (gemv_tma_device.cuh: stage_column PER_BLOCK)
+        static const bool stage_v2 = [] { const char * e = getenv("RWKV_B200_STAGE_V2"); return e && atoi(e) != 0; }();
+        if (stage_v2) return launch_tma_nc<1, true>(batch, grid, smem, stream);
+    }
     static bool attr_set_dev[64] = {};       // the shared-memory opt-in is per device
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     cur_dev = (cur_dev < 0 || cur_dev >= 64) ? 0 : cur_dev;
     bool & attr_set = attr_set_dev[cur_dev];
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tma::gemv_tma_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::CTA_SMEM_BUDGET);
+        cudaError_t e = cudaFuncSetAttribute(tma::gemv_tma_kernel<NC, STAGE_V2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::CTA_SMEM_BUDGET);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -168,7 +175,7 @@ cudaError_t launch_tma_nc(const GemvBatch & batch, int grid, size_t smem, cudaSt
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 1 : 0;
     g_kernel_launches++;
-    return cudaLaunchKernelEx(&cfg, tma::gemv_tma_kernel<NC>, batch);
+    return cudaLaunchKernelEx(&cfg, tma::gemv_tma_kernel<NC, STAGE_V2>, batch);
 }
 
 }  // namespace

@@ -180,7 +180,11 @@ template <int TYPE> __device__ __forceinline__ void load_unit(const uint8_t * ro
 // would multiply with (ggml-cpu.c:253-311 `vec_dot_type`): Q8_0 / Q8_1 blocks for quantised weights (x86 flavour of
 // quantize_row_q8_0 / q8_1, ggml-cpu-quants.c:781-846, 1085-1160; one thread per 32-element block), fp16 for F16
 // weights, fp32 for F32 weights. PRO_LAYERNORM applies rwkv_layer_norm (rwkv_operators.inc:93-97) on the fly.
-template <int UNR = 4>     // float4 loads a thread keeps in flight per round of the quantising loop
+// PER_BLOCK (experimental, RWKV_B200_STAGE_V2=1): one thread quantises a whole 32-element block instead of 8 lanes sharing it --
+// the two IEEE divisions, the scale and the sums once per 32 elements instead of once per 4, no shuffles; ~4x fewer instructions for
+// a stage that is instruction-bound. The staged bytes are identical: the maximum and the integer sum of a block do
+// not depend on the order they are taken in.
+template <int UNR = 4, bool PER_BLOCK = false>     // UNR: float4 loads a thread keeps in flight per round of the quantising loop
 static __device__ void stage_column(const GemvProblem & P, int col_index, uint8_t * col, double * red_d) {
     const int K = P.K, tid = threadIdx.x;
     const float * x = P.x + (long long) col_index * P.ldx;
@@ -216,10 +220,53 @@ static __device__ void stage_column(const GemvProblem & P, int col_index, uint8_
         __half * d = reinterpret_cast<__half *>(col);
         for (int k = tid; k < K; k += CONSUMER_THREADS) d[k] = __float2half_rn(norm(x[k], k));
     } else {
-        // 8 lanes per 32-element block, one float4 each: coalesced loads, amax / sum over the 8 lanes by shuffles
         const bool has_min = (P.type == DT_Q4_1 || P.type == DT_Q5_1);
         const int UB = has_min ? 1 : 2;
         const int nblk = K / 32, nunits = (nblk + UB - 1) / UB;
+        if constexpr (PER_BLOCK) {
+            // two blocks per thread and round (threads tid and tid + 256 blocks apart), all 16 float4 loads issued before the first use
+            for (int blk0 = tid; blk0 < nblk; blk0 += 2 * CONSUMER_THREADS) {
+                float4 v[2][8];
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const int blk = blk0 + r * CONSUMER_THREADS;
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        v[r][j] = (blk < nblk) ? *reinterpret_cast<const float4 *>(x + (size_t) blk * 32 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const int blk = blk0 + r * CONSUMER_THREADS;
+                    if (blk >= nblk) break;
+                    float amax = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float4 & t = v[r][j];
+                        if (ln) { const int k = blk * 32 + j * 4; t.x = norm(t.x, k); t.y = norm(t.y, k + 1); t.z = norm(t.z, k + 2); t.w = norm(t.w, k + 3); }
+                        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+                    }
+                    const float d32 = amax / 127.0f;
+                    const float id = (amax != 0.0f) ? 127.0f / amax : 0.0f;
+                    int isum = 0, words[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 t = v[r][j];
+                        const int q0 = __float2int_rn(t.x * id), q1 = __float2int_rn(t.y * id), q2 = __float2int_rn(t.z * id), q3 = __float2int_rn(t.w * id);
+                        isum += q0 + q1 + q2 + q3;
+                        words[j] = (q0 & 0xFF) | ((q1 & 0xFF) << 8) | ((q2 & 0xFF) << 16) | ((q3 & 0xFF) << 24);
+                    }
+                    const int u = blk / UB, bi = blk % UB;
+                    *reinterpret_cast<int4 *>(col + ((size_t) (bi * 2 + 0) * nunits + u) * 16) = make_int4(words[0], words[1], words[2], words[3]);
+                    *reinterpret_cast<int4 *>(col + ((size_t) (bi * 2 + 1) * nunits + u) * 16) = make_int4(words[4], words[5], words[6], words[7]);
+                    ActScale a;
+                    a.d = round_to_half(d32);
+                    a.s = has_min ? round_to_half(d32 * (float) isum) : (float) isum;
+                    *reinterpret_cast<ActScale *>(col + (size_t) nunits * UB * 32 + ((size_t) bi * nunits + u) * 8) = a;
+                }
+            }
+            return;
+        }
+        // 8 lanes per 32-element block, one float4 each: coalesced loads, amax / sum over the 8 lanes by shuffles
         const int sub = tid & 7;
         // loads of UNR iterations are issued together: the loop is L2-latency bound, not math bound
         const int kpad = (K + 127) & ~127;
