@@ -64,6 +64,11 @@ __device__ __forceinline__ unsigned long long global_timer() {
 __device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void * p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// `bytes` of immutable data starting at p (128-byte aligned) -> L2, spread over the 256 consumer threads
+__device__ __forceinline__ void prefetch_l2_span(const void * p, int bytes) {
+    for (int off = (int) threadIdx.x * 128; off < bytes; off += CONSUMER_THREADS * 128) prefetch_l2(reinterpret_cast<const uint8_t *>(p) + off);
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -196,7 +201,10 @@ __device__ void run_gemv(Shared & sh, uint8_t * ring, uint32_t stage_bytes, uint
     if (marks && threadIdx.x == 0) marks[2] = global_timer();      // this CTA's tiles consumed
 }
 
-template <bool STAGE_V2>       // experimental per-block activation staging (RWKV_B200_STAGE_V2=1), see gemv_tma_device.cuh
+// STAGE_V2 = the experimental bundle selected by RWKV_B200_STAGE_V2=1 (written after the last GPU run of round 1, not yet executed):
+// per-block activation staging (gemv_tma_device.cuh), red.release arrival without separate fences, L2 prefetch of the LayerNorm
+// parameters and the WKV state while waiting in the barrier. The <false> instantiation is the validated kernel, SASS-identical.
+template <bool STAGE_V2>
 __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Args a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ Shared sh;
@@ -254,7 +262,10 @@ __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Arg
         // (1) this phase's record has landed; the previous phase is complete on this CTA: arrive at the grid barrier
         cp_async_wait_all();
         consumer_barrier();
-        if (ph > 0 && tid == 0) { __threadfence(); atomicAdd(a.bar, 1ull); }
+        if (ph > 0 && tid == 0) {
+            if constexpr (STAGE_V2) asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(a.bar) : "memory");     // 1.65 vs 1.95 us per barrier (microbench)
+            else { __threadfence(); atomicAdd(a.bar, 1ull); }
+        }
         const CtaPhase & R = rec[ph & 1];
         const int op = R.op, active = R.active, local = R.local, my_tiles = R.my_tiles;
         // (2) work that needs nothing from the previous phase: the next record, immutable operands of this phase's stage
@@ -263,6 +274,20 @@ __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Arg
         cp_async_commit();
         LerpRegs lr;
         if (op == DOP_LERP) lerp_prefetch(R.u.lerp, lr);
+        if constexpr (STAGE_V2) {
+            // immutable operands of this phase's stage, requested into L2 while the CTA waits for the others: by the time a layer
+            // comes round again its small vectors have been flushed by the 165 MB of weights streamed in between
+            if (op == DOP_LNMIX_GEMV && active) {
+                const LnLocal & L = R.u.ln;
+                prefetch_l2_span(L.ln_w, L.C * 4); prefetch_l2_span(L.ln_b, L.C * 4);
+                prefetch_l2_span(L.coef, L.C * 4); prefetch_l2_span(L.state_in, L.C * 4);
+            } else if (op == DOP_GEMV_WKV && R.head >= 0) {
+                const WkvStep & w = R.u.wkv;
+                const size_t hb = (size_t) R.head * w.S;
+                prefetch_l2_span(w.state_in + hb * w.S, w.S * w.S * 4);
+                if (tid < 2) prefetch_l2((tid == 0 ? w.lnx_w : w.lnx_b) + hb);
+            }
+        }
         // (3) wait for every CTA
         if (tid == 0) {
             if (active) {
@@ -276,7 +301,7 @@ __global__ void __launch_bounds__(THREADS, 2) decode_persistent_kernel(const Arg
                 while (ld_acquire_u64(a.bar) < target) {
                     if ((++spins & 0x3FFu) == 0 && clock64() - t0 > GUARD_CYCLES) __trap();
                 }
-                __threadfence();
+                if constexpr (!STAGE_V2) __threadfence();      // the acquire load above already orders everything after it
             }
             if (a.trace && blockIdx.x == 0) a.trace[ph] = global_timer();
         }
