@@ -38,7 +38,10 @@ def eval_serial(lib, ctx, toks, n_state, n_logits, logits_every=1):
     return logits, state
 
 
-@pytest.mark.parametrize("preset,fmt", [("rwkv4-169m", "Q5_1"), ("rwkv5-1b5", "Q4_0")])
+@pytest.mark.parametrize("preset,fmt", [
+    ("rwkv4-169m", "Q5_1"), ("rwkv5-1b5", "Q4_0"),       # BASELINE.json configs 1 and 2: green on B200 in round 1
+    pytest.param("rwkv7-2b9", "FP16", marks=pytest.mark.xfail(strict=False, reason="config 3 (5.8 GB synthetic file): added after round 1's last GPU run, not yet executed")),
+])
 def test_full_shape_invariants(lib, synth, preset, fmt):
     import synthetic_model as sm
     ctx = lib.rwkv_init_from_file(synth(preset, fmt), 1, 0)
