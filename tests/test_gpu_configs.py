@@ -5,6 +5,7 @@ alone, a clone continues identically; plus the engine's own invariants at these 
 and the tensor-core prefill path stays close to the batch-invariant one (the persistent kernel is checked out of process in
 tests/test_zz_gpu_persistent.py)."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -40,7 +41,9 @@ def eval_serial(lib, ctx, toks, n_state, n_logits, logits_every=1):
 
 @pytest.mark.parametrize("preset,fmt", [
     ("rwkv4-169m", "Q5_1"), ("rwkv5-1b5", "Q4_0"),       # BASELINE.json configs 1 and 2: green on B200 in round 1
-    pytest.param("rwkv7-2b9", "FP16", marks=pytest.mark.xfail(strict=False, reason="config 3 (5.8 GB synthetic file): added after round 1's last GPU run, not yet executed")),
+    # config 3 (5.8 GB synthetic file) was added after round 1's last GPU run: until it has been seen green it only runs in a child
+    # process (tests/test_zz_gpu_persistent.py sets RWKV_RUN_UNVALIDATED=1), where a fault cannot take the suite's CUDA context along
+    pytest.param("rwkv7-2b9", "FP16", marks=pytest.mark.skipif(os.environ.get("RWKV_RUN_UNVALIDATED") != "1", reason="not yet validated on a GPU; runs out of process")),
 ])
 def test_full_shape_invariants(lib, synth, preset, fmt):
     import synthetic_model as sm
