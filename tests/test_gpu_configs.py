@@ -82,7 +82,7 @@ def test_full_shape_invariants(lib, synth, preset, fmt):
         lib.rwkv_free(ctx)
 
 
-@pytest.mark.xfail(strict=False, reason="tolerance not yet calibrated on a GPU: the round's last GPU run lost its CUDA context to an earlier test before reaching this one")
+@pytest.mark.skipif(os.environ.get("RWKV_RUN_UNVALIDATED") != "1", reason="not yet validated on a GPU (round 1's last run lost its CUDA context before reaching it); runs out of process")
 def test_prefill_chunk_128_tensor_core_path_close_to_serial(lib, synth):
     """Config 2 of BASELINE.json: RWKV-5-World-1.5B shape, Q4_0, one 128-token chunk. The tcgen05 path multiplies fp16-rounded
     activations (the reference multiplies int8-quantised ones), so it is compared with the batch-invariant path with a tolerance;
