@@ -902,7 +902,6 @@ int plan_selftest(int arch_major, int arch_minor, int type, int C, int F, int V,
     }
     m.head = mat(type == DT_F32 ? DT_F32 : DT_F16, C, V);
     m.ln_out_w = vec(C); m.ln_out_b = vec(C);
-    std::vector<float> dummy(1);
     float * base = reinterpret_cast<float *>((uintptr_t) 1 << 40);
     const Scratch s = carve(m, base, 1);
     const size_t per_layer = m.state_floats_per_layer();
