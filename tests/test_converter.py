@@ -57,3 +57,19 @@ def test_architecture_detection_and_errors(converter, tmp_path):
         converter.write_state_dict(sc.make_state_dict("v4"), str(tmp_path / "x.bin"), "Q5_1")
     with pytest.raises(ValueError):
         converter.count_layers({"emb.weight": None})
+
+
+def test_reference_known_answer_bytes(converter, tmp_path):
+    """The known-answer vector of the reference's own converter test (python/convert_pytorch_to_ggml.test.py:11-48): a 3 x 2 embedding
+    and one 1-element LayerNorm weight must serialise to exactly these bytes."""
+    import struct
+    import torch
+    state_dict = {"emb.weight": torch.tensor([[1, 2], [3, 4], [5, 6]], dtype=torch.float32),
+                  "blocks.0.ln1.weight": torch.tensor([1], dtype=torch.float32)}
+    path = str(tmp_path / "known.bin")
+    converter.write_state_dict(state_dict, dest_path=path, data_type="FP32")
+    expected = struct.pack("=iiiiii" + "iiiii10sffffff" + "iiii19sf",
+                           0x67676D66, 101, 3, 2, 1, 0,
+                           2, 10, 0, 2, 3, b"emb.weight", 1.0, 2.0, 3.0, 4.0, 5.0, 6.0,
+                           1, 19, 0, 1, b"blocks.0.ln1.weight", 1.0)
+    assert open(path, "rb").read() == expected
