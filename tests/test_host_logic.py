@@ -214,3 +214,15 @@ def test_persistent_decode_planner(lib, name, shape, expect):
                 assert phases == per_layer * shape[-1] + 1
                 assert smem == 3 * stage + region + 4096 and smem <= 110 * 1024 and stage >= 16 * 1024
     assert lib.library.rwkv_b200_plan_selftest(4, 0, DT["Q5_1"], 768, 3072, 50277, 64, 0, 0, 12, 148, None) == -1   # v4: not built
+
+
+def test_quantize_cli_matches_library_call(lib, tmp_path):
+    """rwkv.cpp_b200/quantize.py (the reference's python/quantize.py CLI) writes the file the library call writes."""
+    src = model_path("5v2-730K", "FP16")
+    a, b = tmp_path / "cli.bin", tmp_path / "lib.bin"
+    r = subprocess.run([os.sys.executable, os.path.join(ROOT, "rwkv.cpp_b200", "quantize.py"), src, str(a), "Q4_1"], capture_output=True, text=True)
+    assert r.returncode == 0 and "Done" in r.stdout, r.stderr[-500:]
+    lib.rwkv_quantize_model_file(src, str(b), "Q4_1")
+    assert a.read_bytes() == b.read_bytes()
+    r = subprocess.run([os.sys.executable, os.path.join(ROOT, "rwkv.cpp_b200", "quantize.py"), src, str(a), "Q9_9"], capture_output=True, text=True)
+    assert r.returncode != 0
