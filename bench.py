@@ -45,7 +45,14 @@ def parse_args():
     ap.add_argument("--workload", default="rwkv6-7b:Q5_1", help="<preset>:<format>, presets in tools/synthetic_model.py")
     ap.add_argument("--prefill-steps", type=int, default=8)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-budget-s", type=float, default=25.0, help="CPU seconds the bounded reference sample may take per leg")
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="CPU seconds the bounded reference sample may take per leg")
+    ap.add_argument("--mode", default="decode", choices=["decode", "prefill"],
+                    help="headline metric: single-token decode tokens/s (default) or 128-token-chunk prefill tokens/s (one step = one chunk)")
+    # internal: the reference library only ever runs in child processes (hard timeouts), see cpu_reference_leg
+    ap.add_argument("--ref-child", default=None, choices=["probe", "full"], help=argparse.SUPPRESS)
+    ap.add_argument("--ref-threads", default="8", help=argparse.SUPPRESS)
+    ap.add_argument("--workload-path", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--no-prefill", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -102,27 +109,36 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def host_buffers(n_state, n_logits):
-    """Pinned host buffers for the e2e leg (what a serving process would hold); falls back to pageable numpy."""
-    try:
-        import torch
-        if torch.cuda.is_available():
-            s = torch.zeros(n_state, dtype=torch.float32).pin_memory()
-            l = torch.zeros(n_logits, dtype=torch.float32).pin_memory()
-            return s, l, s.data_ptr(), l.data_ptr(), "pinned"
-    except Exception:
-        pass
+def host_buffers(n_state, n_logits, kind="pinned"):
+    """Host state / logits buffers for the e2e legs: pinned (what a serving process would hold) or pageable numpy arrays (what the
+    reference's Python binding passes, rwkv_cpp_model.py:330-351)."""
+    if kind == "pinned":
+        try:
+            import torch
+            if torch.cuda.is_available():
+                s = torch.zeros(n_state, dtype=torch.float32).pin_memory()
+                l = torch.zeros(n_logits, dtype=torch.float32).pin_memory()
+                return s, l, s.data_ptr(), l.data_ptr(), "pinned"
+        except Exception:
+            pass
     s, l = np.zeros(n_state, np.float32), np.zeros(n_logits, np.float32)
     return s, l, s.ctypes.data, l.ctypes.data, "pageable"
 
 
 def prefill_matmul_flops(preset, n_tokens):
-    """FLOPs of the weight contractions of one chunk (2 * weights * tokens), per-layer matrices only; None for shapes not modelled."""
-    if preset.get("arch", (0, 0))[0] != 6:
-        return None
-    C, F, Lr, mix, dec = preset["C"], preset["F"], preset["L"], preset["mix"], preset["decay"]
-    per_layer = 5 * C * C + C * 5 * mix + 5 * mix * C + 2 * C * dec + 2 * C * F + C * C
-    return 2.0 * per_layer * Lr * n_tokens
+    """FLOPs of the weight contractions of one chunk: 2 * (elements of every per-layer matrix) * tokens (+ the head, one token)."""
+    major, minor = preset["arch"]
+    C, F, Lr, V = preset["C"], preset["F"], preset["L"], preset["V"]
+    if major == 4:
+        per_layer = 4 * C * C + 2 * C * F + C * C
+    elif major == 5:
+        per_layer = (5 if minor >= 2 else 4) * C * C + 2 * C * F + C * C
+    elif major == 6:
+        mix, dec = preset["mix"], preset["decay"]
+        per_layer = 5 * C * C + C * 5 * mix + 5 * mix * C + 2 * C * dec + 2 * C * F + C * C
+    else:
+        per_layer = 4 * C * C + 2 * C * (preset["lora_w"] + preset["lora_a"] + preset["lora_v"] + preset["lora_g"]) + 2 * C * F
+    return 2.0 * per_layer * Lr * n_tokens + 2.0 * C * V
 
 
 def measured_tensor_peak():
@@ -155,70 +171,192 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_timeline(L, ctx, tok_arr, T=1, passes=6, skip=3):
+    """One decode step as the kernels see it: every kernel folds %globaltimer of its CTAs into a [start, end] record (works inside
+    CUDA-graph replays). Returns the traced span and the critical-path attribution per kernel family: a kernel is charged the time by
+    which it pushed the end of the timeline out, so the shares add up to the span exactly."""
+    N = 1024
+    st, en = (ctypes.c_double * N)(), (ctypes.c_double * N)()
+    names = ctypes.create_string_buffer(32 * N)
+    L.rwkv_b200_state_load(ctx.ptr, None)
+    if not L.rwkv_b200_trace_enable(ctx.ptr):
+        return {"span_us": 0.0, "attributed_us": {}, "busy_us": {}, "launches": {}}
+    best = None
+    for i in range(passes):                    # eager, eager, capture, replay ... : keep the shortest replayed step
+        L.rwkv_b200_eval_resident(ctx.ptr, ctypes.cast(ctypes.byref(tok_arr, 4 * i * T), PU), T, True, None)
+        n = L.rwkv_b200_trace_read(ctx.ptr, st, en, ctypes.cast(names, ctypes.c_void_p), N)
+        if i < skip or n <= 0:
+            continue
+        rows = [(names.raw[32 * j:32 * j + 32].split(b"\0")[0].decode(), st[j], en[j]) for j in range(n)]
+        t_begin, t_end = min(r[1] for r in rows), max(r[2] for r in rows)
+        att, busy, cnt, pe = {}, {}, {}, t_begin
+        for nm, s_, e_ in rows:
+            fam = "gemv" if nm.startswith("gemv") else ("gemm_tc" if nm.startswith("gemm_tc") else nm)
+            cnt[fam] = cnt.get(fam, 0) + 1
+            busy[fam] = busy.get(fam, 0.0) + (e_ - s_)
+            if e_ > pe:
+                att[fam] = att.get(fam, 0.0) + (e_ - pe)
+                pe = e_
+        cur = {"span_us": t_end - t_begin, "attributed_us": att, "busy_us": busy, "launches": cnt}
+        if best is None or cur["span_us"] < best["span_us"]:
+            best = cur
+    L.rwkv_b200_trace_disable(ctx.ptr)
+    return best or {"span_us": 0.0, "attributed_us": {}, "busy_us": {}, "launches": {}}
+
+
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_leg(path, preset, n_decode, budget_s, want_prefill=True):
-    """Times the unmodified reference (oracle/_ref) on the host cores: bounded sample of the same workload."""
+def physical_cores():
+    """Distinct (socket, core) pairs among the CPUs this process may run on (hyper-threads counted once)."""
+    allowed = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else set(range(os.cpu_count() or 1))
+    seen, cpu, phys = set(), None, "0"
+    try:
+        for line in open("/proc/cpuinfo"):
+            k, _, v = line.partition(":")
+            k = k.strip()
+            if k == "processor":
+                cpu = int(v)
+            elif k == "physical id":
+                phys = v.strip()
+            elif k == "core id" and cpu in allowed:
+                seen.add((phys, v.strip()))
+    except (OSError, ValueError):
+        pass
+    return len(seen) or len(allowed)
+
+
+def reference_thread_candidates():
+    """ggml's spin barriers collapse when oversubscribed (round 1: 128 threads on the 8-GPU node never returned), so the
+    reference is never given more threads than min(32, cgroup quota / affinity, physical cores)."""
+    if "RWKV_REF_THREADS" in os.environ:
+        return [int(os.environ["RWKV_REF_THREADS"])]
+    cap = max(1, min(32, available_cpus(), physical_cores()))
+    return sorted({max(1, min(cap, c)) for c in (8, 16, 32)})
+
+
+def _ref_bind(path, threads):
     import ref_lib
-    import synthetic_model as sm
     ref = ref_lib.load_reference_library()
     ref.rwkv_set_print_errors(None, False)
-    cores = available_cpus()
-    load_s = 0.0
-    if "RWKV_REF_THREADS" in os.environ:
-        candidates = [int(os.environ["RWKV_REF_THREADS"])]
-    else:   # ggml's spin barriers collapse when oversubscribed: probe a few counts, keep the fastest
-        candidates = sorted({max(1, min(cores, c)) for c in (8, 16, 32, 64, cores)})
-    best = None
+    t0 = time.time()
+    ctx = ref.rwkv_init_from_file(path.encode(), threads, 0)
+    if not ctx:
+        raise RuntimeError("reference failed to load " + path)
+    return ref, ctx, time.time() - t0, os.path.basename(ref_lib.reference_library_path())
+
+
+def ref_child_probe(path, candidates):
+    """Child process: loads the model ONCE, then one clone per candidate thread count (rwkv_clone_context takes n_threads,
+    rwkv.h:80), 1 warm + 2 timed tokens each; one JSON line per candidate as soon as it is known, so a candidate that
+    hangs costs the parent only its own timeout."""
+    ref, ctx, load_s, _ = _ref_bind(path, candidates[0])
+    n_state, n_vocab = ref.rwkv_get_state_len(ctx), ref.rwkv_get_logits_len(ctx)
+    st, lg = np.zeros(n_state, np.float32), np.zeros(n_vocab, np.float32)
+    sp, lp = st.ctypes.data_as(PF), lg.ctypes.data_as(PF)
+    emit({"loaded": True, "load_s": load_s})
     for th in candidates:
-        t0 = time.time()
-        c = ref.rwkv_init_from_file(path.encode(), th, 0)
-        if not c:
-            raise RuntimeError("reference failed to load " + path)
-        load_s = time.time() - t0
-        n_state, n_vocab = ref.rwkv_get_state_len(c), ref.rwkv_get_logits_len(c)
-        st, lg = np.zeros(n_state, np.float32), np.zeros(n_vocab, np.float32)
-        ref.rwkv_init_state(c, st.ctypes.data_as(PF))
-        ref.rwkv_eval(c, 1, st.ctypes.data_as(PF), st.ctypes.data_as(PF), lg.ctypes.data_as(PF))
+        c = ref.rwkv_clone_context(ctx, th)
+        ref.rwkv_init_state(c, sp)
+        ref.rwkv_eval(c, 1, sp, sp, lp)
         t0 = time.perf_counter()
         for t in (2, 3):
-            ref.rwkv_eval(c, t, st.ctypes.data_as(PF), st.ctypes.data_as(PF), lg.ctypes.data_as(PF))
-        dt = (time.perf_counter() - t0) / 2
-        log("reference probe: %d threads -> %.1f ms/token" % (th, dt * 1e3))
+            ref.rwkv_eval(c, t, sp, sp, lp)
+        emit({"threads": th, "ms": (time.perf_counter() - t0) / 2 * 1e3})
         ref.rwkv_free(c)
-        if best is None or dt < best[1]:
-            best = (th, dt)
-        if dt > 4 * best[1]:
-            break
-    threads = best[0]
-    ctx = ref.rwkv_init_from_file(path.encode(), threads, 0)
+    ref.rwkv_free(ctx)
+
+
+def ref_child_full(path, threads, steps, warmup, budget_s, want_prefill):
+    """Child process: `warmup` untimed + up to `steps` timed rwkv_eval calls (bounded by budget_s of CPU time), then one
+    128-token chunk after one warm-up chunk when that fits the budget."""
+    import synthetic_model as sm
+    ref, ctx, load_s, libname = _ref_bind(path, threads)
     n_state, n_vocab = ref.rwkv_get_state_len(ctx), ref.rwkv_get_logits_len(ctx)
     state, logits = np.zeros(n_state, np.float32), np.zeros(n_vocab, np.float32)
     ref.rwkv_init_state(ctx, state.ctypes.data_as(PF))
     toks = sm.synthetic_tokens(4096, n_vocab)
     sp, lp = state.ctypes.data_as(PF), logits.ctypes.data_as(PF)
-    # warm-up (2 tokens: first call builds the scheduler) and a probe to size the sample
+    warmup = max(2, warmup)                      # the first call builds the scheduler
     t0 = time.time()
-    for t in toks[:2]:
+    for t in toks[:warmup]:
         ref.rwkv_eval(ctx, t, sp, sp, lp)
-    probe = (time.time() - t0) / 2
-    n = int(max(4, min(n_decode, budget_s / max(probe, 1e-6))))
+    probe = (time.time() - t0) / warmup
+    n = int(max(4, min(steps, budget_s / max(probe, 1e-6))))
     times = []
-    for t in toks[2:2 + n]:
+    for t in toks[warmup:warmup + n]:
         t0 = time.perf_counter()
         ref.rwkv_eval(ctx, t, sp, sp, lp)
         times.append(time.perf_counter() - t0)
-    med = float(np.median(times))
-    out = {"decode_tokens_per_s": 1.0 / med, "decode_ms_per_token": med * 1e3, "decode_sample_tokens": n, "threads": threads, "cores": cores,
-           "load_s": load_s, "library": os.path.basename(ref_lib.reference_library_path())}
-    if want_prefill and med * PREFILL_TOKENS < 6 * budget_s:
+    med, mean = float(np.median(times)), float(np.mean(times))
+    out = {"decode_tokens_per_s": 1.0 / mean, "decode_ms_per_token": mean * 1e3, "decode_ms_median": med * 1e3, "decode_sample_tokens": n, "warmup": warmup,
+           "threads": threads, "load_s": load_s, "library": libname}
+    if want_prefill and mean * PREFILL_TOKENS < 4 * budget_s:
         arr = (ctypes.c_uint32 * PREFILL_TOKENS)(*toks[:PREFILL_TOKENS])
         ref.rwkv_eval_sequence_in_chunks(ctx, arr, PREFILL_TOKENS, PREFILL_TOKENS, None, sp, lp)   # builds + caches the sequence graph
-        t0 = time.perf_counter()
-        ref.rwkv_eval_sequence_in_chunks(ctx, arr, PREFILL_TOKENS, PREFILL_TOKENS, None, sp, lp)
-        dt = time.perf_counter() - t0
-        out["prefill_tokens_per_s"] = PREFILL_TOKENS / dt
-        out["prefill_sample"] = "1 chunk of 128 tokens after one warm-up chunk"
+        reps = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            ref.rwkv_eval_sequence_in_chunks(ctx, arr, PREFILL_TOKENS, PREFILL_TOKENS, None, sp, lp)
+            reps.append(time.perf_counter() - t0)
+            if reps[-1] > budget_s / 2:
+                break
+        out["prefill_tokens_per_s"] = PREFILL_TOKENS / float(np.mean(reps))
+        out["prefill_ms_per_chunk"] = float(np.mean(reps)) * 1e3
+        out["prefill_sample"] = "%d chunk(s) of 128 tokens after one warm-up chunk" % len(reps)
     ref.rwkv_free(ctx)
+    emit(out)
+
+
+def _run_child(argv, timeout_s, on_line=None):
+    """Runs `bench.py <argv>` as a child; returns its JSON stdout lines. The child is killed when `timeout_s` passes without
+    it finishing (lines printed before that are kept) -- a hung ggml thread pool can never take the bench with it."""
+    proc = subprocess.Popen([sys.executable, os.path.abspath(__file__)] + argv, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    lines, deadline = [], time.time() + timeout_s
+
+    def reader():
+        for ln in proc.stdout:
+            if ln.startswith("{"):
+                lines.append(json.loads(ln))
+                if on_line:
+                    on_line(lines[-1])
+    th = threading.Thread(target=reader, daemon=True)
+    th.start()
+    while proc.poll() is None and time.time() < deadline:
+        time.sleep(0.2)
+    timed_out = proc.poll() is None
+    if timed_out:
+        proc.kill()
+        proc.wait()
+    th.join(timeout=5)
+    return lines, timed_out
+
+
+def cpu_reference_leg(path, preset, n_decode, budget_s, want_prefill=True, warmup=2):
+    """Times the unmodified reference (oracle/_ref) on the host cores: a bounded sample of the same workload. Everything that
+    touches the reference library runs in child processes under hard timeouts; the whole leg is bounded by ~2 x budget_s +
+    two model loads."""
+    cores = available_cpus()
+    candidates = reference_thread_candidates()
+    size_gb = os.path.getsize(path) / 1e9
+    load_allow = 20.0 + 12.0 * size_gb                      # page-cache read + ggml allocation of the file
+    probes = []
+    if len(candidates) > 1:
+        last = {"t": time.time()}
+        lines, timed_out = _run_child(["--impl", "reference", "--ref-child", "probe", "--ref-threads", ",".join(map(str, candidates)), "--workload-path", path],
+                                      load_allow + 30.0 * len(candidates), on_line=lambda _l: last.update(t=time.time()))
+        probes = [l for l in lines if "threads" in l]
+        for pr in probes:
+            log("reference probe: %d threads -> %.1f ms/token" % (pr["threads"], pr["ms"]))
+        if timed_out:
+            log("reference probe: child killed after its timeout; candidates seen: %s" % [p["threads"] for p in probes])
+    threads = min(probes, key=lambda p: p["ms"])["threads"] if probes else candidates[0]
+    lines, timed_out = _run_child(["--impl", "reference", "--ref-child", "full", "--ref-threads", str(threads), "--workload-path", path, "--steps", str(n_decode),
+                                   "--warmup", str(warmup), "--cpu-budget-s", str(budget_s)] + ([] if want_prefill else ["--no-prefill"]),
+                                  load_allow + 5.0 * budget_s + 60.0)
+    full = [l for l in lines if "decode_tokens_per_s" in l]
+    if not full:
+        raise RuntimeError("reference child produced no result (timed out: %s)" % timed_out)
+    out = full[-1]
+    out.update({"cores": cores, "physical_cores": physical_cores(), "candidates": candidates, "probes": probes})
     return out
 
 
@@ -253,20 +391,48 @@ def cpu_model_name():
 
 
 # ------------------------------------------------------------------------------------------------
+def dtype_label(workload):
+    fmt = workload.split(":")[1]
+    return {"Q4_0": "q4_0 weights x q8_0 activations (int8 dot, fp32 accumulate); fp16 head", "Q4_1": "q4_1 weights x q8_1 activations (int8 dot, fp32 accumulate); fp16 head",
+            "Q5_0": "q5_0 weights x q8_0 activations (int8 dot, fp32 accumulate); fp16 head", "Q5_1": "q5_1 weights x q8_1 activations (int8 dot, fp32 accumulate); fp16 head",
+            "Q8_0": "q8_0 weights x q8_0 activations (int8 dot, fp32 accumulate); fp16 head", "FP16": "f16 weights x f16-rounded activations, fp32 accumulate",
+            "FP32": "f32"}.get(fmt, fmt)
+
+
+def workload_label(args, preset):
+    what = "single-token rwkv_eval with logits" if args.mode == "decode" else "%d-token rwkv_eval_sequence_in_chunks chunk with logits" % PREFILL_TOKENS
+    return f"{args.workload} {what} ({preset['L']} layers, n_embed {preset['C']}, ffn {preset['F']}, vocab {preset['V']})"
+
+
 def run_reference(args, rank, world):
+    if args.ref_child:                          # child process of cpu_reference_leg
+        ths = [int(t) for t in args.ref_threads.split(",")]
+        if args.ref_child == "probe":
+            ref_child_probe(args.workload_path, ths)
+        else:
+            ref_child_full(args.workload_path, ths[0], args.steps, args.warmup, args.cpu_budget_s, not args.no_prefill)
+        return
     if rank != 0:
         return
     path, preset = workload_file(args.workload)
-    r = cpu_reference_leg(path, preset, n_decode=args.steps, budget_s=max(args.cpu_budget_s, 10.0))
+    r = cpu_reference_leg(path, preset, n_decode=args.steps, budget_s=max(args.cpu_budget_s, 5.0), warmup=args.warmup)
+    prefill = args.mode == "prefill"
+    if prefill and "prefill_tokens_per_s" not in r:
+        emit({"impl": "reference", "unavailable": "the 128-token chunk did not fit the CPU budget"})
+        return
+    value = r["prefill_tokens_per_s"] if prefill else r["decode_tokens_per_s"]
+    sample = (r["prefill_sample"] if prefill else f"{r['decode_sample_tokens']} rwkv_eval calls (mean) after {r['warmup']} warm-up calls")
     line = {
-        "impl": "reference", "metric": "decode_tokens_per_sec", "value": r["decode_tokens_per_s"], "unit": "tokens/s", "n_gpus": args.gpus,
-        "steps": r["decode_sample_tokens"], "warmup": 2, "ms_per_step": r["decode_ms_per_token"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "q5_1 weights x q8_1 activations (int8 dot, fp32 accumulate)" if "Q" in args.workload else "as file",
-        "data": "synthetic", "config": {"workload": args.workload + " single-token rwkv_eval, reference CPU path (oracle/_ref)", "cpu": cpu_model_name()},
-        "cpu_baseline": {"value": r["decode_tokens_per_s"], "unit": "tokens/s", "cores": r["threads"], "kind": "reference",
-                         "sample": f"{r['decode_sample_tokens']} rwkv_eval calls (median), {r['library']}, {r['threads']} threads of {r['cores']} logical CPUs"},
-        "e2e": {"value": r["decode_tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": "prefill_tokens_per_sec" if prefill else "decode_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "steps_timed": 1 if prefill else r["decode_sample_tokens"],
+        "ms_per_step": r["prefill_ms_per_chunk"] if prefill else r["decode_ms_per_token"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": dtype_label(args.workload), "data": "synthetic",
+        "config": {"workload": workload_label(args, preset), "parallelism": "reference CPU path (oracle/_ref), %d threads" % r["threads"], "cpu": cpu_model_name()},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": r["threads"], "kind": "reference",
+                         "sample": f"{sample}, {r['library']}, {r['threads']} threads (candidates {r['candidates']}; {r['cores']} usable logical CPUs, {r['physical_cores']} physical cores)"},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "prefill": {"tokens_per_s": r.get("prefill_tokens_per_s"), "chunk": PREFILL_TOKENS},
+        "decode": {"tokens_per_s": r["decode_tokens_per_s"], "ms_median": r["decode_ms_median"]},
         "gpu_launches": 0,
     }
     emit(line)
@@ -283,12 +449,14 @@ def run_ours(args, rank, world, dist):
     log("workload file ready: %s" % path)
     local = int(os.environ.get("LOCAL_RANK", rank))
     t0 = time.time()
-    ctx = lib.rwkv_b200_init_from_file_ex(path, local, 0, -1)   # N > 1: one full replica per GPU (multi-GPU)
+    ctx = lib.rwkv_b200_init_from_file_ex(path, local, 0, -1)   # N > 1 replicas: one full model per GPU
     load_s = time.time() - t0
     log("loaded %s in %.1fs" % (path, load_s))
     n_state, n_vocab = lib.rwkv_get_state_len(ctx), lib.rwkv_get_logits_len(ctx)
-    K, W = args.steps, args.warmup
-    toks = sm.synthetic_tokens(max(K + W + 8, (args.prefill_steps + 3) * PREFILL_TOKENS), n_vocab)
+    prefill_mode = args.mode == "prefill"
+    K, W = args.steps, max(args.warmup, 3)
+    P = K if prefill_mode else args.prefill_steps
+    toks = sm.synthetic_tokens(max(K + W + 8, (P + W + 3) * PREFILL_TOKENS), n_vocab)
     tok_arr = (ctypes.c_uint32 * len(toks))(*toks)
     sampler = ClockSampler(local)
     sampler.start()
@@ -299,135 +467,144 @@ def run_ours(args, rank, world, dist):
         if dist:
             dist.barrier()
 
+    def max_over_ranks(*vals):
+        if not dist:
+            return vals if len(vals) > 1 else vals[0]
+        import torch
+        t = torch.tensor(list(vals), device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out = [float(v) for v in t]
+        return out if len(out) > 1 else out[0]
+
     # ---- decode, state resident in HBM, CUDA events on the library's stream -------------------------------
+    KD = K if not prefill_mode else 32
     L.rwkv_b200_state_load(ctx.ptr, None)
-    L.rwkv_b200_eval_resident(ctx.ptr, tok_arr, 1, True, None)   # lazy allocations, graph capture happens in warm-up
+    L.rwkv_b200_eval_resident(ctx.ptr, tok_arr, 1, True, None)   # lazy allocations; graph capture happens in warm-up
     sync_all()
     launches0 = L.rwkv_b200_kernel_launch_count()
     w0 = time.time()
-    ms = L.rwkv_b200_time_resident(ctx.ptr, tok_arr, 1, K, W, True)
+    ms = L.rwkv_b200_time_resident(ctx.ptr, tok_arr, 1, KD, W, True)
     windows.append((w0, time.time()))
-    launches = (L.rwkv_b200_kernel_launch_count() - launches0) * K // (K + W)
+    decode_launches = (L.rwkv_b200_kernel_launch_count() - launches0) * KD // (KD + W)
     assert ms > 0, "device timing failed"
-    ms_max = ms
-    if dist:
-        import torch
-        t = torch.tensor([ms], device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max = float(t.item())
-    decode_tps = world * K / (ms_max / 1e3)
-    persistent = int(L.rwkv_b200_persistent_state(ctx.ptr)) == 1
+    ms_max = max_over_ranks(ms)
+    decode_tps = world * KD / (ms_max / 1e3)
+    step_ms = ms_max / KD
     overlap_groups = int(L.rwkv_b200_overlap_groups(ctx.ptr))
-    log("decode resident: %.3f ms/token (%s)" % (ms_max / K, "one persistent kernel per token" if persistent else "CUDA graph of per-launch kernels"))
+    log("decode resident: %.3f ms/token (CUDA graph of per-launch kernels)" % step_ms)
 
-    # ---- decode end to end through rwkv_eval with host buffers ------------------------------------------------
-    sbuf, lbuf, sp, lp, kind = host_buffers(n_state, n_vocab)
-    lib.rwkv_init_state(ctx, sp)
-    for t in toks[:W]:
-        lib.rwkv_eval(ctx, t, sp, sp, lp)
-    sync_all()
-    w0 = time.time()
-    t0 = time.perf_counter()
-    for t in toks[W:W + K]:
-        lib.rwkv_eval(ctx, t, sp, sp, lp)
-    e2e_s = time.perf_counter() - t0
-    windows.append((w0, time.time()))
-    if dist:
-        import torch
-        t = torch.tensor([e2e_s], device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_tps = world * K / e2e_s
-    log("decode e2e: %.3f ms/token" % (e2e_s / K * 1e3))
+    # ---- decode end to end through rwkv_eval with HOST buffers: pinned (a serving process) and pageable (what the reference's
+    # ---- Python binding hands over, rwkv_cpp_model.py:330-351) ----------------------------------------------------
+    e2e = {}
+    for kind in ("pinned", "pageable"):
+        sbuf, lbuf, sp, lp, got = host_buffers(n_state, n_vocab, kind)
+        lib.rwkv_init_state(ctx, sp)
+        for t in toks[:W]:
+            lib.rwkv_eval(ctx, t, sp, sp, lp)
+        sync_all()
+        w0 = time.time()
+        t0 = time.perf_counter()
+        for t in toks[W:W + KD]:
+            lib.rwkv_eval(ctx, t, sp, sp, lp)
+        dt = time.perf_counter() - t0
+        windows.append((w0, time.time()))
+        dt = max_over_ranks(dt)
+        e2e[kind] = {"tokens_per_s": world * KD / dt, "ms_per_step": dt / KD * 1e3, "buffers": got}
+        log("decode e2e (%s host buffers): %.3f ms/token" % (got, dt / KD * 1e3))
+    sbuf, lbuf, sp, lp, kind = host_buffers(n_state, n_vocab, "pinned")
 
     # ---- prefill: 128-token chunk ----------------------------------------------------------------------------------
-    P = args.prefill_steps
     L.rwkv_b200_state_load(ctx.ptr, None)
+    launches0 = L.rwkv_b200_kernel_launch_count()
     w0 = time.time()
-    pms = L.rwkv_b200_time_resident(ctx.ptr, tok_arr, PREFILL_TOKENS, P, 2, True)
+    pms = L.rwkv_b200_time_resident(ctx.ptr, tok_arr, PREFILL_TOKENS, P, W if prefill_mode else 2, True)
     windows.append((w0, time.time()))
+    prefill_launches = (L.rwkv_b200_kernel_launch_count() - launches0) * P // (P + (W if prefill_mode else 2))
     arr128 = (ctypes.c_uint32 * PREFILL_TOKENS)(*toks[:PREFILL_TOKENS])
-    L.rwkv_eval_sequence_in_chunks(ctx.ptr, arr128, PREFILL_TOKENS, PREFILL_TOKENS, None, ctypes.cast(sp, PF), ctypes.cast(lp, PF))
-    t0 = time.perf_counter()
-    for _ in range(max(2, P // 2)):
+    reps = P if prefill_mode else max(2, P // 2)
+    for _ in range(W if prefill_mode else 1):
         L.rwkv_eval_sequence_in_chunks(ctx.ptr, arr128, PREFILL_TOKENS, PREFILL_TOKENS, None, ctypes.cast(sp, PF), ctypes.cast(lp, PF))
-    pe2e_s = (time.perf_counter() - t0) / max(2, P // 2)
-    if dist:
-        import torch
-        t = torch.tensor([pms, pe2e_s], device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        pms, pe2e_s = float(t[0].item()), float(t[1].item())
+    w0 = time.time()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        L.rwkv_eval_sequence_in_chunks(ctx.ptr, arr128, PREFILL_TOKENS, PREFILL_TOKENS, None, ctypes.cast(sp, PF), ctypes.cast(lp, PF))
+    pe2e_s = (time.perf_counter() - t0) / reps
+    windows.append((w0, time.time()))
+    pms, pe2e_s = max_over_ranks(pms, pe2e_s)
+    chunk_ms = pms / P
+    log("prefill: %.3f ms/chunk resident, %.3f ms/chunk e2e" % (chunk_ms, pe2e_s * 1e3))
 
-    log("prefill: %.3f ms/chunk resident, %.3f ms/chunk e2e" % (pms / P, pe2e_s * 1e3))
-    # ---- roofline leg: events around every GEMV launch of one decode pass ------------------------------------
-    prof = pkg.shared_library.ProfileResult()
-    L.rwkv_b200_state_load(ctx.ptr, None)
-    profs = []
-    for i in range(5):
-        L.rwkv_b200_profile_pass(ctx.ptr, ctypes.cast(ctypes.byref(tok_arr, 4 * i), PU), 1, True, ctypes.byref(prof))
-        profs.append((prof.gemv_ms, prof.gemv_bytes, prof.pass_ms, prof.gemv_launches, prof.total_launches, prof.top_ms, prof.top_bytes))
-    profs = profs[1:]
-    gemv_ms = float(np.median([p[0] for p in profs])); gemv_bytes = profs[0][1]; pass_ms = float(np.median([p[2] for p in profs]))
-    top = min(profs, key=lambda p: p[5])
-    peak, peak_src = measured_peaks()
+    # ---- roofline legs: the dominant kernel's share of a step from the in-kernel %globaltimer timeline (works inside CUDA-graph
+    # ---- replays; per-launch CUDA events would serialise what programmatic dependent launch overlaps) ------------------
+    tl = kernel_timeline(L, ctx, tok_arr, 1)
+    gemv_share = tl["attributed_us"].get("gemv", 0.0) / tl["span_us"] if tl["span_us"] else 0.0
+    tlp = kernel_timeline(L, ctx, tok_arr, PREFILL_TOKENS, passes=3, skip=1)
+    gemm_share = tlp["attributed_us"].get("gemm_tc", 0.0) / tlp["span_us"] if tlp["span_us"] else 0.0
+    gemv_bytes = int(L.rwkv_b200_gemv_bytes_per_token(ctx.ptr, True))
     bytes_tok = int(L.rwkv_b200_bytes_per_token(ctx.ptr, True))
-    step_ms = ms_max / K
+    peak, peak_src = measured_peaks()
+    tpeak, tpeak_src = measured_tensor_peak()
+    gemv_ms = gemv_share * step_ms
+    flops = prefill_matmul_flops(preset, PREFILL_TOKENS)
     sampler.stop()
     clocks = sampler.summary(windows)
-    log("roofline leg done")
+    log("roofline legs done: decode traced %.1f us (gemv share %.3f), chunk traced %.1f us (gemm_tc share %.3f)" % (tl["span_us"], gemv_share, tlp["span_us"], gemm_share))
 
     line = None
     if rank == 0:
-        line = {
-            "metric": "decode_tokens_per_sec", "value": decode_tps, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "q5_1 weights x q8_1 activations (int8 dp4a, fp32 accumulate); fp16 head" if "Q5_1" in args.workload else args.workload.split(":")[1],
-            "data": "synthetic",
-            "config": {"workload": f"{args.workload} single-token rwkv_eval with logits ({preset['L']} layers, n_embed {preset['C']}, ffn {preset['F']}, vocab {preset['V']})",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas, one stream each (single-stream decode does not shard; DESIGN.md)",
-                       "l2": "6.1 GB of weights per step >> 126 MB L2, no flush needed", "bytes_per_token": bytes_tok, "load_s": round(load_s, 2),
-                       "cuda_graph": not persistent, "persistent_kernel": persistent},
-            "clocks": clocks,
-            "e2e": {"value": e2e_tps, "unit": "tokens/s", "h2d_bytes_per_step": n_state * 4 + 4, "d2h_bytes_per_step": n_state * 4 + n_vocab * 4,
-                    "host_buffers": kind, "ms_per_step": e2e_s / K * 1e3,
-                    "state_copies": ("pipelined against %d layer groups on copy streams" % overlap_groups) if overlap_groups else "one upload before, one download after the pass"},
-            "gpu_launches": int(launches),
-            "prefill": {"tokens_per_s": world * P * PREFILL_TOKENS / (pms / 1e3), "ms_per_chunk": pms / P, "chunk": PREFILL_TOKENS, "steps": P,
-                        "e2e_tokens_per_s": world * PREFILL_TOKENS / pe2e_s,
-                        "kernel": "gemm_tc_kernel (tcgen05, TMEM accumulators + TMEM A operand) for every layer matrix; wkv6 / lerp / LN on CUDA cores",
-                        "tensor": (lambda fl, pk: None if fl is None else {"bound": "tensor", "achieved": fl / (pms / P * 1e-3) / 1e12, "peak": pk[0], "unit": "TFLOP/s",
-                                                                            "frac": fl / (pms / P * 1e-3) / 1e12 / pk[0], "peak_source": pk[1],
-                                                                            "note": "whole chunk (GEMMs + recurrence + glue) against the dense bf16 peak"})(
-                            prefill_matmul_flops(preset, PREFILL_TOKENS), measured_tensor_peak())},
-            "roofline": {"bound": "hbm", "kernel": "gemv_kernel (fused dequantize-GEMV, all launches of one decode step)",
-                         "achieved": gemv_bytes / (gemv_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": gemv_bytes / (gemv_ms * 1e-3) / 1e9 / peak,
-                         "peak_source": peak_src, "traffic": ncu_traffic(preset)[0] if "rwkv6-7b:Q5_1" == args.workload else None,
-                         "traffic_launch": ncu_traffic(preset)[1] if "rwkv6-7b:Q5_1" == args.workload else None,
-                         "bytes_per_step": gemv_bytes, "ms_per_step": gemv_ms,
-                         "launches_per_step": int(profs[0][3]), "share_of_step": gemv_ms / pass_ms,
-                         "largest_launch": {"bytes": top[6], "ms": top[5], "gbs": top[6] / (top[5] * 1e-3) / 1e9},
-                         "whole_step": {"bytes": bytes_tok, "ms": step_ms, "gbs": bytes_tok / (step_ms * 1e-3) / 1e9, "frac": bytes_tok / (step_ms * 1e-3) / 1e9 / peak}},
-        }
-    if line is not None and persistent:
-        # the whole token is ONE kernel (plus the embedding gather): that kernel is the dominant kernel, its algorithmic bytes are the
-        # byte model of a token and its duration the CUDA-event time of a step; the per-launch GEMV figures (measured
-        # with the per-launch path, which the profiling leg always uses) stay for comparison.
-        r = line["roofline"]
-        per_launch = {k: r[k] for k in ("kernel", "achieved", "frac", "bytes_per_step", "ms_per_step", "launches_per_step", "share_of_step", "largest_launch")}
-        r.update({"kernel": "decode_persistent_kernel (every layer's fused dequantize-GEMVs, LayerNorm/mix, lerp and WKV of one token in one launch)",
-                  "achieved": r["whole_step"]["gbs"], "frac": r["whole_step"]["frac"], "bytes_per_step": bytes_tok, "ms_per_step": step_ms,
-                  "launches_per_step": 1, "share_of_step": 1.0, "per_launch_path": per_launch})
-        r.pop("largest_launch", None)
+        decode_roofline = {
+            "bound": "hbm", "kernel": "gemv_tma_kernel (fused dequantize-GEMV, all launches of one decode step)",
+            "achieved": gemv_bytes / (gemv_ms * 1e-3) / 1e9 if gemv_ms else None, "peak": peak, "unit": "GB/s",
+            "frac": gemv_bytes / (gemv_ms * 1e-3) / 1e9 / peak if gemv_ms else None, "peak_source": peak_src,
+            "traffic": ncu_traffic(preset)[0] if "rwkv6-7b:Q5_1" == args.workload else None,
+            "traffic_launch": ncu_traffic(preset)[1] if "rwkv6-7b:Q5_1" == args.workload else None,
+            "bytes_per_step": gemv_bytes, "ms_per_step": gemv_ms, "share_of_step": gemv_share,
+            "method": "critical-path attribution of the %globaltimer timeline of a graph-replayed step x the CUDA-event step time",
+            "launches_per_step": tl["launches"], "attributed_us": {k: round(v, 2) for k, v in tl["attributed_us"].items()},
+            "whole_step": {"bytes": bytes_tok, "ms": step_ms, "gbs": bytes_tok / (step_ms * 1e-3) / 1e9, "frac": bytes_tok / (step_ms * 1e-3) / 1e9 / peak}}
+        gemm_ms = gemm_share * chunk_ms
+        prefill_roofline = {
+            "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 + TMEM, all launches of one 128-token chunk)",
+            "achieved": flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None, "peak": tpeak, "unit": "TFLOP/s",
+            "frac": flops / (gemm_ms * 1e-3) / 1e12 / tpeak if gemm_ms else None, "peak_source": tpeak_src, "traffic": None,
+            "flops_per_step": flops, "ms_per_step": gemm_ms, "share_of_step": gemm_share,
+            "launches_per_step": tlp["launches"], "attributed_us": {k: round(v, 2) for k, v in tlp["attributed_us"].items()},
+            "whole_step": {"flops": flops, "ms": chunk_ms, "tflops": flops / (chunk_ms * 1e-3) / 1e12, "frac": flops / (chunk_ms * 1e-3) / 1e12 / tpeak}}
+        prefill_obj = {"tokens_per_s": world * PREFILL_TOKENS / (chunk_ms / 1e3), "ms_per_chunk": chunk_ms, "chunk": PREFILL_TOKENS, "steps": P,
+                       "e2e_tokens_per_s": world * PREFILL_TOKENS / pe2e_s, "gpu_launches": int(prefill_launches)}
+        decode_obj = {"tokens_per_s": decode_tps, "ms_per_token": step_ms, "steps": KD, "e2e_tokens_per_s": e2e["pinned"]["tokens_per_s"],
+                      "e2e_pageable_tokens_per_s": e2e["pageable"]["tokens_per_s"], "gpu_launches": int(decode_launches)}
+        state_copies = ("pipelined against %d layer groups on copy streams" % overlap_groups) if overlap_groups else "one upload before, one download after the pass"
+        common = {"n_gpus": world, "steps": K, "warmup": W, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype_label(args.workload), "data": "synthetic",
+                  "config": {"workload": workload_label(args, preset),
+                             "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (single-stream decode does not shard; DESIGN.md)",
+                             "l2": "%.2f GB of weights per step >> 126 MB L2, no flush needed" % (bytes_tok / 1e9) if bytes_tok > 4 * 126e6 else
+                                   "%.0f MB of weights per step: fits L2, steps run back to back WITHOUT a flush (stated, launch-bound config)" % (bytes_tok / 1e6),
+                             "bytes_per_token": bytes_tok, "load_s": round(load_s, 2), "cuda_graph": True},
+                  "clocks": clocks, "prefill": prefill_obj, "decode": decode_obj}
+        if prefill_mode:
+            line = dict(common, metric="prefill_tokens_per_sec", value=prefill_obj["tokens_per_s"], unit="tokens/s", ms_per_step=chunk_ms,
+                        e2e={"value": prefill_obj["e2e_tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": 4 * PREFILL_TOKENS, "d2h_bytes_per_step": n_state * 4 + n_vocab * 4,
+                             "host_buffers": "pinned", "ms_per_step": pe2e_s * 1e3, "state_copies": state_copies},
+                        gpu_launches=int(prefill_launches), roofline=dict(prefill_roofline, decode=decode_roofline))
+        else:
+            line = dict(common, metric="decode_tokens_per_sec", value=decode_tps, unit="tokens/s", ms_per_step=step_ms,
+                        e2e={"value": e2e["pinned"]["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": n_state * 4 + 4, "d2h_bytes_per_step": n_state * 4 + n_vocab * 4,
+                             "host_buffers": "pinned", "ms_per_step": e2e["pinned"]["ms_per_step"], "state_copies": state_copies,
+                             "pageable": {"value": e2e["pageable"]["tokens_per_s"], "ms_per_step": e2e["pageable"]["ms_per_step"], "buffers": e2e["pageable"]["buffers"]},
+                             "prefill_tokens_per_s": prefill_obj["e2e_tokens_per_s"]},
+                        gpu_launches=int(decode_launches), roofline=dict(decode_roofline, prefill=prefill_roofline))
     lib.rwkv_free(ctx)
     if rank == 0:
         if world == 1 and not args.skip_cpu_baseline:
-            # the reference runs in its own process under a hard timeout: it can never hang or skew the GPU numbers
-            log("cpu baseline (reference arm in a subprocess)")
+            log("cpu baseline (reference library in child processes)")
             try:
-                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", "32",
-                                    "--cpu-budget-s", str(args.cpu_budget_s)], capture_output=True, text=True, timeout=max(240.0, 14 * args.cpu_budget_s))
-                ref_line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-                line["cpu_baseline"] = dict(ref_line["cpu_baseline"], prefill_tokens_per_s=ref_line["prefill"]["tokens_per_s"], cpu=ref_line["config"]["cpu"])
+                r = cpu_reference_leg(path, preset, n_decode=32, budget_s=args.cpu_budget_s, want_prefill=True, warmup=2)
+                v = r.get("prefill_tokens_per_s") if prefill_mode else r["decode_tokens_per_s"]
+                line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": r["threads"], "kind": "reference",
+                                        "sample": f"{r['decode_sample_tokens']} rwkv_eval calls (mean) + {r.get('prefill_sample', 'no prefill chunk')}, {r['library']}, "
+                                                  f"{r['threads']} threads (candidates {r['candidates']}; {r['cores']} usable logical CPUs, {r['physical_cores']} physical cores)",
+                                        "decode_tokens_per_s": r["decode_tokens_per_s"], "prefill_tokens_per_s": r.get("prefill_tokens_per_s"), "cpu": cpu_model_name()}
             except Exception as e:   # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
         emit(line)

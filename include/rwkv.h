@@ -12,7 +12,11 @@
  *   - n_gpu_layers is accepted and ignored: all layers always run on the GPU;
  *   - a missing / unusable CUDA device makes rwkv_init_from_file return NULL with
  *     RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED -- there is no host execution path;
- *   - rwkv_get_system_info_string describes the CUDA device instead of CPU features.
+ *   - rwkv_get_system_info_string describes the CUDA device instead of CPU features;
+ *   - tensor data types: FP32, FP16, Q4_0, Q4_1, Q5_0, Q5_1, Q8_0 -- the formats rwkv.h:212-217 documents. The reference's
+ *     type table (rwkv_file_format.inc:28-47) also lets ggml's Q8_1 / K-quant ids (10..16) through; a file that contains
+ *     such a tensor is refused by rwkv_init_from_file with RWKV_ERROR_MODEL_PARAMS | RWKV_ERROR_UNSUPPORTED, and
+ *     rwkv_quantize_model_file refuses those format names with RWKV_ERROR_ARGS | RWKV_ERROR_DATA_TYPE.
  */
 #ifndef RWKV_H
 #define RWKV_H

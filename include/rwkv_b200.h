@@ -90,6 +90,8 @@ RWKV_API bool rwkv_b200_stage_logits(struct rwkv_context * ctx, float * logits_o
 RWKV_API float rwkv_b200_last_device_ms(const struct rwkv_context * ctx);     /* CUDA-event time of the last pass */
 RWKV_API uint64_t rwkv_b200_kernel_launch_count(void);                         /* kernels enqueued by this process */
 RWKV_API uint64_t rwkv_b200_bytes_per_token(const struct rwkv_context * ctx, bool with_logits);
+/* The part of that byte model the fused dequantize-GEMV kernel streams: every layer matrix (+ the head), at file precision. */
+RWKV_API uint64_t rwkv_b200_gemv_bytes_per_token(const struct rwkv_context * ctx, bool with_logits);
 /* Times `n_steps` back-to-back resident passes of `tokens_per_step` tokens each (after `warmup_steps` untimed ones)
  * with CUDA events on the context's own stream. `tokens` holds (warmup_steps + n_steps) * tokens_per_step ids.
  * Returns the milliseconds of the timed steps, or a negative value on error. Single-token passes replay a CUDA graph. */
@@ -109,6 +111,7 @@ RWKV_API bool rwkv_b200_profile_pass(struct rwkv_context * ctx, const uint32_t *
  * and last CTA into one record, also inside CUDA-graph replays. rwkv_b200_trace_read returns the records of the most recent
  * pass (microseconds relative to the first kernel's start, names up to 31 chars) and re-arms the buffer. */
 RWKV_API bool rwkv_b200_trace_enable(struct rwkv_context * ctx);
+RWKV_API void rwkv_b200_trace_disable(struct rwkv_context * ctx);      /* frees the buffer; graphs are re-captured without trace slots */
 RWKV_API void rwkv_b200_trace_set_marks_buffer(double * marks_us);   /* optional [max_records][4]: intra-kernel marks of CTA 0 */
 RWKV_API int rwkv_b200_trace_read(struct rwkv_context * ctx, double * start_us, double * end_us, char (*names)[32], int max_records);
 
@@ -117,13 +120,6 @@ RWKV_API void rwkv_b200_set_graphs(struct rwkv_context * ctx, bool enabled);
 /* Enables / disables the tcgen05 tensor-core kernel for passes of >= 32 tokens (on by default; off = batch-invariant SIMT path). */
 RWKV_API void rwkv_b200_set_tensor_cores(struct rwkv_context * ctx, bool enabled);
 
-/* Single-token passes as ONE persistent kernel (csrc/kernels/decode_persistent.h): every CTA walks the layer program, the
- * launch boundaries of the per-launch path become grid barriers and the weight stream continues across them. Results are
- * bit-identical to the per-launch path. RWKV v5 / v6 with n_embed <= 4096 and head size <= 64 fit it; everything else keeps
- * using the per-launch path. The environment variable RWKV_B200_PERSISTENT=0/1 sets the default of new contexts.
- * rwkv_b200_persistent_state: 1 = in use, 0 = not tried yet, -1 = this model / device does not fit it. */
-RWKV_API void rwkv_b200_set_persistent(struct rwkv_context * ctx, bool enabled);
-RWKV_API int rwkv_b200_persistent_state(const struct rwkv_context * ctx);
 /* rwkv_eval / rwkv_eval_sequence with caller-owned HOST state: copy the state per layer group (n_layer / 4 groups, at most 8) on
  * dedicated copy streams so that the host-to-device copy of group g+1 and the device-to-host copy of group g-1 overlap the kernels
  * of group g (the ABI state layout is layer-major, so a group is one contiguous slice). Results are bit-identical to the plain
@@ -132,20 +128,6 @@ RWKV_API int rwkv_b200_persistent_state(const struct rwkv_context * ctx);
 RWKV_API void rwkv_b200_set_overlap(struct rwkv_context * ctx, bool enabled);
 /* Number of layer groups the overlapped path uses for this context (0 = overlap off or a single group). */
 RWKV_API int rwkv_b200_overlap_groups(const struct rwkv_context * ctx);
-
-/* Phase timeline of the persistent kernel: the first call arms a device buffer (returns 0); after the next single-token pass a
- * second call returns n_phases + 1 boundaries (microseconds since the kernel's first phase began, %globaltimer of CTA 0). */
-RWKV_API int rwkv_b200_phase_trace(struct rwkv_context * ctx, double * boundaries_us, int max_records);
-/* Intra-phase marks of CTA 0 from the same traced pass: per phase [inputs ready (after LayerNorm), activation column staged,
- * tiles consumed], microseconds on the time base of rwkv_b200_phase_trace, -1 where a phase has no such step. Returns the phase count. */
-RWKV_API int rwkv_b200_phase_marks(struct rwkv_context * ctx, double * marks_us, int max_phases);
-
-/* Host-only self-test of the persistent kernel's planner (no GPU, no file): plans the single-token program of a fake RWKV v5 /
- * v6 model of the given shape for a device with num_sms SMs and replays every CTA's tile walk. 1 = planned and consistent,
- * 0 = the shape does not fit the kernel, -1 = bad arguments. info (optional, 4 ints) = ring stage bytes, activation region
- * bytes, number of phases, dynamic shared memory per CTA. */
-RWKV_API int rwkv_b200_plan_selftest(int arch_major, int arch_minor, int data_type, int n_embed, int ffn, int n_vocab, int head_size, int mix, int decay,
-                                     int n_layer, int num_sms, int * info);
 
 /* Test hook: one fused dequantize-GEMV on host buffers, y[M,T] = W[M,K] . x[K,T] (column-major activations),
  * through exactly the kernel the eval path uses (csrc/kernels/gemv.cu). `weights` holds M rows in the file

@@ -321,6 +321,11 @@ float rwkv_b200_last_device_ms(const struct rwkv_context * ctx) {
 
 uint64_t rwkv_b200_kernel_launch_count(void) { return g_kernel_launches; }
 
+uint64_t rwkv_b200_gemv_bytes_per_token(const struct rwkv_context * ctx, bool with_logits) {
+    const Model & m = *C(ctx)->model;
+    return (uint64_t) (m.gemv_bytes_per_token - (with_logits ? 0 : m.head_matrix_bytes));
+}
+
 uint64_t rwkv_b200_bytes_per_token(const struct rwkv_context * ctx, bool with_logits) {
     const Model & m = *C(ctx)->model;
     return (uint64_t) (m.weight_bytes_per_token - (with_logits ? 0 : m.head_bytes) + 2 * 4 * m.state_len());
@@ -371,60 +376,8 @@ bool rwkv_b200_profile_pass(struct rwkv_context * ctx, const uint32_t * tokens, 
 
 void rwkv_b200_set_graphs(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_graphs = enabled; }
 void rwkv_b200_set_tensor_cores(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_tensor_cores = enabled; }
-void rwkv_b200_set_persistent(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_persistent = enabled; }
 void rwkv_b200_set_overlap(struct rwkv_context * ctx, bool enabled) { C(ctx)->overlap_copies = enabled; }
 int rwkv_b200_overlap_groups(const struct rwkv_context * ctx) { return C(ctx)->overlap_copies && C(ctx)->n_segments > 1 ? C(ctx)->n_segments : 0; }
-int rwkv_b200_persistent_state(const struct rwkv_context * ctx) {
-    const Context * c = C(ctx);
-    int best = 0;
-    for (int i = 0; i < Context::N_SLOTS; i++) {
-        if (c->persistent_state[i] > 0) return 1;
-        if (c->persistent_state[i] < 0) best = -1;
-    }
-    return best;
-}
-
-int rwkv_b200_phase_marks(struct rwkv_context * ctx, double * marks_us, int max_phases) {
-    Context * c = C(ctx);
-    if (!c->phase_trace || !marks_us || cudaSetDevice(c->model->dev.device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
-    int n = 0;
-    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) { const DecodeProgram & pr = c->programs[Context::slot_index(a != 0, b, 0)]; if (pr.supported && pr.n_phases > n) n = pr.n_phases; }
-    if (n > max_phases) n = max_phases;
-    if (n > 700) n = 700;
-    if (n <= 0) return 0;
-    std::vector<unsigned long long> raw((size_t) 1024 + 4 * (size_t) n);
-    if (cudaMemcpy(raw.data(), c->phase_trace, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    for (int i = 0; i < n; i++) for (int k = 0; k < 3; k++) {
-        const unsigned long long v = raw[1024 + 4 * (size_t) i + k];
-        marks_us[3 * i + k] = (v && v >= raw[0]) ? (double) (v - raw[0]) * 1e-3 : -1.0;
-    }
-    return n;
-}
-
-int rwkv_b200_plan_selftest(int arch_major, int arch_minor, int data_type, int n_embed, int ffn, int n_vocab, int head_size, int mix, int decay, int n_layer, int num_sms, int * info) {
-    return plan_selftest(arch_major, arch_minor, data_type, n_embed, ffn, n_vocab, head_size, mix, decay, n_layer, num_sms, info);
-}
-
-int rwkv_b200_phase_trace(struct rwkv_context * ctx, double * boundaries_us, int max_records) {
-    Context * c = C(ctx);
-    if (cudaSetDevice(c->model->dev.device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
-    const int cap = 4096;
-    if (!c->phase_trace) {      // first call arms the buffer; the next single-token pass fills it
-        if (cudaMalloc((void **) &c->phase_trace, (size_t) cap * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return -1; }
-        cudaMemset(c->phase_trace, 0, (size_t) cap * sizeof(unsigned long long));
-        c->phase_trace_len = cap;
-        return 0;
-    }
-    int n = 0;
-    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) { const DecodeProgram & pr = c->programs[Context::slot_index(a != 0, b, 0)]; if (pr.supported && pr.n_phases + 1 > n) n = pr.n_phases + 1; }
-    if (n > max_records) n = max_records;
-    if (n <= 0 || !boundaries_us) return 0;
-    std::vector<unsigned long long> raw((size_t) n);
-    if (cudaMemcpy(raw.data(), c->phase_trace, (size_t) n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    for (int i = 0; i < n; i++) boundaries_us[i] = raw[i] >= raw[0] && raw[i] ? (double) (raw[i] - raw[0]) * 1e-3 : -1.0;
-    return n;
-}
-
 static bool trace_rearm(Context * c) {
     std::vector<TraceRec> init(1024);
     for (auto & r : init) { r.start = ~0ull; r.end = 0; for (auto & m : r.mark) m = 0; }
@@ -438,6 +391,15 @@ bool rwkv_b200_trace_enable(struct rwkv_context * ctx) {
     // graphs captured so far carry no trace slots: drop them so they are re-captured
     for (auto & g : c->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g = Context::GraphSlot(); }
     return trace_rearm(c);
+}
+
+void rwkv_b200_trace_disable(struct rwkv_context * ctx) {
+    Context * c = C(ctx);
+    if (!c->trace_buf || cudaSetDevice(c->model->dev.device) != cudaSuccess) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto & g : c->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g = Context::GraphSlot(); }
+    cudaFree(c->trace_buf);
+    c->trace_buf = nullptr; c->trace_count = 0;
 }
 
 // marks_us: optional [max_records][4] intra-kernel marks of CTA 0 (-1 when absent)
@@ -456,7 +418,7 @@ int rwkv_b200_trace_read(struct rwkv_context * ctx, double * start_us, double * 
         start_us[i] = recs[i].start == ~0ull ? -1.0 : (double) (recs[i].start - t0) * 1e-3;
         end_us[i] = recs[i].end == 0 ? -1.0 : (double) (recs[i].end - t0) * 1e-3;
         if (g_trace_marks_out) for (int k = 0; k < 4; k++) g_trace_marks_out[i * 4 + k] = recs[i].mark[k] ? (double) (recs[i].mark[k] - t0) * 1e-3 : -1.0;
-        const char * nm = g_trace_names[i] ? g_trace_names[i] : "?";
+        const char * nm = c->trace_names[i] ? c->trace_names[i] : "?";
         strncpy(names[i], nm, 31); names[i][31] = 0;
     }
     trace_rearm(c);

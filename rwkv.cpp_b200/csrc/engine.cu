@@ -17,8 +17,6 @@ namespace rwkv {
 
 namespace {
 
-// Single-token passes as one persistent kernel by default? (RWKV_B200_PERSISTENT=0/1 overrides, rwkv_b200_set_persistent per context)
-constexpr bool PERSISTENT_DEFAULT = false;
 // rwkv_eval with host state buffers: pipeline the state copies against layer groups? (RWKV_B200_OVERLAP=0/1, rwkv_b200_set_overlap)
 constexpr bool OVERLAP_DEFAULT = true;
 
@@ -325,176 +323,6 @@ bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T,
     return att_output(ctx, L, s, T);
 }
 
-// ---- persistent single-token kernel: the same launch sequences as att_v5 / att_v6 / ffn above, written as a phase list ----
-void phase_gemv(std::vector<DecodePhase> & prog, const Batch & b, int op = DOP_GEMV) {
-    DecodePhase d{};
-    d.op = op;
-    d.batch = b.b;
-    prog.push_back(d);
-}
-DecodePhase & phase_lnmix(std::vector<DecodePhase> & prog, const Batch & b, const LnMixParams & lp, const int * mix_of_problem) {
-    phase_gemv(prog, b, DOP_LNMIX_GEMV);
-    DecodePhase & d = prog.back();
-    d.ln.x = lp.x; d.ln.ln_w = lp.ln_w; d.ln.ln_b = lp.ln_b;
-    d.ln.state_in = lp.state_in; d.ln.state_out = lp.state_out;
-    d.ln.formula = lp.formula; d.ln.C = lp.C;
-    d.ln.out_xx = lp.out_xx; d.ln.out_sx = lp.out_sx;
-    for (int i = 0; i < b.b.n; i++) d.ln.coef[i] = lp.coef[mix_of_problem[i]];
-    return d;
-}
-
-void program_ffn(const Model & m, const Layer & L, const Scratch & s, const float * st_in, float * st_out, std::vector<DecodePhase> & prog) {
-    const int C = m.n_embed;
-    LnMixParams lp{};
-    lp.x = s.x; lp.ln_w = L.ln2_w.data; lp.ln_b = L.ln2_b.data;
-    lp.state_in = st_in; lp.state_out = st_out; lp.C = C; lp.T = 1;
-    if (m.arch_major == 6) { lp.formula = 1; lp.coef[0] = L.ffn_maa_k.data; lp.coef[1] = L.ffn_maa_r.data; }
-    else { lp.formula = 0; lp.coef[0] = L.ffn_time_mix_k.data; lp.coef[1] = L.ffn_time_mix_r.data; }
-    {
-        Batch b(1);
-        b.add(L.ffn_key, s.mix[0], s.ffn_k, EPI_RELU_SQR);
-        b.add(L.ffn_receptance, s.mix[1], s.ffn_r, EPI_SIGMOID);
-        const int mixes[2] = {0, 1};
-        phase_lnmix(prog, b, lp, mixes);
-    }
-    {
-        Batch b(1);
-        GemvProblem & p = b.add(L.ffn_value, s.ffn_k, s.x, EPI_MUL_ADD);
-        p.res = s.x; p.ldres = C;
-        p.gate = s.ffn_r; p.ldgate = C;
-        phase_gemv(prog, b);
-    }
-}
-
-void program_att_output(const Model & m, const Layer & L, const Scratch & s, std::vector<DecodePhase> & prog) {
-    Batch b(1);
-    GemvProblem & p = b.add(L.att_output, s.y, s.x, EPI_ADD);
-    p.res = s.x; p.ldres = m.n_embed;
-    phase_gemv(prog, b);
-}
-
-void program_att_v5(const Model & m, const Layer & L, const Scratch & s, const float * st_in, float * st_out, std::vector<DecodePhase> & prog) {
-    const int C = m.n_embed;
-    const bool v52 = m.arch_minor >= 2;
-    LnMixParams lp{};
-    lp.x = s.x; lp.ln_w = L.ln1_w.data; lp.ln_b = L.ln1_b.data;
-    lp.state_in = st_in + C; lp.state_out = st_out + C; lp.C = C; lp.T = 1;
-    lp.formula = 0;
-    lp.coef[0] = L.att_time_mix_k.data; lp.coef[1] = L.att_time_mix_v.data; lp.coef[2] = L.att_time_mix_r.data;
-    if (v52) lp.coef[3] = L.att_time_mix_g.data;
-    {
-        Batch b(1);
-        b.add(L.att_receptance, s.mix[2], s.r);
-        b.add(L.att_key, s.mix[0], s.k);
-        b.add(L.att_value, s.mix[1], s.v);
-        if (v52) b.add(L.att_gate, s.mix[3], s.g, EPI_SILU);
-        const int mixes[4] = {2, 0, 1, 3};
-        phase_lnmix(prog, b, lp, mixes);
-    }
-    {
-        Batch none(1);
-        phase_gemv(prog, none, DOP_GEMV_WKV);
-        Wkv6Params & wp = prog.back().wkv;
-        wp.r = s.r; wp.k = s.k; wp.v = s.v;
-        wp.td = L.att_time_decay.data; wp.td_per_token = 0;
-        wp.tf = v52 ? L.att_time_faaaa.data : L.att_time_first.data;
-        wp.per_head_scalars = v52 ? 0 : 1;
-        wp.state_in = st_in + 2 * C; wp.state_out = st_out + 2 * C;
-        wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
-        wp.g = v52 ? s.g : nullptr;
-        wp.y = s.y; wp.eps = 1e-5f; wp.H = m.head_count; wp.S = m.head_size; wp.T = 1;
-    }
-    program_att_output(m, L, s, prog);
-}
-
-void program_att_v6(const Model & m, const Layer & L, const Scratch & s, const float * st_in, float * st_out, std::vector<DecodePhase> & prog) {
-    const int C = m.n_embed;
-    LnMixParams lp{};
-    lp.x = s.x; lp.ln_w = L.ln1_w.data; lp.ln_b = L.ln1_b.data;
-    lp.state_in = st_in + C; lp.state_out = st_out + C; lp.C = C; lp.T = 1;
-    lp.formula = 1; lp.coef[0] = L.att_maa_x.data;
-    lp.out_xx = s.xx; lp.out_sx = s.sx;
-    {
-        Batch b(1);
-        b.add(L.att_maa_w1, s.mix[0], s.lora[0], EPI_TANH);
-        const int mixes[1] = {0};
-        phase_lnmix(prog, b, lp, mixes);
-    }
-    {
-        Batch none(1);
-        phase_gemv(prog, none, DOP_LERP);
-        V6LerpParams & vp = prog.back().lerp;
-        vp.w2 = L.att_maa_w2.data; vp.z = s.lora[0]; vp.xx = s.xx; vp.sx = s.sx;
-        vp.maa[0] = L.att_maa_w.data; vp.maa[1] = L.att_maa_k.data; vp.maa[2] = L.att_maa_v.data;
-        vp.maa[3] = L.att_maa_r.data; vp.maa[4] = L.att_maa_g.data;
-        for (int j = 0; j < 5; j++) vp.out[j] = s.mix[1 + j];
-        vp.C = C; vp.T = 1; vp.mix = L.maa_mix;
-    }
-    {
-        Batch b(1);
-        b.add(L.att_receptance, s.mix[4], s.r);
-        b.add(L.att_key, s.mix[2], s.k);
-        b.add(L.att_value, s.mix[3], s.v);
-        b.add(L.att_gate, s.mix[5], s.g, EPI_SILU);
-        b.add(L.att_decay_w1, s.mix[1], s.lora[1], EPI_TANH);
-        phase_gemv(prog, b);
-    }
-    {
-        Batch b(1);
-        GemvProblem & p = b.add(L.att_decay_w2, s.lora[1], s.w, EPI_BIAS_EXPNEGEXP);
-        p.bias = L.att_time_decay.data;
-        phase_gemv(prog, b, DOP_GEMV_WKV);
-        Wkv6Params & wp = prog.back().wkv;
-        wp.r = s.r; wp.k = s.k; wp.v = s.v;
-        wp.td = s.w; wp.td_per_token = 1; wp.tf = L.att_time_faaaa.data; wp.per_head_scalars = 0;
-        wp.state_in = st_in + 2 * C; wp.state_out = st_out + 2 * C;
-        wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
-        wp.g = s.g; wp.y = s.y; wp.eps = 64e-5f; wp.H = m.head_count; wp.S = m.head_size; wp.T = 1;
-    }
-    program_att_output(m, L, s, prog);
-}
-
-// Builds (once) the program of a single-token pass for this [want_logits][phase]; false = use the per-launch path.
-bool ensure_program(Context * ctx, bool want_logits, int phase, int seg) {
-    const int slot = Context::slot_index(want_logits, phase, seg);
-    int & state = ctx->persistent_state[slot];
-    if (state != 0) return state > 0;
-    state = -1;
-    const Model & m = *ctx->model;
-    if (m.arch_major != 5 && m.arch_major != 6) return false;
-    int l0, l1;
-    segment_range(ctx, seg, l0, l1);
-    const Scratch s = carve(m, ctx->scratch, 1);
-    const size_t per_layer = m.state_floats_per_layer();
-    std::vector<DecodePhase> prog;
-    for (int i = l0; i < l1; i++) {
-        const Layer & L = m.layers[i];
-        const float * st_in = ctx->state_a + (size_t) i * per_layer;
-        float * st_out = ctx->state_b + (size_t) i * per_layer;
-        if (m.arch_major == 6) program_att_v6(m, L, s, st_in, st_out, prog);
-        else program_att_v5(m, L, s, st_in, st_out, prog);
-        program_ffn(m, L, s, st_in, st_out, prog);
-    }
-    if (want_logits && l1 == m.n_layer) {
-        Batch b(1);
-        GemvProblem & p = b.add(m.head, s.x, ctx->logits);
-        p.pro = PRO_LAYERNORM; p.ln_w = m.ln_out_w.data; p.ln_b = m.ln_out_b.data;
-        phase_gemv(prog, b);
-    }
-    if (!ctx->grid_barrier) {
-        if (cudaMalloc(reinterpret_cast<void **>(&ctx->grid_barrier), sizeof(unsigned long long)) != cudaSuccess ||
-            cudaMemset(ctx->grid_barrier, 0, sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return false; }
-        ctx->grid_barrier_value = 0;
-    }
-    if (!decode_program_build(prog, m.dev, ctx->programs[slot])) return false;
-    state = 1;
-    return true;
-}
-
-void drop_programs(Context * ctx) {
-    for (int i = 0; i < Context::N_SLOTS; i++) { decode_program_free(ctx->programs[i]); ctx->persistent_state[i] = 0; }
-}
-
 bool ensure_capacity(Context * ctx, int T) {
     if (T <= ctx->capacity_T) return true;
     const Model & m = *ctx->model;
@@ -510,7 +338,6 @@ bool ensure_capacity(Context * ctx, int T) {
         ctx->slot_used[i] = false;
     }
     for (auto & g : ctx->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g = Context::GraphSlot(); }
-    drop_programs(ctx);
     ctx->capacity_T = 0;
     const size_t n = scratch_floats_for(m, cap);
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ctx->scratch), n * sizeof(float));
@@ -524,7 +351,7 @@ bool ensure_capacity(Context * ctx, int T) {
     if (cap >= 32) {   // fp16 staging for the tensor-core path: up to 8 distinct inputs of max(C, F) x round16(cap)
         Dims d = model_dims(m);
         const size_t kmax = d.F > d.C ? d.F : d.C;
-        ctx->act16_bytes = (size_t) GEMV_MAX_PROBLEMS * (kmax * (size_t) ((cap + 15) / 16 * 16) * 2 + 256);
+        ctx->act16_bytes = (size_t) GEMV_MAX_PROBLEMS * (kmax * (size_t) ((cap + 15) / 16 * 16) * 2 + 256 + (size_t) ((cap + 15) / 16 * 16) * 4 + 256);   // + a per-token scale vector
         e = cudaMalloc(&ctx->act16, ctx->act16_bytes);
         RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, false, e == cudaSuccess, "Failed to allocate fp16 staging: %s", cudaGetErrorString(e));
     }
@@ -566,7 +393,10 @@ bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase, int seg) {
         p.pro = PRO_LAYERNORM; p.ln_w = m.ln_out_w.data; p.ln_b = m.ln_out_b.data;
         if (!run_batch(ctx, b)) return false;
     }
-    if (ctx->trace_buf) ctx->trace_count = g_trace_next;
+    if (ctx->trace_buf) {
+        ctx->trace_count = g_trace_next;
+        for (int i = 0; i < g_trace_next; i++) ctx->trace_names[i] = g_trace_names[i];
+    }
     g_trace_base = nullptr;
     return true;
 }
@@ -597,29 +427,8 @@ bool run_layers(Context * ctx, int T, bool want_logits, int seg) {
     segment_range(ctx, seg, l0, l1);
     want_logits = want_logits && l1 == m.n_layer;        // only the group that ends the model can run the head
     const int slot = Context::slot_index(want_logits, phase, seg);
-    // Single-token passes: one persistent kernel per token when enabled and the model fits it (kernels/decode_persistent.h)
-    bool done = false;
-    if (T == 1 && ctx->use_persistent && !ctx->profiling && !ctx->trace_buf && ensure_program(ctx, want_logits, phase, seg)) {
-        const DecodeProgram & prog = ctx->programs[slot];
-        if (l0 == 0) {
-            const Scratch hs = carve(m, ctx->scratch, 1);
-            CUDA_OK(ctx, cudaMemcpyAsync(ctx->tokens, ctx->tokens_host[phase], sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            CUDA_OK(ctx, launch_embed_ln0(m.emb.data, m.emb.type, m.emb.pitch, ctx->tokens, 1, m.n_embed, m.ln0_w.data, m.ln0_b.data, hs.x, ctx->stream));
-        }
-        unsigned long long * tr = (seg == 0 && ctx->phase_trace && ctx->phase_trace_len > prog.n_phases) ? ctx->phase_trace : nullptr;
-        const cudaError_t e = decode_program_launch(prog, ctx->grid_barrier, ctx->grid_barrier_value, tr, ctx->stream);
-        if (e == cudaSuccess) {
-            ctx->grid_barrier_value += decode_program_barrier_arrivals(prog);
-            done = true;
-        } else {
-            cudaGetLastError();
-            fprintf(stderr, "rwkv_b200: persistent decode kernel launch failed (%s); falling back to the per-launch path\n", cudaGetErrorString(e));
-            ctx->persistent_state[slot] = -1;
-        }
-    }
-    Context::GraphSlot * g = (!done && T == 1 && ctx->use_graphs && !ctx->profiling) ? &ctx->graphs[slot] : nullptr;
-    if (done) {
-    } else if (g && g->exec) {
+    Context::GraphSlot * g = (T == 1 && ctx->use_graphs && !ctx->profiling) ? &ctx->graphs[slot] : nullptr;
+    if (g && g->exec) {
         CUDA_OK(ctx, cudaGraphLaunch(g->exec, ctx->stream));
         g_kernel_launches += g->launches;
     } else if (g && g->uses >= 1) {
@@ -693,7 +502,6 @@ Context * create_context(Model * model, ErrorSink sink, int batch_n) {
     ctx->model = model;
     model->refcount.fetch_add(1);
     ctx->print_errors = *sink.print;
-    { const char * e = getenv("RWKV_B200_PERSISTENT"); ctx->use_persistent = e ? atoi(e) != 0 : PERSISTENT_DEFAULT; }
     { const char * e = getenv("RWKV_B200_OVERLAP"); ctx->overlap_copies = e ? atoi(e) != 0 : OVERLAP_DEFAULT; }
     {   // layer groups of the overlapped host-state path: at least 4 layers each, at most MAX_SEGMENTS groups
         const int n = model->layer_end - model->layer_begin;
@@ -703,7 +511,7 @@ Context * create_context(Model * model, ErrorSink sink, int batch_n) {
     }
     const size_t n = model->state_len();
     const size_t seqs = batch_n > 0 ? (size_t) batch_n : 1;
-    if (batch_n > 0) { ctx->batch_n = batch_n; ctx->batch_stride = (long long) n; ctx->use_persistent = false; ctx->overlap_copies = false; }
+    if (batch_n > 0) { ctx->batch_n = batch_n; ctx->batch_stride = (long long) n; ctx->overlap_copies = false; }
     bool ok = cudaSetDevice(model->dev.device) == cudaSuccess
         && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess
         && cudaEventCreate(&ctx->ev_start) == cudaSuccess && cudaEventCreate(&ctx->ev_stop) == cudaSuccess
@@ -740,8 +548,6 @@ void destroy_context(Context * ctx) {
         if (ctx->slot_free[i]) cudaEventDestroy(ctx->slot_free[i]);
     }
     for (auto & g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-    drop_programs(ctx);
-    cudaFree(ctx->grid_barrier); cudaFree(ctx->phase_trace);
     if (ctx->copy_in) { cudaStreamSynchronize(ctx->copy_in); cudaStreamDestroy(ctx->copy_in); }
     if (ctx->copy_out) { cudaStreamSynchronize(ctx->copy_out); cudaStreamDestroy(ctx->copy_out); }
     if (ctx->pass_begin) cudaEventDestroy(ctx->pass_begin);
@@ -860,69 +666,6 @@ bool forward(Context * ctx, const uint32_t * tokens, size_t T, bool want_logits)
         done += n;
     }
     return true;
-}
-
-// Host-only check of the persistent-kernel planner (no GPU, no model file): lays out a fake model of the given shape
-// (pointers are dummies, never dereferenced), builds its single-token program and runs decode_program_plan on it.
-int plan_selftest(int arch_major, int arch_minor, int type, int C, int F, int V, int S, int mix, int decay, int n_layer, int num_sms, int * info) {
-    if (C <= 0 || F <= 0 || V <= 0 || S <= 0 || C % S != 0 || n_layer <= 0 || n_layer > 256 || !dtype_supported(type) || C % 32 || F % 32) return -1;
-    if (arch_major == 6 && (mix <= 0 || decay <= 0 || (5 * mix) % 32 || decay % 32)) return -1;
-    if (arch_major != 5 && arch_major != 6) return -1;
-    Model m;
-    m.arch_major = arch_major; m.arch_minor = arch_minor; m.n_embed = C; m.n_vocab = V; m.n_layer = n_layer;
-    m.head_size = S; m.head_count = C / S; m.layer_begin = 0; m.layer_end = n_layer;
-    m.dev.num_sms = num_sms;
-    uint8_t * fake = reinterpret_cast<uint8_t *>((uintptr_t) 1 << 20);
-    auto mat = [&](int t, int K, int M) {
-        DevMatrix d;
-        d.data = fake; d.type = t; d.K = K; d.M = M;
-        size_t bytes = tensor_nbytes(t, (uint64_t) K, 1, 1);
-        if (t == DT_Q4_0 || t == DT_Q5_0 || t == DT_Q8_0) bytes = (size_t) ((K / 32 + 1) / 2 * 2) * dtype_block_bytes(t);
-        d.pitch = (long long) ((bytes + 15) / 16 * 16);
-        fake += ((size_t) d.pitch * M + 255) / 256 * 256;
-        return d;
-    };
-    auto vec = [&](size_t n) { DevVec v; v.data = reinterpret_cast<const float *>(fake); v.n = n; fake += (n * 4 + 255) / 256 * 256; return v; };
-    m.layers.resize((size_t) n_layer);
-    for (Layer & L : m.layers) {
-        L.ln1_w = vec(C); L.ln1_b = vec(C); L.ln2_w = vec(C); L.ln2_b = vec(C);
-        L.att_key = mat(type, C, C); L.att_value = mat(type, C, C); L.att_receptance = mat(type, C, C); L.att_output = mat(type, C, C);
-        L.att_gate = mat(type, C, C);
-        L.att_ln_x_w = vec(C); L.att_ln_x_b = vec(C); L.att_time_decay = vec(C); L.att_time_faaaa = vec(C); L.att_time_first = vec(C);
-        L.att_time_mix_k = vec(C); L.att_time_mix_v = vec(C); L.att_time_mix_r = vec(C); L.att_time_mix_g = vec(C);
-        if (arch_major == 6) {
-            L.att_maa_x = vec(C); L.att_maa_w = vec(C); L.att_maa_k = vec(C); L.att_maa_v = vec(C); L.att_maa_r = vec(C); L.att_maa_g = vec(C);
-            L.att_maa_w1 = mat(type, C, 5 * mix); L.att_decay_w1 = mat(type, C, decay); L.att_decay_w2 = mat(type, decay, C);
-            L.att_maa_w2 = vec((size_t) 5 * C * mix); L.maa_mix = mix;
-            L.ffn_maa_k = vec(C); L.ffn_maa_r = vec(C);
-        } else {
-            L.ffn_time_mix_k = vec(C); L.ffn_time_mix_r = vec(C);
-        }
-        L.ffn_key = mat(type, C, F); L.ffn_value = mat(type, F, C); L.ffn_receptance = mat(type, C, C);
-    }
-    m.head = mat(type == DT_F32 ? DT_F32 : DT_F16, C, V);
-    m.ln_out_w = vec(C); m.ln_out_b = vec(C);
-    float * base = reinterpret_cast<float *>((uintptr_t) 1 << 40);
-    const Scratch s = carve(m, base, 1);
-    const size_t per_layer = m.state_floats_per_layer();
-    float * st_a = reinterpret_cast<float *>((uintptr_t) 1 << 41), * st_b = reinterpret_cast<float *>((uintptr_t) 1 << 42);
-    std::vector<DecodePhase> prog;
-    for (int i = 0; i < n_layer; i++) {
-        const Layer & L = m.layers[(size_t) i];
-        if (arch_major == 6) program_att_v6(m, L, s, st_a + i * per_layer, st_b + i * per_layer, prog);
-        else program_att_v5(m, L, s, st_a + i * per_layer, st_b + i * per_layer, prog);
-        program_ffn(m, L, s, st_a + i * per_layer, st_b + i * per_layer, prog);
-    }
-    {
-        Batch b(1);
-        GemvProblem & p = b.add(m.head, s.x, base);
-        p.pro = PRO_LAYERNORM; p.ln_w = m.ln_out_w.data; p.ln_b = m.ln_out_b.data;
-        phase_gemv(prog, b);
-    }
-    DecodeProgram program;
-    const bool ok = decode_program_plan_check_records(prog, num_sms, program);
-    if (info) { info[0] = (int) program.stage_bytes; info[1] = (int) program.region_bytes; info[2] = program.n_phases; info[3] = (int) program.smem_bytes; }
-    return ok ? 1 : 0;
 }
 
 bool batch_set_state(Context * ctx, int seq, const float * state_in) {

@@ -7,7 +7,6 @@
 #include <vector>
 
 #include "model.h"
-#include "kernels/decode_persistent.h"
 
 namespace rwkv {
 
@@ -51,16 +50,6 @@ struct Context {
     GraphSlot graphs[N_SLOTS];
     bool use_graphs = true;
 
-    // Persistent single-token kernel (kernels/decode_persistent.h): one program per slot, built on first use.
-    // `persistent_state`: 0 = not tried yet, 1 = in use, -1 = this model / device does not fit it (per-launch path is used).
-    DecodeProgram programs[N_SLOTS];
-    int persistent_state[N_SLOTS] = {};
-    bool use_persistent = false;
-    unsigned long long * grid_barrier = nullptr;     // device counter of the kernel's grid barrier
-    unsigned long long grid_barrier_value = 0;       // its value once everything enqueued so far has run
-    unsigned long long * phase_trace = nullptr;      // optional device buffer: %globaltimer of CTA 0 at every phase boundary
-    int phase_trace_len = 0;
-
     // Profiling mode (bench.py roofline leg): CUDA events around every GEMV launch, graphs off.
     bool profiling = false;
     struct ProfRecord { cudaEvent_t start, stop; double bytes; };
@@ -68,6 +57,7 @@ struct Context {
 
     TraceRec * trace_buf = nullptr;  // in-kernel timeline records (rwkv_b200_trace_*), 1024 slots
     int trace_count = 0;             // slots used by the last enqueued / captured pass
+    const char * trace_names[1024] = {};   // kernel name per slot (string literals)
 
     // Pipeline-stage hand-off: device pointers of the caller for the pass being enqueued, or NULL.
     // Layout: x f32[C x T], then (v7 only) v_first f32[C x T].
@@ -140,9 +130,6 @@ bool sample_token(Context * ctx, float temperature, float top_p, double u, const
 
 size_t stage_hidden_len(const Model & m, size_t T);
 
-// Host-only self-test of the persistent-kernel planner on a fake model of the given shape: 1 = a program was planned and passed
-// its tile-walk check, 0 = the shape does not fit the kernel, -1 = bad arguments. info[4] = stage bytes, region bytes, phases, smem.
-int plan_selftest(int arch_major, int arch_minor, int type, int C, int F, int V, int S, int mix, int decay, int n_layer, int num_sms, int * info);
 bool stage_forward(Context * ctx, const uint32_t * tokens, size_t T, const float * hidden_in, float * hidden_out, bool want_logits, cudaStream_t stream);
 
 }  // namespace rwkv

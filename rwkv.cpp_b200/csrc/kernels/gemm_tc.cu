@@ -199,6 +199,7 @@ struct TcShared {
     uint32_t tmem_base;
     long long t0;            // clock64 at kernel start (trace marks)
     GemvProblem P;
+    float colscale[MAX_N];
 };
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
@@ -206,7 +207,7 @@ __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf
 // 32 accumulator columns of one row -> fused epilogue -> column-major store. Everything the loop needs sits in registers
 // (the problem record lives in shared memory: re-reading it per element made the unrolled body 250 instructions long).
 struct EpiRow { float * y; long long ldy; const float * res; long long ldres; const float * gate; long long ldgate; float bias; };
-template <int EPI> __device__ __forceinline__ void store_cols(const EpiRow & e, const uint32_t (&acc)[32], int c0, int T) {
+template <int EPI> __device__ __forceinline__ void store_cols(const EpiRow & e, const uint32_t (&acc)[32], const float * cs, int c0, int T) {
     // the residual / gate inputs of all 32 columns are requested before the first store: the output may alias the residual
     // (x += ...), so a load placed after a store would have to wait for it, one L2 round trip per column
     float rv[32], gv[32];
@@ -222,7 +223,7 @@ template <int EPI> __device__ __forceinline__ void store_cols(const EpiRow & e, 
     for (int j = 0; j < 32; j++) {
         const int col = c0 + j;
         if (col >= T) break;
-        float v = __uint_as_float(acc[j]);
+        float v = __uint_as_float(acc[j]) * cs[col];
         if constexpr (EPI == EPI_SIGMOID) v = sigmoidf_(v);
         else if constexpr (EPI == EPI_SILU) v = v / (1.0f + expf(-v));
         else if constexpr (EPI == EPI_TANH) v = tanhf(v);
@@ -237,7 +238,7 @@ template <int EPI> __device__ __forceinline__ void store_cols(const EpiRow & e, 
 }
 // warp w owns TMEM lanes 32 (w % 4) .. + 31 = rows row0 + 32 (w % 4) + lane; warps 0-3 take the even 32-column groups of the
 // accumulator, warps 4-7 the odd ones
-__device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, uint32_t tmem_base, int row0, int npad, int T) {
+__device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, const float * cs, uint32_t tmem_base, int row0, int npad, int T) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3;
     const int row = row0 + q * 32 + lane;
@@ -254,16 +255,16 @@ __device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, uint32_t 
         tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) c0, acc);
         if (!live) continue;
         switch (epi) {
-            case EPI_SIGMOID: store_cols<EPI_SIGMOID>(e, acc, c0, T); break;
-            case EPI_SILU: store_cols<EPI_SILU>(e, acc, c0, T); break;
-            case EPI_TANH: store_cols<EPI_TANH>(e, acc, c0, T); break;
-            case EPI_RELU_SQR: store_cols<EPI_RELU_SQR>(e, acc, c0, T); break;
-            case EPI_ADD: store_cols<EPI_ADD>(e, acc, c0, T); break;
-            case EPI_MUL_ADD: store_cols<EPI_MUL_ADD>(e, acc, c0, T); break;
-            case EPI_BIAS_EXPNEGEXP: store_cols<EPI_BIAS_EXPNEGEXP>(e, acc, c0, T); break;
-            case EPI_BIAS_SIGMOID: store_cols<EPI_BIAS_SIGMOID>(e, acc, c0, T); break;
-            case EPI_BIAS_W7: store_cols<EPI_BIAS_W7>(e, acc, c0, T); break;
-            default: store_cols<EPI_NONE>(e, acc, c0, T); break;
+            case EPI_SIGMOID: store_cols<EPI_SIGMOID>(e, acc, cs, c0, T); break;
+            case EPI_SILU: store_cols<EPI_SILU>(e, acc, cs, c0, T); break;
+            case EPI_TANH: store_cols<EPI_TANH>(e, acc, cs, c0, T); break;
+            case EPI_RELU_SQR: store_cols<EPI_RELU_SQR>(e, acc, cs, c0, T); break;
+            case EPI_ADD: store_cols<EPI_ADD>(e, acc, cs, c0, T); break;
+            case EPI_MUL_ADD: store_cols<EPI_MUL_ADD>(e, acc, cs, c0, T); break;
+            case EPI_BIAS_EXPNEGEXP: store_cols<EPI_BIAS_EXPNEGEXP>(e, acc, cs, c0, T); break;
+            case EPI_BIAS_SIGMOID: store_cols<EPI_BIAS_SIGMOID>(e, acc, cs, c0, T); break;
+            case EPI_BIAS_W7: store_cols<EPI_BIAS_W7>(e, acc, cs, c0, T); break;
+            default: store_cols<EPI_NONE>(e, acc, cs, c0, T); break;
         }
     }
 }
@@ -338,12 +339,13 @@ struct TcBatch {
     int raw_stage_bytes;             // ring slot size: the largest 128-row chunk of the batch's formats, 128-byte multiple
     int b_stages;                    // A/B ring depth, 2 .. MAX_STAGES
     const __half * act16[GEMV_MAX_PROBLEMS];   // canonical-layout fp16 activations per problem (convert_f16_kernel)
+    const float * colscale[GEMV_MAX_PROBLEMS]; // [npad] power-of-two factor per token that the epilogue multiplies back in
     GemvProblem p[GEMV_MAX_PROBLEMS];          // first_cta / n_cta = tiles of 128 rows
     TraceRec * trace;
 };
 
 template <int TYPE>
-__device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, const __half * act16, int tile) {
+__device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, const __half * act16, const float * colscale, int tile) {
     using RT = RawTraits<TYPE>;
     const GemvProblem & P = sh.P;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -468,10 +470,12 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
         }
         {
             pdl_prologue();     // residual / gate inputs come from the previous kernels
+            if (tid < NPAD) sh.colscale[tid] = colscale[tid];
+            asm volatile("bar.sync 2, 256;" ::: "memory");      // the 8 transform / epilogue warps
             mbar_wait(&sh.acc_done, 0);
             const bool acct_e = batch.trace != nullptr && blockIdx.x == 0 && tid == 0;
             tc_fence_after_sync();
-            tc_epilogue_rows(P, sh.tmem_base, row0, NPAD, batch.T);
+            tc_epilogue_rows(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T);
             (void) acct_e;
         }
     }
@@ -501,53 +505,102 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
     const int tile = (int) blockIdx.x - sh.P.first_cta;
     const __half * act16 = batch.act16[pi];
     switch (sh.P.type) {
-        case DT_Q4_0: tc_tile<DT_Q4_0>(sh, smem, batch, act16, tile); break;
-        case DT_Q4_1: tc_tile<DT_Q4_1>(sh, smem, batch, act16, tile); break;
-        case DT_Q5_0: tc_tile<DT_Q5_0>(sh, smem, batch, act16, tile); break;
-        case DT_Q5_1: tc_tile<DT_Q5_1>(sh, smem, batch, act16, tile); break;
-        case DT_Q8_0: tc_tile<DT_Q8_0>(sh, smem, batch, act16, tile); break;
-        default: tc_tile<DT_F16>(sh, smem, batch, act16, tile); break;
+        case DT_Q4_0: tc_tile<DT_Q4_0>(sh, smem, batch, act16, batch.colscale[pi], tile); break;
+        case DT_Q4_1: tc_tile<DT_Q4_1>(sh, smem, batch, act16, batch.colscale[pi], tile); break;
+        case DT_Q5_0: tc_tile<DT_Q5_0>(sh, smem, batch, act16, batch.colscale[pi], tile); break;
+        case DT_Q5_1: tc_tile<DT_Q5_1>(sh, smem, batch, act16, batch.colscale[pi], tile); break;
+        case DT_Q8_0: tc_tile<DT_Q8_0>(sh, smem, batch, act16, batch.colscale[pi], tile); break;
+        default: tc_tile<DT_F16>(sh, smem, batch, act16, batch.colscale[pi], tile); break;
     }
     if (threadIdx.x < 32) tmem_dealloc(sh.tmem_base, (uint32_t) batch.tmem_cols);
     trace_end(batch.trace);
 }
 
-// x fp32 [K, T] column-major (column t contiguous) -> fp16 in the UMMA canonical layout, one contiguous B stage per
-// K-step:  [K / 64][kc = 8][g = npad / 8][8 tokens][8 k]  (tokens >= T zero-filled). One thread = one 16-byte chunk; all
-// distinct inputs of a GEMM batch (up to 8: x_r, x_k, x_v, x_g, x_w of the time mix) go through ONE launch, blockIdx.y = input.
+// x fp32 [K, T] column-major (column t contiguous) -> the fp16 B operand in the UMMA canonical layout, one contiguous B stage per
+// K-step:  [K / 64][kc = 8][g = npad / 8][8 tokens][8 k]  (tokens >= T zero-filled). One CTA = one token column of one distinct
+// input of the GEMM batch (blockIdx.y = input; up to 8: x_r, x_k, x_v, x_g, x_w of the time mix).
+//
+// What the halves hold. For QUANTISED weights the reference multiplies Q8_0 / Q8_1 activation blocks (ggml-cpu.c:7439-7458,
+// quantize_row_q8_0 / q8_1 ggml-cpu-quants.c:781-846, 1085-1160): per 32 elements d = fp16(amax / 127), q = rint(x * 127 / amax),
+// and the dot product sees d * q. So does this path: the half written is d * q (exact in fp32: 11 x 7 bits) rounded once to fp16,
+// i.e. the tensor cores contract the reference's own operand values instead of a "more accurate" fp16 rounding of x, and the
+// >= 32-token path tracks the dp4a path to fp16 rounding of the products (2^-12 relative per element) instead of to the Q8
+// quantisation noise (~4e-3 of the block maximum). For F16 weights the reference rounds activations to fp16
+// (ggml-cpu.c:259-264): the half is fp16(x).
+// Range. fp16 ends at 65504 where the reference's operands do not (d is fp16 but q * d goes up to amax): every token column
+// carries a power-of-two scale 2^-e, e = max(0, exponent(column maximum) - 15), applied before the rounding (exact) and taken
+// out by the GEMM epilogue through colscale[t] = 2^e, so activations up to 3e38 / 127 stay finite and equally precise.
 struct ConvertBatch {
     int n, T, npad;
     const float * x[GEMV_MAX_PROBLEMS];
     long long ldx[GEMV_MAX_PROBLEMS];
     int K[GEMV_MAX_PROBLEMS];
+    int quant[GEMV_MAX_PROBLEMS];      // 1: Q8 block values (quantised weights), 0: plain fp16 rounding (F16 weights)
     __half * out[GEMV_MAX_PROBLEMS];
+    float * colscale[GEMV_MAX_PROBLEMS];   // [npad] per input
     TraceRec * trace;
 };
-__global__ void convert_f16_kernel(const ConvertBatch cb) {
+constexpr int CVT_THREADS = 256;
+__global__ void __launch_bounds__(CVT_THREADS) convert_f16_kernel(const ConvertBatch cb) {
+    __shared__ float red[CVT_THREADS / 32];
     trace_begin(cb.trace);
     pdl_prologue();
-    const int q = blockIdx.y, T = cb.T, npad = cb.npad, K = cb.K[q];
-    const float * x = cb.x[q];
-    const long long ldx = cb.ldx[q];
-    __half * out = cb.out[q];
-    const int NG = npad / 8;
-    const long long nchunks = (long long) npad * K / 8;
-    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < nchunks; i += (long long) gridDim.x * blockDim.x) {
-        const int t8 = (int) (i & 7);
-        const long long j = i >> 3;
-        const int g = (int) (j % NG);
-        const long long j2 = j / NG;
-        const int kc = (int) (j2 & 7), ks = (int) (j2 >> 3);
-        const int t = g * 8 + t8, k = ks * KSTEP + kc * 8;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if (t < T) {
-            const float4 v0 = *reinterpret_cast<const float4 *>(x + (long long) t * ldx + k);
-            const float4 v1 = *reinterpret_cast<const float4 *>(x + (long long) t * ldx + k + 4);
-            __half2 a = __floats2half2_rn(v0.x, v0.y), b = __floats2half2_rn(v0.z, v0.w);
-            __half2 c = __floats2half2_rn(v1.x, v1.y), d = __floats2half2_rn(v1.z, v1.w);
-            o = make_uint4(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b), *reinterpret_cast<uint32_t *>(&c), *reinterpret_cast<uint32_t *>(&d));
+    const int q = blockIdx.y, t = blockIdx.x, T = cb.T, npad = cb.npad, K = cb.K[q];
+    const int tid = threadIdx.x;
+    uint4 * out = reinterpret_cast<uint4 *>(cb.out[q]);
+    const int NG = npad / 8, g = t >> 3, t8 = t & 7;
+    const int nblk = K / 32;
+    // 16-byte chunk (ks, kc) of this token sits at ((ks * 8 + kc) * NG + g) * 8 + t8
+    if (t >= T) {
+        for (int c = tid; c < K / 8; c += CVT_THREADS) out[((size_t) c * NG + g) * 8 + t8] = make_uint4(0, 0, 0, 0);
+        if (tid == 0) cb.colscale[q][t] = 1.0f;
+        return;
+    }
+    const float4 * x4 = reinterpret_cast<const float4 *>(cb.x[q] + (long long) t * cb.ldx[q]);
+    float cmax = 0.f;
+    for (int i = tid; i < K / 4; i += CVT_THREADS) {
+        const float4 v = x4[i];
+        cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    if ((tid & 31) == 0) red[tid >> 5] = cmax;
+    __syncthreads();
+    cmax = red[0];
+#pragma unroll
+    for (int i = 1; i < CVT_THREADS / 32; i++) cmax = fmaxf(cmax, red[i]);
+    int ex = 0;
+    if (cmax > 32768.0f && cmax <= 3.0e38f) { (void) frexpf(cmax, &ex); ex -= 15; }      // cmax <= 2^ex_raw  ->  cmax * 2^-ex <= 2^15
+    const float down = ex > 0 ? exp2f((float) -ex) : 1.0f;
+    if (tid == 0) cb.colscale[q][t] = ex > 0 ? exp2f((float) ex) : 1.0f;
+    const bool quant = cb.quant[q] != 0;
+    for (int blk = tid; blk < nblk; blk += CVT_THREADS) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = x4[blk * 8 + j];      // second touch of the column: L1 / L2
+        if (quant) {
+            float amax = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
+            const float d = __half2float(__float2half_rn(amax / 127.0f)) * down;
+            const float id = (amax != 0.0f) ? 127.0f / amax : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                v[j].x = (float) __float2int_rn(v[j].x * id) * d; v[j].y = (float) __float2int_rn(v[j].y * id) * d;
+                v[j].z = (float) __float2int_rn(v[j].z * id) * d; v[j].w = (float) __float2int_rn(v[j].w * id) * d;
+            }
+        } else if (ex > 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { v[j].x *= down; v[j].y *= down; v[j].z *= down; v[j].w *= down; }
         }
-        *reinterpret_cast<uint4 *>(out + i * 8) = o;
+        const int c0 = blk * 4;            // first of the block's four 8-element chunks
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+            __half2 a = __floats2half2_rn(v[2 * cc].x, v[2 * cc].y), b = __floats2half2_rn(v[2 * cc].z, v[2 * cc].w);
+            __half2 c = __floats2half2_rn(v[2 * cc + 1].x, v[2 * cc + 1].y), d2 = __floats2half2_rn(v[2 * cc + 1].z, v[2 * cc + 1].w);
+            out[((size_t) (c0 + cc) * NG + g) * 8 + t8] =
+                make_uint4(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b), *reinterpret_cast<uint32_t *>(&c), *reinterpret_cast<uint32_t *>(&d2));
+        }
     }
     trace_end(cb.trace);
 }
@@ -609,40 +662,42 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
     tb.tmem_cols = 32;
     while (tb.tmem_cols < tb.npad + tc::MAX_STAGES * 32) tb.tmem_cols *= 2;      // accumulator + A stages
 
-    __half * scratch = reinterpret_cast<__half *>(act16_scratch);
+    uint8_t * scratch = reinterpret_cast<uint8_t *>(act16_scratch);
     size_t used = 0;
     int next = 0;
     tc::ConvertBatch cvt;
     memset(&cvt, 0, sizeof(cvt));
     cvt.T = batch.T; cvt.npad = tb.npad;
-    int cvt_kmax = 0;
+    int share_of[GEMV_MAX_PROBLEMS];
     for (int i = 0; i < batch.n; i++) {
         GemvProblem & p = batch.p[i];
-        const size_t need = (size_t) tb.npad * p.K * sizeof(__half);
-        // problems that share an input share the converted copy
-        const __half * shared = nullptr;
-        for (int j = 0; j < i; j++) if (batch.p[j].x == p.x && batch.p[j].K == p.K && batch.p[j].ldx == p.ldx) shared = tb.act16[j];
-        if (!shared) {
+        const int quant = p.type != DT_F16;
+        const size_t need = (((size_t) tb.npad * p.K * sizeof(__half) + 255) & ~(size_t) 255) + (((size_t) tb.npad * sizeof(float) + 255) & ~(size_t) 255);
+        // problems that share an input (and its operand kind) share the converted copy
+        int shared = -1;
+        for (int j = 0; j < i; j++)
+            if (batch.p[j].x == p.x && batch.p[j].K == p.K && batch.p[j].ldx == p.ldx && (batch.p[j].type != DT_F16) == (quant != 0)) shared = share_of[j];
+        if (shared < 0) {
             if (used + need > scratch_bytes) return cudaErrorMemoryAllocation;
-            __half * dst = scratch + used / sizeof(__half);
-            cvt.x[cvt.n] = p.x; cvt.ldx[cvt.n] = p.ldx; cvt.K[cvt.n] = p.K; cvt.out[cvt.n] = dst;
+            shared = cvt.n;
+            cvt.x[cvt.n] = p.x; cvt.ldx[cvt.n] = p.ldx; cvt.K[cvt.n] = p.K; cvt.quant[cvt.n] = quant;
+            cvt.out[cvt.n] = reinterpret_cast<__half *>(scratch + used);
+            cvt.colscale[cvt.n] = reinterpret_cast<float *>(scratch + used + (((size_t) tb.npad * p.K * sizeof(__half) + 255) & ~(size_t) 255));
             cvt.n++;
-            if (p.K > cvt_kmax) cvt_kmax = p.K;
-            shared = dst;
-            used += (need + 255) & ~(size_t) 255;
+            used += need;
         }
-        tb.act16[i] = shared;
+        share_of[i] = shared;
+        tb.act16[i] = cvt.out[shared];
+        tb.colscale[i] = cvt.colscale[shared];
         p.first_cta = next;
         p.n_cta = (p.M + tc::TILE_M - 1) / tc::TILE_M;
         next += p.n_cta;
         tb.p[i] = p;
     }
-    {   // every distinct input of the batch -> fp16 canonical layout, one launch
-        const long long n8 = (long long) tb.npad * cvt_kmax / 8;
-        const int blocks = (int) ((n8 + 255) / 256 < 592 ? (n8 + 255) / 256 : 592);
+    {   // every distinct input of the batch -> fp16 canonical layout, one launch: one CTA per (token column, input)
         cvt.trace = trace_slot("convert_f16");
         g_kernel_launches++;
-        cudaError_t e = launch_pdl(tc::convert_f16_kernel, dim3(blocks, cvt.n), dim3(256), 0, stream, cvt);
+        cudaError_t e = launch_pdl(tc::convert_f16_kernel, dim3(tb.npad, cvt.n), dim3(tc::CVT_THREADS), 0, stream, cvt);
         if (e != cudaSuccess) return e;
     }
     // shared memory: 3 raw chunks (sized for the widest format of this batch) and as many B stages as fit, at most 8. The ring has
@@ -664,14 +719,9 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
     if (nb < 2) return cudaErrorInvalidValue;
     tb.b_stages = nb;
     const size_t smem = fixed + (size_t) nb * b_bytes;
-    static bool attr_set[64] = {};           // the opt-in is per device
-    int cur_dev = 0;
-    cudaGetDevice(&cur_dev);
-    if (cur_dev < 0 || cur_dev >= 64 || !attr_set[cur_dev]) {
-        cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_budget);
-        if (e != cudaSuccess) return e;
-        if (cur_dev >= 0 && cur_dev < 64) attr_set[cur_dev] = true;
-    }
+    static PerDeviceOnce once;               // the opt-in is per device
+    const cudaError_t ae = once.run([&] { return cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_budget); });
+    if (ae != cudaSuccess) return ae;
     tb.trace = trace_slot("gemm_tc");
     g_kernel_launches++;
     return launch_pdl(tc::gemm_tc_kernel, dim3(next), dim3(tc::THREADS), smem, stream, tb);

@@ -21,10 +21,10 @@
 
 namespace rwkv {
 
-unsigned long long g_kernel_launches = 0;
-TraceRec * g_trace_base = nullptr;
-int g_trace_next = 0;
-const char * g_trace_names[1024];
+std::atomic<unsigned long long> g_kernel_launches{0};
+thread_local TraceRec * g_trace_base = nullptr;
+thread_local int g_trace_next = 0;
+thread_local const char * g_trace_names[1024];
 
 namespace {
 
@@ -290,16 +290,9 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvBatch batc
 
 template <int NC>
 cudaError_t launch_nc(const GemvBatch & batch, int grid, size_t smem, int max_optin, cudaStream_t stream) {
-    static bool attr_set_dev[64] = {};       // the shared-memory opt-in is per device
-    int cur_dev = 0;
-    cudaGetDevice(&cur_dev);
-    cur_dev = (cur_dev < 0 || cur_dev >= 64) ? 0 : cur_dev;
-    bool & attr_set = attr_set_dev[cur_dev];
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemv_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static PerDeviceOnce once;                // the shared-memory opt-in is per device
+    const cudaError_t ae = once.run([&] { return cudaFuncSetAttribute(gemv_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024); });
+    if (ae != cudaSuccess) return ae;
     g_kernel_launches++;
     return launch_pdl(gemv_kernel<NC>, dim3(grid), dim3(GEMV_THREADS), smem, stream, batch);
 }

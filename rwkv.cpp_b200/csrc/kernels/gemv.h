@@ -4,6 +4,7 @@
 // 504-510, 708; CPU ggml-cpu.c:7377 + quant vec_dot kernels; CUDA ggml-cuda/mmvq.cu:55, mmv.cu:5).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 
 namespace rwkv {
@@ -41,9 +42,11 @@ struct GemvProblem {
 // In-kernel timeline (our stand-in for nsys, which this image lacks): when a trace slot is attached, thread 0 of every
 // CTA folds %globaltimer into [min start, max end] of the slot. Works inside CUDA-graph replays.
 struct TraceRec { unsigned long long start, end, mark[4]; };   // mark[]: optional intra-kernel points of CTA 0
-extern TraceRec * g_trace_base;        // device buffer, or nullptr when tracing is off
-extern int g_trace_next;               // next free slot of the current pass
-extern const char * g_trace_names[1024];
+// The cursor belongs to the host thread that is enqueuing a pass (contexts are evaluated one thread each, rwkv.h:94-96): thread_local,
+// so two clones traced from two threads never share slots; enqueue_pass copies the names into its Context when the pass is complete.
+extern thread_local TraceRec * g_trace_base;        // device buffer, or nullptr when tracing is off
+extern thread_local int g_trace_next;               // next free slot of the current pass
+extern thread_local const char * g_trace_names[1024];
 inline TraceRec * trace_slot(const char * name) {
     if (!g_trace_base || g_trace_next >= 1024) return nullptr;
     g_trace_names[g_trace_next] = name;
@@ -114,6 +117,20 @@ __device__ __forceinline__ void pdl_prologue() {
 #endif
 
 // Per-launch count of kernels this module has enqueued (bench.py reports it as gpu_launches).
-extern unsigned long long g_kernel_launches;
+extern std::atomic<unsigned long long> g_kernel_launches;
+
+// One-time per-device function attribute (dynamic shared-memory opt-in): several host threads may launch concurrently.
+struct PerDeviceOnce {
+    std::atomic<bool> done[64] = {};
+    template <typename F> cudaError_t run(F && set) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) return set();
+        if (done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+        const cudaError_t e = set();               // idempotent: a second thread repeating it is harmless
+        if (e == cudaSuccess) done[dev].store(true, std::memory_order_release);
+        return e;
+    }
+};
 
 }  // namespace rwkv

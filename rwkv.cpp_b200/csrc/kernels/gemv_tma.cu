@@ -154,16 +154,9 @@ cudaError_t launch_tma_nc(const GemvBatch & batch, int grid, size_t smem, cudaSt
         static const bool stage_v2 = [] { const char * e = getenv("RWKV_B200_STAGE_V2"); return e && atoi(e) != 0; }();
         if (stage_v2) return launch_tma_nc<1, true>(batch, grid, smem, stream);
     }
-    static bool attr_set_dev[64] = {};       // the shared-memory opt-in is per device
-    int cur_dev = 0;
-    cudaGetDevice(&cur_dev);
-    cur_dev = (cur_dev < 0 || cur_dev >= 64) ? 0 : cur_dev;
-    bool & attr_set = attr_set_dev[cur_dev];
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tma::gemv_tma_kernel<NC, STAGE_V2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::CTA_SMEM_BUDGET);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static PerDeviceOnce once;                // the shared-memory opt-in is per device
+    const cudaError_t ae = once.run([&] { return cudaFuncSetAttribute(tma::gemv_tma_kernel<NC, STAGE_V2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::CTA_SMEM_BUDGET); });
+    if (ae != cudaSuccess) return ae;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned) grid);
     cfg.blockDim = dim3(tma::THREADS);

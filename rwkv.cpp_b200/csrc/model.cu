@@ -331,8 +331,8 @@ Model * load_model(const char * path, int device, int layer_begin, int layer_end
             }
             const size_t bytes = t.nbytes;
             if (r.name == "emb.weight") m.weight_bytes_per_token += row_bytes;
-            else if (r.name == "head.weight") { m.weight_bytes_per_token += bytes; m.head_bytes += bytes; }
-            else m.weight_bytes_per_token += bytes;
+            else if (r.name == "head.weight") { m.weight_bytes_per_token += bytes; m.head_bytes += bytes; m.gemv_bytes_per_token += bytes; m.head_matrix_bytes += bytes; }
+            else { m.weight_bytes_per_token += bytes; m.gemv_bytes_per_token += bytes; }
         } else {
             DevVec & d = *r.vec;
             d.n = (size_t) (t.ne[0] * t.ne[1] * t.ne[2]);

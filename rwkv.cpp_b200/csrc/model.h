@@ -66,6 +66,8 @@ struct Model {
     size_t tiled_bytes = 0;              // of which: tile-major prefill copies of the layer matrices
     size_t weight_bytes_per_token = 0;   // byte model of SURVEY.md 8(d), resident layers, with head
     size_t head_bytes = 0;
+    size_t gemv_bytes_per_token = 0;     // of which: matrices streamed by the fused dequantize-GEMV (layer matrices + head)
+    size_t head_matrix_bytes = 0;
     std::atomic<int> refcount{0};
     std::string device_name;
 

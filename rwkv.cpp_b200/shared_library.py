@@ -110,24 +110,18 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_trace_enable.restype = ctypes.c_bool
         lib.rwkv_b200_trace_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_void_p, ctypes.c_int]
         lib.rwkv_b200_trace_read.restype = ctypes.c_int
+        lib.rwkv_b200_trace_disable.argtypes = [vp]
+        lib.rwkv_b200_trace_disable.restype = None
+        lib.rwkv_b200_gemv_bytes_per_token.argtypes = [vp, ctypes.c_bool]
+        lib.rwkv_b200_gemv_bytes_per_token.restype = ctypes.c_uint64
         lib.rwkv_b200_set_graphs.argtypes = [vp, ctypes.c_bool]
         lib.rwkv_b200_set_graphs.restype = None
         lib.rwkv_b200_set_tensor_cores.argtypes = [vp, ctypes.c_bool]
         lib.rwkv_b200_set_tensor_cores.restype = None
-        lib.rwkv_b200_set_persistent.argtypes = [vp, ctypes.c_bool]
-        lib.rwkv_b200_set_persistent.restype = None
         lib.rwkv_b200_set_overlap.argtypes = [vp, ctypes.c_bool]
         lib.rwkv_b200_set_overlap.restype = None
         lib.rwkv_b200_overlap_groups.argtypes = [vp]
         lib.rwkv_b200_overlap_groups.restype = ctypes.c_int
-        lib.rwkv_b200_persistent_state.argtypes = [vp]
-        lib.rwkv_b200_persistent_state.restype = ctypes.c_int
-        lib.rwkv_b200_phase_trace.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_int]
-        lib.rwkv_b200_phase_trace.restype = ctypes.c_int
-        lib.rwkv_b200_phase_marks.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_int]
-        lib.rwkv_b200_phase_marks.restype = ctypes.c_int
-        lib.rwkv_b200_plan_selftest.argtypes = [ctypes.c_int] * 11 + [ctypes.POINTER(ctypes.c_int)]
-        lib.rwkv_b200_plan_selftest.restype = ctypes.c_int
         lib.rwkv_b200_batch_create.argtypes = [vp, ctypes.c_size_t]
         lib.rwkv_b200_batch_create.restype = vp
         lib.rwkv_b200_batch_set_state.argtypes = [vp, ctypes.c_size_t, P_FLOAT]

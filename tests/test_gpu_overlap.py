@@ -13,9 +13,8 @@ pytestmark = pytest.mark.gpu
 P_F = ctypes.POINTER(ctypes.c_float)
 
 
-def run(lib, ctx, toks, overlap, persistent, n_state, n_logits, skip_logits=False, seq=0):
+def run(lib, ctx, toks, overlap, n_state, n_logits, skip_logits=False, seq=0):
     lib.library.rwkv_b200_set_overlap(ctx.ptr, overlap)
-    lib.library.rwkv_b200_set_persistent(ctx.ptr, persistent)
     state = np.zeros(n_state, dtype=np.float32)
     logits = np.zeros(n_logits, dtype=np.float32)
     i = 0
@@ -40,12 +39,12 @@ def test_overlapped_copies_bitwise(lib, ver, fmt):
     try:
         n_state, n_logits = lib.rwkv_get_state_buffer_element_count(ctx), lib.rwkv_get_logits_buffer_element_count(ctx)
         toks = LONG_PROMPT[:20]
-        want = run(lib, ctx, toks, False, False, n_state, n_logits)
-        for skip in (False, True):      # (the persistent kernel x overlap combination is checked out of process, test_zz_gpu_persistent.py)
-            got = run(lib, ctx, toks, True, False, n_state, n_logits, skip_logits=skip)
+        want = run(lib, ctx, toks, False, n_state, n_logits)
+        for skip in (False, True):
+            got = run(lib, ctx, toks, True, n_state, n_logits, skip_logits=skip)
             assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes(), (ver, fmt, skip)
-        want_seq = run(lib, ctx, toks, False, False, n_state, n_logits, seq=7)
-        got_seq = run(lib, ctx, toks, True, False, n_state, n_logits, seq=7)
+        want_seq = run(lib, ctx, toks, False, n_state, n_logits, seq=7)
+        got_seq = run(lib, ctx, toks, True, n_state, n_logits, seq=7)
         assert got_seq[0].tobytes() == want_seq[0].tobytes() and got_seq[1].tobytes() == want_seq[1].tobytes()
         assert want_seq[1].tobytes() == want[1].tobytes()          # and sequence mode == serial, as ever
         # state_out == NULL (logits only) and state_in == NULL with overlap on
@@ -54,7 +53,7 @@ def test_overlapped_copies_bitwise(lib, ver, fmt):
         assert lib.library.rwkv_eval(ctx.ptr, toks[0], None, None, lg.ctypes.data_as(P_F))
         st = np.zeros(n_state, dtype=np.float32)
         assert lib.library.rwkv_eval(ctx.ptr, toks[0], None, st.ctypes.data_as(P_F), None)
-        ref_l, ref_s = run(lib, ctx, toks[:1], False, False, n_state, n_logits)
+        ref_l, ref_s = run(lib, ctx, toks[:1], False, n_state, n_logits)
         assert lg.tobytes() == ref_l.tobytes() and st.tobytes() == ref_s.tobytes()
     finally:
         lib.rwkv_free(ctx)
@@ -69,11 +68,10 @@ def test_overlap_with_pinned_buffers_real_head_size(pkg, lib, tmp_path):
     try:
         n_state, n_logits = lib.rwkv_get_state_buffer_element_count(ctx), lib.rwkv_get_logits_buffer_element_count(ctx)
         toks = sm.synthetic_tokens(6, n_logits)
-        want = run(lib, ctx, toks, False, False, n_state, n_logits)
+        want = run(lib, ctx, toks, False, n_state, n_logits)
         state = torch.zeros(n_state, dtype=torch.float32).pin_memory()
         logits = torch.zeros(n_logits, dtype=torch.float32).pin_memory()
         lib.library.rwkv_b200_set_overlap(ctx.ptr, True)
-        lib.library.rwkv_b200_set_persistent(ctx.ptr, False)
         for i, t in enumerate(toks):
             sp = ctypes.cast(state.data_ptr(), P_F)
             assert lib.library.rwkv_eval(ctx.ptr, t, None if i == 0 else sp, sp, ctypes.cast(logits.data_ptr(), P_F))

@@ -98,12 +98,57 @@ def test_chunked_equals_serial_bitwise(models, ref_outputs, ver, fmt):
                 assert state.tobytes() == want_state.tobytes(), (ver, fmt, chunk)
                 assert logits.tobytes() == want_logits.tobytes(), (ver, fmt, chunk)
             else:
-                # passes of >= 32 tokens of non-F32 weights run on the tensor cores with fp16 (not Q8) activations
-                assert np.abs(logits - want_logits).max() <= 5 * TOL["Q"], (ver, fmt, chunk, np.abs(logits - want_logits).max())
+                # passes of >= 32 tokens of non-F32 weights run on the tensor cores (fp16 operands holding the reference's Q8
+                # activation values): not bit-identical to the dp4a path, but within the bar we hold against the reference
+                assert np.abs(logits - want_logits).max() <= TOL["Q"], (ver, fmt, chunk, np.abs(logits - want_logits).max())
     if fmt == "FP32":   # after 70 tokens FP32 still tracks the reference closely
         logits, state = serial(m, LONG_PROMPT)
         assert np.abs(logits - ref_outputs[f"{ver}/FP32/long_logits"]).max() <= 1e-3
         assert np.abs(state - ref_outputs[f"{ver}/FP32/long_state"]).max() <= 1e-2
+
+
+@pytest.mark.parametrize("ver", VERSIONS)
+@pytest.mark.parametrize("fmt", ["FP16", "Q5_0", "Q5_1"])
+def test_long_prompt_vs_reference_all_paths(models, ref_outputs, ver, fmt):
+    """The 70-token prompt of tests/test_eval_sequence_in_chunks.c against the compiled reference's outputs on the same file
+    (tests/golden/ref_outputs.npz: */long_logits, */long_state): serial, one sequence call (tensor-core path for non-F32
+    weights) and chunks of 32 / 64 -- the reference computes all of them identically (memcmp, :54), so each must sit within
+    the bar of the 3-token test. This pins the >= 32-token path to the reference."""
+    m = models(model_path(ver, fmt))
+    tol = TOL.get(fmt, TOL["Q"])
+    want_l, want_s = ref_outputs[f"{ver}/{fmt}/long_logits"], ref_outputs[f"{ver}/{fmt}/long_state"]
+    runs = {"serial": serial(m, LONG_PROMPT), "sequence": m.eval_sequence(LONG_PROMPT, None, use_numpy=True)}
+    for chunk in (32, 64):
+        runs[f"chunks of {chunk}"] = m.eval_sequence_in_chunks(LONG_PROMPT, None, chunk_size=chunk, use_numpy=True)
+    for how, (logits, state) in runs.items():
+        assert np.isfinite(logits).all() and np.isfinite(state).all(), (ver, fmt, how)
+        el, es = np.abs(logits - want_l).max(), np.abs(state - want_s).max()
+        assert el <= tol, (ver, fmt, how, el)
+        assert es <= 10 * tol, (ver, fmt, how, es)
+
+
+def test_large_activations_stay_finite_on_the_tensor_core_path(pkg, lib):
+    """activations beyond the fp16 range (65504) must not turn into inf / NaN on the >= 32-token path of quantised
+    weights (the reference quantises them to Q8 blocks and stays finite), and the result must still agree with the dp4a path:
+    the fp16 operands carry a per-token power-of-two scale that the epilogue takes out again. The carried token-shift state is
+    set to 3e5, so the mixed inputs of the first token of every matrix exceed 65504."""
+    toks = [(7919 * i + 3) % 256 for i in range(40)]
+    for ver, C, L in (("6v0-3m", 128, 12), ("5v2-730K", 64, 12)):
+        m = pkg.RWKVModel(lib, model_path(ver, "Q5_1"), thread_count=1)
+        try:
+            state = np.zeros(m.state_len, np.float32)
+            per_layer = state.size // L
+            for layer in range(L):
+                state[layer * per_layer: layer * per_layer + 2 * C] = 3.0e5
+            l_seq, s_seq = m.eval_sequence(toks, state.copy(), use_numpy=True)
+            st, lg = state.copy(), None
+            for t in toks:
+                lg, st = m.eval(t, st, use_numpy=True)
+            assert np.isfinite(l_seq).all() and np.isfinite(s_seq).all(), ver
+            assert np.isfinite(lg).all(), ver
+            assert np.abs(l_seq - lg).max() <= 2 * TOL["Q"], (ver, np.abs(l_seq - lg).max())
+        finally:
+            m.free()
 
 
 @pytest.mark.parametrize("ver", VERSIONS)
@@ -233,3 +278,39 @@ def test_reference_c_tests_run_against_our_library(lib, tmp_path):
     for exe in sorted(os.listdir(bindir)):
         r = subprocess.run([os.path.join(bindir, exe)], cwd=work, env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, (exe, r.stderr[-2000:])
+
+
+def test_two_clones_on_two_host_threads(lib):
+    """rwkv.h:65-67, 94-96: one evaluation at a time per context, but clones may run concurrently on different threads. Two clones
+    evaluate different token streams from two host threads (ctypes releases the GIL), one of them with the in-kernel timeline
+    switched on; each must produce exactly what it produces alone."""
+    import threading
+    path = model_path("6v0-3m", "Q5_1")
+    ctx = lib.rwkv_init_from_file(path, 1, 0)
+    clone = lib.rwkv_clone_context(ctx, 1)
+    n, v = lib.rwkv_get_state_len(ctx), lib.rwkv_get_logits_len(ctx)
+    P = ctypes.POINTER(ctypes.c_float)
+    streams = {0: [(31 * i + 7) % 256 for i in range(150)], 1: [(17 * i + 3) % 256 for i in range(150)]}
+
+    def run(c, toks, out):
+        state, logits = np.zeros(n, np.float32), np.zeros(v, np.float32)
+        for i, t in enumerate(toks):
+            assert lib.library.rwkv_eval(c.ptr, t, None if i == 0 else state.ctypes.data_as(P), state.ctypes.data_as(P), logits.ctypes.data_as(P))
+        out.append((logits.copy(), state.copy()))
+
+    alone = {0: [], 1: []}
+    run(ctx, streams[0], alone[0])
+    run(clone, streams[1], alone[1])
+    assert lib.library.rwkv_b200_trace_enable(clone.ptr)
+    for _ in range(3):
+        together = {0: [], 1: []}
+        th = [threading.Thread(target=run, args=(ctx, streams[0], together[0])), threading.Thread(target=run, args=(clone, streams[1], together[1]))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for k in (0, 1):
+            assert together[k] and together[k][0][0].tobytes() == alone[k][0][0].tobytes() and together[k][0][1].tobytes() == alone[k][0][1].tobytes(), k
+    lib.library.rwkv_b200_trace_disable(clone.ptr)
+    lib.rwkv_free(clone)
+    lib.rwkv_free(ctx)
