@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--workload", default="rwkv6-7b:Q5_1", help="<preset>:<format>, presets in tools/synthetic_model.py")
     ap.add_argument("--prefill-steps", type=int, default=8)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="A/B aid, not a bench line: resident decode timing + kernel timeline only")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="CPU seconds the bounded reference sample may take per leg")
     ap.add_argument("--mode", default="decode", choices=["decode", "prefill"],
                     help="headline metric: single-token decode tokens/s (default) or 128-token-chunk prefill tokens/s (one step = one chunk)")
@@ -492,6 +493,17 @@ def run_ours(args, rank, world, dist):
     step_ms = ms_max / KD
     overlap_groups = int(L.rwkv_b200_overlap_groups(ctx.ptr))
     log("decode resident: %.3f ms/token (CUDA graph of per-launch kernels)" % step_ms)
+    if args.quick:
+        tl = kernel_timeline(L, ctx, tok_arr, 1)
+        bytes_tok = int(L.rwkv_b200_bytes_per_token(ctx.ptr, True))
+        sampler.stop()
+        if rank == 0:
+            emit({"quick": True, "workload": args.workload, "ms_per_token": step_ms, "tokens_per_s": decode_tps, "gpu_launches": int(decode_launches),
+                  "whole_step_frac": bytes_tok / (step_ms * 1e-3) / 1e9 / measured_peaks()[0], "traced_us": tl["span_us"],
+                  "attributed_us": {k: round(v, 1) for k, v in tl["attributed_us"].items()}, "launches": tl["launches"],
+                  "env": {k: v for k, v in os.environ.items() if k.startswith("RWKV_B200_") and k != "RWKV_B200_BENCH_DIR"}})
+        lib.rwkv_free(ctx)
+        return
 
     # ---- decode end to end through rwkv_eval with HOST buffers: pinned (a serving process) and pageable (what the reference's
     # ---- Python binding hands over, rwkv_cpp_model.py:330-351) ----------------------------------------------------

@@ -137,6 +137,35 @@ cudaError_t do_wkv4(Context * ctx, const Wkv4Params & wp) {
     return ctx->batch_stride ? launch_wkv4_batch(wp, ctx->batch_stride, ctx->stream) : launch_wkv4(wp, ctx->stream);
 }
 
+// LayerNorm + token shift + mix in front of a batch of GEMVs. Single-token passes fold it into the GEMV launch itself (PRO_LN_MIX:
+// every CTA recomputes the 16 KB LayerNorm in its prologue; one launch and one dependency hand-off fewer per block); multi-token
+// passes, batch contexts and shapes the streaming kernel cannot take run ln_mix_kernel first. Both produce the same bits.
+// Every problem of `b` must have been added with x = the lp.out[j] it reads.
+bool ln_mix_then(Context * ctx, const LnMixParams & lp, Batch & b) {
+    static const bool no_fuse = getenv("RWKV_B200_NO_FUSE_LN") != nullptr || getenv("RWKV_B200_GENERIC_GEMV") != nullptr;
+    bool fuse = lp.T == 1 && !ctx->batch_stride && !no_fuse && ctx->fuse_ln_mix;
+    if (fuse) {
+        GemvBatch probe = b.b;
+        fuse = gemv_lnmix_supported(probe);
+    }
+    if (!fuse) {
+        CUDA_OK(ctx, do_ln_mix(ctx, lp));
+        return true;
+    }
+    for (int i = 0; i < b.b.n; i++) {
+        GemvProblem & p = b.b.p[i];
+        int j = 0;
+        while (j < lp.n_out && lp.out[j] != p.x) j++;
+        RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, j < lp.n_out, "internal: GEMV input is not a mix output");
+        p.x = lp.x; p.ldx = lp.C;
+        p.pro = PRO_LN_MIX;
+        p.ln_w = lp.ln_w; p.ln_b = lp.ln_b;
+        p.mix_prev = lp.state_in; p.mix_coef = lp.coef[j]; p.mix_formula = lp.formula;
+        p.ln_state_out = lp.state_out; p.ln_xx_out = lp.out_xx; p.ln_sx_out = lp.out_sx;
+    }
+    return true;
+}
+
 // Channel mixing, all versions (rwkv_ffn_v4_v5 :484-511, rwkv_ffn_v6 :513-531, rwkv_ffn_v7 :533-543).
 bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
     const Model & m = *ctx->model;
@@ -155,12 +184,11 @@ bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const float *
         lp.coef[0] = L.ffn_time_mix_k.data; lp.out[0] = s.mix[0];
         lp.coef[1] = L.ffn_time_mix_r.data; lp.out[1] = s.mix[1];
     }
-    CUDA_OK(ctx, do_ln_mix(ctx, lp));
     {
         Batch b(T);
         b.add(L.ffn_key, s.mix[0], s.ffn_k, EPI_RELU_SQR);
         if (m.arch_major != 7) b.add(L.ffn_receptance, s.mix[1], s.ffn_r, EPI_SIGMOID);
-        if (!run_batch(ctx, b)) return false;
+        if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     }
     {
         Batch b(T);
@@ -188,12 +216,11 @@ bool att_v4(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     lp.coef[0] = L.att_time_mix_k.data; lp.out[0] = s.mix[0];
     lp.coef[1] = L.att_time_mix_v.data; lp.out[1] = s.mix[1];
     lp.coef[2] = L.att_time_mix_r.data; lp.out[2] = s.mix[2];
-    CUDA_OK(ctx, do_ln_mix(ctx, lp));
     Batch b(T);
     b.add(L.att_receptance, s.mix[2], s.r, EPI_SIGMOID);
     b.add(L.att_key, s.mix[0], s.k);
     b.add(L.att_value, s.mix[1], s.v);
-    if (!run_batch(ctx, b)) return false;
+    if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     Wkv4Params wp{};
     wp.k = s.k; wp.v = s.v; wp.r = s.r;
     wp.time_first = L.att_time_first.data; wp.time_decay = L.att_time_decay.data;
@@ -216,13 +243,12 @@ bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     lp.coef[1] = L.att_time_mix_v.data; lp.out[1] = s.mix[1];
     lp.coef[2] = L.att_time_mix_r.data; lp.out[2] = s.mix[2];
     if (v52) { lp.coef[3] = L.att_time_mix_g.data; lp.out[3] = s.mix[3]; }
-    CUDA_OK(ctx, do_ln_mix(ctx, lp));
     Batch b(T);
     b.add(L.att_receptance, s.mix[2], s.r);
     b.add(L.att_key, s.mix[0], s.k);
     b.add(L.att_value, s.mix[1], s.v);
     if (v52) b.add(L.att_gate, s.mix[3], s.g, EPI_SILU);
-    if (!run_batch(ctx, b)) return false;
+    if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     Wkv6Params wp{};
     wp.r = s.r; wp.k = s.k; wp.v = s.v;
     wp.td = L.att_time_decay.data; wp.td_per_token = 0;
@@ -244,11 +270,10 @@ bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     lp.state_in = st_in + C; lp.state_out = st_out + C; lp.C = C; lp.T = T;
     lp.formula = 1; lp.n_out = 1; lp.coef[0] = L.att_maa_x.data; lp.out[0] = s.mix[0];
     lp.out_xx = s.xx; lp.out_sx = s.sx;
-    CUDA_OK(ctx, do_ln_mix(ctx, lp));
     {   // :313-321  tanh(W1 . xxx)
         Batch b(T);
         b.add(L.att_maa_w1, s.mix[0], s.lora[0], EPI_TANH);
-        if (!run_batch(ctx, b)) return false;
+        if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     }
     V6LerpParams vp{};   // :323-346
     vp.w2 = L.att_maa_w2.data; vp.z = s.lora[0]; vp.xx = s.xx; vp.sx = s.sx;
@@ -291,7 +316,6 @@ bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T,
     lp.state_in = st_in + C; lp.state_out = st_out + C; lp.C = C; lp.T = T;
     lp.formula = 1; lp.n_out = 6;
     for (int j = 0; j < 6; j++) { lp.coef[j] = L.att_x_rwkvag.data + (size_t) j * C; lp.out[j] = s.mix[j]; }   // r w k v a g
-    CUDA_OK(ctx, launch_ln_mix(lp, ctx->stream));
     float * v_dst = first ? s.v_first : s.v;
     {   // :415-432, 439, 447 -- first halves of the LoRA pairs
         Batch b(T);
@@ -302,7 +326,7 @@ bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T,
         b.add(L.att_a1, s.mix[4], s.lora[1]);
         b.add(L.att_g1, s.mix[5], s.lora[2], EPI_SIGMOID);
         if (!first) b.add(L.att_v1, s.mix[3], s.lora[3]);
-        if (!run_batch(ctx, b)) return false;
+        if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     }
     {   // second halves
         Batch b(T);
