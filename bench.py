@@ -623,9 +623,11 @@ def run_ours(args, rank, world, dist):
 
 
 def run_pipeline(args, rank, world, dist):
-    """N > 1: layer pipeline (rwkv.cpp_b200/pipeline.py). Rank g holds layers [g*L/N, (g+1)*L/N) and their slice of
-    the recurrent state; `world` sequences are in flight, one per stage; x f32[C x T] crosses each stage boundary by NCCL
-    send/recv on the stream the stage kernels run on. One step = one token of every in-flight sequence (`world` tokens)."""
+    """N > 1: layer pipeline. Rank g holds a contiguous block of layers (balanced by BYTES: the last stage also
+    streams the head) and their slice of the recurrent state; `world` sequences are in flight, one per stage. The hand-off is
+    inside the library (csrc/kernels/pipe.cu): x f32[C x T] goes into the next GPU's mailbox with NVLink peer stores from the last
+    kernel of the stage's pass, flags + device-side item counters order it -- NCCL only carries the 64-byte IPC handles at set-up
+    and the barriers / reductions of the measurement. One step = one token of every in-flight sequence (`world` tokens)."""
     import torch
     import __graft_entry__
     import synthetic_model as sm
@@ -635,7 +637,10 @@ def run_pipeline(args, rank, world, dist):
     L = lib.library
     path, preset = workload_file(args.workload, rank, world, lambda: dist.barrier())
     local = int(os.environ.get("LOCAL_RANK", rank))
-    begin, end = pipeline.stage_layers(preset["L"], world, rank)
+    info = lib.rwkv_b200_inspect_file(path)
+    head_bytes = preset["C"] * preset["V"] * (4 if args.workload.endswith("FP32") else 2)
+    layer_bytes = (info.bytes_per_token - head_bytes - 8 * info.state_len) / preset["L"]
+    begin, end = pipeline.stage_layers_balanced(preset["L"], world, rank, head_layers=head_bytes / layer_bytes)
     t0 = time.time()
     ctxs = [lib.rwkv_b200_init_from_file_ex(path, local, begin, end)]
     for _ in range(world - 1):
@@ -643,49 +648,58 @@ def run_pipeline(args, rank, world, dist):
     load_s = time.time() - t0
     log("rank %d: layers [%d, %d) loaded in %.1fs" % (rank, begin, end, load_s))
     n_vocab = lib.rwkv_get_logits_len(ctxs[0])
+    first, last = rank == 0, rank == world - 1
+    # ---- connect the stages: 64-byte CUDA IPC handles of the mailboxes, all_gathered once ----
+    hsz = int(L.rwkv_b200_pipe_handle_size())
+    hbuf = ctypes.create_string_buffer(hsz)
+    assert L.rwkv_b200_pipe_export(ctxs[0].ptr, hbuf), "pipe_export failed"
+    mine = torch.frombuffer(bytearray(hbuf.raw), dtype=torch.uint8).to(f"cuda:{local}")
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    handles = [bytes(g.cpu().numpy().tobytes()) for g in gathered]
+    assert L.rwkv_b200_pipe_connect(ctxs[0].ptr, None if first else handles[rank - 1], None if last else handles[rank + 1]), "pipe_connect failed"
+    dist.barrier()
     for c in ctxs:
         L.rwkv_b200_state_load(c.ptr, None)
         L.rwkv_b200_synchronize(c.ptr)
-    K, W, P = args.steps, args.warmup, args.prefill_steps
-    first, last = rank == 0, rank == world - 1
-    # a dedicated (non-default) stream: torch's NCCL send / recv and the stage kernels are all ordered on it. (The legacy default
-    # stream has handle 0, which rwkv_b200_stage_eval reads as "use the context's own stream".)
+    K, W, P = args.steps, max(args.warmup, 3), args.prefill_steps
+    # one stream per stage: a link's hand-offs are enqueued in item order (the legacy default stream has handle 0, which
+    # rwkv_b200_pipe_eval reads as "use the context's own stream")
     stream = torch.cuda.Stream(device=local)
     torch.cuda.set_stream(stream)
     sp = ctypes.c_void_p(stream.cuda_stream)
     assert stream.cuda_stream != 0
-    transport = pipeline.Transport(dist, rank, world)
     sampler = ClockSampler(local)
     sampler.start()
     windows = []
     logits_host = torch.zeros(n_vocab, dtype=torch.float32).pin_memory()
     bytes_tok = int(L.rwkv_b200_bytes_per_token(ctxs[0].ptr, True))   # this stage's share of the byte model
+    kept = {}
 
-    def leg(T, steps, warm, read_logits):
-        """`steps` timed steps of `world` work items each (one per in-flight sequence), after `warm` untimed ones."""
-        toks = sm.synthetic_tokens((steps + warm) * world * T + T, n_vocab)
+    def leg(T, steps, warm, read_logits, n_seq=world, keep=None):
+        """`steps` timed steps of `n_seq` work items each (one per in-flight sequence), after `warm` untimed ones. Every rank simply
+        enqueues its stage for every item in order; the flags in the mailboxes make a stage wait for its neighbour ON THE DEVICE."""
+        n_items = (steps + warm) * n_seq
+        toks = sm.synthetic_tokens(n_items * T + T, n_vocab)
         arr = (ctypes.c_uint32 * len(toks))(*toks)
-        n_hidden = L.rwkv_b200_stage_hidden_len(ctxs[0].ptr, T)
-        recv = torch.empty(n_hidden, dtype=torch.float32, device=f"cuda:{local}")
-        send = torch.empty(n_hidden, dtype=torch.float32, device=f"cuda:{local}")
-        state = {"u": 0}
 
-        def stage(seq, step, hin, hout):
-            u = state["u"]; state["u"] += 1
-            ok = L.rwkv_b200_stage_eval(ctxs[seq].ptr, ctypes.cast(ctypes.byref(arr, 4 * u * T), PU), T,
-                                        ctypes.c_void_p(hin.data_ptr()) if hin is not None else None,
-                                        ctypes.c_void_p(hout.data_ptr()) if hout is not None else None, True, sp)
-            assert ok, "stage_eval failed"
-            if read_logits and last:
-                assert L.rwkv_b200_stage_logits(ctxs[seq].ptr, ctypes.cast(logits_host.data_ptr(), PF), sp)
+        def run(u0, u1):
+            for u in range(u0, u1):
+                seq = u % n_seq
+                ok = L.rwkv_b200_pipe_eval(ctxs[seq].ptr, ctypes.cast(ctypes.byref(arr, 4 * u * T), PU) if first else None, T, True, sp)
+                assert ok, "pipe_eval failed"
+                if read_logits and last:
+                    assert L.rwkv_b200_stage_logits(ctxs[seq].ptr, ctypes.cast(logits_host.data_ptr(), PF), sp)
+                    if keep is not None and seq == 0 and len(keep) < 4:
+                        keep.append((list(toks[u * T:(u + 1) * T]), logits_host.numpy().copy()))
 
-        pipeline.run_ticks(transport, pipeline.schedule(world, world, warm * world, rank), stage, recv, send)
+        run(0, warm * n_seq)
         torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = L.rwkv_b200_kernel_launch_count()
         w0 = time.time(); t0 = time.perf_counter()
         e0.record(stream)
-        pipeline.run_ticks(transport, pipeline.schedule(world, world, steps * world, rank), stage, recv, send)
+        run(warm * n_seq, n_items)
         e1.record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -696,15 +710,43 @@ def run_pipeline(args, rank, world, dist):
         sm_ = t.clone(); dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
         return float(mx[0]), float(mx[1]), float(sm_[2])
 
-    dev_ms, _, launches = leg(1, K, max(W, 3), False)                      # decode, logits stay on the last stage's GPU
+    def reset_states():
+        for c in ctxs:
+            L.rwkv_b200_state_load(c.ptr, None)
+            L.rwkv_b200_synchronize(c.ptr)
+        dist.barrier()
+
+    # ---- correctness inside the bench: the pipeline's logits of sequence 0 vs the same tokens on ONE GPU (last rank loads the whole model)
+    check = []
+    leg(1, 4, 0, True, keep=check)
+    check_out = None
+    if last:
+        whole = lib.rwkv_b200_init_from_file_ex(path, local, 0, -1)
+        lg = np.zeros(n_vocab, np.float32)
+        L.rwkv_b200_state_load(whole.ptr, None)
+        worst, same = 0.0, True
+        for toks_u, got in check:
+            arr1 = (ctypes.c_uint32 * 1)(*toks_u)
+            assert L.rwkv_b200_eval_resident(whole.ptr, arr1, 1, True, lg.ctypes.data_as(PF))
+            worst = max(worst, float(np.abs(lg - got).max()))
+            same = same and lg.tobytes() == got.tobytes()
+        lib.rwkv_free(whole)
+        check_out = {"tokens": len(check), "max_abs_diff_vs_single_gpu": worst, "bitwise_equal": same}
+        log("pipeline check: %s" % check_out)
+    reset_states()
+    dev_ms, _, launches = leg(1, K, W, False)                         # decode, logits stay on the last stage's GPU
     log("pipeline decode: %.3f ms per step of %d tokens" % (dev_ms / K, world))
-    _, e2e_ms, _ = leg(1, K, max(W, 3), True)                              # + token H2D on stage 0, logits D2H on the last stage, per token
+    _, e2e_ms, _ = leg(1, K, W, True)                                 # + token H2D on stage 0, logits D2H on the last stage, per token
+    lat_ms, _, _ = leg(1, max(8, K // 2), 2, False, n_seq=1)          # ONE sequence through all stages: the single-stream latency
+    lat_steps = max(8, K // 2)
     pdev_ms, _, _ = leg(PREFILL_TOKENS, P, 2, False)
     _, pe2e_ms, _ = leg(PREFILL_TOKENS, P, 1, True)
     sampler.stop()
     clocks = sampler.summary(windows)
     stage_bytes = torch.tensor([float(bytes_tok)], device=f"cuda:{local}")
     dist.all_reduce(stage_bytes, op=dist.ReduceOp.MAX)
+    chk = [check_out]
+    dist.broadcast_object_list(chk, src=world - 1)
     for c in ctxs[1:]:
         lib.rwkv_free(c)
     lib.rwkv_free(ctxs[0])
@@ -712,20 +754,23 @@ def run_pipeline(args, rank, world, dist):
         peak, peak_src = measured_peaks()
         tick_ms = dev_ms / (K * world)                                      # one token leaves the pipeline per tick
         gbs = float(stage_bytes.item()) / (tick_ms * 1e-3) / 1e9
+        blocks = [pipeline.stage_layers_balanced(preset["L"], world, r, head_layers=head_bytes / layer_bytes) for r in range(world)]
         line = {
-            "metric": "decode_tokens_per_sec", "value": world * K / (dev_ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "q5_1 weights x q8_1 activations (int8 dp4a, fp32 accumulate); fp16 head" if "Q5_1" in args.workload else args.workload.split(":")[1],
-            "data": "synthetic",
-            "config": {"workload": f"{args.workload} single-token eval with logits ({preset['L']} layers, n_embed {preset['C']}, ffn {preset['F']}, vocab {preset['V']})",
-                       "parallelism": f"pp{world}: {preset['L'] // world} layers + their state slice per GPU, {world} sequences in flight (one per stage), "
-                                      f"x f32[{preset['C']}] per token over NCCL send/recv; one step = {world} tokens",
-                       "l2": "each stage streams its share of 6.1 GB of weights per token >> 126 MB L2, no flush needed", "load_s": round(load_s, 2), "cuda_graph": True},
+            "metric": "decode_tokens_per_sec", "value": world * K / (dev_ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype_label(args.workload), "data": "synthetic",
+            "config": {"workload": workload_label(args, preset),
+                       "parallelism": f"pp{world}: layer blocks {blocks} balanced by bytes (head = {head_bytes / layer_bytes:.1f} layers) + their state slice per GPU, "
+                                      f"{world} sequences in flight (one per stage), x f32[{preset['C']}] per token by NVLink peer stores + flags inside the library "
+                                      f"(csrc/kernels/pipe.cu); one step = {world} tokens",
+                       "l2": "each stage streams its share of the weights per token >> 126 MB L2, no flush needed", "load_s": round(load_s, 2), "cuda_graph": True},
             "clocks": clocks,
             "e2e": {"value": world * K / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": 4 * world, "d2h_bytes_per_step": 4 * n_vocab * world,
                     "host_buffers": "pinned", "ms_per_step": e2e_ms / K,
                     "note": "token ids enter on stage 0, logits leave from the last stage; the recurrent state stays resident on its stage"},
             "gpu_launches": int(launches),
+            "single_stream": {"tokens_per_s": lat_steps / (lat_ms / 1e3), "ms_per_token": lat_ms / lat_steps,
+                              "note": "ONE sequence through all stages (layer i+1 needs layer i: a pipeline cannot speed a single stream up; this is its latency)"},
+            "pipeline_check": chk[0],
             "prefill": {"tokens_per_s": world * P * PREFILL_TOKENS / (pdev_ms / 1e3), "ms_per_chunk": pdev_ms / (P * world), "chunk": PREFILL_TOKENS, "steps": P,
                         "e2e_tokens_per_s": world * P * PREFILL_TOKENS / (pe2e_ms / 1e3)},
             "roofline": {"bound": "hbm", "kernel": "whole pipeline tick of the slowest stage (fused dequant-GEMV launches + glue)",

@@ -86,6 +86,23 @@ RWKV_API bool rwkv_b200_stage_eval(struct rwkv_context * ctx, const uint32_t * t
                                    bool want_logits, void * cuda_stream);
 RWKV_API bool rwkv_b200_stage_logits(struct rwkv_context * ctx, float * logits_out, void * cuda_stream);
 
+/* The same pipeline with the hand-off INSIDE the library: every stage owns a mailbox in its HBM that the previous stage fills with
+ * NVLink peer stores from the last kernel of its pass, and a credit word the next stage writes back (csrc/kernels/pipe.cu) -- no
+ * NCCL call, no host synchronisation and no data-dependent launch parameter per token, so single-token passes keep replaying
+ * their CUDA graph. Set-up (once): every stage exports a handle, the handles travel between the ranks by any means (an
+ * all_gather of rwkv_b200_pipe_handle_size() bytes; NCCL / gloo are needed for nothing else), every stage connects to its
+ * neighbours. One process driving several GPUs uses rwkv_b200_pipe_connect_local instead (peer access, no IPC).
+ *   rwkv_b200_pipe_eval: receive (unless first stage) -> resident layers -> send (unless last stage), all enqueued on cuda_stream
+ *   (NULL = the context's own). Every context of a stage shares the stage's link: enqueue a link's passes in item order on ONE
+ *   stream. The last stage computes logits when asked (rwkv_b200_stage_logits fetches them). A neighbour that never shows up
+ *   makes the waiting kernel trap after ~20 s instead of hanging the GPU. */
+RWKV_API void * rwkv_b200_stream(struct rwkv_context * ctx);            /* the context's own cudaStream_t */
+RWKV_API size_t rwkv_b200_pipe_handle_size(void);
+RWKV_API bool rwkv_b200_pipe_export(struct rwkv_context * ctx, void * handle_out);
+RWKV_API bool rwkv_b200_pipe_connect(struct rwkv_context * ctx, const void * prev_handle, const void * next_handle);
+RWKV_API bool rwkv_b200_pipe_connect_local(struct rwkv_context * ctx, struct rwkv_context * prev, struct rwkv_context * next);
+RWKV_API bool rwkv_b200_pipe_eval(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, bool want_logits, void * cuda_stream);
+
 /* Measurement hooks. */
 RWKV_API float rwkv_b200_last_device_ms(const struct rwkv_context * ctx);     /* CUDA-event time of the last pass */
 RWKV_API uint64_t rwkv_b200_kernel_launch_count(void);                         /* kernels enqueued by this process */

@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "librwkv.so")
 
 SOURCES = [
     "api.cpp", "ggml_file.cpp", "quantizer.cpp", "model.cu", "engine.cu",
-    "kernels/gemv.cu", "kernels/gemv_tma.cu", "kernels/gemm_tc.cu", "kernels/glue.cu", "kernels/wkv.cu", "kernels/sampling.cu", "kernels/batch.cu",
+    "kernels/gemv.cu", "kernels/gemv_tma.cu", "kernels/gemm_tc.cu", "kernels/pipe.cu", "kernels/glue.cu", "kernels/wkv.cu", "kernels/sampling.cu", "kernels/batch.cu",
 ]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

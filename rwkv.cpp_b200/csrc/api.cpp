@@ -300,6 +300,88 @@ bool rwkv_b200_stage_eval(struct rwkv_context * ctx, const uint32_t * tokens, si
     return stage_forward(c, tokens, n_tokens, hidden_in, hidden_out, want_logits && last, reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
+// ---- layer pipeline over peer memory (kernels/pipe.cu) ----
+void * rwkv_b200_stream(struct rwkv_context * ctx) { return ctx ? reinterpret_cast<void *>(C(ctx)->stream) : nullptr; }
+size_t rwkv_b200_pipe_handle_size(void) { return sizeof(cudaIpcMemHandle_t); }
+
+bool rwkv_b200_pipe_export(struct rwkv_context * ctx, void * handle_out) {
+    Context * c = C(ctx);
+    c->last_error = RWKV_ERROR_NONE;
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, handle_out != nullptr, "handle_out is NULL");
+    if (!pipe_ensure_box(c)) return false;
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, c->model->link.box);
+    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, e == cudaSuccess, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    memcpy(handle_out, &h, sizeof(h));
+    return true;
+}
+
+static bool pipe_open(Context * c, const void * handle, PipeBox ** out) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void * p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, e == cudaSuccess, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+    *out = reinterpret_cast<PipeBox *>(p);
+    return true;
+}
+
+bool rwkv_b200_pipe_connect(struct rwkv_context * ctx, const void * prev_handle, const void * next_handle) {
+    Context * c = C(ctx);
+    c->last_error = RWKV_ERROR_NONE;
+    Model & m = *c->model;
+    if (!pipe_ensure_box(c)) return false;
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, (m.layer_begin == 0) == (prev_handle == nullptr) && (m.layer_end == m.n_layer) == (next_handle == nullptr),
+               "Stage [%d, %d): a first stage has no previous neighbour, a last stage no next one, every other stage both", m.layer_begin, m.layer_end);
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, !m.link.prev && !m.link.next, "The stage is already connected");
+    if (cudaSetDevice(m.dev.device) != cudaSuccess) return false;
+    if (prev_handle) { if (!pipe_open(c, prev_handle, &m.link.prev)) return false; m.link.prev_ipc = true; }
+    if (next_handle) { if (!pipe_open(c, next_handle, &m.link.next)) return false; m.link.next_ipc = true; }
+    return true;
+}
+
+bool rwkv_b200_pipe_connect_local(struct rwkv_context * ctx, struct rwkv_context * prev, struct rwkv_context * next) {
+    Context * c = C(ctx);
+    c->last_error = RWKV_ERROR_NONE;
+    Model & m = *c->model;
+    if (!pipe_ensure_box(c)) return false;
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, (m.layer_begin == 0) == (prev == nullptr) && (m.layer_end == m.n_layer) == (next == nullptr),
+               "Stage [%d, %d): a first stage has no previous neighbour, a last stage no next one, every other stage both", m.layer_begin, m.layer_end);
+    for (struct rwkv_context * other : {prev, next}) {
+        if (!other) continue;
+        Context * o = C(other);
+        if (!pipe_ensure_box(o)) return false;
+        if (o->model->dev.device != m.dev.device) {      // one process, two GPUs: peer access in both directions
+            for (int pass = 0; pass < 2; pass++) {
+                const int from = pass ? o->model->dev.device : m.dev.device, to = pass ? m.dev.device : o->model->dev.device;
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, from, to);
+                RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, can, "Device %d cannot access device %d's memory", from, to);
+                cudaSetDevice(from);
+                const cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, e == cudaSuccess, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e));
+            }
+        }
+        (other == prev ? m.link.prev : m.link.next) = o->model->link.box;
+    }
+    return true;
+}
+
+bool rwkv_b200_pipe_eval(struct rwkv_context * ctx, const uint32_t * tokens, size_t n_tokens, bool want_logits, void * cuda_stream) {
+    Context * c = C(ctx);
+    c->last_error = RWKV_ERROR_NONE;
+    const Model & m = *c->model;
+    const bool first = m.layer_begin == 0;
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, n_tokens > 0 && n_tokens <= (size_t) MAX_TOKENS_PER_PASS, "A stage pass takes 1 .. %d tokens", MAX_TOKENS_PER_PASS);
+    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->batch_n == 0, "Batch contexts cannot be pipeline stages");
+    RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, !first || tokens != nullptr, "The first stage needs tokens");
+    if (first)
+        for (size_t i = 0; i < n_tokens; i++)
+            RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, tokens[i] < (uint32_t) m.n_vocab, "Token at index %zu (%" PRIu32 ") is out of range (0 .. %d)", i, tokens[i], m.n_vocab - 1);
+    return pipe_forward(c, tokens, n_tokens, want_logits, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
 bool rwkv_b200_stage_logits(struct rwkv_context * ctx, float * logits_out, void * cuda_stream) {
     Context * c = C(ctx);
     c->last_error = RWKV_ERROR_NONE;
@@ -454,14 +536,14 @@ bool rwkv_b200_matvec(int data_type, int K, int M, int T, const void * weights, 
         p.W = dW; p.pitch = (long long) pitch; p.type = data_type; p.K = K; p.M = M;
         p.x = dx; p.ldx = K; p.y = dy; p.ldy = M; p.epi = epilogue; p.pro = PRO_NONE;
         void * act16 = nullptr, * tiled = nullptr;
-        const size_t act16_bytes = (size_t) ((T + 15) / 16 * 16) * K * 2 + 256;
+        const size_t act16_bytes = gemm_tc_workspace_bytes(T, (size_t) ((T + 15) / 16 * 16) * K + 128);
         // passes of >= 32 tokens go through the tensor-core kernel, which streams the tile-major copy of the matrix
         if (T >= 32 && gemm_tc_eligible(data_type, K) && !getenv("RWKV_B200_NO_TC")) {
             ok = cudaMalloc(&tiled, gemm_tc_tiled_bytes(data_type, M, K)) == cudaSuccess && gemm_tc_repack(dW, (long long) pitch, data_type, M, K, tiled, 0) == cudaSuccess;
             p.Wt = tiled;
         }
         const bool use_tc = ok && gemm_tc_supported(p, T);
-        if (use_tc) ok = cudaMalloc(&act16, act16_bytes) == cudaSuccess && gemm_tc_launch(b, di, 0, act16, act16_bytes) == cudaSuccess;
+        if (use_tc) ok = cudaMalloc(&act16, act16_bytes) == cudaSuccess && cudaMemset(act16, 0, GEMM_TC_COUNTER_BYTES) == cudaSuccess && gemm_tc_launch(b, di, 0, act16, act16_bytes) == cudaSuccess;
         else ok = gemv_launch(b, di, 0) == cudaSuccess;
         ok = ok && cudaDeviceSynchronize() == cudaSuccess && cudaMemcpy(y, dy, sizeof(float) * M * T, cudaMemcpyDeviceToHost) == cudaSuccess;
         cudaFree(act16); cudaFree(tiled);

@@ -375,8 +375,9 @@ bool ensure_capacity(Context * ctx, int T) {
     if (cap >= 32) {   // fp16 staging for the tensor-core path: up to 8 distinct inputs of max(C, F) x round16(cap)
         Dims d = model_dims(m);
         const size_t kmax = d.F > d.C ? d.F : d.C;
-        ctx->act16_bytes = (size_t) GEMV_MAX_PROBLEMS * (kmax * (size_t) ((cap + 15) / 16 * 16) * 2 + 256 + (size_t) ((cap + 15) / 16 * 16) * 4 + 256);   // + a per-token scale vector
+        ctx->act16_bytes = gemm_tc_workspace_bytes(cap, (size_t) GEMV_MAX_PROBLEMS * (kmax * (size_t) ((cap + 15) / 16 * 16) + 128));
         e = cudaMalloc(&ctx->act16, ctx->act16_bytes);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->act16, 0, GEMM_TC_COUNTER_BYTES, ctx->stream);      // split-K tile counters
         RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, false, e == cudaSuccess, "Failed to allocate fp16 staging: %s", cudaGetErrorString(e));
     }
     ctx->scratch_floats = n;
@@ -766,6 +767,42 @@ bool sample_token(Context * ctx, float temperature, float top_p, double u, const
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     *token_out = ctx->sample_token_host[0];
     return true;
+}
+
+bool pipe_ensure_box(Context * ctx) {
+    Model & m = *ctx->model;
+    if (m.link.box) return true;
+    CUDA_OK(ctx, cudaSetDevice(m.dev.device));
+    m.link.slot_floats = stage_hidden_len(m, (size_t) MAX_TOKENS_PER_PASS);
+    m.link.bytes = sizeof(PipeBox) + (size_t) PIPE_SLOTS * m.link.slot_floats * sizeof(float);
+    CUDA_OK(ctx, cudaMalloc(reinterpret_cast<void **>(&m.link.box), m.link.bytes));
+    CUDA_OK(ctx, cudaMemset(m.link.box, 0, sizeof(PipeBox)));
+    CUDA_OK(ctx, cudaMalloc(reinterpret_cast<void **>(&m.link.counters), 8 * sizeof(unsigned long long)));
+    CUDA_OK(ctx, cudaMemset(m.link.counters, 0, 8 * sizeof(unsigned long long)));
+    CUDA_OK(ctx, cudaDeviceSynchronize());
+    return true;
+}
+
+bool pipe_forward(Context * ctx, const uint32_t * tokens, size_t T, bool want_logits, cudaStream_t stream) {
+    Model & m = *ctx->model;
+    const bool first = m.layer_begin == 0, last = m.layer_end == m.n_layer;
+    RWKV_CHECK(ctx->sink(), RWKV_ERROR_ARGS, false, m.link.box && (first || m.link.prev) && (last || m.link.next), "The stage is not connected to its neighbours");
+    CUDA_OK(ctx, cudaSetDevice(m.dev.device));
+    cudaStream_t own = ctx->stream;
+    if (stream) ctx->stream = stream;
+    bool ok = begin_pass(ctx, tokens, (int) T);
+    if (ok) {
+        const Scratch hs = carve(m, ctx->scratch, (int) T);
+        const size_t n = (size_t) m.n_embed * T, nv = m.arch_major == 7 ? n : 0;
+        cudaError_t e = cudaSuccess;
+        if (!first) e = launch_pipe_recv(m.link.box, m.link.prev, m.link.counters, m.link.slot_floats, hs.x, n, hs.v_first, nv, ctx->stream);
+        ok = e == cudaSuccess && run_layers(ctx, (int) T, want_logits && last, 0);
+        if (ok && !last) e = launch_pipe_send(m.link.box, m.link.next, m.link.counters, m.link.slot_floats, hs.x, n, hs.v_first, nv, ctx->stream);
+        ok = ok && e == cudaSuccess && end_pass(ctx, (int) T, want_logits && last);
+        if (e != cudaSuccess) { ctx->last_error |= RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED; if (ctx->print_errors) fprintf(stderr, "pipeline hand-off launch failed: %s\n", cudaGetErrorString(e)); }
+    }
+    ctx->stream = own;
+    return ok;
 }
 
 size_t stage_hidden_len(const Model & m, size_t T) { return (size_t) (m.arch_major == 7 ? 2 : 1) * (size_t) m.n_embed * T; }

@@ -132,5 +132,10 @@ bool sample_token(Context * ctx, float temperature, float top_p, double u, const
 size_t stage_hidden_len(const Model & m, size_t T);
 
 bool stage_forward(Context * ctx, const uint32_t * tokens, size_t T, const float * hidden_in, float * hidden_out, bool want_logits, cudaStream_t stream);
+// The same with the hand-off done by peer-memory kernels on the stream (kernels/pipe.cu): receive from the previous stage's
+// stores (unless this stage embeds tokens), run the resident layers, store into the next stage's mailbox (unless this is the last).
+bool pipe_forward(Context * ctx, const uint32_t * tokens, size_t T, bool want_logits, cudaStream_t stream);
+// Allocates (once) the stage's mailbox for passes of up to MAX_TOKENS_PER_PASS tokens.
+bool pipe_ensure_box(Context * ctx);
 
 }  // namespace rwkv

@@ -100,6 +100,26 @@ __device__ __forceinline__ void bulk_load(void * dst, const void * src, uint32_t
                  "r"(smem_u32(bar))
                  : "memory");
 }
+// ---- thread-block clusters: the CTAs of a cluster work on neighbouring row tiles of the SAME matrix over the same K range, so they
+// need the same B (activation) stage; each loads 1/CS of it and multicasts the slice into every member's shared memory.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_multicast(void * dst, const void * src, uint32_t bytes, uint64_t * bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t * bar, uint32_t cta) {      // the barrier at the same offset in CTA `cta` of the cluster
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
@@ -154,6 +174,9 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t * r) {
 __device__ __forceinline__ void umma_commit(uint64_t * bar) {   // arrives on `bar` when every MMA issued so far has completed
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void umma_commit_multicast(uint64_t * bar, uint16_t mask) {   // ... on the barrier at this offset in every CTA of `mask`
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t * r) {   // 32 lanes x 32 consecutive columns
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -200,6 +223,7 @@ struct TcShared {
     long long t0;            // clock64 at kernel start (trace marks)
     GemvProblem P;
     float colscale[MAX_N];
+    int split_rank;          // arrival order of this CTA among the K-splits of its tile (split-K epilogue)
 };
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
@@ -237,8 +261,13 @@ template <int EPI> __device__ __forceinline__ void store_cols(const EpiRow & e, 
     }
 }
 // warp w owns TMEM lanes 32 (w % 4) .. + 31 = rows row0 + 32 (w % 4) + lane; warps 0-3 take the even 32-column groups of the
-// accumulator, warps 4-7 the odd ones
-__device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, const float * cs, uint32_t tmem_base, int row0, int npad, int T) {
+// accumulator, warps 4-7 the odd ones.
+//   MODE 0  single split: accumulator -> fused epilogue -> y
+//   MODE 1  one of several K-splits: accumulator -> this split's slot of the partial buffer (row-major [128][npad], full-line stores)
+//   MODE 2  the split that arrived last: partials of ALL splits, added in split order from the buffer -> fused epilogue -> y
+template <int MODE>
+__device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, const float * cs, uint32_t tmem_base, int row0, int npad, int T,
+                                              float * part0, int nsplit, size_t slot_floats) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3;
     const int row = row0 + q * 32 + lane;
@@ -248,11 +277,33 @@ __device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, const flo
     e.y = Psh.y + row; e.ldy = Psh.ldy;
     e.res = Psh.res ? Psh.res + row : nullptr; e.ldres = Psh.ldres;
     e.gate = Psh.gate ? Psh.gate + row : nullptr; e.ldgate = Psh.ldgate;
-    e.bias = (live && Psh.bias) ? Psh.bias[row] : 0.f;
+    e.bias = (MODE != 1 && live && Psh.bias) ? Psh.bias[row] : 0.f;
+    float * prow = part0 + (size_t) (q * 32 + lane) * npad;
 #pragma unroll 1
     for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += 64) {
         uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) c0, acc);
+        if constexpr (MODE == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) acc[j] = 0u;          // +0.0f
+            for (int sp = 0; sp < nsplit; sp++) {
+                const float4 * src = reinterpret_cast<const float4 *>(prow + (size_t) sp * slot_floats + c0);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float4 v = __ldcg(src + j);            // written by other SMs: L2, not L1
+                    acc[4 * j] = __float_as_uint(__uint_as_float(acc[4 * j]) + v.x); acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + v.y);
+                    acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + v.z); acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + v.w);
+                }
+            }
+        } else {
+            tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) c0, acc);
+        }
+        if constexpr (MODE == 1) {
+            float4 * dst = reinterpret_cast<float4 *>(prow + c0);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                __stcg(dst + j, make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3])));
+            continue;
+        }
         if (!live) continue;
         switch (epi) {
             case EPI_SIGMOID: store_cols<EPI_SIGMOID>(e, acc, cs, c0, T); break;
@@ -340,17 +391,29 @@ struct TcBatch {
     int b_stages;                    // A/B ring depth, 2 .. MAX_STAGES
     const __half * act16[GEMV_MAX_PROBLEMS];   // canonical-layout fp16 activations per problem (convert_f16_kernel)
     const float * colscale[GEMV_MAX_PROBLEMS]; // [npad] power-of-two factor per token that the epilogue multiplies back in
-    GemvProblem p[GEMV_MAX_PROBLEMS];          // first_cta / n_cta = tiles of 128 rows
+    GemvProblem p[GEMV_MAX_PROBLEMS];          // first_cta / n_cta: CTA range of the problem = splits x tpad
+    // Work decomposition. A problem's CTAs are [split][tile padded to a multiple of the cluster size]; the CTAs of one cluster are
+    // cs neighbouring tiles of one split (tiles >= `tiles` are stand-ins that only take part in the B multicast). With splits > 1
+    // every CTA contracts `steps_per_split` K-steps and leaves its 128 x npad partial tile in `partial`; the CTA that arrives last
+    // at the tile's counter adds the partials up in split order (a fixed order: deterministic) and runs the epilogue.
+    int cs;                                    // cluster size: 1, 2 or 4
+    int tiles[GEMV_MAX_PROBLEMS], tpad[GEMV_MAX_PROBLEMS], splits[GEMV_MAX_PROBLEMS], steps_per_split[GEMV_MAX_PROBLEMS];
+    int slot0[GEMV_MAX_PROBLEMS];              // first partial slot / counter of the problem (slot = slot0 + tile * splits + split)
+    float * partial;                           // [slots][128][npad] fp32
+    int * counters;                            // one per (problem, tile) with splits > 1, at index slot0 + tile * splits; zero between launches
     TraceRec * trace;
 };
 
+// What one CTA does: rows [tile * 128, +128) of problem `pi` against all tokens over K-steps [ks0, ks1).
+struct TcWork { int pi, tile, split, ks0, ks1; bool standin; };
+
 template <int TYPE>
-__device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, const __half * act16, const float * colscale, int tile) {
+__device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, const TcWork w) {
     using RT = RawTraits<TYPE>;
     const GemvProblem & P = sh.P;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int K = P.K, NPAD = batch.npad, NG = NPAD / 8;
-    const int row0 = tile * TILE_M;
+    const int NPAD = batch.npad, NG = NPAD / 8;
+    const int row0 = w.tile * TILE_M;
     const uint32_t b_bytes = (uint32_t) NPAD * KSTEP * 2;
     constexpr uint32_t raw_bytes = (uint32_t) TILE_M * RT::ROW_STRIDE;
     uint8_t * const b_base = smem;
@@ -358,34 +421,51 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
     const int nb = batch.b_stages;
     uint8_t * const raw_base = b_base + (size_t) nb * b_bytes;
     const uint32_t raw_slot = (uint32_t) batch.raw_stage_bytes;
-    const int nsteps = K / KSTEP;
+    const int nsteps_total = P.K / KSTEP;
     const int nraw = batch.raw_stages;
+    const int CS = batch.cs;
+    const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
+    const uint16_t all_mask = (uint16_t) ((1u << CS) - 1u);
+    const __half * act16 = batch.act16[w.pi];
+    const int nsplit = batch.splits[w.pi];
 
     if (warp == WARP_RAW) {
-        if (lane == 0) {
-            const int nchunks = (nsteps + RT::CHUNK_STEPS - 1) / RT::CHUNK_STEPS;
+        if (lane == 0 && !w.standin) {
+            const int nchunks_total = (nsteps_total + RT::CHUNK_STEPS - 1) / RT::CHUNK_STEPS;
+            const int c0 = w.ks0 / RT::CHUNK_STEPS, c1 = (w.ks1 + RT::CHUNK_STEPS - 1) / RT::CHUNK_STEPS;     // split boundaries are chunk-aligned
             const uint8_t * wt = reinterpret_cast<const uint8_t *>(P.Wt);
             int rs = 0; uint32_t ph = 0;
-            for (int c = 0; c < nchunks; c++) {
+            for (int c = c0; c < c1; c++) {
                 mbar_wait(&sh.raw_empty[rs], ph ^ 1);
                 mbar_expect_tx(&sh.raw_full[rs], raw_bytes);
-                bulk_load(raw_base + (size_t) rs * raw_slot, wt + ((size_t) tile * nchunks + c) * raw_bytes, raw_bytes, &sh.raw_full[rs]);
+                bulk_load(raw_base + (size_t) rs * raw_slot, wt + ((size_t) w.tile * nchunks_total + c) * raw_bytes, raw_bytes, &sh.raw_full[rs]);
                 if (++rs == nraw) { rs = 0; ph ^= 1; }
             }
         }
     } else if (warp == WARP_B) {
         if (lane == 0) {
             pdl_prologue();     // the activations come from the previous kernels
+            const uint32_t slice = b_bytes / (uint32_t) CS;
             int s = 0; uint32_t ph = 0;
-            for (int ks = 0; ks < nsteps; ks++) {
-                mbar_wait(&sh.ab_empty[s], ph ^ 1);
-                mbar_expect_tx(&sh.b_full[s], b_bytes);
-                bulk_load(b_base + (size_t) s * b_bytes, act16 + (size_t) ks * KSTEP * NPAD, b_bytes, &sh.b_full[s]);
+            for (int ks = w.ks0; ks < w.ks1; ks++) {
+                mbar_wait(&sh.ab_empty[s], ph ^ 1);        // every CTA of the cluster has consumed this stage
+                mbar_expect_tx(&sh.b_full[s], b_bytes);    // my barrier sees the whole stage: CS slices, one from each member
+                const uint8_t * src = reinterpret_cast<const uint8_t *>(act16 + (size_t) ks * KSTEP * NPAD);
+                if (CS == 1) bulk_load(b_base + (size_t) s * b_bytes, src, b_bytes, &sh.b_full[s]);
+                else bulk_load_multicast(b_base + (size_t) s * b_bytes + (size_t) rank * slice, src + (size_t) rank * slice, slice, &sh.b_full[s], all_mask);
                 if (++s == nb) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == WARP_MMA) {
-        if (lane == 0) {
+        if (lane == 0 && w.standin) {
+            // a stand-in has no rows: it releases every stage as soon as the stage's data has landed in its shared memory
+            int s = 0; uint32_t ph = 0;
+            for (int ks = w.ks0; ks < w.ks1; ks++) {
+                mbar_wait(&sh.b_full[s], ph);
+                for (int c = 0; c < CS; c++) mbar_arrive_remote(&sh.ab_empty[s], (uint32_t) c);
+                if (++s == nb) { s = 0; ph ^= 1; }
+            }
+        } else if (lane == 0) {
             const uint32_t idesc = make_idesc(TILE_M, NPAD);
             // everything the issue loop needs sits in registers: TMEM addresses, the constant descriptor half and the 14-bit
             // start-address field of each B stage; per K-step the thread does two waits, 4 MMAs and ONE commit
@@ -393,7 +473,7 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
             const uint64_t desc_fixed = make_desc(0, (uint32_t) NG * 128, 128);
             const uint32_t b_addr0 = smem_u32(b_base) >> 4, b_stage16 = b_bytes >> 4, b_k16 = (uint32_t) (2 * NG * 128) >> 4;
             int s = 0; uint32_t ph = 0;
-            for (int ks = 0; ks < nsteps; ks++) {
+            for (int ks = w.ks0; ks < w.ks1; ks++) {
                 const uint32_t a_col = tmem_a0 + (uint32_t) (s * 32);
                 const uint64_t d0 = desc_fixed | (uint64_t) ((b_addr0 + (uint32_t) s * b_stage16) & 0x3FFFu);
                 const uint64_t d1 = desc_fixed | (uint64_t) ((b_addr0 + (uint32_t) s * b_stage16 + b_k16) & 0x3FFFu);
@@ -402,31 +482,31 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
                 mbar_wait(&sh.b_full[s], ph);
                 mbar_wait(&sh.a_full[s], ph);
                 tc_fence_after_sync();
-                umma_f16_ts(tmem_d, a_col, d0, idesc, ks > 0 ? 1u : 0u);
+                umma_f16_ts(tmem_d, a_col, d0, idesc, ks > w.ks0 ? 1u : 0u);
                 umma_f16_ts(tmem_d, a_col + 8, d1, idesc, 1u);
                 umma_f16_ts(tmem_d, a_col + 16, d2, idesc, 1u);
                 umma_f16_ts(tmem_d, a_col + 24, d3, idesc, 1u);
-                umma_commit(&sh.ab_empty[s]);          // the A and B stage are free once these MMAs have read them
+                // the A stage (mine) and the B stage (everybody's copy is written by everybody) are free once these MMAs have read them
+                if (CS == 1) umma_commit(&sh.ab_empty[s]); else umma_commit_multicast(&sh.ab_empty[s], all_mask);
                 if (++s == nb) { s = 0; ph ^= 1; }
             }
             umma_commit(&sh.acc_done);                 // ... and the accumulator is final
         }
-    } else {
+    } else if (!w.standin) {
         // transform: thread = row r of the tile, BOTH blocks of a K-step (two independent dequantisation chains in
         // flight, one wait / store / arrive per 64 k); warps 0-3 take the even K-steps, warps 4-7 the odd ones, so two
         // A stages are being filled at any time. Warp w owns TMEM lanes 32 * (w % 4) .. + 31 = its 32 rows.
         const int r = tid & (TILE_M - 1), grp = tid >> 7;
         const uint32_t raw_row0 = smem_u32(raw_base) + (uint32_t) r * RT::ROW_STRIDE;
         const uint32_t tmem_a_mine = tmem_a0 + ((uint32_t) ((warp & 3) * 32) << 16);
-        // trace marks of CTA 0 (cycles, stored as start + cycles): [0] transform waited for raw chunks, [1] for a free A
-        // stage, [2] the MMA issuer waited for operands, [3] the whole K loop
         // trace marks of CTA 0, thread 0 (cycles, stored as start + cycles): [0] waiting for raw chunks, [1] reading + dequantising
         // two blocks, [2] waiting for a free A stage, [3] tcgen05.st + fences + arrive
         const bool acct = batch.trace != nullptr && blockIdx.x == 0 && tid == 0;
         long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, tq = acct ? clock64() : 0;
         auto tick = [&](long long & a) { if (acct) { const long long now = clock64(); a += now - tq; tq = now; } };
-        int s = grp, rs = 0, cur_chunk = -1; uint32_t ph = 0, rph = 0;
-        for (int ks = grp; ks < nsteps; ks += 2) {
+        int s = grp % nb, rs = 0, cur_chunk = -1; uint32_t ph = 0, rph = 0;
+        if (grp >= nb) ph ^= 1;        // (nb >= 2 always)
+        for (int ks = w.ks0 + grp; ks < w.ks1; ks += 2) {
             const int c = ks / RT::CHUNK_STEPS, sc = ks % RT::CHUNK_STEPS;
             if (c != cur_chunk) {
                 if (cur_chunk >= 0 && ++rs == nraw) { rs = 0; rph ^= 1; }
@@ -438,7 +518,7 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
             read_block<TYPE>(raw_row0 + (uint32_t) rs * raw_slot, sc * 2, regs0);
             read_block<TYPE>(raw_row0 + (uint32_t) rs * raw_slot, sc * 2 + 1, regs1);
             // last step of this warp inside the chunk: the raw rows are in registers, hand the slot back
-            const bool last_in_chunk = sc + 2 >= RT::CHUNK_STEPS || ks + 2 >= nsteps;
+            const bool last_in_chunk = sc + 2 >= RT::CHUNK_STEPS || ks + 2 >= w.ks1;
             uint4 h0[4], h1[4];
             block_to_half<TYPE>(regs0, h0);
             block_to_half<TYPE>(regs1, h1);
@@ -469,15 +549,31 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
             t->mark[2] = t->start + (unsigned long long) c2; t->mark[3] = t->start + (unsigned long long) c3;
         }
         {
-            pdl_prologue();     // residual / gate inputs come from the previous kernels
-            if (tid < NPAD) sh.colscale[tid] = colscale[tid];
+            pdl_prologue();     // residual / gate inputs (and, with K-splits, the partial buffer) belong to the previous kernels until here
+            if (tid < NPAD) sh.colscale[tid] = batch.colscale[w.pi][tid];
             asm volatile("bar.sync 2, 256;" ::: "memory");      // the 8 transform / epilogue warps
             mbar_wait(&sh.acc_done, 0);
-            const bool acct_e = batch.trace != nullptr && blockIdx.x == 0 && tid == 0;
             tc_fence_after_sync();
-            tc_epilogue_rows(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T);
-            (void) acct_e;
+            if (nsplit == 1) {
+                tc_epilogue_rows<0>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, nullptr, 1, 0);
+            } else {
+                const size_t slot_floats = (size_t) TILE_M * NPAD;
+                const int slot_first = batch.slot0[w.pi] + w.tile * nsplit;
+                float * part0 = batch.partial + (size_t) slot_first * slot_floats;
+                tc_epilogue_rows<1>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, part0 + (size_t) w.split * slot_floats, nsplit, slot_floats);
+                __threadfence();                                    // my partial is visible device-wide before I take a ticket
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (tid == 0) sh.split_rank = atomicAdd(batch.counters + slot_first, 1);
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (sh.split_rank == nsplit - 1) {                  // every other split's partial has been published before its ticket
+                    __threadfence();
+                    tc_epilogue_rows<2>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, part0, nsplit, slot_floats);
+                    if (tid == 0) batch.counters[slot_first] = 0;   // ready for the next launch (ordered by kernel completion)
+                }
+            }
         }
+    } else {
+        pdl_prologue();
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -494,7 +590,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
         sh.t0 = clock64();
         sh.P = batch.p[pi];
         for (int s = 0; s < MAX_RAW_STAGES; s++) { mbar_init(&sh.raw_full[s], 1); mbar_init(&sh.raw_empty[s], XFORM_WARPS); }
-        for (int s = 0; s < MAX_STAGES; s++) { mbar_init(&sh.a_full[s], XFORM_WARPS / 2); mbar_init(&sh.b_full[s], 1); mbar_init(&sh.ab_empty[s], 1); }
+        for (int s = 0; s < MAX_STAGES; s++) { mbar_init(&sh.a_full[s], XFORM_WARPS / 2); mbar_init(&sh.b_full[s], 1); mbar_init(&sh.ab_empty[s], (uint32_t) batch.cs); }
         mbar_init(&sh.acc_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -502,16 +598,27 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const int tile = (int) blockIdx.x - sh.P.first_cta;
-    const __half * act16 = batch.act16[pi];
-    switch (sh.P.type) {
-        case DT_Q4_0: tc_tile<DT_Q4_0>(sh, smem, batch, act16, batch.colscale[pi], tile); break;
-        case DT_Q4_1: tc_tile<DT_Q4_1>(sh, smem, batch, act16, batch.colscale[pi], tile); break;
-        case DT_Q5_0: tc_tile<DT_Q5_0>(sh, smem, batch, act16, batch.colscale[pi], tile); break;
-        case DT_Q5_1: tc_tile<DT_Q5_1>(sh, smem, batch, act16, batch.colscale[pi], tile); break;
-        case DT_Q8_0: tc_tile<DT_Q8_0>(sh, smem, batch, act16, batch.colscale[pi], tile); break;
-        default: tc_tile<DT_F16>(sh, smem, batch, act16, batch.colscale[pi], tile); break;
+    if (batch.cs > 1) cluster_sync_all();          // nobody multicasts into, or arrives on, a barrier that is not initialised yet
+    TcWork w;
+    w.pi = pi;
+    {
+        const int local = (int) blockIdx.x - sh.P.first_cta, tpad = batch.tpad[pi];
+        w.split = local / tpad;
+        w.tile = local % tpad;
+        w.standin = w.tile >= batch.tiles[pi];
+        const int nsteps = sh.P.K / KSTEP, per = batch.steps_per_split[pi];
+        w.ks0 = w.split * per;
+        w.ks1 = min(nsteps, w.ks0 + per);
     }
+    switch (sh.P.type) {
+        case DT_Q4_0: tc_tile<DT_Q4_0>(sh, smem, batch, w); break;
+        case DT_Q4_1: tc_tile<DT_Q4_1>(sh, smem, batch, w); break;
+        case DT_Q5_0: tc_tile<DT_Q5_0>(sh, smem, batch, w); break;
+        case DT_Q5_1: tc_tile<DT_Q5_1>(sh, smem, batch, w); break;
+        case DT_Q8_0: tc_tile<DT_Q8_0>(sh, smem, batch, w); break;
+        default: tc_tile<DT_F16>(sh, smem, batch, w); break;
+    }
+    if (batch.cs > 1) cluster_sync_all();          // my shared memory and barriers stay valid until every member is done with them
     if (threadIdx.x < 32) tmem_dealloc(sh.tmem_base, (uint32_t) batch.tmem_cols);
     trace_end(batch.trace);
 }
@@ -652,19 +759,27 @@ bool gemm_tc_supported(const GemvProblem & p, int T) {
            (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.Wt) & 15) == 0;
 }
 
-// act16_scratch: device buffer of at least sum over problems of npad * K halves.
-cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream, void * act16_scratch, size_t scratch_bytes) {
-    (void) dev;
+// Workspace layout (gemm_tc_workspace_bytes): [split-K tile counters, zero between launches][split-K partial tiles][fp16 operands +
+// per-token scales of the batch's distinct inputs]. The caller zeroes the counter block once after allocating.
+size_t gemm_tc_workspace_bytes(int T, size_t operand_halves) {
+    const size_t npad = (size_t) (T + 15) / 16 * 16;
+    return GEMM_TC_COUNTER_BYTES + GEMM_TC_PARTIAL_BYTES + operand_halves * 2 + (size_t) GEMV_MAX_PROBLEMS * (npad * 4 + 512);
+}
+
+cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream, void * workspace, size_t workspace_bytes) {
+    if (workspace_bytes < GEMM_TC_COUNTER_BYTES + GEMM_TC_PARTIAL_BYTES) return cudaErrorMemoryAllocation;
     tc::TcBatch tb;
     memset(&tb, 0, sizeof(tb));
     tb.n = batch.n; tb.T = batch.T;
     tb.npad = (batch.T + 15) / 16 * 16;
     tb.tmem_cols = 32;
     while (tb.tmem_cols < tb.npad + tc::MAX_STAGES * 32) tb.tmem_cols *= 2;      // accumulator + A stages
+    tb.counters = reinterpret_cast<int *>(workspace);
+    tb.partial = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(workspace) + GEMM_TC_COUNTER_BYTES);
 
-    uint8_t * scratch = reinterpret_cast<uint8_t *>(act16_scratch);
+    uint8_t * scratch = reinterpret_cast<uint8_t *>(workspace) + GEMM_TC_COUNTER_BYTES + GEMM_TC_PARTIAL_BYTES;
+    const size_t scratch_bytes = workspace_bytes - GEMM_TC_COUNTER_BYTES - GEMM_TC_PARTIAL_BYTES;
     size_t used = 0;
-    int next = 0;
     tc::ConvertBatch cvt;
     memset(&cvt, 0, sizeof(cvt));
     cvt.T = batch.T; cvt.npad = tb.npad;
@@ -689,8 +804,43 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
         share_of[i] = shared;
         tb.act16[i] = cvt.out[shared];
         tb.colscale[i] = cvt.colscale[shared];
+    }
+    // ---- work decomposition: cluster size, K-splits ----
+    // Clusters of 4 neighbouring row tiles share every B stage through multicast: a CTA pulls 1/4 of the activations it multiplies
+    // out of L2 (the B operand, re-read by every row tile, is 3x the weight bytes of a 128-row tile per K-step). Launches that
+    // would leave most of the 148 SMs idle (matrices with 4096 rows: 32 tiles; the LoRA matrices: 1-2 tiles) are cut along K.
+    static const int force_cs = [] { const char * e = getenv("RWKV_B200_TC_CLUSTER"); return e ? atoi(e) : 0; }();
+    static const int force_split = [] { const char * e = getenv("RWKV_B200_TC_SPLITK"); return e ? atoi(e) : -1; }();
+    int base = 0;
+    for (int i = 0; i < batch.n; i++) { tb.tiles[i] = (batch.p[i].M + tc::TILE_M - 1) / tc::TILE_M; base += tb.tiles[i]; }
+    tb.cs = base >= 16 ? 4 : 1;
+    if (force_cs == 1 || force_cs == 2 || force_cs == 4) tb.cs = force_cs;
+    int total = 0;
+    for (int i = 0; i < batch.n; i++) { tb.tpad[i] = (tb.tiles[i] + tb.cs - 1) / tb.cs * tb.cs; total += tb.tpad[i]; }
+    const int sms = dev.num_sms > 0 ? dev.num_sms : 148;
+    int want = total * 5 < sms * 3 ? sms / total : 1;      // below 60 % of the SMs: split
+    if (force_split >= 0) want = force_split < 1 ? 1 : force_split;
+    const size_t slot_bytes = (size_t) tc::TILE_M * tb.npad * sizeof(float);
+    const int slot_cap = (int) (GEMM_TC_PARTIAL_BYTES / slot_bytes), ctr_cap = (int) (GEMM_TC_COUNTER_BYTES / sizeof(int));
+    int next = 0, slots = 0;
+    for (int i = 0; i < batch.n; i++) {
+        GemvProblem & p = batch.p[i];
+        const int nsteps = p.K / tc::KSTEP, chunk = tc::raw_geom(p.type).chunk_steps;
+        int splits = want;
+        if (splits > 32) splits = 32;
+        const int max_splits = (nsteps + chunk - 1) / chunk;          // at least one raw chunk per split
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+        int per = (nsteps + splits - 1) / splits;
+        per = (per + chunk - 1) / chunk * chunk;                       // split boundaries on raw-chunk boundaries
+        splits = (nsteps + per - 1) / per;
+        if (splits > 1 && (slots + tb.tiles[i] * splits > slot_cap || slots + tb.tiles[i] * splits > ctr_cap)) { splits = 1; per = nsteps; }
+        tb.splits[i] = splits;
+        tb.steps_per_split[i] = splits == 1 ? nsteps : per;
+        tb.slot0[i] = slots;
+        if (splits > 1) slots += tb.tiles[i] * splits;
         p.first_cta = next;
-        p.n_cta = (p.M + tc::TILE_M - 1) / tc::TILE_M;
+        p.n_cta = tb.tpad[i] * splits;
         next += p.n_cta;
         tb.p[i] = p;
     }
@@ -724,7 +874,18 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
     if (ae != cudaSuccess) return ae;
     tb.trace = trace_slot("gemm_tc");
     g_kernel_launches++;
-    return launch_pdl(tc::gemm_tc_kernel, dim3(next), dim3(tc::THREADS), smem, stream, tb);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned) next);
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (g_use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+    if (tb.cs > 1) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = (unsigned) tb.cs; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; na++; }
+    cfg.attrs = attr;
+    cfg.numAttrs = (unsigned) na;
+    return cudaLaunchKernelEx(&cfg, tc::gemm_tc_kernel, tb);
 }
 
 }  // namespace rwkv

@@ -91,7 +91,12 @@ bool gemm_tc_supported(const GemvProblem & p, int T);
 bool gemm_tc_eligible(int type, int K);
 size_t gemm_tc_tiled_bytes(int type, int M, int K);
 cudaError_t gemm_tc_repack(const void * W, long long pitch, int type, int M, int K, void * dst, cudaStream_t stream);
-cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream, void * act16_scratch, size_t scratch_bytes);
+// workspace: gemm_tc_workspace_bytes(T, sum over the batch's distinct inputs of round16(T) * K) bytes of device memory whose first
+// GEMM_TC_COUNTER_BYTES were zeroed once after the allocation (split-K tile counters; every launch leaves them zero again).
+constexpr size_t GEMM_TC_COUNTER_BYTES = 4096;
+constexpr size_t GEMM_TC_PARTIAL_BYTES = (size_t) 24 << 20;      // split-K partial tiles: 384 slots of 128 x 128 fp32
+size_t gemm_tc_workspace_bytes(int T, size_t operand_halves);
+cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream, void * workspace, size_t workspace_bytes);
 
 // Programmatic dependent launch for every kernel of the eval path (RWKV_B200_NO_PDL=1 turns it off).
 extern bool g_use_pdl;

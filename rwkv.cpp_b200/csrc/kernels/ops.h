@@ -100,6 +100,19 @@ cudaError_t launch_ln_mix_batch(const LnMixParams & p, long long seq_stride, cud
 cudaError_t launch_wkv6_batch(const Wkv6Params & p, long long seq_stride, cudaStream_t s);
 cudaError_t launch_wkv4_batch(const Wkv4Params & p, long long seq_stride, cudaStream_t s);
 
+// Layer-pipeline hand-off over peer memory (pipe.cu). A PipeBox sits at the start of every stage's mailbox allocation, followed by
+// PIPE_SLOTS data areas of slot_floats floats each.
+constexpr int PIPE_SLOTS = 2;
+constexpr int PIPE_CTAS = 8;               // every hand-off launch has this many CTAs (the device-side item counters rely on it)
+struct PipeBox {
+    unsigned long long credit;             // written by the NEXT stage: items of mine it has drained
+    unsigned long long pad0[15];
+    unsigned long long full[PIPE_SLOTS];   // written by the PREVIOUS stage: item + 1 that the slot holds
+    unsigned long long pad1[16 - PIPE_SLOTS];
+};
+cudaError_t launch_pipe_recv(PipeBox * mine, PipeBox * prev, unsigned long long * counters, size_t slot_floats, float * x, size_t nx, float * v, size_t nv, cudaStream_t s);
+cudaError_t launch_pipe_send(PipeBox * mine, PipeBox * next, unsigned long long * counters, size_t slot_floats, float * x, size_t nx, float * v, size_t nv, cudaStream_t s);
+
 // On-device sampling from the logits of the last evaluated token (reference python/sampling.py:10-52); see sampling.cu.
 struct SampleParams {
     const float * logits;             // [n_vocab] device

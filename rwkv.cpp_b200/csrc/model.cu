@@ -15,10 +15,12 @@
 namespace rwkv {
 
 Model::~Model() {
-    if (arena) {
-        cudaSetDevice(dev.device);
-        cudaFree(arena);
-    }
+    if (arena || link.box) cudaSetDevice(dev.device);
+    if (link.prev && link.prev_ipc) cudaIpcCloseMemHandle(link.prev);
+    if (link.next && link.next_ipc) cudaIpcCloseMemHandle(link.next);
+    cudaFree(link.box);
+    cudaFree(link.counters);
+    if (arena) cudaFree(arena);
 }
 
 namespace {

@@ -11,6 +11,7 @@
 #include "errors.h"
 #include "ggml_file.h"
 #include "kernels/gemv.h"
+#include "kernels/ops.h"
 
 namespace rwkv {
 
@@ -48,6 +49,17 @@ struct Layer {
     DevMatrix ffn_key, ffn_value, ffn_receptance;
 };
 
+// Peer-memory hand-off of a pipeline stage (kernels/pipe.cu): the stage's own mailbox + credit word (`box`, exported through CUDA
+// IPC or shared inside the process) and the mappings of its neighbours'. One per model: every context (in-flight sequence) of a
+// stage sends and receives through the same link, in item order, on one stream.
+struct PipeLink {
+    PipeBox * box = nullptr;               // my mailbox allocation: PipeBox + PIPE_SLOTS x slot_floats floats
+    size_t slot_floats = 0, bytes = 0;
+    PipeBox * prev = nullptr, * next = nullptr;
+    bool prev_ipc = false, next_ipc = false;
+    unsigned long long * counters = nullptr;   // device: tickets / completions of the hand-off kernels
+};
+
 struct Model {
     FileHeader header{};
     int arch_major = 4, arch_minor = 0;
@@ -69,6 +81,7 @@ struct Model {
     size_t gemv_bytes_per_token = 0;     // of which: matrices streamed by the fused dequantize-GEMV (layer matrices + head)
     size_t head_matrix_bytes = 0;
     std::atomic<int> refcount{0};
+    PipeLink link;
     std::string device_name;
 
     size_t state_floats_per_layer() const {

@@ -26,6 +26,37 @@ def stage_layers(n_layer: int, world: int, rank: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+def stage_layers_balanced(n_layer: int, world: int, rank: int, head_layers: float = 0.0, embed_layers: float = 0.0) -> Tuple[int, int]:
+    """Contiguous blocks that minimise the heaviest stage when the last stage also streams the head (`head_layers` = head bytes /
+    bytes of one layer: 3.2 at RWKV-6-7B with an FP16 head) and the first one gathers embeddings (`embed_layers`, ~0). A pipeline
+    ticks at the pace of its slowest stage, so an even split of the LAYERS leaves N - 1 stages idle while the last one reads the
+    head. Exact min-max partition by dynamic programming over the cut positions; every stage keeps at least one layer."""
+    if not (0 <= rank < world) or world < 1 or n_layer < world:
+        raise ValueError(f"cannot split {n_layer} layers over {world} stages (rank {rank})")
+    INF = float("inf")
+
+    def cost(stage: int, a: int, b: int) -> float:
+        return (b - a) + (head_layers if stage == world - 1 else 0.0) + (embed_layers if stage == 0 else 0.0)
+    # best[s][e]: smallest possible maximum over stages 0..s when stage s ends at layer e
+    best = [[INF] * (n_layer + 1) for _ in range(world)]
+    cut = [[0] * (n_layer + 1) for _ in range(world)]
+    for e in range(1, n_layer + 1):
+        best[0][e] = cost(0, 0, e)
+    for st in range(1, world):
+        for e in range(st + 1, n_layer + 1):
+            for a in range(st, e):
+                v = max(best[st - 1][a], cost(st, a, e))
+                if v < best[st][e] - 1e-12:
+                    best[st][e], cut[st][e] = v, a
+    bounds, e = [n_layer], n_layer
+    for st in range(world - 1, 0, -1):
+        e = cut[st][e]
+        bounds.append(e)
+    bounds.append(0)
+    bounds.reverse()
+    return bounds[rank], bounds[rank + 1]
+
+
 def schedule(world: int, n_sequences: int, n_items: int, rank: int) -> List[Optional[Tuple[int, int]]]:
     """What `rank` does at each of the n_items + world - 1 ticks: None while the pipeline fills / drains, else (sequence, step).
     Work item u (u = 0 .. n_items - 1) is step u // n_sequences of sequence u % n_sequences; it enters stage 0 at tick u and reaches

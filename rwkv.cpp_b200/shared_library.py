@@ -110,6 +110,18 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_trace_enable.restype = ctypes.c_bool
         lib.rwkv_b200_trace_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_void_p, ctypes.c_int]
         lib.rwkv_b200_trace_read.restype = ctypes.c_int
+        lib.rwkv_b200_stream.argtypes = [vp]
+        lib.rwkv_b200_stream.restype = ctypes.c_void_p
+        lib.rwkv_b200_pipe_handle_size.argtypes = []
+        lib.rwkv_b200_pipe_handle_size.restype = ctypes.c_size_t
+        lib.rwkv_b200_pipe_export.argtypes = [vp, ctypes.c_void_p]
+        lib.rwkv_b200_pipe_export.restype = ctypes.c_bool
+        lib.rwkv_b200_pipe_connect.argtypes = [vp, ctypes.c_void_p, ctypes.c_void_p]
+        lib.rwkv_b200_pipe_connect.restype = ctypes.c_bool
+        lib.rwkv_b200_pipe_connect_local.argtypes = [vp, vp, vp]
+        lib.rwkv_b200_pipe_connect_local.restype = ctypes.c_bool
+        lib.rwkv_b200_pipe_eval.argtypes = [vp, P_U32, ctypes.c_size_t, ctypes.c_bool, ctypes.c_void_p]
+        lib.rwkv_b200_pipe_eval.restype = ctypes.c_bool
         lib.rwkv_b200_trace_disable.argtypes = [vp]
         lib.rwkv_b200_trace_disable.restype = None
         lib.rwkv_b200_gemv_bytes_per_token.argtypes = [vp, ctypes.c_bool]

@@ -55,3 +55,55 @@ def test_two_stages_on_one_gpu_match_the_whole_model(pkg, lib, ver, fmt):
         assert not L.rwkv_b200_stage_eval(a.ptr, arr, 1, None, None, False, None)
     finally:
         lib.rwkv_free(a); lib.rwkv_free(b); whole.free()
+
+
+@pytest.mark.parametrize("ver,fmt", [("6v0-3m", "Q5_1"), ("7v0-834K", "FP16"), ("4v0-660K", "FP32"), ("5v2-730K", "Q5_1")])
+def test_peer_memory_pipeline_three_stages_two_sequences(pkg, lib, ver, fmt):
+    """The hand-off inside the library (csrc/kernels/pipe.cu: mailbox + credit flags written with peer stores, device-side item
+    counters): three stages on ONE GPU connected with rwkv_b200_pipe_connect_local, two sequences in flight (one context per
+    sequence and stage), every stage on its own stream, the host never waiting for a neighbour. Logits must equal the whole
+    model's bit for bit, token by token (graph replays) and for multi-token passes; v7 carries v_first through the mailbox."""
+    L = lib.library
+    path = model_path(ver, fmt)
+    whole = [pkg.RWKVModel(lib, path, thread_count=1) for _ in range(2)]
+    n_layer, n_vocab = lib.rwkv_get_n_layer(whole[0]._ctx), lib.rwkv_get_logits_len(whole[0]._ctx)
+    cuts = [pkg.pipeline.stage_layers(n_layer, 3, r) for r in range(3)]
+    stages = [lib.rwkv_b200_init_from_file_ex(path, 0, b, e) for b, e in cuts]
+    seqs = [[s] + [lib.rwkv_clone_context(s, 1)] for s in stages]          # seqs[stage][sequence]
+    try:
+        for r in range(3):
+            assert L.rwkv_b200_pipe_connect_local(stages[r].ptr, stages[r - 1].ptr if r > 0 else None, stages[r + 1].ptr if r < 2 else None)
+            for c in seqs[r]:
+                assert L.rwkv_b200_state_load(c.ptr, None)
+        sp = [ctypes.c_void_p(L.rwkv_b200_stream(stages[r].ptr)) for r in range(3)]      # ONE stream per stage: a link's items are enqueued in order
+        streams = {0: LONG_PROMPT[:14], 1: [(5 * i + 11) % 256 for i in range(14)]}
+        states = [None, None]
+        got = np.zeros(n_vocab, np.float32)
+        for i in range(14):                     # one token per pass; the third pass on replays the captured graphs
+            for q in (0, 1):
+                tok = (ctypes.c_uint32 * 1)(streams[q][i])
+                for r in range(3):
+                    assert L.rwkv_b200_pipe_eval(seqs[r][q].ptr, tok if r == 0 else None, 1, True, sp[r]), (r, q, i)
+            for q in (0, 1):
+                want, states[q] = whole[q].eval(streams[q][i], states[q], use_numpy=True)
+                # the last stage evaluated sequence 0 then 1 on ONE context each: read each one's logits
+                assert L.rwkv_b200_stage_logits(seqs[2][q].ptr, got.ctypes.data_as(PF), sp[2])
+                assert np.array_equal(got, want), (ver, fmt, i, q)
+        for q in (0, 1):                        # a 9-token pass and a 40-token pass (tensor-core path for non-F32 weights)
+            for n in (9, 40):
+                seq = [(7 * j + 3 * q + n) % 256 for j in range(n)]
+                arr = (ctypes.c_uint32 * n)(*seq)
+                for r in range(3):
+                    assert L.rwkv_b200_pipe_eval(seqs[r][q].ptr, arr if r == 0 else None, n, True, sp[r])
+                want, states[q] = whole[q].eval_sequence(seq, states[q], use_numpy=True)
+                assert L.rwkv_b200_stage_logits(seqs[2][q].ptr, got.ctypes.data_as(PF), sp[2])
+                if n < 32 or fmt == "FP32":
+                    assert np.array_equal(got, want), (ver, fmt, n, q)
+                else:       # K-splits of the tensor-core GEMM depend on the stage's matrix set only through the launch shape: same bits expected too
+                    assert np.abs(got - want).max() <= 5e-2, (ver, fmt, n, q, np.abs(got - want).max())
+        assert not L.rwkv_b200_pipe_eval(seqs[0][0].ptr, None, 1, False, None)          # the first stage needs tokens
+    finally:
+        for r in range(3):
+            lib.rwkv_free(seqs[r][1]); lib.rwkv_free(seqs[r][0])
+        for w in whole:
+            w.free()

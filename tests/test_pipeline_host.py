@@ -29,6 +29,23 @@ def test_stage_layers_cover_every_layer_once():
         pipeline.stage_layers(4, 8, 0)
 
 
+def test_balanced_partition_accounts_for_the_head():
+    """The last stage also streams the head (3.2 layers' worth of bytes at RWKV-6-7B): blocks are contiguous, cover every layer once,
+    and the heaviest stage is as light as a contiguous partition allows (checked against brute force on small cases)."""
+    import itertools
+    for n_layer, world, head in ((32, 8, 3.2), (32, 4, 3.2), (32, 2, 3.2), (24, 8, 1.5), (12, 4, 6.0), (12, 4, 0.0), (9, 3, 2.0)):
+        blocks = [pipeline.stage_layers_balanced(n_layer, world, r, head_layers=head) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n_layer and all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+        assert all(e > b for b, e in blocks)
+        got = max((e - b) + (head if r == world - 1 else 0.0) for r, (b, e) in enumerate(blocks))
+        if n_layer <= 12:
+            best = min(max((c[i + 1] - c[i]) + (head if i == world - 1 else 0.0) for i in range(world))
+                       for cuts in itertools.combinations(range(1, n_layer), world - 1) for c in [(0,) + cuts + (n_layer,)])
+            assert abs(got - best) < 1e-9, (n_layer, world, head, got, best)
+    assert [pipeline.stage_layers_balanced(32, 8, r, head_layers=3.2) for r in range(8)][-1] == (31, 32)
+    assert pipeline.stage_layers_balanced(12, 4, 2, head_layers=0.0) == (6, 9)
+
+
 def test_schedule_keeps_a_sequence_on_one_stage_at_a_time():
     world, n_seq, items = 4, 4, 16
     plans = [pipeline.schedule(world, n_seq, items, r) for r in range(world)]
