@@ -96,6 +96,14 @@ RWKV_API bool rwkv_b200_stage_logits(struct rwkv_context * ctx, float * logits_o
  *   (NULL = the context's own). Every context of a stage shares the stage's link: enqueue a link's passes in item order on ONE
  *   stream. The last stage computes logits when asked (rwkv_b200_stage_logits fetches them). A neighbour that never shows up
  *   makes the waiting kernel trap after ~20 s instead of hanging the GPU. */
+/* The whole pipeline inside ONE process, behind the plain rwkv.h entry points: rwkv_b200_init_pipeline loads one stage per listed CUDA
+ * device (layer blocks balanced by bytes, the head on the last one), connects them with peer access, and returns a handle that
+ * rwkv_eval / rwkv_eval_sequence / rwkv_eval_sequence_in_chunks / rwkv_clone_context / rwkv_free accept like any other: every stage
+ * takes and returns its own slice of the caller's state buffer, the token ids enter stage 0, the logits leave the last stage.
+ * rwkv_init_from_file does the same when the environment holds RWKV_B200_PIPELINE_DEVICES="0,1,2,3" -- an unchanged consumer of the
+ * reference binding reaches several GPUs that way (capacity; clones evaluated from several threads fill the stages concurrently). */
+RWKV_API struct rwkv_context * rwkv_b200_init_pipeline(const char * model_file_path, const int * devices, size_t n_devices);
+RWKV_API size_t rwkv_b200_pipeline_stages(const struct rwkv_context * ctx);   /* 0 for an ordinary context */
 RWKV_API void * rwkv_b200_stream(struct rwkv_context * ctx);            /* the context's own cudaStream_t */
 RWKV_API size_t rwkv_b200_pipe_handle_size(void);
 RWKV_API bool rwkv_b200_pipe_export(struct rwkv_context * ctx, void * handle_out);

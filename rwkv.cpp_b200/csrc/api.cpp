@@ -42,9 +42,41 @@ struct rwkv_context * rwkv_b200_init_from_file_ex(const char * file_path, int de
     return static_cast<struct rwkv_context *>(ctx);
 }
 
+// RWKV_B200_PIPELINE_DEVICES="0,1,2,3": one stage per listed CUDA device (a device may repeat), all inside this process
+static std::vector<int> pipeline_devices() {
+    std::vector<int> d;
+    const char * e = getenv("RWKV_B200_PIPELINE_DEVICES");
+    if (!e) return d;
+    for (const char * p = e; *p;) {
+        char * end = nullptr;
+        const long v = strtol(p, &end, 10);
+        if (end == p) break;
+        d.push_back((int) v);
+        p = *end == ',' ? end + 1 : end;
+    }
+    return d;
+}
+
+struct rwkv_context * rwkv_b200_init_pipeline(const char * file_path, const int * devices, size_t n_devices) {
+    g_last_error = RWKV_ERROR_NONE;
+    ErrorSink sink = global_sink();
+    RWKV_CHECK(sink, RWKV_ERROR_ARGS, nullptr, file_path && devices && n_devices >= 2, "A pipeline needs a model file and at least two devices");
+    Context * head = create_pipeline(file_path, std::vector<int>(devices, devices + n_devices), sink);
+    RWKV_PROPAGATE(sink, nullptr, head != nullptr);
+    return static_cast<struct rwkv_context *>(head);
+}
+
+size_t rwkv_b200_pipeline_stages(const struct rwkv_context * ctx) { return ctx && C(ctx)->group ? C(ctx)->stages.size() + 1 : 0; }
+
+static bool whole_model(const Context * c) {
+    return (c->group || (c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer)) && c->batch_n == 0;
+}
+
 struct rwkv_context * rwkv_init_from_file(const char * file_path, const uint32_t n_threads, const uint32_t n_gpu_layers) {
     (void) n_gpu_layers;   // every layer always lives on the GPU
-    struct rwkv_context * ctx = rwkv_b200_init_from_file_ex(file_path, default_device(), 0, -1);
+    const std::vector<int> devs = pipeline_devices();
+    struct rwkv_context * ctx = devs.size() >= 2 ? rwkv_b200_init_pipeline(file_path, devs.data(), devs.size())
+                                                 : rwkv_b200_init_from_file_ex(file_path, default_device(), 0, -1);
     if (ctx) C(ctx)->n_threads = n_threads;
     return ctx;
 }
@@ -54,7 +86,7 @@ struct rwkv_context * rwkv_clone_context(struct rwkv_context * ctx, const uint32
     bool print = C(ctx)->print_errors;
     int flags = 0;
     ErrorSink sink{&flags, &print};
-    Context * clone = create_context(C(ctx)->model, sink);
+    Context * clone = C(ctx)->group ? clone_pipeline(C(ctx), sink) : create_context(C(ctx)->model, sink);
     if (!clone) { g_last_error |= flags; return nullptr; }
     clone->n_threads = n_threads;
     clone->print_errors = C(ctx)->print_errors;
@@ -66,8 +98,9 @@ bool rwkv_eval(struct rwkv_context * ctx, const uint32_t token, const float * st
     c->last_error = RWKV_ERROR_NONE;
     const size_t n_vocab = (size_t) c->model->n_vocab;
     RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, token < n_vocab, "Token (%" PRIu32 ") is out of range (0 .. %zu)", token, n_vocab - 1);
-    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer && c->batch_n == 0,
+    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, whole_model(c),
                "This context holds only a pipeline stage or is a batch context; use the rwkv_b200 stage / batch API");
+    if (c->group) return pipeline_eval_host(c, &token, 1, 0, state_in, state_out, logits_out);
     return eval_host(c, &token, 1, state_in, state_out, logits_out);
 }
 
@@ -79,8 +112,9 @@ bool rwkv_eval_sequence(struct rwkv_context * ctx, const uint32_t * sequence, co
     const size_t n_vocab = (size_t) c->model->n_vocab;
     for (size_t i = 0; i < sequence_len; i++)
         RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, sequence[i] < n_vocab, "Token at index %zu (%" PRIu32 ") is out of range (0 .. %zu)", i, sequence[i], n_vocab - 1);
-    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer && c->batch_n == 0,
+    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, whole_model(c),
                "This context holds only a pipeline stage or is a batch context; use the rwkv_b200 stage / batch API");
+    if (c->group) return pipeline_eval_host(c, sequence, sequence_len, 0, state_in, state_out, logits_out);
     return eval_host(c, sequence, sequence_len, state_in, state_out, logits_out);
 }
 
@@ -94,8 +128,9 @@ bool rwkv_eval_sequence_in_chunks(struct rwkv_context * ctx, const uint32_t * to
     const size_t n_vocab = (size_t) c->model->n_vocab;
     for (size_t i = 0; i < sequence_len; i++)
         RWKV_CHECK(c->sink(), RWKV_ERROR_ARGS, false, tokens[i] < n_vocab, "Token at index %zu (%" PRIu32 ") is out of range (0 .. %zu)", i, tokens[i], n_vocab - 1);
-    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, c->model->layer_begin == 0 && c->model->layer_end == c->model->n_layer && c->batch_n == 0,
+    RWKV_CHECK(c->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, whole_model(c),
                "This context holds only a pipeline stage or is a batch context; use the rwkv_b200 stage / batch API");
+    if (c->group) return pipeline_eval_host(c, tokens, sequence_len, chunk_size, state_in, state_out, logits_out);
     return eval_host_chunks(c, tokens, sequence_len, chunk_size, state_in, state_out, logits_out);
 }
 
@@ -211,7 +246,7 @@ struct rwkv_context * rwkv_b200_batch_create(struct rwkv_context * ctx, size_t n
         if (print) fprintf(stderr, "A batch holds 1 .. %d sequences\n", MAX_TOKENS_PER_PASS);
     } else if (m.layer_begin != 0 || m.layer_end != m.n_layer || !batch_shape_supported(m.arch_major, m.n_embed, m.head_size)) {
         flags |= RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED;
-        if (print) fprintf(stderr, "Batched decode supports whole RWKV v4 / v5 / v6 models with n_embed <= 4096 and head size <= 64\n");
+        if (print) fprintf(stderr, "Batched decode supports whole RWKV v4 / v5 / v6 / v7 models with n_embed <= 4096 and head size <= 64 (v7: 128)\n");
     } else {
         b = create_context(c->model, sink, (int) n_sequences);
     }

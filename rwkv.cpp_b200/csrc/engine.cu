@@ -4,6 +4,7 @@
 // except the token upload.
 #include "engine.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +28,8 @@ struct Scratch {      // carve-up of ctx->scratch for T tokens
     float * ffn_k, * ffn_r;
     float * lora[4];
 };
+
+constexpr int BATCH_TC_MIN = 16;
 
 struct Dims { size_t C, F, R; };
 
@@ -76,6 +79,12 @@ Scratch carve(const Model & m, float * base, int T) {
 struct Batch {
     GemvBatch b;
     explicit Batch(int T) { memset(&b, 0, sizeof(b)); b.T = T; }
+    // L2 look-ahead: the matrices of the launch(es) after this one (single-token passes; opt-in RWKV_B200_XPF=1 until measured)
+    void prefetch(const DevMatrix & W) {
+        static const bool on = [] { const char * e = getenv("RWKV_B200_XPF"); return e && atoi(e) != 0; }();
+        if (!on || !W.data || b.T != 1 || b.pf_n >= GEMV_MAX_PREFETCH) return;
+        b.pf_ptr[b.pf_n] = W.data; b.pf_bytes[b.pf_n] = (long long) W.pitch * W.M; b.pf_n++;
+    }
     GemvProblem & add(const DevMatrix & W, const float * x, float * y, int epi = EPI_NONE) {
         GemvProblem & p = b.p[b.n++];
         p.W = W.data; p.Wt = W.tiled; p.pitch = W.pitch; p.type = W.type; p.K = W.K; p.M = W.M;
@@ -95,7 +104,9 @@ struct Batch {
 // gemm_tc.cu; the rest (and all shorter passes) use the batch-invariant GEMV, so serial == sequence stays bit-exact
 // wherever the reference's tests compare states.
 bool launch_batch(Context * ctx, GemvBatch & b) {
-    if (b.T >= 32 && ctx->use_tensor_cores && ctx->act16) {
+    // tensor cores: chunks of >= 32 tokens; batch contexts (one token of each of B sequences: nothing to stay bit-identical with
+    // across pass sizes) from 16 sequences on, where the multi-column SIMT consumer is instruction-bound
+    if ((b.T >= 32 || (ctx->batch_n > 0 && b.T >= BATCH_TC_MIN)) && ctx->use_tensor_cores && ctx->act16) {
         GemvBatch tcb, rest;
         memset(&tcb, 0, sizeof(tcb)); memset(&rest, 0, sizeof(rest));
         tcb.T = rest.T = b.T;
@@ -167,7 +178,7 @@ bool ln_mix_then(Context * ctx, const LnMixParams & lp, Batch & b) {
 }
 
 // Channel mixing, all versions (rwkv_ffn_v4_v5 :484-511, rwkv_ffn_v6 :513-531, rwkv_ffn_v7 :533-543).
-bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
+bool ffn(Context * ctx, const Layer & L, const Layer * next, const Scratch & s, int T, const float * st_in, float * st_out) {
     const Model & m = *ctx->model;
     const int C = m.n_embed;
     LnMixParams lp{};
@@ -188,6 +199,7 @@ bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const float *
         Batch b(T);
         b.add(L.ffn_key, s.mix[0], s.ffn_k, EPI_RELU_SQR);
         if (m.arch_major != 7) b.add(L.ffn_receptance, s.mix[1], s.ffn_r, EPI_SIGMOID);
+        b.prefetch(L.ffn_value);
         if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     }
     {
@@ -195,6 +207,12 @@ bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const float *
         GemvProblem & p = b.add(L.ffn_value, s.ffn_k, s.x, m.arch_major == 7 ? EPI_ADD : EPI_MUL_ADD);
         p.res = s.x; p.ldres = C;
         p.gate = s.ffn_r; p.ldgate = C;
+        if (next) {      // the next layer's first big launch
+            b.prefetch(next->att_maa_w1); b.prefetch(next->att_receptance); b.prefetch(next->att_key); b.prefetch(next->att_value); b.prefetch(next->att_gate);
+            b.prefetch(next->att_decay_w1); b.prefetch(next->att_w1);
+        } else if (ctx->model->head.data && ctx->model->layer_end == ctx->model->n_layer) {
+            b.prefetch(ctx->model->head);
+        }
         if (!run_batch(ctx, b)) return false;
     }
     return true;
@@ -204,6 +222,7 @@ bool att_output(Context * ctx, const Layer & L, const Scratch & s, int T) {
     Batch b(T);
     GemvProblem & p = b.add(L.att_output, s.y, s.x, EPI_ADD);   // x + Wo.y  (:182/:291/:384/:481 + residual :667-679)
     p.res = s.x; p.ldres = ctx->model->n_embed;
+    b.prefetch(L.ffn_key); b.prefetch(L.ffn_receptance);
     return run_batch(ctx, b);
 }
 
@@ -220,6 +239,7 @@ bool att_v4(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     b.add(L.att_receptance, s.mix[2], s.r, EPI_SIGMOID);
     b.add(L.att_key, s.mix[0], s.k);
     b.add(L.att_value, s.mix[1], s.v);
+    b.prefetch(L.att_output);
     if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     Wkv4Params wp{};
     wp.k = s.k; wp.v = s.v; wp.r = s.r;
@@ -248,6 +268,7 @@ bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     b.add(L.att_key, s.mix[0], s.k);
     b.add(L.att_value, s.mix[1], s.v);
     if (v52) b.add(L.att_gate, s.mix[3], s.g, EPI_SILU);
+    b.prefetch(L.att_output);
     if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     Wkv6Params wp{};
     wp.r = s.r; wp.k = s.k; wp.v = s.v;
@@ -289,17 +310,29 @@ bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
         b.add(L.att_value, s.mix[3], s.v);
         b.add(L.att_gate, s.mix[5], s.g, EPI_SILU);
         b.add(L.att_decay_w1, s.mix[1], s.lora[1], EPI_TANH);
+        b.prefetch(L.att_decay_w2); b.prefetch(L.att_output);
         if (!run_batch(ctx, b)) return false;
     }
-    {   // :357-367  w = exp(-exp(Wd2 . tanh(..) + time_decay))
+    // :357-367  w = exp(-exp(Wd2 . tanh(..) + time_decay)): folded into the WKV kernel (every head computes its own rows) unless the
+    // pass takes the tensor-core path or the context is a batch -- the choice depends on the weight type and the pass kind only, so
+    // all passes that must agree bit for bit (T < 32, and every T for F32 weights) use the same arithmetic
+    bool fused_decay;
+    {
         Batch b(T);
         GemvProblem & p = b.add(L.att_decay_w2, s.lora[1], s.w, EPI_BIAS_EXPNEGEXP);
         p.bias = L.att_time_decay.data;
-        if (!run_batch(ctx, b)) return false;
+        static const bool no_fuse = getenv("RWKV_B200_NO_FUSE_DECAY") != nullptr;
+        const bool tc = (T >= 32 || (ctx->batch_n > 0 && T >= BATCH_TC_MIN)) && ctx->use_tensor_cores && ctx->act16 && gemm_tc_supported(p, T);
+        fused_decay = !no_fuse && !ctx->batch_stride && !tc && L.att_decay_w2.K <= WKV6_FUSED_DECAY_MAX_K && L.att_decay_w2.K % 32 == 0;
+        if (!fused_decay && !run_batch(ctx, b)) return false;
     }
     Wkv6Params wp{};   // :370-382
     wp.r = s.r; wp.k = s.k; wp.v = s.v;
     wp.td = s.w; wp.td_per_token = 1; wp.tf = L.att_time_faaaa.data; wp.per_head_scalars = 0;
+    if (fused_decay) {
+        wp.dw2 = L.att_decay_w2.data; wp.dw2_pitch = L.att_decay_w2.pitch; wp.dw2_type = L.att_decay_w2.type; wp.dw2_K = L.att_decay_w2.K;
+        wp.dw2_x = s.lora[1]; wp.dw2_bias = L.att_time_decay.data;
+    }
     wp.state_in = st_in + 2 * C; wp.state_out = st_out + 2 * C;
     wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
     wp.g = s.g; wp.y = s.y; wp.eps = 64e-5f; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
@@ -326,6 +359,7 @@ bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T,
         b.add(L.att_a1, s.mix[4], s.lora[1]);
         b.add(L.att_g1, s.mix[5], s.lora[2], EPI_SIGMOID);
         if (!first) b.add(L.att_v1, s.mix[3], s.lora[3]);
+        b.prefetch(L.att_w2); b.prefetch(L.att_a2); b.prefetch(L.att_g2); b.prefetch(L.att_v2); b.prefetch(L.att_output);
         if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     }
     {   // second halves
@@ -343,7 +377,7 @@ bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T,
     wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
     wp.state_in = st_in + 2 * C; wp.state_out = st_out + 2 * C;
     wp.y = s.y; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
-    CUDA_OK(ctx, launch_wkv7(wp, ctx->stream));
+    CUDA_OK(ctx, ctx->batch_stride ? launch_wkv7_batch(wp, ctx->batch_stride, ctx->stream) : launch_wkv7(wp, ctx->stream));
     return att_output(ctx, L, s, T);
 }
 
@@ -372,7 +406,7 @@ bool ensure_capacity(Context * ctx, int T) {
         e = cudaMallocHost(reinterpret_cast<void **>(&ctx->tokens_host[i]), (size_t) cap * sizeof(int));
         RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, false, e == cudaSuccess, "Failed to allocate pinned token staging: %s", cudaGetErrorString(e));
     }
-    if (cap >= 32) {   // fp16 staging for the tensor-core path: up to 8 distinct inputs of max(C, F) x round16(cap)
+    if (cap >= BATCH_TC_MIN) {   // fp16 staging for the tensor-core path: up to 8 distinct inputs of max(C, F) x round16(cap)
         Dims d = model_dims(m);
         const size_t kmax = d.F > d.C ? d.F : d.C;
         ctx->act16_bytes = gemm_tc_workspace_bytes(cap, (size_t) GEMV_MAX_PROBLEMS * (kmax * (size_t) ((cap + 15) / 16 * 16) + 128));
@@ -410,7 +444,7 @@ bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase, int seg) {
             case 5: ok = att_v5(ctx, L, s, T, st_in, st_out); break;
             default: ok = att_v4(ctx, L, s, T, st_in, st_out); break;
         }
-        if (!ok || !ffn(ctx, L, s, T, st_in, st_out)) return false;
+        if (!ok || !ffn(ctx, L, i + 1 < l1 ? &m.layers[i + 1] : nullptr, s, T, st_in, st_out)) return false;
     }
     if (want_logits && l1 == m.n_layer) {   // :705-708 / :851-854  head . LN(x_last; ln_out); a batch context wants every column
         Batch b(ctx->batch_n ? T : 1);
@@ -563,6 +597,15 @@ Context * create_context(Model * model, ErrorSink sink, int batch_n) {
 
 void destroy_context(Context * ctx) {
     if (!ctx) return;
+    for (Context * s : ctx->stages) destroy_context(s);
+    ctx->stages.clear();
+    if (PipeGroup * g = ctx->group) {
+        ctx->group = nullptr;
+        if (g->refs.fetch_sub(1) == 1) {
+            for (size_t r = 0; r < g->streams.size(); r++) { cudaSetDevice(g->devices[r]); cudaStreamSynchronize(g->streams[r]); cudaStreamDestroy(g->streams[r]); }
+            delete g;
+        }
+    }
     Model * model = ctx->model;
     if (model) cudaSetDevice(model->dev.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -803,6 +846,152 @@ bool pipe_forward(Context * ctx, const uint32_t * tokens, size_t T, bool want_lo
     }
     ctx->stream = own;
     return ok;
+}
+
+// ---- in-process pipeline behind rwkv.h ---------------------------------------------------------------------------
+namespace {
+
+// contiguous min-max partition of n_layer layers over `world` stages, the last one carrying `head_layers` extra (pipeline.py:
+// stage_layers_balanced is the same recurrence)
+std::vector<int> balanced_cuts(int n_layer, int world, double head_layers) {
+    const double INF = 1e300;
+    std::vector<std::vector<double>> best((size_t) world, std::vector<double>((size_t) n_layer + 1, INF));
+    std::vector<std::vector<int>> cut((size_t) world, std::vector<int>((size_t) n_layer + 1, 0));
+    auto cost = [&](int st, int a, int b) { return (double) (b - a) + (st == world - 1 ? head_layers : 0.0); };
+    for (int e = 1; e <= n_layer; e++) best[0][(size_t) e] = cost(0, 0, e);
+    for (int st = 1; st < world; st++)
+        for (int e = st + 1; e <= n_layer; e++)
+            for (int a = st; a < e; a++) {
+                const double v = std::max(best[(size_t) st - 1][(size_t) a], cost(st, a, e));
+                if (v < best[(size_t) st][(size_t) e] - 1e-12) { best[(size_t) st][(size_t) e] = v; cut[(size_t) st][(size_t) e] = a; }
+            }
+    std::vector<int> bounds((size_t) world + 1, 0);
+    bounds[(size_t) world] = n_layer;
+    for (int st = world - 1, e = n_layer; st >= 1; st--) { e = cut[(size_t) st][(size_t) e]; bounds[(size_t) st] = e; }
+    return bounds;
+}
+
+Context * stage_of(Context * head, size_t r) { return r == 0 ? head : head->stages[r - 1]; }
+
+bool connect_stages(Context * head, ErrorSink sink) {
+    const size_t n = head->stages.size() + 1;
+    for (size_t r = 0; r < n; r++) if (!pipe_ensure_box(stage_of(head, r))) return false;
+    for (size_t r = 0; r < n; r++) {
+        Model & m = *stage_of(head, r)->model;
+        for (int dir = 0; dir < 2; dir++) {
+            if ((dir == 0 && r == 0) || (dir == 1 && r + 1 == n)) continue;
+            Model & o = *stage_of(head, dir == 0 ? r - 1 : r + 1)->model;
+            if (o.dev.device != m.dev.device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, m.dev.device, o.dev.device);
+                RWKV_CHECK(sink, RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, can, "Device %d cannot access device %d's memory", m.dev.device, o.dev.device);
+                cudaSetDevice(m.dev.device);
+                const cudaError_t e = cudaDeviceEnablePeerAccess(o.dev.device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else RWKV_CHECK(sink, RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, e == cudaSuccess, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e));
+            }
+            (dir == 0 ? m.link.prev : m.link.next) = o.link.box;
+        }
+    }
+    return true;
+}
+
+}  // namespace
+
+Context * create_pipeline(const char * path, const std::vector<int> & devices, ErrorSink sink) {
+    ModelFile mf;
+    if (!scan_model_file(path, mf, sink)) return nullptr;
+    const int n_layer = (int) mf.header.n_layer, world = (int) devices.size();
+    RWKV_CHECK(sink, RWKV_ERROR_ARGS, nullptr, world >= 2 && world <= n_layer, "A pipeline needs 2 .. n_layer (%d) stages, got %d", n_layer, world);
+    double layer_bytes = 0, head_bytes = 0;
+    for (const TensorInfo & t : mf.tensors) {
+        if (t.name == "head.weight") head_bytes += (double) t.nbytes;
+        else if (t.name.compare(0, 7, "blocks.") == 0) layer_bytes += (double) t.nbytes;
+    }
+    layer_bytes /= n_layer;
+    const std::vector<int> bounds = balanced_cuts(n_layer, world, layer_bytes > 0 ? head_bytes / layer_bytes : 0.0);
+    Context * head = nullptr;
+    PipeGroup * group = new (std::nothrow) PipeGroup();
+    RWKV_CHECK(sink, RWKV_ERROR_CTX | RWKV_ERROR_ALLOC, nullptr, group, "Failed to allocate the pipeline group");
+    group->devices = devices;
+    bool ok = true;
+    for (int r = 0; r < world && ok; r++) {
+        Model * m = load_model(path, devices[(size_t) r], bounds[(size_t) r], bounds[(size_t) r + 1], sink);
+        Context * c = m ? create_context(m, sink) : nullptr;
+        if (!c) { ok = false; break; }
+        c->overlap_copies = false;
+        if (r == 0) { head = c; head->group = group; group->refs.fetch_add(1); } else head->stages.push_back(c);
+        cudaStream_t s = nullptr;
+        ok = cudaSetDevice(devices[(size_t) r]) == cudaSuccess && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
+        group->streams.push_back(s);
+    }
+    ok = ok && connect_stages(head, sink);
+    if (!ok) {
+        if (head) destroy_context(head); else delete group;
+        return nullptr;
+    }
+    return head;
+}
+
+Context * clone_pipeline(Context * src, ErrorSink sink) {
+    Context * head = create_context(src->model, sink);
+    if (!head) return nullptr;
+    head->overlap_copies = false;
+    head->group = src->group;
+    src->group->refs.fetch_add(1);
+    for (Context * s : src->stages) {
+        Context * c = create_context(s->model, sink);
+        if (!c) { destroy_context(head); return nullptr; }
+        c->overlap_copies = false;
+        head->stages.push_back(c);
+    }
+    return head;
+}
+
+bool pipeline_eval_host(Context * head, const uint32_t * tokens, size_t T, size_t chunk, const float * state_in, float * state_out, float * logits_out) {
+    PipeGroup & g = *head->group;
+    const size_t n = head->stages.size() + 1;
+    const size_t per_layer = head->model->state_floats_per_layer();
+    {
+        std::lock_guard<std::mutex> lock(g.order);      // the passes of one evaluation enter every link back to back
+        for (size_t r = 0; r < n; r++) {                // every stage takes ITS slice of the caller's state (layer-major ABI layout)
+            Context * c = stage_of(head, r);
+            const Model & m = *c->model;
+            CUDA_OK(head, cudaSetDevice(m.dev.device));
+            const size_t off = (size_t) m.layer_begin * per_layer, cnt = (size_t) (m.layer_end - m.layer_begin) * per_layer;
+            CUDA_OK(head, cudaMemcpyAsync(c->state_a + off, state_in ? state_in + off : c->state_init + off, cnt * sizeof(float), cudaMemcpyDefault, g.streams[r]));
+        }
+        // chunk boundaries as the reference loop (rwkv_eval.inc:179-218), each cut further into passes the kernels take
+        size_t off = 0;
+        while (off < T) {
+            size_t nchunk = T - off;
+            if (chunk && nchunk > chunk) nchunk = chunk;
+            size_t done = 0;
+            while (done < nchunk) {
+                const size_t np = nchunk - done < (size_t) MAX_TOKENS_PER_PASS ? nchunk - done : (size_t) MAX_TOKENS_PER_PASS;
+                const bool final_pass = off + done + np == T;
+                for (size_t r = 0; r < n; r++) {
+                    Context * c = stage_of(head, r);
+                    if (!pipe_forward(c, tokens + off + done, np, final_pass && logits_out != nullptr, g.streams[r])) { head->last_error |= c->last_error; return false; }
+                }
+                done += np;
+            }
+            off += nchunk;
+        }
+        for (size_t r = 0; r < n; r++) {
+            Context * c = stage_of(head, r);
+            const Model & m = *c->model;
+            CUDA_OK(head, cudaSetDevice(m.dev.device));
+            const size_t so = (size_t) m.layer_begin * per_layer, cnt = (size_t) (m.layer_end - m.layer_begin) * per_layer;
+            if (state_out) CUDA_OK(head, cudaMemcpyAsync(state_out + so, c->state_a + so, cnt * sizeof(float), cudaMemcpyDefault, g.streams[r]));
+            if (logits_out && r + 1 == n) CUDA_OK(head, cudaMemcpyAsync(logits_out, c->logits, (size_t) m.n_vocab * sizeof(float), cudaMemcpyDefault, g.streams[r]));
+        }
+    }
+    for (size_t r = 0; r < n; r++) {
+        CUDA_OK(head, cudaSetDevice(g.devices[r]));
+        CUDA_OK(head, cudaStreamSynchronize(g.streams[r]));
+    }
+    return true;
 }
 
 size_t stage_hidden_len(const Model & m, size_t T) { return (size_t) (m.arch_major == 7 ? 2 : 1) * (size_t) m.n_embed * T; }

@@ -3,15 +3,30 @@
 // rwkv_eval.inc:25-35): there is no graph IR -- the launch sequence is written out per architecture.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
+#include <mutex>
 #include <vector>
 
 #include "model.h"
 
 namespace rwkv {
 
+// One process, several GPUs, behind the plain rwkv.h API (RWKV_B200_PIPELINE_DEVICES=0,1,...): the layers are cut into stages, one
+// per listed device, connected by the peer-memory hand-off (kernels/pipe.cu). The handle the caller holds is the stage-0 context;
+// it owns one context per further stage. All contexts of a stage (the original and its clones) enqueue on the stage's ONE stream,
+// and one pass over all stages is enqueued under `order`, so items travel through every link in the same order.
+struct PipeGroup {
+    std::vector<cudaStream_t> streams;     // one per stage, on that stage's device
+    std::vector<int> devices;
+    std::mutex order;
+    std::atomic<int> refs{0};
+};
+
 struct Context {
     Model * model = nullptr;
+    PipeGroup * group = nullptr;           // set on the stage-0 context of an in-process pipeline
+    std::vector<Context *> stages;         // ... which owns the contexts of stages 1 .. N-1
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
 
@@ -92,6 +107,14 @@ constexpr int MAX_TOKENS_PER_PASS = 256;
 
 Context * create_context(Model * model, ErrorSink sink, int batch_n = 0);   // batch_n > 0: a batch context for that many sequences
 void destroy_context(Context * ctx);
+
+// In-process pipeline over `devices` (one stage per entry, layer blocks balanced by bytes with the head on the last stage).
+Context * create_pipeline(const char * path, const std::vector<int> & devices, ErrorSink sink);
+Context * clone_pipeline(Context * head, ErrorSink sink);
+// rwkv_eval / rwkv_eval_sequence / rwkv_eval_sequence_in_chunks for a pipeline handle: every stage takes its slice of the caller's
+// host state, passes of <= MAX_TOKENS_PER_PASS tokens run through all stages (the state stays resident in between), every stage
+// hands its slice back, the last one the logits. chunk == 0: plain sequence evaluation.
+bool pipeline_eval_host(Context * head, const uint32_t * tokens, size_t T, size_t chunk, const float * state_in, float * state_out, float * logits_out);
 
 // Host image of a fresh state (rwkv_init_state, rwkv_eval.inc:224-241).
 void fill_init_state(const Model & m, float * state);

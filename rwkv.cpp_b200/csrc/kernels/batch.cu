@@ -113,6 +113,7 @@ __global__ void wkv4_batch_kernel(const Wkv4Params p, const long long seq_stride
 bool batch_shape_supported(int arch_major, int n_embed, int head_size) {
     if (arch_major == 4) return n_embed <= 256 * steps::LN_MAXCH;
     if (arch_major == 5 || arch_major == 6) return n_embed <= 256 * steps::LN_MAXCH && (head_size == 8 || head_size == 16 || head_size == 32 || head_size == 64);
+    if (arch_major == 7) return n_embed <= 256 * steps::LN_MAXCH && (head_size == 8 || head_size == 16 || head_size == 32 || head_size == 64 || head_size == 128);
     return false;
 }
 

@@ -755,7 +755,7 @@ cudaError_t gemm_tc_repack(const void * W, long long pitch, int type, int M, int
 }
 
 bool gemm_tc_supported(const GemvProblem & p, int T) {
-    return T >= 32 && T <= tc::MAX_N && p.Wt != nullptr && gemm_tc_eligible(p.type, p.K) && (p.ldx % 4) == 0 &&
+    return T >= 16 && T <= tc::MAX_N && p.Wt != nullptr && gemm_tc_eligible(p.type, p.K) && (p.ldx % 4) == 0 &&
            (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.Wt) & 15) == 0;
 }
 

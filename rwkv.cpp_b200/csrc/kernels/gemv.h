@@ -65,11 +65,17 @@ inline TraceRec * trace_slot(const char * name) {
 }
 
 constexpr int GEMV_MAX_PROBLEMS = 8;
+constexpr int GEMV_MAX_PREFETCH = 8;
 struct GemvBatch {
     int n, T;
     TraceRec * trace;
     long long max_col_bytes, stage_bytes; // streaming kernel only: shared-memory carve-up
     int prefetch_tiles;                   // streaming kernel only: tiles beyond the ring each CTA asks L2 to fetch at kernel start
+    // Weights of the launches that FOLLOW this one (the engine knows the order): every CTA asks L2 for its slice of each region at
+    // kernel start, so HBM keeps streaming through the dependency bubbles between launches and the next launch finds its tiles in L2.
+    int pf_n;
+    const void * pf_ptr[GEMV_MAX_PREFETCH];
+    long long pf_bytes[GEMV_MAX_PREFETCH];
     GemvProblem p[GEMV_MAX_PROBLEMS];
 };
 

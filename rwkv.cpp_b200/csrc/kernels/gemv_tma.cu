@@ -138,6 +138,17 @@ __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch ba
                 const int row0 = (local_cta + i * P.n_cta) * P.tile_rows;
                 bulk_prefetch_l2(Wb + (size_t) row0 * (size_t) P.pitch, (uint32_t) ((size_t) min(P.tile_rows, P.M - row0) * (size_t) P.pitch));
             }
+            // ... and for this CTA's slice of the weights of the launches that follow (cross-launch look-ahead through L2)
+            for (int r = 0; r < batch.pf_n; r++) {
+                const long long bytes = batch.pf_bytes[r];
+                long long per = (bytes + gridDim.x - 1) / gridDim.x;
+                per = (per + 127) / 128 * 128;
+                const long long lo = (long long) blockIdx.x * per, hi = lo + per < bytes ? lo + per : bytes;
+                for (long long o = lo; o < hi; o += 16384) {
+                    const long long n = (hi - o < 16384 ? hi - o : 16384) / 16 * 16;
+                    if (n > 0) bulk_prefetch_l2(reinterpret_cast<const uint8_t *>(batch.pf_ptr[r]) + o, (uint32_t) n);
+                }
+            }
             int it = 0;
             for (int g = 0; g < n_groups; g++) {
                 for (int i = 0; i < my_tiles; i++, it++) {

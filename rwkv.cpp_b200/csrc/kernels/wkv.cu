@@ -3,6 +3,10 @@
 // whole chunk; one CTA per head (v5+), one thread per state column (v5/v6) or row (v7).
 #include "ops.h"
 #include "gemv.h"   // g_kernel_launches
+#include "quant_decode.cuh"
+#include "../formats.h"
+
+#include <cuda_fp16.h>
 
 namespace rwkv {
 namespace {
@@ -97,6 +101,12 @@ __global__ void __launch_bounds__(Wkv6Layout<S>::BLOCK) wkv6_kernel(const Wkv6Pa
     __shared__ Wkv6Chunk<S> buf[2];
     __shared__ __align__(16) float sf[S], sdc[S];
     __shared__ __align__(16) float ybuf[2][TB][S];
+    // fused decay GEMV: the chunk's z columns as the operand the reference would multiply (Q8 blocks / fp16-rounded / fp32)
+    constexpr int DMAXB = WKV6_FUSED_DECAY_MAX_K / 32;
+    __shared__ __align__(16) unsigned char zraw[TB * WKV6_FUSED_DECAY_MAX_K * 4];       // one buffer, two views (quantised / float operand)
+    int (* zq)[DMAXB][8] = reinterpret_cast<int (*)[DMAXB][8]>(zraw);
+    ActScale (* zs)[DMAXB] = reinterpret_cast<ActScale (*)[DMAXB]>(zraw + sizeof(int) * TB * DMAXB * 8);
+    float (* zf)[WKV6_FUSED_DECAY_MAX_K] = reinterpret_cast<float (*)[WKV6_FUSED_DECAY_MAX_K]>(zraw);
     trace_begin(p.trace);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int h = blockIdx.x, tid = threadIdx.x, C = p.H * S;
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(Wkv6Layout<S>::BLOCK) wkv6_kernel(const Wkv6Pa
             wkv_cp16(&B.k[tt][f], p.k + o);
             wkv_cp16(&B.r[tt][f], p.r + o);
             wkv_cp16(&B.v[tt][f], p.v + o);
-            if (p.td_per_token) wkv_cp16(&B.d[tt][f], p.td + o);
+            if (p.td_per_token && !p.dw2) wkv_cp16(&B.d[tt][f], p.td + o);
         }
     };
     // trace marks of CTA 0 (cycles, stored as start + cycles): [0] staging + wait for the chunk, [1] phase A,
@@ -151,12 +161,102 @@ __global__ void __launch_bounds__(Wkv6Layout<S>::BLOCK) wkv6_kernel(const Wkv6Pa
     const bool acct = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
     long long a0 = 0, a1 = 0, a2 = 0, a3 = 0, tq = acct ? clock64() : 0;
     auto tick = [&](long long & a) { if (acct) { const long long now = clock64(); a += now - tq; tq = now; } };
+    // ---- decay rows of this head for the tokens of chunk c -> B.d (fused form) ----
+    const bool fused_decay = p.dw2 != nullptr;
+    const float dbias = (fused_decay && tid < S) ? p.dw2_bias[h * S + tid] : 0.f;
+    auto decay_rows = [&](int c) {
+        Wkv6Chunk<S> & B = buf[c & 1];
+        const int t0 = c * TB, nt = min(TB, p.T - t0);
+        const int K = p.dw2_K, nblk = K / 32, type = p.dw2_type;
+        const bool quant = type != DT_F16 && type != DT_F32;
+        if (quant) {                 // one thread per (token, 32-element block): x86 flavour of quantize_row_q8_0 / q8_1
+            const bool has_min = type == DT_Q4_1 || type == DT_Q5_1;
+            for (int w = tid; w < nt * nblk; w += BLOCK) {
+                const int tt = w / nblk, blk = w % nblk;
+                const float4 * x4 = reinterpret_cast<const float4 *>(p.dw2_x + (size_t) (t0 + tt) * K + blk * 32);
+                float4 v[8];
+                float amax = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; j++) { v[j] = x4[j]; amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w)))); }
+                const float d32 = amax / 127.0f;
+                const float id = (amax != 0.0f) ? 127.0f / amax : 0.0f;
+                int isum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int q0 = __float2int_rn(v[j].x * id), q1 = __float2int_rn(v[j].y * id), q2 = __float2int_rn(v[j].z * id), q3 = __float2int_rn(v[j].w * id);
+                    isum += q0 + q1 + q2 + q3;
+                    zq[tt][blk][j] = (q0 & 0xFF) | ((q1 & 0xFF) << 8) | ((q2 & 0xFF) << 16) | ((q3 & 0xFF) << 24);
+                }
+                ActScale a;
+                a.d = __half2float(__float2half_rn(d32));
+                a.s = has_min ? __half2float(__float2half_rn(d32 * (float) isum)) : (float) isum;
+                zs[tt][blk] = a;
+            }
+        } else {
+            for (int w = tid; w < nt * K; w += BLOCK) {
+                const int tt = w / K, k = w % K;
+                const float x = p.dw2_x[(size_t) (t0 + tt) * K + k];
+                zf[tt][k] = type == DT_F16 ? __half2float(__float2half_rn(x)) : x;
+            }
+        }
+        __syncthreads();
+        if (tid < S) {
+            const uint8_t * wrow = reinterpret_cast<const uint8_t *>(p.dw2) + (size_t) (h * S + tid) * (size_t) p.dw2_pitch;
+            float acc[TB];
+#pragma unroll
+            for (int tt = 0; tt < TB; tt++) acc[tt] = 0.f;
+            auto blocks = [&](auto tag) {
+                constexpr int TYPE = decltype(tag)::value;
+                using TR = QTraits<TYPE>;
+                const int nunits = (nblk + TR::UNIT_BLOCKS - 1) / TR::UNIT_BLOCKS;
+                for (int u = 0; u < nunits; u++) {
+                    uint32_t w[TR::UNIT_WORDS];
+#pragma unroll
+                    for (int i = 0; i < TR::UNIT_WORDS; i++) w[i] = reinterpret_cast<const uint32_t *>(wrow)[u * TR::UNIT_WORDS + i];
+#pragma unroll
+                    for (int bi = 0; bi < TR::UNIT_BLOCKS; bi++) {
+                        const int blk = u * TR::UNIT_BLOCKS + bi;
+                        if (blk >= nblk) break;
+                        BlockQ bq;
+                        decode_block<TYPE>(w, bi, bq);
+#pragma unroll
+                        for (int tt = 0; tt < TB; tt++) if (tt < nt) acc[tt] = block_dot<TYPE>(bq, zq[tt][blk], zs[tt][blk], acc[tt]);
+                    }
+                }
+            };
+            switch (type) {
+                case DT_Q4_0: blocks(std::integral_constant<int, DT_Q4_0>{}); break;
+                case DT_Q4_1: blocks(std::integral_constant<int, DT_Q4_1>{}); break;
+                case DT_Q5_0: blocks(std::integral_constant<int, DT_Q5_0>{}); break;
+                case DT_Q5_1: blocks(std::integral_constant<int, DT_Q5_1>{}); break;
+                case DT_Q8_0: blocks(std::integral_constant<int, DT_Q8_0>{}); break;
+                case DT_F16:
+                    for (int k = 0; k < K; k++) {
+                        const float wv = __half2float(reinterpret_cast<const __half *>(wrow)[k]);
+#pragma unroll
+                        for (int tt = 0; tt < TB; tt++) if (tt < nt) acc[tt] = __fmaf_rn(wv, zf[tt][k], acc[tt]);
+                    }
+                    break;
+                default:
+                    for (int k = 0; k < K; k++) {
+                        const float wv = reinterpret_cast<const float *>(wrow)[k];
+#pragma unroll
+                        for (int tt = 0; tt < TB; tt++) if (tt < nt) acc[tt] = __fmaf_rn(wv, zf[tt][k], acc[tt]);
+                    }
+                    break;
+            }
+#pragma unroll
+            for (int tt = 0; tt < TB; tt++) if (tt < nt) B.d[tt][tid] = expf(-expf(__fadd_rn(acc[tt], dbias)));
+        }
+        // B.d becomes visible to phase A through the barrier that follows the cp.async wait
+    };
     float tfr[8];     // time_first of my key rows
     stage(0);
     wkv_cp_commit();
     for (int c = 0; c < nchunks; c++) {
         if (c + 1 < nchunks) stage(c + 1);     // buf[(c+1)&1] was last read by phase A of chunk c-1, two barriers ago
         wkv_cp_commit();
+        if (fused_decay) decay_rows(c);        // zq / zs / zf were last read before the previous iteration's barriers
         wkv_cp_wait<1>();
         __syncthreads();
         tick(a0);
@@ -259,19 +359,23 @@ __global__ void __launch_bounds__(Wkv6Layout<S>::BLOCK) wkv6_kernel(const Wkv6Pa
 // v7: rwkv_att_v7 (rwkv_graph.inc:432-479) around rwkv_wkv_v7_impl (rwkv_operators_wkv_v7.inc:63-101).
 // Thread i owns state row S[i][.] (value index i, key index j).
 // ---------------------------------------------------------------------------------------------
+// seq_stride > 0 (batch contexts, grid = heads x sequences): the block handles ONE token, column blockIdx.y, on the state of sequence
+// blockIdx.y, which lives seq_stride floats after sequence 0's.
 template <int S>
-__global__ void __launch_bounds__(S) wkv7_kernel(const Wkv7Params p) {
+__global__ void __launch_bounds__(S) wkv7_kernel(const Wkv7Params p, const long long seq_stride) {
     __shared__ float sr[S], sw[S], sk[S], sa[S], sb[S], red[S];
     trace_begin(p.trace);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int h = blockIdx.x, i = threadIdx.x, C = p.H * S, c = h * S + i;
+    const long long so = seq_stride ? (long long) blockIdx.y * seq_stride : 0;
+    const int t_begin = seq_stride ? (int) blockIdx.y : 0, t_end = seq_stride ? (int) blockIdx.y + 1 : p.T;
     float st[S];
 #pragma unroll
-    for (int j = 0; j < S; j++) st[j] = p.state_in[((size_t) h * S + i) * S + j];
+    for (int j = 0; j < S; j++) st[j] = p.state_in[so + ((size_t) h * S + i) * S + j];
     const float kk_w = p.k_k[c], ka_w = p.k_a[c], rk_w = p.r_k[c];
     const float lw = p.lnx_w[c], lb = p.lnx_b[c];
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int t = 0; t < p.T; t++) {
+    for (int t = t_begin; t < t_end; t++) {
         const size_t o = (size_t) t * C + c;
         const float r = p.r[o], w = p.w[o], k0 = p.k[o], a = p.a[o];
         float v = p.v[o];
@@ -316,7 +420,7 @@ __global__ void __launch_bounds__(S) wkv7_kernel(const Wkv7Params p) {
         p.y[o] = __fmul_rn(n, p.g[o]);
     }
 #pragma unroll
-    for (int j = 0; j < S; j++) p.state_out[((size_t) h * S + i) * S + j] = st[j];
+    for (int j = 0; j < S; j++) p.state_out[so + ((size_t) h * S + i) * S + j] = st[j];
     trace_end(p.trace);
 }
 
@@ -330,13 +434,13 @@ cudaError_t launch_wkv4(const Wkv4Params & p_in, cudaStream_t s) {
     return launch_pdl(wkv4_kernel, dim3((p.C + threads - 1) / threads), dim3(threads), 0, s, p);
 }
 
-#define RWKV_DISPATCH_HEAD_SIZE(S_, KERNEL, PARAMS, STREAM)                              \
+#define RWKV_DISPATCH_HEAD_SIZE(S_, KERNEL, PARAMS, STREAM, GRID, STRIDE)                              \
     switch (S_) {                                                                        \
-        case 8: return launch_pdl(KERNEL<8>, dim3(PARAMS.H), dim3(8), 0, STREAM, PARAMS);         \
-        case 16: return launch_pdl(KERNEL<16>, dim3(PARAMS.H), dim3(16), 0, STREAM, PARAMS);      \
-        case 32: return launch_pdl(KERNEL<32>, dim3(PARAMS.H), dim3(32), 0, STREAM, PARAMS);      \
-        case 64: return launch_pdl(KERNEL<64>, dim3(PARAMS.H), dim3(64), 0, STREAM, PARAMS);      \
-        case 128: return launch_pdl(KERNEL<128>, dim3(PARAMS.H), dim3(128), 0, STREAM, PARAMS);   \
+        case 8: return launch_pdl(KERNEL<8>, GRID, dim3(8), 0, STREAM, PARAMS, STRIDE);         \
+        case 16: return launch_pdl(KERNEL<16>, GRID, dim3(16), 0, STREAM, PARAMS, STRIDE);      \
+        case 32: return launch_pdl(KERNEL<32>, GRID, dim3(32), 0, STREAM, PARAMS, STRIDE);      \
+        case 64: return launch_pdl(KERNEL<64>, GRID, dim3(64), 0, STREAM, PARAMS, STRIDE);      \
+        case 128: return launch_pdl(KERNEL<128>, GRID, dim3(128), 0, STREAM, PARAMS, STRIDE);   \
         default: return cudaErrorInvalidValue;                                           \
     }
 
@@ -358,7 +462,16 @@ cudaError_t launch_wkv7(const Wkv7Params & p_in, cudaStream_t s) {
     Wkv7Params p = p_in;
     p.trace = trace_slot("wkv7");
     g_kernel_launches++;
-    RWKV_DISPATCH_HEAD_SIZE(p.S, wkv7_kernel, p, s)
+    const long long none = 0;
+    RWKV_DISPATCH_HEAD_SIZE(p.S, wkv7_kernel, p, s, dim3(p.H), none)
+}
+
+// batch contexts: one token of each of p.T sequences, column t on the state of sequence t
+cudaError_t launch_wkv7_batch(const Wkv7Params & p_in, long long seq_stride, cudaStream_t s) {
+    Wkv7Params p = p_in;
+    p.trace = trace_slot("wkv7_batch");
+    g_kernel_launches++;
+    RWKV_DISPATCH_HEAD_SIZE(p.S, wkv7_kernel, p, s, dim3(p.H, p.T), seq_stride)
 }
 
 }  // namespace rwkv

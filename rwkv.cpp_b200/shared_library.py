@@ -110,6 +110,10 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_trace_enable.restype = ctypes.c_bool
         lib.rwkv_b200_trace_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_void_p, ctypes.c_int]
         lib.rwkv_b200_trace_read.restype = ctypes.c_int
+        lib.rwkv_b200_init_pipeline.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.c_size_t]
+        lib.rwkv_b200_init_pipeline.restype = vp
+        lib.rwkv_b200_pipeline_stages.argtypes = [vp]
+        lib.rwkv_b200_pipeline_stages.restype = ctypes.c_size_t
         lib.rwkv_b200_stream.argtypes = [vp]
         lib.rwkv_b200_stream.restype = ctypes.c_void_p
         lib.rwkv_b200_pipe_handle_size.argtypes = []

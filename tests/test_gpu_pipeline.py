@@ -107,3 +107,65 @@ def test_peer_memory_pipeline_three_stages_two_sequences(pkg, lib, ver, fmt):
             lib.rwkv_free(seqs[r][1]); lib.rwkv_free(seqs[r][0])
         for w in whole:
             w.free()
+
+
+@pytest.mark.parametrize("ver,fmt", [("6v0-3m", "Q5_1"), ("7v0-834K", "FP32"), ("5v1-730K", "FP16")])
+def test_in_process_pipeline_behind_rwkv_h(pkg, lib, ver, fmt):
+    """rwkv_b200_init_pipeline / RWKV_B200_PIPELINE_DEVICES: several stages inside one process behind the PLAIN rwkv.h calls (here four
+    stages on device 0; on a multi-GPU box one per device). rwkv_eval, rwkv_eval_sequence(_in_chunks), aliased / NULL buffers, clones
+    evaluated from two host threads: everything must equal the single-context evaluation bit for bit (below the tensor-core
+    threshold), and the stages' state slices must tile the caller's state buffer exactly."""
+    import threading
+    L = lib.library
+    path = model_path(ver, fmt)
+    one = pkg.RWKVModel(lib, path, thread_count=1)
+    devs = (ctypes.c_int * 4)(0, 0, 0, 0)
+    ptr = L.rwkv_b200_init_pipeline(path.encode(), devs, 4)
+    assert ptr and L.rwkv_b200_pipeline_stages(ptr) == 4 and L.rwkv_b200_pipeline_stages(one._ctx.ptr) == 0
+    pipe = ctypes.c_void_p(ptr)
+    n, v = one.state_len, one.n_vocab
+    try:
+        assert lib.library.rwkv_get_state_len(pipe) == n and lib.library.rwkv_get_n_layer(pipe) == one.n_layer
+        toks = LONG_PROMPT[:20]
+        state, logits = np.zeros(n, np.float32), np.zeros(v, np.float32)
+        want_state = None
+        for i, t in enumerate(toks):             # serial, state_in aliases state_out from the second call on
+            want, want_state = one.eval(t, want_state, use_numpy=True)
+            assert L.rwkv_eval(pipe, t, None if i == 0 else state.ctypes.data_as(PF), state.ctypes.data_as(PF), logits.ctypes.data_as(PF))
+            assert logits.tobytes() == want.tobytes() and state.tobytes() == want_state.tobytes(), (ver, fmt, i)
+        arr = (ctypes.c_uint32 * len(toks))(*toks)
+        s2, l2 = np.zeros(n, np.float32), np.zeros(v, np.float32)
+        assert L.rwkv_eval_sequence(pipe, arr, len(toks), None, s2.ctypes.data_as(PF), l2.ctypes.data_as(PF))
+        assert s2.tobytes() == want_state.tobytes() and l2.tobytes() == want.tobytes()
+        s3, l3 = np.zeros(n, np.float32), np.zeros(v, np.float32)
+        assert L.rwkv_eval_sequence_in_chunks(pipe, arr, len(toks), 7, None, s3.ctypes.data_as(PF), l3.ctypes.data_as(PF))
+        assert s3.tobytes() == want_state.tobytes() and l3.tobytes() == want.tobytes()
+        assert L.rwkv_eval(pipe, toks[0], None, None, None)                       # every output optional
+        # two clones on two threads: their passes interleave on the stages' streams
+        clones = [ctypes.c_void_p(L.rwkv_clone_context(pipe, 1)) for _ in range(2)]
+        streams = [[(13 * i + 5 * q) % 256 for i in range(40)] for q in range(2)]
+        wants = []
+        for q in range(2):
+            st = None
+            for t in streams[q]:
+                lg, st = one.eval(t, st, use_numpy=True)
+            wants.append((lg.copy(), st.copy()))
+        outs = [None, None]
+
+        def run(q):
+            st, lg = np.zeros(n, np.float32), np.zeros(v, np.float32)
+            for i, t in enumerate(streams[q]):
+                assert L.rwkv_eval(clones[q], t, None if i == 0 else st.ctypes.data_as(PF), st.ctypes.data_as(PF), lg.ctypes.data_as(PF))
+            outs[q] = (lg, st)
+        th = [threading.Thread(target=run, args=(q,)) for q in range(2)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for q in range(2):
+            assert outs[q][0].tobytes() == wants[q][0].tobytes() and outs[q][1].tobytes() == wants[q][1].tobytes(), q
+        for c in clones:
+            L.rwkv_free(c)
+    finally:
+        L.rwkv_free(pipe)
+        one.free()
