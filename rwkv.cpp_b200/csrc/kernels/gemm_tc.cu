@@ -263,7 +263,7 @@ template <int EPI> __device__ __forceinline__ void store_cols(const EpiRow & e, 
 // warp w owns TMEM lanes 32 (w % 4) .. + 31 = rows row0 + 32 (w % 4) + lane; warps 0-3 take the even 32-column groups of the
 // accumulator, warps 4-7 the odd ones.
 //   MODE 0  single split: accumulator -> fused epilogue -> y
-//   MODE 1  one of several K-splits: accumulator -> this split's slot of the partial buffer (row-major [128][npad], full-line stores)
+//   MODE 1  one of several K-splits: accumulator -> this split's slot of the partial buffer (row-major [128][npad rounded up to 32], full-line stores)
 //   MODE 2  the split that arrived last: partials of ALL splits, added in split order from the buffer -> fused epilogue -> y
 template <int MODE>
 __device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, const float * cs, uint32_t tmem_base, int row0, int npad, int T,
@@ -278,7 +278,9 @@ __device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, const flo
     e.res = Psh.res ? Psh.res + row : nullptr; e.ldres = Psh.ldres;
     e.gate = Psh.gate ? Psh.gate + row : nullptr; e.ldgate = Psh.ldgate;
     e.bias = (MODE != 1 && live && Psh.bias) ? Psh.bias[row] : 0.f;
-    float * prow = part0 + (size_t) (q * 32 + lane) * npad;
+    // partial rows are (npad rounded up to 32) floats apart: the loop below moves whole 32-column groups, and with a stride of npad the
+    // last group of a row would spill into the next row's partial whenever npad is not a multiple of 32
+    float * prow = part0 + (size_t) (q * 32 + lane) * (size_t) ((npad + 31) & ~31);
 #pragma unroll 1
     for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += 64) {
         uint32_t acc[32];
@@ -557,7 +559,7 @@ __device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, co
             if (nsplit == 1) {
                 tc_epilogue_rows<0>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, nullptr, 1, 0);
             } else {
-                const size_t slot_floats = (size_t) TILE_M * NPAD;
+                const size_t slot_floats = (size_t) TILE_M * (size_t) ((NPAD + 31) & ~31);
                 const int slot_first = batch.slot0[w.pi] + w.tile * nsplit;
                 float * part0 = batch.partial + (size_t) slot_first * slot_floats;
                 tc_epilogue_rows<1>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, part0 + (size_t) w.split * slot_floats, nsplit, slot_floats);
@@ -820,7 +822,7 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
     const int sms = dev.num_sms > 0 ? dev.num_sms : 148;
     int want = total * 5 < sms * 3 ? sms / total : 1;      // below 60 % of the SMs: split
     if (force_split >= 0) want = force_split < 1 ? 1 : force_split;
-    const size_t slot_bytes = (size_t) tc::TILE_M * tb.npad * sizeof(float);
+    const size_t slot_bytes = (size_t) tc::TILE_M * (size_t) ((tb.npad + 31) & ~31) * sizeof(float);
     const int slot_cap = (int) (GEMM_TC_PARTIAL_BYTES / slot_bytes), ctr_cap = (int) (GEMM_TC_COUNTER_BYTES / sizeof(int));
     int next = 0, slots = 0;
     for (int i = 0; i < batch.n; i++) {

@@ -34,6 +34,10 @@ struct GemvProblem {
     long long pitch;
     int type, K, M;
     const float * x;  long long ldx;      // input  column t at x + t*ldx
+    // Single-token launches of the streaming kernel: x[:, 0] already in the staged layout of this problem's (type, K) (act_stage.cuh),
+    // emitted by the kernel that produced x. The consumers copy it instead of quantising x; NULL = stage from x. Ignored by the
+    // generic kernel and the tensor-core path.
+    const unsigned char * xq;
     float * y;        long long ldy;      // output column t at y + t*ldy
     const float * res;  long long ldres;
     const float * gate; long long ldgate;

@@ -174,8 +174,16 @@ __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch ba
     for (int g = 0; g < n_groups; g++) {
         const int c0 = g * NC, nc = min(NC, batch.T - c0);
         if (g > 0) consumer_barrier();   // everyone finished reading the previous group's activations
-        if (lnmix) stage_column_lnmix(P, act, sh.slots, blockIdx.x == 0);
-        else for (int c = 0; c < nc; c++) stage_column<4, STAGE_V2>(P, c0 + c, act + c * colb, sh.red_d);
+        if (lnmix) {
+            stage_column_lnmix(P, act, sh.slots, blockIdx.x == 0);
+        } else if (P.xq && NC == 1 && batch.T == 1) {
+            // the producer of x left the staged column in global memory (act_stage.cuh): one 16-byte-per-thread copy out of L2
+            const int4 * src = reinterpret_cast<const int4 *>(P.xq);
+            int4 * dst = reinterpret_cast<int4 *>(act);
+            for (int i = threadIdx.x; i < (int) (colb / 16); i += CONSUMER_THREADS) dst[i] = __ldcg(src + i);
+        } else {
+            for (int c = 0; c < nc; c++) stage_column<4, STAGE_V2>(P, c0 + c, act + c * colb, sh.red_d);
+        }
         consumer_barrier();
         trace_mark(batch.trace, 1);
         const int it0 = g * my_tiles;
@@ -240,8 +248,9 @@ bool plan_wk(GemvProblem & p) {
 template <int NC, bool STAGE_V2 = false>
 cudaError_t launch_tma_nc(const GemvBatch & batch, int grid, size_t smem, cudaStream_t stream) {
     if constexpr (NC == 1 && !STAGE_V2) {
-        // experimental: single-column launches with the per-block activation staging (gemv_tma_device.cuh: stage_column PER_BLOCK)
-        static const bool stage_v2 = [] { const char * e = getenv("RWKV_B200_STAGE_V2"); return e && atoi(e) != 0; }();
+        // single-column launches stage their activation column one thread per 32-element block (gemv_tma_device.cuh: stage_column
+        // PER_BLOCK; bit-identical bytes, -0.36 ms per 7B token); RWKV_B200_STAGE_V2=0 selects the 8-lanes-per-block variant
+        static const bool stage_v2 = [] { const char * e = getenv("RWKV_B200_STAGE_V2"); return !e || atoi(e) != 0; }();
         if (stage_v2) return launch_tma_nc<1, true>(batch, grid, smem, stream);
     }
     static PerDeviceOnce once;                // the shared-memory opt-in is per device

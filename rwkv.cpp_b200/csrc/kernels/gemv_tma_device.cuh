@@ -4,6 +4,7 @@
 #pragma once
 #include "gemv.h"
 #include "quant_decode.cuh"
+#include "act_stage.cuh"
 
 #include <cuda_fp16.h>
 
@@ -133,18 +134,9 @@ __device__ __forceinline__ float apply_epilogue(const GemvProblem & P, float v, 
 }
 
 // ---- shared-memory layout:  [ ring: NSTAGES x stage_bytes ][ act: NC columns ][ red ] ----------------------------
-// Blocks of a quantised activation column rounded up to whole units (pairs for the 2-byte-aligned formats).
-__host__ __device__ inline int padded_blocks(int type, int K) {
-    const int nblk = K / 32;
-    return (type == DT_Q4_1 || type == DT_Q5_1) ? nblk : (nblk + 1) / 2 * 2;
-}
-__host__ __device__ inline size_t act_bytes_per_column(int type, int K) {
-    size_t b;
-    if (type == DT_F32) b = (size_t) K * 4;
-    else if (type == DT_F16) b = (size_t) K * 2;
-    else b = (size_t) padded_blocks(type, K) * (32 + sizeof(ActScale));
-    return (b + 15) & ~(size_t) 15;
-}
+// The activation column's layout is act_stage.cuh's (producer kernels can emit it ready-made).
+__host__ __device__ inline int padded_blocks(int type, int K) { return act::padded_blocks(type, K); }
+__host__ __device__ inline size_t act_bytes_per_column(int type, int K) { return act::bytes_per_column(type, K); }
 
 struct Shared {
     uint64_t full[NSTAGES];

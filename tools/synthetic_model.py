@@ -22,10 +22,17 @@ import ggml_file as gf  # noqa: E402
 # name -> (arch_major, arch_minor, C, F, L, V, head_size, extras)
 PRESETS = {
     # BASELINE.json configs / north star
-    "rwkv4-169m": dict(arch=(4, 0), C=768, F=3072, L=12, V=50277),
-    "rwkv5-1b5": dict(arch=(5, 2), C=2048, F=7168, L=24, V=65536, S=64),
-    "rwkv6-7b": dict(arch=(6, 0), C=4096, F=14336, L=32, V=65536, S=64, mix=64, decay=128),
-    "rwkv7-2b9": dict(arch=(7, 0), C=2560, F=10240, L=32, V=65536, S=64, lora_w=96, lora_a=96, lora_v=64, lora_g=320),
+    # out_scale: factor on the two matrices that write into the residual stream (att.output, ffn.value). With 1.0 every block adds a
+    # vector as large as the stream itself and a 24-32 layer random network is chaotic: the unmodified reference then differs from
+    # ITSELF (AVX2 vs AVX-512 build, same file) by 2.1 in the logits of the 2.9B FP16 shape after one token (tools/ref_self_spread.py),
+    # so no end-to-end comparison means anything. Trained checkpoints are nothing like that (RWKV initialises both matrices to zero);
+    # 0.1 keeps the residual stream embedding-dominated, as in a trained model, and rounding flips stay local.
+    # lora_fan_in: LoRA matrices (v6 time_maa / time_decay, v7 w/a/v/g pairs) get std 0.5/sqrt(fan_in) instead of a flat 0.05, which
+    # at n_embed = 4096 drives every tanh / sigmoid of the data-dependent mixes into saturation (pre-activations of std 3.2).
+    "rwkv4-169m": dict(arch=(4, 0), C=768, F=3072, L=12, V=50277, out_scale=0.1),
+    "rwkv5-1b5": dict(arch=(5, 2), C=2048, F=7168, L=24, V=65536, S=64, out_scale=0.1),
+    "rwkv6-7b": dict(arch=(6, 0), C=4096, F=14336, L=32, V=65536, S=64, mix=64, decay=128, out_scale=0.1, lora_fan_in=True),
+    "rwkv7-2b9": dict(arch=(7, 0), C=2560, F=10240, L=32, V=65536, S=64, lora_w=96, lora_a=96, lora_v=64, lora_g=320, out_scale=0.1, lora_fan_in=True),
     # small shapes for parity tests (head size 64 like real models)
     "rwkv4-small": dict(arch=(4, 0), C=256, F=1024, L=3, V=1000),
     "rwkv5.1-small": dict(arch=(5, 1), C=256, F=896, L=3, V=1000, S=64),
@@ -158,6 +165,18 @@ def _small_values(kind, ne, rng):
     raise ValueError(kind)
 
 
+def _mat_std(p, name, ne):
+    """std of a 2-D weight: 1/sqrt(fan_in), damped by the preset's out_scale for the matrices that write into the residual stream."""
+    s = 1.0 / np.sqrt(ne[0])
+    if name.endswith(("att.output.weight", "ffn.value.weight")):
+        s *= p.get("out_scale", 1.0)
+    return s
+
+
+def _lora_std(p, ne):
+    return 0.5 / np.sqrt(ne[0]) if p.get("lora_fan_in") else 0.05
+
+
 def _dense(ne, rng, scale):
     """[M, K] float32 (ggml ne = (K, M))."""
     K, M = ne[0], int(np.prod(ne[1:]))
@@ -174,16 +193,16 @@ def write_master(path, preset, dtype="FP16", seed=0):
     def gen():
         for name, kind, ne, _ in _Spec(p).tensors():
             if kind in ("mat", "head"):
-                yield name, wide, ne, conv(_dense(ne, rng, 1.0 / np.sqrt(ne[0])))
+                yield name, wide, ne, conv(_dense(ne, rng, _mat_std(p, name, ne)))
             elif kind == "emb":
                 yield name, wide, ne, conv(_dense(ne, rng, 0.1))
             elif kind in ("lora", "lora_keep"):
                 # v6 LoRA matrices keep FP32 even in FP16 files (names contain `.time_`); v7's become FP16
                 t = gf.TYPE_FP32 if (kind == "lora" or dtype != "FP16") else gf.TYPE_FP16
-                a = _dense(ne, rng, 0.05)
+                a = _dense(ne, rng, _lora_std(p, ne))
                 yield name, t, ne, (a if t == gf.TYPE_FP32 else _f16(a))
             elif kind == "lora_f32":
-                yield name, gf.TYPE_FP32, ne, (0.05 * rng.standard_normal(int(np.prod(ne)))).astype(np.float32)
+                yield name, gf.TYPE_FP32, ne, (_lora_std(p, ne) * rng.standard_normal(int(np.prod(ne)))).astype(np.float32)
             else:
                 t, a = _vec(_small_values(kind, ne, rng))
                 yield name, t, ne, a
@@ -227,22 +246,22 @@ def write_direct(path, preset, fmt, seed=0):
         for name, kind, ne, _ in _Spec(p).tensors():
             if kind == "mat":
                 if quant:
-                    t, raw = _random_blocks(fmt, ne, rng, 1.0 / np.sqrt(ne[0]))
+                    t, raw = _random_blocks(fmt, ne, rng, _mat_std(p, name, ne))
                     yield name, t, ne, raw
                 else:
-                    a = _dense(ne, rng, 1.0 / np.sqrt(ne[0]))
+                    a = _dense(ne, rng, _mat_std(p, name, ne))
                     yield name, (gf.TYPE_FP16 if fmt == "FP16" else gf.TYPE_FP32), ne, (_f16(a) if fmt == "FP16" else a)
             elif kind == "lora":
                 if quant:
-                    t, raw = _random_blocks(fmt, ne, rng, 0.05)
+                    t, raw = _random_blocks(fmt, ne, rng, _lora_std(p, ne))
                     yield name, t, ne, raw
                 else:
-                    yield name, gf.TYPE_FP32, ne, _dense(ne, rng, 0.05)
+                    yield name, gf.TYPE_FP32, ne, _dense(ne, rng, _lora_std(p, ne))
             elif kind == "lora_keep":
-                a = _dense(ne, rng, 0.05)
+                a = _dense(ne, rng, _lora_std(p, ne))
                 yield name, (gf.TYPE_FP32 if fmt == "FP32" else gf.TYPE_FP16), ne, (a if fmt == "FP32" else _f16(a))
             elif kind == "lora_f32":
-                yield name, gf.TYPE_FP32, ne, (0.05 * rng.standard_normal(int(np.prod(ne)))).astype(np.float32)
+                yield name, gf.TYPE_FP32, ne, (_lora_std(p, ne) * rng.standard_normal(int(np.prod(ne)))).astype(np.float32)
             elif kind in ("emb", "head"):
                 a = _dense(ne, rng, 0.1 if kind == "emb" else 1.0 / np.sqrt(ne[0]))
                 yield name, (gf.TYPE_FP32 if fmt == "FP32" else gf.TYPE_FP16), ne, (a if fmt == "FP32" else _f16(a))
