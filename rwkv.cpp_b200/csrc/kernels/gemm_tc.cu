@@ -1,32 +1,27 @@
 // Chunked-prefill contraction on the 5th-generation tensor cores:  Y[M, T] = epilogue(W[M, K] . X[K, T])  for T >= 32.
 //
 // This is the one place of the eval path where the chunk x embedding contraction is dense enough for tensor cores
-// (~325 FLOP/B at T = 128). Per CTA: one 128-row tile of W against all T (<= 256) tokens, warp-specialised:
+// (SURVEY.md 8d). Round-2 design, after measuring the round-1 kernel (quantised tiles dequantised by 8 SIMT warps into TMEM:
+// 9-13 % of the tensor peak, every K-step a chain of four mbarrier hand-offs; profiles/r2_c3_pf_*.json):
 //
-//   warp 8   raw producer   one contiguous bulk copy (cp.async.bulk, 50 KB) per K-chunk (8 K-steps: 128 rows x 16 ggml blocks,
-//                           still quantised) out of the TILE-MAJOR prefill copy of the matrix (tc_repack_kernel) into a
-//                           2-deep shared-memory ring; weights do not depend on the previous kernel, so this starts
-//                           before the programmatic-dependency wait. (A 2-D TMA box over the row-major matrix needed
-//                           ~58 cycles per 416-byte row: 3.7 us per chunk, which capped the K loop at ~1000 cycles per step.)
-//   warp 9   B producer     fp16 activations, stored by convert_f16_kernel directly in the UMMA canonical layout, one
-//                           contiguous bulk copy (16-32 KB) per K-step of 64
-//   warps 0-7 transform     each thread owns (row, block) of the K-step: read the raw block from shared memory, dequantise
-//                           to fp16 in packed-half arithmetic ((q - offset) * d + m, rounded once), store into the A stage
-//                           in the canonical K-major no-swizzle layout (8-row x 16-byte core matrices), proxy fence,
-//                           arrive. These threads never have a global load in flight, so the fence costs nothing (it is a
-//                           MEMBAR.ALL.CTA in SASS: with in-flight LDGs it serialised every K-step at HBM latency)
-//   warp 10  MMA issuer     one thread issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = T padded to 16, K = 16) four
-//                           times per K-step; the fp32 accumulator lives in TMEM (N columns x 128 lanes); tcgen05.commit
-//                           frees the A/B stage through an mbarrier
-//   epilogue warps 0-3 pull the accumulator with tcgen05.ld (32x32b), apply the same fused epilogues as the GEMV
-//                           (activation, bias, residual, gate) and store column-major.
+//   * Weights for this path are expanded ONCE, at load time, to fp16 -- the value the old kernel computed on the fly,
+//     (q - offset) * d + m rounded once -- and stored tile-major in the UMMA canonical no-swizzle K-major layout: one
+//     [128 rows x 64 k] operand block = 16 KB contiguous, core matrices (8 rows x 16 bytes) back to back. 180 GB of HBM
+//     pays for it (2 bytes per weight: 17 GB at 7B next to the 6 GB the decode path streams).
+//   * The kernel is the canonical sm_100 pipeline and nothing else: ONE producer thread moves both operands with 1-D bulk
+//     copies (cp.async.bulk, SASS UBLKCP; no tensor map needed because the global layout already is the shared-memory
+//     layout) into a ring of up to 8 stages, ONE thread issues tcgen05.mma.cta_group::1.kind::f16 (M 128, N = tokens padded
+//     to 16, K 16; A and B from shared memory, fp32 accumulator in TMEM), tcgen05.commit hands the stage back, four
+//     epilogue warps pull the accumulator with tcgen05.ld and apply the GEMV's fused epilogues. One mbarrier pair per
+//     stage, no __syncthreads in the K loop.
+//   * At T = 128 the contraction is HBM-bound on the fp16 weights (128 FLOP per weight byte, ridge 221): the target is the
+//     copy bandwidth, i.e. 17 GB / 6.5 TB/s = 2.6 ms per 7B chunk = 58 % of the sustained bf16 peak, not the tensor peak.
+//   * Launches whose tiles would leave most SMs idle (4096-row matrices: 32 tiles; LoRA matrices: 1-2) are cut along K;
+//     the CTA that arrives last at a tile's counter adds the partial tiles up in split order (deterministic).
 //
-// There is no __syncthreads in the K loop: every hand-off is an mbarrier (raw_full/raw_empty, a_full/b_full/ab_empty).
-//
-// Numerics: weights exactly as the file stores them, activations rounded to fp16, fp32 accumulate -- what the reference
-// does for F16 weights (ggml-cpu.c:259-264, 1463); for quantised weights the reference rounds activations to int8
-// blocks instead, so this path is (slightly) more accurate than the reference, and NOT bit-identical to the decode GEMV.
-// The engine therefore uses it only for passes of >= 32 tokens and never for F32 weights, which keeps every
+// Numerics: weights exactly as the file stores them, rounded once to fp16 after dequantisation; activations are fp16 of the
+// reference's own operand values (convert_f16_kernel below); fp32 accumulation in the tensor core. Not bit-identical to the
+// dp4a decode path, so the engine uses it only for passes of >= 32 tokens and never for F32 weights, which keeps every
 // serial == sequence memcmp test of the reference (tests/test_eval_sequence_in_chunks.c: chunks of 1, 2, 8, 10) exact.
 #include "gemv.h"
 #include "quant_decode.cuh"
@@ -39,36 +34,13 @@ namespace rwkv {
 namespace tc {
 
 constexpr int TILE_M = 128;
-constexpr int KSTEP = 64;                 // K elements per A/B stage = 4 MMAs of K = 16
-constexpr int XFORM_WARPS = 8;
-constexpr int WARP_RAW = 8, WARP_B = 9, WARP_MMA = 10;
-constexpr int THREADS = 352;
-constexpr int MAX_STAGES = 8;             // A/B ring depth (runtime: as many B stages as fit shared memory, <= 8). A stage = 32 columns of
-                                          // TENSOR MEMORY (dequantised weights) + NPAD x 64 halves of shared memory (activations)
-constexpr int MAX_RAW_STAGES = 3;         // raw (quantised) ring, in K-chunks
+constexpr int KSTEP = 64;                 // K elements per ring stage = 4 MMAs of K = 16
+constexpr int THREADS = 192;              // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue (TMEM lane quarters 2, 3, 0, 1)
+constexpr int EPI_WARP0 = 2, EPI_THREADS = 128;
+constexpr int MAX_STAGES = 8;
 constexpr int MAX_N = 256;
-// Tile-major prefill copy of a matrix: [tile of 128 rows][K-chunk][row][ROW_STRIDE bytes]; ROW_STRIDE = chunk bytes + a
-// pad that puts the 32 rows a warp reads on distinct shared-memory banks (64-bit loads for Q5_1, 128-bit for F16, 32-bit
-// for the rest), so one chunk of one tile is ONE contiguous, bank-conflict-free bulk copy.
-constexpr int QUANT_CHUNK_STEPS = 4;       // K-steps per raw chunk of the block formats (18-35 KB per bulk copy)
-template <int TYPE> struct RawTraits {
-    static constexpr int BLOCK_BYTES = QTraits<TYPE>::BLOCK_BYTES;
-    static constexpr int CHUNK_STEPS = QUANT_CHUNK_STEPS;
-    static constexpr int CHUNK_BYTES = CHUNK_STEPS * 2 * BLOCK_BYTES;
-    static constexpr int ROW_STRIDE = CHUNK_BYTES + (TYPE == DT_Q5_1 ? 8 : 4);
-};
-template <> struct RawTraits<DT_F16> {
-    static constexpr int BLOCK_BYTES = 64, CHUNK_STEPS = 2, CHUNK_BYTES = 256, ROW_STRIDE = CHUNK_BYTES + 16;
-};
-struct RawGeom { int block_bytes, chunk_steps, chunk_bytes, row_stride; };
-inline RawGeom raw_geom(int type) {
-    RawGeom g;
-    g.block_bytes = type == DT_F16 ? 64 : dtype_block_bytes(type);
-    g.chunk_steps = type == DT_F16 ? 2 : QUANT_CHUNK_STEPS;
-    g.chunk_bytes = g.chunk_steps * 2 * g.block_bytes;
-    g.row_stride = g.chunk_bytes + (type == DT_F16 ? 16 : type == DT_Q5_1 ? 8 : 4);
-    return g;
-}
+constexpr uint32_t A_BYTES = TILE_M * KSTEP * 2;      // one weight operand block: 16 KB
+constexpr uint32_t A_LBO = (TILE_M / 8) * 128;        // bytes between core matrices adjacent along K (16 row groups x 128 B)
 
 __device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t * bar, uint32_t count) {
@@ -100,35 +72,11 @@ __device__ __forceinline__ void bulk_load(void * dst, const void * src, uint32_t
                  "r"(smem_u32(bar))
                  : "memory");
 }
-// ---- thread-block clusters: the CTAs of a cluster work on neighbouring row tiles of the SAME matrix over the same K range, so they
-// need the same B (activation) stage; each loads 1/CS of it and multicasts the slice into every member's shared memory.
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_load_multicast(void * dst, const void * src, uint32_t bytes, uint64_t * bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t * bar, uint32_t cta) {      // the barrier at the same offset in CTA `cta` of the cluster
-    asm volatile(
-        "{\n"
-        ".reg .b32 ra;\n"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
-}
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
     uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
 }
-__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
 // ---- tcgen05 wrappers (PTX ISA 8.6+, sm_100a) ----------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t * dst_in_smem, uint32_t ncols) {   // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_in_smem)), "r"(ncols) : "memory");
@@ -149,33 +97,8 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// A operand from tensor memory (128 lanes x 8 columns of packed fp16 per K = 16), B from shared memory
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// 32 lanes (this warp's quarter of TMEM) x 32 consecutive columns <- registers; r[j] goes to column j of the lane's row
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t * r) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
-        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
-        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void umma_commit(uint64_t * bar) {   // arrives on `bar` when every MMA issued so far has completed
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_commit_multicast(uint64_t * bar, uint16_t mask) {   // ... on the barrier at this offset in every CTA of `mask`
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t * r) {   // 32 lanes x 32 consecutive columns
     asm volatile(
@@ -207,20 +130,13 @@ __host__ __device__ inline uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
 }
 
-// Dynamic shared memory: [B stages][raw stages]
-//   B stage: NPAD x KSTEP halves : chunk (kc, g) at (kc * NG + g) * 128 bytes   (kc = k / 8, g = token / 8)
-//   raw stage: TILE_M rows x ROW_STRIDE bytes of quantised blocks, exactly as the tile-major copy stores them
-// Tensor memory: columns [0, NPAD) fp32 accumulator, then up to MAX_STAGES x 32 columns of A: lane = tile row, column j of a stage =
-//   fp16 pair (k = 2j, 2j + 1) of the K-step. The tensor core reads A from there (tcgen05.mma with a TMEM A operand), so
-//   the dequantised weights never touch shared memory: its bandwidth (128 B/clk) is left to the B operand and the TMA
-//   writes -- with A in shared memory the MMAs, the transform stores and the TMA traffic together needed ~600 cycles of
-//   shared-memory time per K-step against 262 cycles of tensor-core math.
+// Dynamic shared memory: `stages` ring slots of [A: 128 rows x 64 k fp16 = 16 KB][B: NPAD tokens x 64 k fp16], both in the UMMA
+// canonical K-major no-swizzle layout: element (row, k) at (k / 8) * LBO + (row / 8) * 128 + (row % 8) * 16 + (k % 8) * 2 bytes,
+// LBO = (rows / 8) * 128. Tensor memory: columns [0, NPAD) = the fp32 accumulator, lane = tile row.
 struct TcShared {
-    uint64_t raw_full[MAX_RAW_STAGES], raw_empty[MAX_RAW_STAGES];
-    uint64_t a_full[MAX_STAGES], b_full[MAX_STAGES], ab_empty[MAX_STAGES];
+    uint64_t full[MAX_STAGES], empty[MAX_STAGES];
     uint64_t acc_done;
     uint32_t tmem_base;
-    long long t0;            // clock64 at kernel start (trace marks)
     GemvProblem P;
     float colscale[MAX_N];
     int split_rank;          // arrival order of this CTA among the K-splits of its tile (split-K epilogue)
@@ -260,8 +176,7 @@ template <int EPI> __device__ __forceinline__ void store_cols(const EpiRow & e, 
         e.y[(long long) col * e.ldy] = v;
     }
 }
-// warp w owns TMEM lanes 32 (w % 4) .. + 31 = rows row0 + 32 (w % 4) + lane; warps 0-3 take the even 32-column groups of the
-// accumulator, warps 4-7 the odd ones.
+// Epilogue warp w owns TMEM lanes 32 (w % 4) .. + 31 = rows row0 + 32 (w % 4) + lane and walks all 32-column groups of the accumulator.
 //   MODE 0  single split: accumulator -> fused epilogue -> y
 //   MODE 1  one of several K-splits: accumulator -> this split's slot of the partial buffer (row-major [128][npad rounded up to 32], full-line stores)
 //   MODE 2  the split that arrived last: partials of ALL splits, added in split order from the buffer -> fused epilogue -> y
@@ -282,7 +197,7 @@ __device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, const flo
     // last group of a row would spill into the next row's partial whenever npad is not a multiple of 32
     float * prow = part0 + (size_t) (q * 32 + lane) * (size_t) ((npad + 31) & ~31);
 #pragma unroll 1
-    for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += 64) {
+    for (int c0 = 0; c0 < npad; c0 += 32) {
         uint32_t acc[32];
         if constexpr (MODE == 2) {
 #pragma unroll
@@ -388,240 +303,122 @@ template <int TYPE> __device__ __forceinline__ void block_to_half(const BlockReg
 struct TcBatch {
     int n, T, npad;                  // problems, tokens, tokens padded to a multiple of 16
     int tmem_cols;                   // power of two >= 32
-    int raw_stages;                  // 2 or 3
-    int raw_stage_bytes;             // ring slot size: the largest 128-row chunk of the batch's formats, 128-byte multiple
-    int b_stages;                    // A/B ring depth, 2 .. MAX_STAGES
+    int stages;                      // ring depth, 2 .. MAX_STAGES
     const __half * act16[GEMV_MAX_PROBLEMS];   // canonical-layout fp16 activations per problem (convert_f16_kernel)
     const float * colscale[GEMV_MAX_PROBLEMS]; // [npad] power-of-two factor per token that the epilogue multiplies back in
-    GemvProblem p[GEMV_MAX_PROBLEMS];          // first_cta / n_cta: CTA range of the problem = splits x tpad
-    // Work decomposition. A problem's CTAs are [split][tile padded to a multiple of the cluster size]; the CTAs of one cluster are
-    // cs neighbouring tiles of one split (tiles >= `tiles` are stand-ins that only take part in the B multicast). With splits > 1
-    // every CTA contracts `steps_per_split` K-steps and leaves its 128 x npad partial tile in `partial`; the CTA that arrives last
-    // at the tile's counter adds the partials up in split order (a fixed order: deterministic) and runs the epilogue.
-    int cs;                                    // cluster size: 1, 2 or 4
-    int tiles[GEMV_MAX_PROBLEMS], tpad[GEMV_MAX_PROBLEMS], splits[GEMV_MAX_PROBLEMS], steps_per_split[GEMV_MAX_PROBLEMS];
+    GemvProblem p[GEMV_MAX_PROBLEMS];          // first_cta / n_cta: CTA range of the problem = splits x tiles
+    // Work decomposition: a problem's CTAs are [split][tile]. With splits > 1 every CTA contracts `steps_per_split` K-steps and
+    // leaves its 128 x npad partial tile in `partial`; the CTA that arrives last at the tile's counter adds the partials up in split
+    // order (a fixed order: deterministic) and runs the epilogue.
+    int tiles[GEMV_MAX_PROBLEMS], splits[GEMV_MAX_PROBLEMS], steps_per_split[GEMV_MAX_PROBLEMS];
     int slot0[GEMV_MAX_PROBLEMS];              // first partial slot / counter of the problem (slot = slot0 + tile * splits + split)
-    float * partial;                           // [slots][128][npad] fp32
+    float * partial;                           // [slots][128][npad rounded up to 32] fp32
     int * counters;                            // one per (problem, tile) with splits > 1, at index slot0 + tile * splits; zero between launches
     TraceRec * trace;
 };
-
-// What one CTA does: rows [tile * 128, +128) of problem `pi` against all tokens over K-steps [ks0, ks1).
-struct TcWork { int pi, tile, split, ks0, ks1; bool standin; };
-
-template <int TYPE>
-__device__ void tc_tile(TcShared & sh, uint8_t * smem, const TcBatch & batch, const TcWork w) {
-    using RT = RawTraits<TYPE>;
-    const GemvProblem & P = sh.P;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int NPAD = batch.npad, NG = NPAD / 8;
-    const int row0 = w.tile * TILE_M;
-    const uint32_t b_bytes = (uint32_t) NPAD * KSTEP * 2;
-    constexpr uint32_t raw_bytes = (uint32_t) TILE_M * RT::ROW_STRIDE;
-    uint8_t * const b_base = smem;
-    const uint32_t tmem_a0 = sh.tmem_base + (uint32_t) NPAD;      // + stage * 32 columns
-    const int nb = batch.b_stages;
-    uint8_t * const raw_base = b_base + (size_t) nb * b_bytes;
-    const uint32_t raw_slot = (uint32_t) batch.raw_stage_bytes;
-    const int nsteps_total = P.K / KSTEP;
-    const int nraw = batch.raw_stages;
-    const int CS = batch.cs;
-    const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
-    const uint16_t all_mask = (uint16_t) ((1u << CS) - 1u);
-    const __half * act16 = batch.act16[w.pi];
-    const int nsplit = batch.splits[w.pi];
-
-    if (warp == WARP_RAW) {
-        if (lane == 0 && !w.standin) {
-            const int nchunks_total = (nsteps_total + RT::CHUNK_STEPS - 1) / RT::CHUNK_STEPS;
-            const int c0 = w.ks0 / RT::CHUNK_STEPS, c1 = (w.ks1 + RT::CHUNK_STEPS - 1) / RT::CHUNK_STEPS;     // split boundaries are chunk-aligned
-            const uint8_t * wt = reinterpret_cast<const uint8_t *>(P.Wt);
-            int rs = 0; uint32_t ph = 0;
-            for (int c = c0; c < c1; c++) {
-                mbar_wait(&sh.raw_empty[rs], ph ^ 1);
-                mbar_expect_tx(&sh.raw_full[rs], raw_bytes);
-                bulk_load(raw_base + (size_t) rs * raw_slot, wt + ((size_t) w.tile * nchunks_total + c) * raw_bytes, raw_bytes, &sh.raw_full[rs]);
-                if (++rs == nraw) { rs = 0; ph ^= 1; }
-            }
-        }
-    } else if (warp == WARP_B) {
-        if (lane == 0) {
-            pdl_prologue();     // the activations come from the previous kernels
-            const uint32_t slice = b_bytes / (uint32_t) CS;
-            int s = 0; uint32_t ph = 0;
-            for (int ks = w.ks0; ks < w.ks1; ks++) {
-                mbar_wait(&sh.ab_empty[s], ph ^ 1);        // every CTA of the cluster has consumed this stage
-                mbar_expect_tx(&sh.b_full[s], b_bytes);    // my barrier sees the whole stage: CS slices, one from each member
-                const uint8_t * src = reinterpret_cast<const uint8_t *>(act16 + (size_t) ks * KSTEP * NPAD);
-                if (CS == 1) bulk_load(b_base + (size_t) s * b_bytes, src, b_bytes, &sh.b_full[s]);
-                else bulk_load_multicast(b_base + (size_t) s * b_bytes + (size_t) rank * slice, src + (size_t) rank * slice, slice, &sh.b_full[s], all_mask);
-                if (++s == nb) { s = 0; ph ^= 1; }
-            }
-        }
-    } else if (warp == WARP_MMA) {
-        if (lane == 0 && w.standin) {
-            // a stand-in has no rows: it releases every stage as soon as the stage's data has landed in its shared memory
-            int s = 0; uint32_t ph = 0;
-            for (int ks = w.ks0; ks < w.ks1; ks++) {
-                mbar_wait(&sh.b_full[s], ph);
-                for (int c = 0; c < CS; c++) mbar_arrive_remote(&sh.ab_empty[s], (uint32_t) c);
-                if (++s == nb) { s = 0; ph ^= 1; }
-            }
-        } else if (lane == 0) {
-            const uint32_t idesc = make_idesc(TILE_M, NPAD);
-            // everything the issue loop needs sits in registers: TMEM addresses, the constant descriptor half and the 14-bit
-            // start-address field of each B stage; per K-step the thread does two waits, 4 MMAs and ONE commit
-            const uint32_t tmem_d = sh.tmem_base;
-            const uint64_t desc_fixed = make_desc(0, (uint32_t) NG * 128, 128);
-            const uint32_t b_addr0 = smem_u32(b_base) >> 4, b_stage16 = b_bytes >> 4, b_k16 = (uint32_t) (2 * NG * 128) >> 4;
-            int s = 0; uint32_t ph = 0;
-            for (int ks = w.ks0; ks < w.ks1; ks++) {
-                const uint32_t a_col = tmem_a0 + (uint32_t) (s * 32);
-                const uint64_t d0 = desc_fixed | (uint64_t) ((b_addr0 + (uint32_t) s * b_stage16) & 0x3FFFu);
-                const uint64_t d1 = desc_fixed | (uint64_t) ((b_addr0 + (uint32_t) s * b_stage16 + b_k16) & 0x3FFFu);
-                const uint64_t d2 = desc_fixed | (uint64_t) ((b_addr0 + (uint32_t) s * b_stage16 + 2 * b_k16) & 0x3FFFu);
-                const uint64_t d3 = desc_fixed | (uint64_t) ((b_addr0 + (uint32_t) s * b_stage16 + 3 * b_k16) & 0x3FFFu);
-                mbar_wait(&sh.b_full[s], ph);
-                mbar_wait(&sh.a_full[s], ph);
-                tc_fence_after_sync();
-                umma_f16_ts(tmem_d, a_col, d0, idesc, ks > w.ks0 ? 1u : 0u);
-                umma_f16_ts(tmem_d, a_col + 8, d1, idesc, 1u);
-                umma_f16_ts(tmem_d, a_col + 16, d2, idesc, 1u);
-                umma_f16_ts(tmem_d, a_col + 24, d3, idesc, 1u);
-                // the A stage (mine) and the B stage (everybody's copy is written by everybody) are free once these MMAs have read them
-                if (CS == 1) umma_commit(&sh.ab_empty[s]); else umma_commit_multicast(&sh.ab_empty[s], all_mask);
-                if (++s == nb) { s = 0; ph ^= 1; }
-            }
-            umma_commit(&sh.acc_done);                 // ... and the accumulator is final
-        }
-    } else if (!w.standin) {
-        // transform: thread = row r of the tile, BOTH blocks of a K-step (two independent dequantisation chains in
-        // flight, one wait / store / arrive per 64 k); warps 0-3 take the even K-steps, warps 4-7 the odd ones, so two
-        // A stages are being filled at any time. Warp w owns TMEM lanes 32 * (w % 4) .. + 31 = its 32 rows.
-        const int r = tid & (TILE_M - 1), grp = tid >> 7;
-        const uint32_t raw_row0 = smem_u32(raw_base) + (uint32_t) r * RT::ROW_STRIDE;
-        const uint32_t tmem_a_mine = tmem_a0 + ((uint32_t) ((warp & 3) * 32) << 16);
-        // trace marks of CTA 0, thread 0 (cycles, stored as start + cycles): [0] waiting for raw chunks, [1] reading + dequantising
-        // two blocks, [2] waiting for a free A stage, [3] tcgen05.st + fences + arrive
-        const bool acct = batch.trace != nullptr && blockIdx.x == 0 && tid == 0;
-        long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, tq = acct ? clock64() : 0;
-        auto tick = [&](long long & a) { if (acct) { const long long now = clock64(); a += now - tq; tq = now; } };
-        int s = grp % nb, rs = 0, cur_chunk = -1; uint32_t ph = 0, rph = 0;
-        if (grp >= nb) ph ^= 1;        // (nb >= 2 always)
-        for (int ks = w.ks0 + grp; ks < w.ks1; ks += 2) {
-            const int c = ks / RT::CHUNK_STEPS, sc = ks % RT::CHUNK_STEPS;
-            if (c != cur_chunk) {
-                if (cur_chunk >= 0 && ++rs == nraw) { rs = 0; rph ^= 1; }
-                cur_chunk = c;
-                mbar_wait(&sh.raw_full[rs], rph);
-            }
-            tick(c0);
-            BlockRegs<TYPE> regs0, regs1;
-            read_block<TYPE>(raw_row0 + (uint32_t) rs * raw_slot, sc * 2, regs0);
-            read_block<TYPE>(raw_row0 + (uint32_t) rs * raw_slot, sc * 2 + 1, regs1);
-            // last step of this warp inside the chunk: the raw rows are in registers, hand the slot back
-            const bool last_in_chunk = sc + 2 >= RT::CHUNK_STEPS || ks + 2 >= w.ks1;
-            uint4 h0[4], h1[4];
-            block_to_half<TYPE>(regs0, h0);
-            block_to_half<TYPE>(regs1, h1);
-            if (last_in_chunk) { __syncwarp(); if (lane == 0) mbar_arrive(&sh.raw_empty[rs]); }
-            tick(c1);
-            mbar_wait(&sh.ab_empty[s], ph ^ 1);
-            tick(c2);
-            tc_fence_after_sync();
-            {
-                uint32_t w32[32];
-#pragma unroll
-                for (int cc = 0; cc < 4; cc++) {
-                    w32[4 * cc] = h0[cc].x; w32[4 * cc + 1] = h0[cc].y; w32[4 * cc + 2] = h0[cc].z; w32[4 * cc + 3] = h0[cc].w;
-                    w32[16 + 4 * cc] = h1[cc].x; w32[16 + 4 * cc + 1] = h1[cc].y; w32[16 + 4 * cc + 2] = h1[cc].z; w32[16 + 4 * cc + 3] = h1[cc].w;
-                }
-                tmem_st32(tmem_a_mine + (uint32_t) (s * 32), w32);
-            }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sh.a_full[s]);
-            tick(c3);
-            s += 2;
-            if (s >= nb) { s -= nb; ph ^= 1; }
-        }
-        if (acct) {
-            TraceRec * t = batch.trace;
-            t->mark[0] = t->start + (unsigned long long) c0; t->mark[1] = t->start + (unsigned long long) c1;
-            t->mark[2] = t->start + (unsigned long long) c2; t->mark[3] = t->start + (unsigned long long) c3;
-        }
-        {
-            pdl_prologue();     // residual / gate inputs (and, with K-splits, the partial buffer) belong to the previous kernels until here
-            if (tid < NPAD) sh.colscale[tid] = batch.colscale[w.pi][tid];
-            asm volatile("bar.sync 2, 256;" ::: "memory");      // the 8 transform / epilogue warps
-            mbar_wait(&sh.acc_done, 0);
-            tc_fence_after_sync();
-            if (nsplit == 1) {
-                tc_epilogue_rows<0>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, nullptr, 1, 0);
-            } else {
-                const size_t slot_floats = (size_t) TILE_M * (size_t) ((NPAD + 31) & ~31);
-                const int slot_first = batch.slot0[w.pi] + w.tile * nsplit;
-                float * part0 = batch.partial + (size_t) slot_first * slot_floats;
-                tc_epilogue_rows<1>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, part0 + (size_t) w.split * slot_floats, nsplit, slot_floats);
-                __threadfence();                                    // my partial is visible device-wide before I take a ticket
-                asm volatile("bar.sync 2, 256;" ::: "memory");
-                if (tid == 0) sh.split_rank = atomicAdd(batch.counters + slot_first, 1);
-                asm volatile("bar.sync 2, 256;" ::: "memory");
-                if (sh.split_rank == nsplit - 1) {                  // every other split's partial has been published before its ticket
-                    __threadfence();
-                    tc_epilogue_rows<2>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, part0, nsplit, slot_floats);
-                    if (tid == 0) batch.counters[slot_first] = 0;   // ready for the next launch (ordered by kernel completion)
-                }
-            }
-        }
-    } else {
-        pdl_prologue();
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-}
 
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ TcShared sh;
     trace_begin(batch.trace);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int pi = 0;
     for (int i = 1; i < batch.n; i++) if ((int) blockIdx.x >= batch.p[i].first_cta) pi = i;
-    if (threadIdx.x == 0) {
-        sh.t0 = clock64();
+    const int nst = batch.stages;
+    if (tid == 0) {
         sh.P = batch.p[pi];
-        for (int s = 0; s < MAX_RAW_STAGES; s++) { mbar_init(&sh.raw_full[s], 1); mbar_init(&sh.raw_empty[s], XFORM_WARPS); }
-        for (int s = 0; s < MAX_STAGES; s++) { mbar_init(&sh.a_full[s], XFORM_WARPS / 2); mbar_init(&sh.b_full[s], 1); mbar_init(&sh.ab_empty[s], (uint32_t) batch.cs); }
+        for (int s = 0; s < MAX_STAGES; s++) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
         mbar_init(&sh.acc_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < 32) tmem_alloc(&sh.tmem_base, (uint32_t) batch.tmem_cols);
+    if (warp == 0) tmem_alloc(&sh.tmem_base, (uint32_t) batch.tmem_cols);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    if (batch.cs > 1) cluster_sync_all();          // nobody multicasts into, or arrives on, a barrier that is not initialised yet
-    TcWork w;
-    w.pi = pi;
-    {
-        const int local = (int) blockIdx.x - sh.P.first_cta, tpad = batch.tpad[pi];
-        w.split = local / tpad;
-        w.tile = local % tpad;
-        w.standin = w.tile >= batch.tiles[pi];
-        const int nsteps = sh.P.K / KSTEP, per = batch.steps_per_split[pi];
-        w.ks0 = w.split * per;
-        w.ks1 = min(nsteps, w.ks0 + per);
+    const GemvProblem & P = sh.P;
+    const int NPAD = batch.npad, NG = NPAD / 8;
+    const uint32_t b_bytes = (uint32_t) NPAD * KSTEP * 2, stage_bytes = A_BYTES + b_bytes;
+    const int nsteps_total = P.K / KSTEP;
+    const int local = (int) blockIdx.x - P.first_cta, ntiles = batch.tiles[pi];
+    const int split = local / ntiles, tile = local % ntiles;
+    const int nsplit = batch.splits[pi];
+    const int ks0 = split * batch.steps_per_split[pi], ks1 = min(nsteps_total, ks0 + batch.steps_per_split[pi]);
+    const int n = ks1 - ks0;                   // K-steps of this CTA (>= 1 by construction)
+    const int row0 = tile * TILE_M;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== producer: weights do not depend on the previous kernel -- the first ring-full of A blocks is on its way before
+            // the programmatic-dependency wait; the activations (B) follow once the kernels that produced them are done
+            const uint8_t * a_src = reinterpret_cast<const uint8_t *>(P.Wt) + ((size_t) tile * nsteps_total + ks0) * A_BYTES;
+            const uint8_t * b_src = reinterpret_cast<const uint8_t *>(batch.act16[pi]) + (size_t) ks0 * b_bytes;
+            const int pre = n < nst ? n : nst;
+            for (int i = 0; i < pre; i++) {
+                mbar_expect_tx(&sh.full[i], stage_bytes);
+                bulk_load(smem + (size_t) i * stage_bytes, a_src + (size_t) i * A_BYTES, A_BYTES, &sh.full[i]);
+            }
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            for (int i = 0; i < pre; i++) bulk_load(smem + (size_t) i * stage_bytes + A_BYTES, b_src + (size_t) i * b_bytes, b_bytes, &sh.full[i]);
+            for (int it = pre; it < n; it++) {
+                const int s = it % nst;
+                mbar_wait(&sh.empty[s], (uint32_t) (((it / nst) - 1) & 1));
+                mbar_expect_tx(&sh.full[s], stage_bytes);
+                bulk_load(smem + (size_t) s * stage_bytes, a_src + (size_t) it * A_BYTES, A_BYTES, &sh.full[s]);
+                bulk_load(smem + (size_t) s * stage_bytes + A_BYTES, b_src + (size_t) it * b_bytes, b_bytes, &sh.full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer: per K-step one wait, 4 MMAs (K = 16 each: two core-matrix columns of A and of B), one commit
+            const uint32_t idesc = make_idesc(TILE_M, NPAD);
+            const uint32_t tmem_d = sh.tmem_base;
+            const uint64_t a_fixed = make_desc(0, A_LBO, 128), b_fixed = make_desc(0, (uint32_t) NG * 128, 128);
+            const uint32_t smem0 = smem_u32(smem) >> 4, stage16 = stage_bytes >> 4;
+            const uint32_t a_k16 = (2 * A_LBO) >> 4, b_k16 = (uint32_t) (2 * NG * 128) >> 4;
+            for (int it = 0; it < n; it++) {
+                const int s = it % nst;
+                const uint32_t a0 = smem0 + (uint32_t) s * stage16, b0 = a0 + (A_BYTES >> 4);
+                mbar_wait(&sh.full[s], (uint32_t) ((it / nst) & 1));
+                tc_fence_after_sync();
+#pragma unroll
+                for (int k = 0; k < KSTEP / 16; k++)
+                    umma_f16(tmem_d, a_fixed | (uint64_t) ((a0 + (uint32_t) k * a_k16) & 0x3FFFu), b_fixed | (uint64_t) ((b0 + (uint32_t) k * b_k16) & 0x3FFFu), idesc,
+                             (it > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&sh.empty[s]);                 // the stage is free once these MMAs have read it
+            }
+            umma_commit(&sh.acc_done);                     // ... and the accumulator is final
+        }
+    } else {
+        // ===== epilogue (warps 2-5): residual / gate inputs (and, with K-splits, the partial buffer) belong to the previous kernels
+        // until the programmatic-dependency wait
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const int et = tid - EPI_WARP0 * 32;
+        for (int i = et; i < NPAD; i += EPI_THREADS) sh.colscale[i] = batch.colscale[pi][i];
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        mbar_wait(&sh.acc_done, 0);
+        tc_fence_after_sync();
+        if (nsplit == 1) {
+            tc_epilogue_rows<0>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, nullptr, 1, 0);
+        } else {
+            const size_t slot_floats = (size_t) TILE_M * (size_t) ((NPAD + 31) & ~31);
+            const int slot_first = batch.slot0[pi] + tile * nsplit;
+            float * part0 = batch.partial + (size_t) slot_first * slot_floats;
+            tc_epilogue_rows<1>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, part0 + (size_t) split * slot_floats, nsplit, slot_floats);
+            __threadfence();                                    // my partial is visible device-wide before I take a ticket
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (et == 0) sh.split_rank = atomicAdd(batch.counters + slot_first, 1);
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (sh.split_rank == nsplit - 1) {                  // every other split's partial has been published before its ticket
+                __threadfence();
+                tc_epilogue_rows<2>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, part0, nsplit, slot_floats);
+                if (et == 0) batch.counters[slot_first] = 0;    // ready for the next launch (ordered by kernel completion)
+            }
+        }
     }
-    switch (sh.P.type) {
-        case DT_Q4_0: tc_tile<DT_Q4_0>(sh, smem, batch, w); break;
-        case DT_Q4_1: tc_tile<DT_Q4_1>(sh, smem, batch, w); break;
-        case DT_Q5_0: tc_tile<DT_Q5_0>(sh, smem, batch, w); break;
-        case DT_Q5_1: tc_tile<DT_Q5_1>(sh, smem, batch, w); break;
-        case DT_Q8_0: tc_tile<DT_Q8_0>(sh, smem, batch, w); break;
-        default: tc_tile<DT_F16>(sh, smem, batch, w); break;
-    }
-    if (batch.cs > 1) cluster_sync_all();          // my shared memory and barriers stay valid until every member is done with them
-    if (threadIdx.x < 32) tmem_dealloc(sh.tmem_base, (uint32_t) batch.tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(sh.tmem_base, (uint32_t) batch.tmem_cols);
     trace_end(batch.trace);
 }
 
@@ -714,23 +511,40 @@ __global__ void __launch_bounds__(CVT_THREADS) convert_f16_kernel(const ConvertB
     trace_end(cb.trace);
 }
 
-// Row-major matrix (rows of `pitch` bytes) -> tile-major prefill copy. One thread per 4-byte word of the destination.
-__global__ void tc_repack_kernel(const uint8_t * src, long long pitch, int M, int nchunks, int chunk_bytes, int row_stride, uint8_t * dst) {
-    const int words_per_row = row_stride / 4;
-    const long long stage_words = (long long) TILE_M * words_per_row;
-    const long long total = (long long) gridDim.y * nchunks * stage_words;      // gridDim.y = tiles
-    for (long long w = (long long) blockIdx.x * blockDim.x + threadIdx.x + (long long) blockIdx.y * nchunks * stage_words;
-         w < ((long long) blockIdx.y + 1) * nchunks * stage_words && w < total; w += (long long) gridDim.x * blockDim.x) {
-        const long long in_tile = w - (long long) blockIdx.y * nchunks * stage_words;
-        const int c = (int) (in_tile / stage_words);
-        const int rem = (int) (in_tile % stage_words);
-        const int r = rem / words_per_row, off = (rem % words_per_row) * 4;
-        const int row = blockIdx.y * TILE_M + r;
-        const long long col = (long long) c * chunk_bytes + off;
+// Load-time expansion: row-major matrix (rows of `pitch` bytes, quantised or f16) -> the fp16 operand blocks gemm_tc_kernel streams.
+// One CTA = one (row tile, K-step): the 128 rows' two blocks of the K-step are staged in shared memory, thread r dequantises row r
+// (block_to_half: packed-half (q - offset) * d + m, rounded once) and writes its eight 16-byte k-groups into the canonical layout
+// (warp-contiguous 512-byte runs). Rows >= M are zero.
+template <int TYPE>
+__global__ void __launch_bounds__(TILE_M) tc_expand_kernel(const uint8_t * src, long long pitch, int M, int nsteps, uint4 * dst) {
+    constexpr int BB = TYPE == DT_F16 ? 64 : QTraits<TYPE == DT_F16 ? DT_Q4_0 : TYPE>::BLOCK_BYTES;
+    constexpr int ROW_WORDS = 2 * BB / 4;                       // the two blocks of a K-step start on a 4-byte boundary of the row
+    constexpr int ROW_STRIDE = (2 * BB + 15) / 16 * 16;         // shared-memory row pitch: keeps 64- / 128-bit reads aligned
+    __shared__ __align__(16) uint8_t rows[TILE_M * ROW_STRIDE];
+    const int ks = blockIdx.x, tile = blockIdx.y, r = threadIdx.x;
+    for (int i = threadIdx.x; i < TILE_M * ROW_WORDS; i += TILE_M) {
+        const int rr = i / ROW_WORDS, w = i % ROW_WORDS;
+        const int row = tile * TILE_M + rr;
         uint32_t v = 0;
-        if (row < M && off < chunk_bytes && col + 4 <= pitch) v = *reinterpret_cast<const uint32_t *>(src + (long long) row * pitch + col);
-        reinterpret_cast<uint32_t *>(dst)[w] = v;
+        if (row < M) v = *reinterpret_cast<const uint32_t *>(src + (long long) row * pitch + (long long) ks * 2 * BB + w * 4);
+        *reinterpret_cast<uint32_t *>(rows + rr * ROW_STRIDE + w * 4) = v;
     }
+    __syncthreads();
+    uint4 h[8];
+    if (tile * TILE_M + r < M) {
+        const uint32_t row_addr = smem_u32(rows) + (uint32_t) r * ROW_STRIDE;
+        BlockRegs<TYPE> r0, r1;
+        read_block<TYPE>(row_addr, 0, r0);
+        read_block<TYPE>(row_addr, 1, r1);
+        block_to_half<TYPE>(r0, h);
+        block_to_half<TYPE>(r1, h + 4);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) h[i] = make_uint4(0, 0, 0, 0);
+    }
+    uint4 * blk = dst + ((size_t) tile * nsteps + ks) * (A_BYTES / 16);
+#pragma unroll
+    for (int kc = 0; kc < 8; kc++) blk[(kc * (TILE_M / 8) + (r >> 3)) * 8 + (r & 7)] = h[kc];
 }
 
 }  // namespace tc
@@ -739,20 +553,25 @@ bool gemm_tc_eligible(int type, int K) { return type != DT_F32 && K % tc::KSTEP 
 
 size_t gemm_tc_tiled_bytes(int type, int M, int K) {
     if (!gemm_tc_eligible(type, K)) return 0;
-    const tc::RawGeom g = tc::raw_geom(type);
-    const size_t nsteps = (size_t) K / tc::KSTEP, nchunks = (nsteps + g.chunk_steps - 1) / g.chunk_steps, ntiles = ((size_t) M + tc::TILE_M - 1) / tc::TILE_M;
-    return ntiles * nchunks * tc::TILE_M * (size_t) g.row_stride;
+    const size_t nsteps = (size_t) K / tc::KSTEP, ntiles = ((size_t) M + tc::TILE_M - 1) / tc::TILE_M;
+    return ntiles * nsteps * tc::A_BYTES;
 }
 
 cudaError_t gemm_tc_repack(const void * W, long long pitch, int type, int M, int K, void * dst, cudaStream_t stream) {
     if (!gemm_tc_eligible(type, K)) return cudaErrorInvalidValue;
-    const tc::RawGeom g = tc::raw_geom(type);
-    const int nsteps = K / tc::KSTEP, nchunks = (nsteps + g.chunk_steps - 1) / g.chunk_steps, ntiles = (M + tc::TILE_M - 1) / tc::TILE_M;
-    const long long words_per_tile = (long long) nchunks * tc::TILE_M * (g.row_stride / 4);
-    int bx = (int) ((words_per_tile + 255) / 256);
-    if (bx > 64) bx = 64;
-    tc::tc_repack_kernel<<<dim3(bx, ntiles), 256, 0, stream>>>(reinterpret_cast<const uint8_t *>(W), pitch, M, nchunks, g.chunk_bytes, g.row_stride,
-                                                               reinterpret_cast<uint8_t *>(dst));
+    const int nsteps = K / tc::KSTEP, ntiles = (M + tc::TILE_M - 1) / tc::TILE_M;
+    const dim3 grid((unsigned) nsteps, (unsigned) ntiles);
+    const uint8_t * src = reinterpret_cast<const uint8_t *>(W);
+    uint4 * out = reinterpret_cast<uint4 *>(dst);
+    switch (type) {
+        case DT_Q4_0: tc::tc_expand_kernel<DT_Q4_0><<<grid, tc::TILE_M, 0, stream>>>(src, pitch, M, nsteps, out); break;
+        case DT_Q4_1: tc::tc_expand_kernel<DT_Q4_1><<<grid, tc::TILE_M, 0, stream>>>(src, pitch, M, nsteps, out); break;
+        case DT_Q5_0: tc::tc_expand_kernel<DT_Q5_0><<<grid, tc::TILE_M, 0, stream>>>(src, pitch, M, nsteps, out); break;
+        case DT_Q5_1: tc::tc_expand_kernel<DT_Q5_1><<<grid, tc::TILE_M, 0, stream>>>(src, pitch, M, nsteps, out); break;
+        case DT_Q8_0: tc::tc_expand_kernel<DT_Q8_0><<<grid, tc::TILE_M, 0, stream>>>(src, pitch, M, nsteps, out); break;
+        case DT_F16: tc::tc_expand_kernel<DT_F16><<<grid, tc::TILE_M, 0, stream>>>(src, pitch, M, nsteps, out); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
@@ -775,7 +594,7 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
     tb.n = batch.n; tb.T = batch.T;
     tb.npad = (batch.T + 15) / 16 * 16;
     tb.tmem_cols = 32;
-    while (tb.tmem_cols < tb.npad + tc::MAX_STAGES * 32) tb.tmem_cols *= 2;      // accumulator + A stages
+    while (tb.tmem_cols < tb.npad) tb.tmem_cols *= 2;      // the accumulator
     tb.counters = reinterpret_cast<int *>(workspace);
     tb.partial = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(workspace) + GEMM_TC_COUNTER_BYTES);
 
@@ -807,34 +626,25 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
         tb.act16[i] = cvt.out[shared];
         tb.colscale[i] = cvt.colscale[shared];
     }
-    // ---- work decomposition: cluster size, K-splits ----
-    // Clusters of 4 neighbouring row tiles share every B stage through multicast: a CTA pulls 1/4 of the activations it multiplies
-    // out of L2 (the B operand, re-read by every row tile, is 3x the weight bytes of a 128-row tile per K-step). Launches that
-    // would leave most of the 148 SMs idle (matrices with 4096 rows: 32 tiles; the LoRA matrices: 1-2 tiles) are cut along K.
-    static const int force_cs = [] { const char * e = getenv("RWKV_B200_TC_CLUSTER"); return e ? atoi(e) : 0; }();
+    // ---- work decomposition: one CTA per (row tile, K-split). Every CTA streams its share of the weights from HBM, so what matters
+    // is that close to all SMs have a CTA: launches with few tiles (4096-row matrices: 32; LoRA: 1-2) are cut along K.
     static const int force_split = [] { const char * e = getenv("RWKV_B200_TC_SPLITK"); return e ? atoi(e) : -1; }();
-    int base = 0;
-    for (int i = 0; i < batch.n; i++) { tb.tiles[i] = (batch.p[i].M + tc::TILE_M - 1) / tc::TILE_M; base += tb.tiles[i]; }
-    tb.cs = base >= 16 ? 4 : 1;
-    if (force_cs == 1 || force_cs == 2 || force_cs == 4) tb.cs = force_cs;
     int total = 0;
-    for (int i = 0; i < batch.n; i++) { tb.tpad[i] = (tb.tiles[i] + tb.cs - 1) / tb.cs * tb.cs; total += tb.tpad[i]; }
+    for (int i = 0; i < batch.n; i++) { tb.tiles[i] = (batch.p[i].M + tc::TILE_M - 1) / tc::TILE_M; total += tb.tiles[i]; }
     const int sms = dev.num_sms > 0 ? dev.num_sms : 148;
-    int want = total * 5 < sms * 3 ? sms / total : 1;      // below 60 % of the SMs: split
+    int want = total * 4 < sms * 3 ? sms / total : 1;      // below 75 % of the SMs: split, but never into a second wave
     if (force_split >= 0) want = force_split < 1 ? 1 : force_split;
     const size_t slot_bytes = (size_t) tc::TILE_M * (size_t) ((tb.npad + 31) & ~31) * sizeof(float);
     const int slot_cap = (int) (GEMM_TC_PARTIAL_BYTES / slot_bytes), ctr_cap = (int) (GEMM_TC_COUNTER_BYTES / sizeof(int));
     int next = 0, slots = 0;
     for (int i = 0; i < batch.n; i++) {
         GemvProblem & p = batch.p[i];
-        const int nsteps = p.K / tc::KSTEP, chunk = tc::raw_geom(p.type).chunk_steps;
+        const int nsteps = p.K / tc::KSTEP;
         int splits = want;
         if (splits > 32) splits = 32;
-        const int max_splits = (nsteps + chunk - 1) / chunk;          // at least one raw chunk per split
-        if (splits > max_splits) splits = max_splits;
+        if (splits > nsteps / 4) splits = nsteps / 4;                   // at least four K-steps per split
         if (splits < 1) splits = 1;
         int per = (nsteps + splits - 1) / splits;
-        per = (per + chunk - 1) / chunk * chunk;                       // split boundaries on raw-chunk boundaries
         splits = (nsteps + per - 1) / per;
         if (splits > 1 && (slots + tb.tiles[i] * splits > slot_cap || slots + tb.tiles[i] * splits > ctr_cap)) { splits = 1; per = nsteps; }
         tb.splits[i] = splits;
@@ -842,7 +652,7 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
         tb.slot0[i] = slots;
         if (splits > 1) slots += tb.tiles[i] * splits;
         p.first_cta = next;
-        p.n_cta = tb.tpad[i] * splits;
+        p.n_cta = tb.tiles[i] * splits;
         next += p.n_cta;
         tb.p[i] = p;
     }
@@ -852,42 +662,20 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
         cudaError_t e = launch_pdl(tc::convert_f16_kernel, dim3(tb.npad, cvt.n), dim3(tc::CVT_THREADS), 0, stream, cvt);
         if (e != cudaSuccess) return e;
     }
-    // shared memory: 3 raw chunks (sized for the widest format of this batch) and as many B stages as fit, at most 8. The ring has
-    // to be deep: a stage comes back only after store -> arrive -> MMA issue -> MMA -> commit -> wake-up, and each of the two
-    // transform groups owns every other stage
+    // shared memory: as many [A | B] ring stages as fit, at most 8
     constexpr size_t smem_budget = 227 * 1024 - 2048;
-    size_t raw_slot = 0;
-    for (int i = 0; i < batch.n; i++) {
-        const size_t b = (size_t) tc::TILE_M * tc::raw_geom(batch.p[i].type).row_stride;
-        if (b > raw_slot) raw_slot = b;
-    }
-    raw_slot = (raw_slot + 127) & ~(size_t) 127;
-    tb.raw_stages = tc::MAX_RAW_STAGES;
-    tb.raw_stage_bytes = (int) raw_slot;
-    const size_t fixed = (size_t) tb.raw_stages * raw_slot;
-    const size_t b_bytes = (size_t) tb.npad * tc::KSTEP * 2;
-    int nb = (int) ((smem_budget - fixed) / b_bytes);
-    if (nb > tc::MAX_STAGES) nb = tc::MAX_STAGES;
-    if (nb < 2) return cudaErrorInvalidValue;
-    tb.b_stages = nb;
-    const size_t smem = fixed + (size_t) nb * b_bytes;
+    const size_t stage_bytes = (size_t) tc::A_BYTES + (size_t) tb.npad * tc::KSTEP * 2;
+    int nst = (int) (smem_budget / stage_bytes);
+    if (nst > tc::MAX_STAGES) nst = tc::MAX_STAGES;
+    if (nst < 2) return cudaErrorInvalidValue;
+    tb.stages = nst;
+    const size_t smem = (size_t) nst * stage_bytes;
     static PerDeviceOnce once;               // the opt-in is per device
     const cudaError_t ae = once.run([&] { return cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_budget); });
     if (ae != cudaSuccess) return ae;
     tb.trace = trace_slot("gemm_tc");
     g_kernel_launches++;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned) next);
-    cfg.blockDim = dim3(tc::THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    int na = 0;
-    if (g_use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; na++; }
-    if (tb.cs > 1) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = (unsigned) tb.cs; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; na++; }
-    cfg.attrs = attr;
-    cfg.numAttrs = (unsigned) na;
-    return cudaLaunchKernelEx(&cfg, tc::gemm_tc_kernel, tb);
+    return launch_pdl(tc::gemm_tc_kernel, dim3((unsigned) next), dim3(tc::THREADS), smem, stream, tb);
 }
 
 }  // namespace rwkv

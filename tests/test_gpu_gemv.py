@@ -131,10 +131,11 @@ def test_tensor_core_gemm_is_deterministic_and_scales_large_columns(lib):
     whose values exceed the fp16 range carries a power-of-two scale through the GEMM and comes out finite and accurate."""
     M, K, T = 160, 4096, 64          # 2 row tiles, 64 K-steps: cut along K
     rng = np.random.default_rng(77)
-    tid, raw = make_weights("Q5_1", M, K, rng)
+    # Q5_0 weights: their activations are Q8_0 blocks, whose only fp16 field is d = fp16(amax / 127) -- finite up to a block maximum of
+    # 65504 * 127 = 8.3e6 (ggml-cpu-quants.c:796-803). (Q8_1 blocks, which Q4_1 / Q5_1 weights multiply, also carry s = fp16(d * sum q)
+    # and overflow in the reference -- and in the dp4a path that mirrors it -- from block maxima of a few 1e4 on: out of its range.)
+    tid, raw = make_weights("Q5_0", M, K, rng)
     x = rng.standard_normal((K, T)).astype(np.float32)
-    # beyond fp16's 65504, but inside what the reference itself survives: its Q8 block scale d = fp16(amax / 127) turns into inf once a
-    # block maximum exceeds 65504 * 127 = 8.3e6 (ggml-cpu-quants.c:796-803), and so does the dp4a path that mirrors it
     x[:, 3] *= 3.0e5
     x[:, 7] *= 1.0e6
     a = run(lib, tid, K, M, T, raw, x)

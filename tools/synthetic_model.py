@@ -34,13 +34,13 @@ PRESETS = {
     "rwkv6-7b": dict(arch=(6, 0), C=4096, F=14336, L=32, V=65536, S=64, mix=64, decay=128, out_scale=0.1, lora_fan_in=True),
     "rwkv7-2b9": dict(arch=(7, 0), C=2560, F=10240, L=32, V=65536, S=64, lora_w=96, lora_a=96, lora_v=64, lora_g=320, out_scale=0.1, lora_fan_in=True),
     # small shapes for parity tests (head size 64 like real models)
-    "rwkv4-small": dict(arch=(4, 0), C=256, F=1024, L=3, V=1000),
-    "rwkv5.1-small": dict(arch=(5, 1), C=256, F=896, L=3, V=1000, S=64),
-    "rwkv5-small": dict(arch=(5, 2), C=256, F=896, L=3, V=1000, S=64),
-    "rwkv6-small": dict(arch=(6, 0), C=512, F=1792, L=4, V=2000, S=64, mix=32, decay=64),
-    "rwkv6-mid": dict(arch=(6, 0), C=2048, F=7168, L=2, V=4000, S=64, mix=32, decay=64),      # ffn rows split over 2 warps
-    "rwkv6-wide": dict(arch=(6, 0), C=4096, F=14336, L=1, V=2000, S=64, mix=64, decay=128),   # one layer of the 7B shape
-    "rwkv7-small": dict(arch=(7, 0), C=512, F=2048, L=4, V=2000, S=64, lora_w=64, lora_a=64, lora_v=32, lora_g=128),
+    "rwkv4-small": dict(arch=(4, 0), C=256, F=1024, L=3, V=1000, out_scale=0.1),
+    "rwkv5.1-small": dict(arch=(5, 1), C=256, F=896, L=3, V=1000, S=64, out_scale=0.1),
+    "rwkv5-small": dict(arch=(5, 2), C=256, F=896, L=3, V=1000, S=64, out_scale=0.1),
+    "rwkv6-small": dict(arch=(6, 0), C=512, F=1792, L=4, V=2000, S=64, mix=32, decay=64, out_scale=0.1, lora_fan_in=True),
+    "rwkv6-mid": dict(arch=(6, 0), C=2048, F=7168, L=2, V=4000, S=64, mix=32, decay=64, out_scale=0.1, lora_fan_in=True),      # ffn rows split over 2 warps
+    "rwkv6-wide": dict(arch=(6, 0), C=4096, F=14336, L=1, V=2000, S=64, mix=64, decay=128, out_scale=0.1, lora_fan_in=True),   # one layer of the 7B shape
+    "rwkv7-small": dict(arch=(7, 0), C=512, F=2048, L=4, V=2000, S=64, lora_w=64, lora_a=64, lora_v=32, lora_g=128, out_scale=0.1, lora_fan_in=True),
 }
 
 
