@@ -562,7 +562,8 @@ bool rwkv_b200_matvec(int data_type, int K, int M, int T, const void * weights, 
               cudaMalloc((void **) &dy, sizeof(float) * M * T) == cudaSuccess;
     ok = ok && cudaMemset(dW, 0, pitch * M + 256) == cudaSuccess &&
          cudaMemcpy2D(dW, pitch, weights, row_bytes, row_bytes, M, cudaMemcpyHostToDevice) == cudaSuccess &&
-         cudaMemcpy(dx, x, sizeof(float) * K * T, cudaMemcpyHostToDevice) == cudaSuccess;
+         cudaMemcpy(dx, x, sizeof(float) * K * T, cudaMemcpyHostToDevice) == cudaSuccess &&
+         weights_to_device_layout(dW, (long long) pitch, data_type, M, K, 0) == cudaSuccess;       // what the model loader does after an upload
     if (ok) {
         GemvBatch b;
         memset(&b, 0, sizeof(b));

@@ -11,7 +11,6 @@
 #include <new>
 #include <vector>
 
-#include "kernels/act_stage.cuh"
 #include "kernels/gemv.h"
 #include "kernels/ops.h"
 
@@ -95,25 +94,6 @@ struct Batch {
         return p;
     }
 };
-
-// ---- staged activation columns (act_stage.cuh) ----------------------------------------------------------------------------------
-// In a single-token pass the kernel that produces a GEMV's input vector (ln_mix, the v6 lerp, a WKV kernel) also writes it in the
-// layout the streaming GEMV keeps in shared memory, so the consumer copies 5 KB instead of quantising 16 KB of fp32 on its critical
-// path. One slot per (producer, output); a slot serves every consumer whose weight type multiplies the same staged format.
-constexpr int XQ_SLOTS = 16;
-enum XqSlot { XQ_ATT_MIX = 0 /* .. 5 */, XQ_LERP = 6 /* .. 10 */, XQ_WKV = 11, XQ_FFN_MIX = 12 /* .. 13 */ };
-
-// The slot to fill for a consumer matrix W of this pass, or NULL when the pass / shape cannot use the hand-off.
-unsigned char * xq_slot(const Context * ctx, int T, int slot, const DevMatrix & W) {
-    static const bool off = getenv("RWKV_B200_NO_XQ") != nullptr || getenv("RWKV_B200_GENERIC_GEMV") != nullptr;
-    if (off || T != 1 || ctx->batch_stride || !ctx->xq || !W.data || W.K % 32 != 0 || W.type == DT_F32 || act::stage_class(W.type) == act::SC_NONE) return nullptr;
-    if (act::bytes_per_column(W.type, W.K) > ctx->xq_slot_bytes) return nullptr;
-    return ctx->xq + (size_t) slot * ctx->xq_slot_bytes;
-}
-// Point problem p at a staged copy of its input that was written for weight type q_type.
-void xq_bind(GemvProblem & p, const unsigned char * q, int q_type) {
-    if (q && act::stage_class(p.type) == act::stage_class(q_type)) p.xq = q;
-}
 
 #define CUDA_OK(ctx, call)                                                                               \
     do { cudaError_t _e = (call);                                                                        \
@@ -217,12 +197,10 @@ bool ffn(Context * ctx, const Layer & L, const Layer * next, const Scratch & s, 
         lp.coef[0] = L.ffn_time_mix_k.data; lp.out[0] = s.mix[0];
         lp.coef[1] = L.ffn_time_mix_r.data; lp.out[1] = s.mix[1];
     }
-    lp.q_out[0] = xq_slot(ctx, T, XQ_FFN_MIX, L.ffn_key); lp.q_type[0] = L.ffn_key.type;
-    if (m.arch_major != 7) { lp.q_out[1] = xq_slot(ctx, T, XQ_FFN_MIX + 1, L.ffn_receptance); lp.q_type[1] = L.ffn_receptance.type; }
     {
         Batch b(T);
-        xq_bind(b.add(L.ffn_key, s.mix[0], s.ffn_k, EPI_RELU_SQR), lp.q_out[0], lp.q_type[0]);
-        if (m.arch_major != 7) xq_bind(b.add(L.ffn_receptance, s.mix[1], s.ffn_r, EPI_SIGMOID), lp.q_out[1], lp.q_type[1]);
+        b.add(L.ffn_key, s.mix[0], s.ffn_k, EPI_RELU_SQR);
+        if (m.arch_major != 7) b.add(L.ffn_receptance, s.mix[1], s.ffn_r, EPI_SIGMOID);
         b.prefetch(L.ffn_value);
         if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     }
@@ -242,11 +220,10 @@ bool ffn(Context * ctx, const Layer & L, const Layer * next, const Scratch & s, 
     return true;
 }
 
-bool att_output(Context * ctx, const Layer & L, const Scratch & s, int T, const unsigned char * yq) {
+bool att_output(Context * ctx, const Layer & L, const Scratch & s, int T) {
     Batch b(T);
     GemvProblem & p = b.add(L.att_output, s.y, s.x, EPI_ADD);   // x + Wo.y  (:182/:291/:384/:481 + residual :667-679)
     p.res = s.x; p.ldres = ctx->model->n_embed;
-    xq_bind(p, yq, L.att_output.type);
     b.prefetch(L.ffn_key); b.prefetch(L.ffn_receptance);
     return run_batch(ctx, b);
 }
@@ -260,12 +237,10 @@ bool att_v4(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     lp.coef[0] = L.att_time_mix_k.data; lp.out[0] = s.mix[0];
     lp.coef[1] = L.att_time_mix_v.data; lp.out[1] = s.mix[1];
     lp.coef[2] = L.att_time_mix_r.data; lp.out[2] = s.mix[2];
-    const DevMatrix * cons[3] = {&L.att_key, &L.att_value, &L.att_receptance};
-    for (int j = 0; j < 3; j++) { lp.q_out[j] = xq_slot(ctx, T, XQ_ATT_MIX + j, *cons[j]); lp.q_type[j] = cons[j]->type; }
     Batch b(T);
-    xq_bind(b.add(L.att_receptance, s.mix[2], s.r, EPI_SIGMOID), lp.q_out[2], lp.q_type[2]);
-    xq_bind(b.add(L.att_key, s.mix[0], s.k), lp.q_out[0], lp.q_type[0]);
-    xq_bind(b.add(L.att_value, s.mix[1], s.v), lp.q_out[1], lp.q_type[1]);
+    b.add(L.att_receptance, s.mix[2], s.r, EPI_SIGMOID);
+    b.add(L.att_key, s.mix[0], s.k);
+    b.add(L.att_value, s.mix[1], s.v);
     b.prefetch(L.att_output);
     if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     Wkv4Params wp{};
@@ -274,9 +249,8 @@ bool att_v4(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     wp.aa_in = st_in + 2 * C; wp.bb_in = st_in + 3 * C; wp.pp_in = st_in + 4 * C;
     wp.aa_out = st_out + 2 * C; wp.bb_out = st_out + 3 * C; wp.pp_out = st_out + 4 * C;
     wp.y = s.y; wp.C = C; wp.T = T;
-    wp.q_out = (C % 32 == 0) ? xq_slot(ctx, T, XQ_WKV, L.att_output) : nullptr; wp.q_type = L.att_output.type;
     CUDA_OK(ctx, do_wkv4(ctx, wp));
-    return att_output(ctx, L, s, T, wp.q_out);
+    return att_output(ctx, L, s, T);
 }
 
 bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
@@ -291,13 +265,11 @@ bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     lp.coef[1] = L.att_time_mix_v.data; lp.out[1] = s.mix[1];
     lp.coef[2] = L.att_time_mix_r.data; lp.out[2] = s.mix[2];
     if (v52) { lp.coef[3] = L.att_time_mix_g.data; lp.out[3] = s.mix[3]; }
-    const DevMatrix * cons[4] = {&L.att_key, &L.att_value, &L.att_receptance, &L.att_gate};
-    for (int j = 0; j < lp.n_out; j++) { lp.q_out[j] = xq_slot(ctx, T, XQ_ATT_MIX + j, *cons[j]); lp.q_type[j] = cons[j]->type; }
     Batch b(T);
-    xq_bind(b.add(L.att_receptance, s.mix[2], s.r), lp.q_out[2], lp.q_type[2]);
-    xq_bind(b.add(L.att_key, s.mix[0], s.k), lp.q_out[0], lp.q_type[0]);
-    xq_bind(b.add(L.att_value, s.mix[1], s.v), lp.q_out[1], lp.q_type[1]);
-    if (v52) xq_bind(b.add(L.att_gate, s.mix[3], s.g, EPI_SILU), lp.q_out[3], lp.q_type[3]);
+    b.add(L.att_receptance, s.mix[2], s.r);
+    b.add(L.att_key, s.mix[0], s.k);
+    b.add(L.att_value, s.mix[1], s.v);
+    if (v52) b.add(L.att_gate, s.mix[3], s.g, EPI_SILU);
     b.prefetch(L.att_output);
     if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     Wkv6Params wp{};
@@ -309,9 +281,8 @@ bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
     wp.g = v52 ? s.g : nullptr;
     wp.y = s.y; wp.eps = 1e-5f; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
-    wp.q_out = (m.head_size % 32 == 0) ? xq_slot(ctx, T, XQ_WKV, L.att_output) : nullptr; wp.q_type = L.att_output.type;
     CUDA_OK(ctx, do_wkv6(ctx, wp));
-    return att_output(ctx, L, s, T, wp.q_out);
+    return att_output(ctx, L, s, T);
 }
 
 bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
@@ -322,10 +293,9 @@ bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     lp.state_in = st_in + C; lp.state_out = st_out + C; lp.C = C; lp.T = T;
     lp.formula = 1; lp.n_out = 1; lp.coef[0] = L.att_maa_x.data; lp.out[0] = s.mix[0];
     lp.out_xx = s.xx; lp.out_sx = s.sx;
-    lp.q_out[0] = xq_slot(ctx, T, XQ_ATT_MIX, L.att_maa_w1); lp.q_type[0] = L.att_maa_w1.type;
     {   // :313-321  tanh(W1 . xxx)
         Batch b(T);
-        xq_bind(b.add(L.att_maa_w1, s.mix[0], s.lora[0], EPI_TANH), lp.q_out[0], lp.q_type[0]);
+        b.add(L.att_maa_w1, s.mix[0], s.lora[0], EPI_TANH);
         if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     }
     V6LerpParams vp{};   // :323-346
@@ -334,20 +304,14 @@ bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     vp.maa[3] = L.att_maa_r.data; vp.maa[4] = L.att_maa_g.data;
     for (int j = 0; j < 5; j++) vp.out[j] = s.mix[1 + j];   // w, k, v, r, g
     vp.C = C; vp.T = T; vp.mix = L.maa_mix;
-    {   // staged columns for the five consumers (w, k, v, r, g order of the lerp outputs): all or none
-        const DevMatrix * cons[5] = {&L.att_decay_w1, &L.att_key, &L.att_value, &L.att_receptance, &L.att_gate};
-        bool all = C % 32 == 0;
-        for (int j = 0; j < 5; j++) { vp.q_out[j] = xq_slot(ctx, T, XQ_LERP + j, *cons[j]); vp.q_type[j] = cons[j]->type; all = all && vp.q_out[j]; }
-        if (!all) for (int j = 0; j < 5; j++) vp.q_out[j] = nullptr;
-    }
     CUDA_OK(ctx, launch_v6_lerp(vp, ctx->stream));
     {   // :349-363
         Batch b(T);
-        xq_bind(b.add(L.att_receptance, s.mix[4], s.r), vp.q_out[3], vp.q_type[3]);
-        xq_bind(b.add(L.att_key, s.mix[2], s.k), vp.q_out[1], vp.q_type[1]);
-        xq_bind(b.add(L.att_value, s.mix[3], s.v), vp.q_out[2], vp.q_type[2]);
-        xq_bind(b.add(L.att_gate, s.mix[5], s.g, EPI_SILU), vp.q_out[4], vp.q_type[4]);
-        xq_bind(b.add(L.att_decay_w1, s.mix[1], s.lora[1], EPI_TANH), vp.q_out[0], vp.q_type[0]);
+        b.add(L.att_receptance, s.mix[4], s.r);
+        b.add(L.att_key, s.mix[2], s.k);
+        b.add(L.att_value, s.mix[3], s.v);
+        b.add(L.att_gate, s.mix[5], s.g, EPI_SILU);
+        b.add(L.att_decay_w1, s.mix[1], s.lora[1], EPI_TANH);
         b.prefetch(L.att_decay_w2); b.prefetch(L.att_output);
         if (!run_batch(ctx, b)) return false;
     }
@@ -376,9 +340,8 @@ bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     wp.state_in = st_in + 2 * C; wp.state_out = st_out + 2 * C;
     wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
     wp.g = s.g; wp.y = s.y; wp.eps = 64e-5f; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
-    wp.q_out = (m.head_size % 32 == 0) ? xq_slot(ctx, T, XQ_WKV, L.att_output) : nullptr; wp.q_type = L.att_output.type;
     CUDA_OK(ctx, do_wkv6(ctx, wp));
-    return att_output(ctx, L, s, T, wp.q_out);
+    return att_output(ctx, L, s, T);
 }
 
 bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T, const float * st_in, float * st_out) {
@@ -391,20 +354,15 @@ bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T,
     lp.formula = 1; lp.n_out = 6;
     for (int j = 0; j < 6; j++) { lp.coef[j] = L.att_x_rwkvag.data + (size_t) j * C; lp.out[j] = s.mix[j]; }   // r w k v a g
     float * v_dst = first ? s.v_first : s.v;
-    {   // the staged column of each mix output is written for its first consumer; att_v1 shares x_v with att_value only if both
-        // multiply the same staged format (in quantised files the LoRA matrices stay fp16)
-        const DevMatrix * cons[6] = {&L.att_receptance, &L.att_w1, &L.att_key, &L.att_value, &L.att_a1, &L.att_g1};
-        for (int j = 0; j < 6; j++) { lp.q_out[j] = xq_slot(ctx, T, XQ_ATT_MIX + j, *cons[j]); lp.q_type[j] = cons[j]->type; }
-    }
     {   // :415-432, 439, 447 -- first halves of the LoRA pairs
         Batch b(T);
-        xq_bind(b.add(L.att_receptance, s.mix[0], s.r), lp.q_out[0], lp.q_type[0]);
-        xq_bind(b.add(L.att_key, s.mix[2], s.k), lp.q_out[2], lp.q_type[2]);
-        xq_bind(b.add(L.att_value, s.mix[3], v_dst), lp.q_out[3], lp.q_type[3]);
-        xq_bind(b.add(L.att_w1, s.mix[1], s.lora[0], EPI_TANH), lp.q_out[1], lp.q_type[1]);
-        xq_bind(b.add(L.att_a1, s.mix[4], s.lora[1]), lp.q_out[4], lp.q_type[4]);
-        xq_bind(b.add(L.att_g1, s.mix[5], s.lora[2], EPI_SIGMOID), lp.q_out[5], lp.q_type[5]);
-        if (!first) xq_bind(b.add(L.att_v1, s.mix[3], s.lora[3]), lp.q_out[3], lp.q_type[3]);
+        b.add(L.att_receptance, s.mix[0], s.r);
+        b.add(L.att_key, s.mix[2], s.k);
+        b.add(L.att_value, s.mix[3], v_dst);
+        b.add(L.att_w1, s.mix[1], s.lora[0], EPI_TANH);
+        b.add(L.att_a1, s.mix[4], s.lora[1]);
+        b.add(L.att_g1, s.mix[5], s.lora[2], EPI_SIGMOID);
+        if (!first) b.add(L.att_v1, s.mix[3], s.lora[3]);
         b.prefetch(L.att_w2); b.prefetch(L.att_a2); b.prefetch(L.att_g2); b.prefetch(L.att_v2); b.prefetch(L.att_output);
         if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     }
@@ -423,9 +381,8 @@ bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T,
     wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
     wp.state_in = st_in + 2 * C; wp.state_out = st_out + 2 * C;
     wp.y = s.y; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
-    wp.q_out = (m.head_size % 32 == 0) ? xq_slot(ctx, T, XQ_WKV, L.att_output) : nullptr; wp.q_type = L.att_output.type;
     CUDA_OK(ctx, ctx->batch_stride ? launch_wkv7_batch(wp, ctx->batch_stride, ctx->stream) : launch_wkv7(wp, ctx->stream));
-    return att_output(ctx, L, s, T, wp.q_out);
+    return att_output(ctx, L, s, T);
 }
 
 bool ensure_capacity(Context * ctx, int T) {
@@ -627,10 +584,6 @@ Context * create_context(Model * model, ErrorSink sink, int batch_n) {
         && cudaMalloc(reinterpret_cast<void **>(&ctx->state_b), seqs * n * sizeof(float)) == cudaSuccess
         && cudaMalloc(reinterpret_cast<void **>(&ctx->state_init), n * sizeof(float)) == cudaSuccess
         && cudaMalloc(reinterpret_cast<void **>(&ctx->logits), seqs * (size_t) model->n_vocab * sizeof(float)) == cudaSuccess;
-    if (ok && batch_n == 0) {      // staged-column hand-off slots: every handed-off vector has n_embed elements, at most 2 bytes each
-        ctx->xq_slot_bytes = ((size_t) 2 * model->n_embed + 64 + 255) / 256 * 256;
-        ok = cudaMalloc(reinterpret_cast<void **>(&ctx->xq), (size_t) XQ_SLOTS * ctx->xq_slot_bytes) == cudaSuccess;
-    }
     if (ok) {
         std::vector<float> init(n);
         fill_init_state(*model, init.data());
@@ -661,7 +614,7 @@ void destroy_context(Context * ctx) {
     if (model) cudaSetDevice(model->dev.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->state_a); cudaFree(ctx->state_b); cudaFree(ctx->state_init); cudaFree(ctx->logits);
-    cudaFree(ctx->tokens); cudaFree(ctx->scratch); cudaFree(ctx->trace_buf); cudaFree(ctx->act16); cudaFree(ctx->xq);
+    cudaFree(ctx->tokens); cudaFree(ctx->scratch); cudaFree(ctx->trace_buf); cudaFree(ctx->act16);
     for (int i = 0; i < 2; i++) {
         if (ctx->tokens_host[i]) cudaFreeHost(ctx->tokens_host[i]);
         if (ctx->slot_free[i]) cudaEventDestroy(ctx->slot_free[i]);

@@ -37,8 +37,6 @@ struct Context {
     float * logits = nullptr;        // [n_vocab]
     int * tokens = nullptr;          // [capacity_T]
     float * scratch = nullptr;       // activation arena for capacity_T tokens
-    unsigned char * xq = nullptr;    // staged activation columns handed from producer kernels to single-token GEMVs (act_stage.cuh): XQ_SLOTS slots
-    size_t xq_slot_bytes = 0;
     void * act16 = nullptr;          // fp16 copies of GEMM inputs for the tensor-core prefill path
     size_t act16_bytes = 0;
     bool use_tensor_cores = true;

@@ -304,6 +304,7 @@ struct TcBatch {
     int n, T, npad;                  // problems, tokens, tokens padded to a multiple of 16
     int tmem_cols;                   // power of two >= 32
     int stages;                      // ring depth, 2 .. MAX_STAGES
+    int stagger;                     // 1: every CTA starts its K range at a different step (RWKV_B200_TC_STAGGER=0 turns it off)
     const __half * act16[GEMV_MAX_PROBLEMS];   // canonical-layout fp16 activations per problem (convert_f16_kernel)
     const float * colscale[GEMV_MAX_PROBLEMS]; // [npad] power-of-two factor per token that the epilogue multiplies back in
     GemvProblem p[GEMV_MAX_PROBLEMS];          // first_cta / n_cta: CTA range of the problem = splits x tiles
@@ -353,19 +354,25 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
             // the programmatic-dependency wait; the activations (B) follow once the kernels that produced them are done
             const uint8_t * a_src = reinterpret_cast<const uint8_t *>(P.Wt) + ((size_t) tile * nsteps_total + ks0) * A_BYTES;
             const uint8_t * b_src = reinterpret_cast<const uint8_t *>(batch.act16[pi]) + (size_t) ks0 * b_bytes;
+            // Every CTA of a problem multiplies the SAME activation block at K-step ks. Marching through K in lockstep, ~130 CTAs would
+            // pull the same 16-32 KB out of the same few L2 slices at the same moment (measured: 1-2 us per K-step however the weights
+            // arrive). So CTA (tile, split) starts at K-step `rot` of its range and wraps around: at any moment the CTAs read different
+            // blocks. The accumulation order of a tile is then a function of its tile index: fixed from run to run.
+            const int rot = batch.stagger ? (int) (((unsigned) tile * 29u + (unsigned) split * 11u) % (unsigned) n) : 0;
+            auto kstep = [&](int it) { const int k = it + rot; return k >= n ? k - n : k; };
             const int pre = n < nst ? n : nst;
             for (int i = 0; i < pre; i++) {
                 mbar_expect_tx(&sh.full[i], stage_bytes);
-                bulk_load(smem + (size_t) i * stage_bytes, a_src + (size_t) i * A_BYTES, A_BYTES, &sh.full[i]);
+                bulk_load(smem + (size_t) i * stage_bytes, a_src + (size_t) kstep(i) * A_BYTES, A_BYTES, &sh.full[i]);
             }
             asm volatile("griddepcontrol.wait;" ::: "memory");
-            for (int i = 0; i < pre; i++) bulk_load(smem + (size_t) i * stage_bytes + A_BYTES, b_src + (size_t) i * b_bytes, b_bytes, &sh.full[i]);
+            for (int i = 0; i < pre; i++) bulk_load(smem + (size_t) i * stage_bytes + A_BYTES, b_src + (size_t) kstep(i) * b_bytes, b_bytes, &sh.full[i]);
             for (int it = pre; it < n; it++) {
                 const int s = it % nst;
                 mbar_wait(&sh.empty[s], (uint32_t) (((it / nst) - 1) & 1));
                 mbar_expect_tx(&sh.full[s], stage_bytes);
-                bulk_load(smem + (size_t) s * stage_bytes, a_src + (size_t) it * A_BYTES, A_BYTES, &sh.full[s]);
-                bulk_load(smem + (size_t) s * stage_bytes + A_BYTES, b_src + (size_t) it * b_bytes, b_bytes, &sh.full[s]);
+                bulk_load(smem + (size_t) s * stage_bytes, a_src + (size_t) kstep(it) * A_BYTES, A_BYTES, &sh.full[s]);
+                bulk_load(smem + (size_t) s * stage_bytes + A_BYTES, b_src + (size_t) kstep(it) * b_bytes, b_bytes, &sh.full[s]);
             }
         }
     } else if (warp == 1) {
@@ -376,10 +383,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
             const uint64_t a_fixed = make_desc(0, A_LBO, 128), b_fixed = make_desc(0, (uint32_t) NG * 128, 128);
             const uint32_t smem0 = smem_u32(smem) >> 4, stage16 = stage_bytes >> 4;
             const uint32_t a_k16 = (2 * A_LBO) >> 4, b_k16 = (uint32_t) (2 * NG * 128) >> 4;
+            // trace marks of CTA 0 (cycles, stored as start + cycles): [0] MMA thread waiting for operands, [1] whole K loop, [2] epilogue
+            const bool acct = batch.trace != nullptr && blockIdx.x == 0;
+            long long waited = 0;
+            const long long loop0 = acct ? clock64() : 0;
             for (int it = 0; it < n; it++) {
                 const int s = it % nst;
                 const uint32_t a0 = smem0 + (uint32_t) s * stage16, b0 = a0 + (A_BYTES >> 4);
+                const long long w0 = acct ? clock64() : 0;
                 mbar_wait(&sh.full[s], (uint32_t) ((it / nst) & 1));
+                if (acct) waited += clock64() - w0;
                 tc_fence_after_sync();
 #pragma unroll
                 for (int k = 0; k < KSTEP / 16; k++)
@@ -388,6 +401,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
                 umma_commit(&sh.empty[s]);                 // the stage is free once these MMAs have read it
             }
             umma_commit(&sh.acc_done);                     // ... and the accumulator is final
+            if (acct) {
+                batch.trace->mark[0] = batch.trace->start + (unsigned long long) waited;
+                batch.trace->mark[1] = batch.trace->start + (unsigned long long) (clock64() - loop0);
+            }
         }
     } else {
         // ===== epilogue (warps 2-5): residual / gate inputs (and, with K-splits, the partial buffer) belong to the previous kernels
@@ -398,6 +415,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
         asm volatile("bar.sync 2, 128;" ::: "memory");
         mbar_wait(&sh.acc_done, 0);
         tc_fence_after_sync();
+        const long long e0 = (batch.trace != nullptr && blockIdx.x == 0 && et == 0) ? clock64() : 0;
         if (nsplit == 1) {
             tc_epilogue_rows<0>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, nullptr, 1, 0);
         } else {
@@ -415,6 +433,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
                 if (et == 0) batch.counters[slot_first] = 0;    // ready for the next launch (ordered by kernel completion)
             }
         }
+        if (e0) batch.trace->mark[2] = batch.trace->start + (unsigned long long) (clock64() - e0);
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -669,13 +688,15 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
     if (nst > tc::MAX_STAGES) nst = tc::MAX_STAGES;
     if (nst < 2) return cudaErrorInvalidValue;
     tb.stages = nst;
+    static const int stagger = [] { const char * e = getenv("RWKV_B200_TC_STAGGER"); return e ? atoi(e) : 1; }();
+    tb.stagger = stagger;
     const size_t smem = (size_t) nst * stage_bytes;
     static PerDeviceOnce once;               // the opt-in is per device
     const cudaError_t ae = once.run([&] { return cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_budget); });
     if (ae != cudaSuccess) return ae;
     tb.trace = trace_slot("gemm_tc");
     g_kernel_launches++;
-    return launch_pdl(tc::gemm_tc_kernel, dim3((unsigned) next), dim3(tc::THREADS), smem, stream, tb);
+    return launch_pdl(tc::gemm_tc_kernel, dim3((unsigned) next), dim3(tc::THREADS), smem, stream, tb);      // (launch_pdl also pins the carve-out)
 }
 
 }  // namespace rwkv

@@ -18,6 +18,9 @@
 
 #include <cuda_fp16.h>
 #include <cstdlib>
+#include <mutex>
+#include <set>
+#include <utility>
 
 namespace rwkv {
 
@@ -298,6 +301,41 @@ cudaError_t launch_nc(const GemvBatch & batch, int grid, size_t smem, int max_op
 }
 
 }  // namespace
+
+namespace {
+// one thread per quant block: the block's qh word (2 bytes into a Q5_0 block, 4 bytes into a Q5_1 block; 2-byte aligned) -> device order
+__global__ void qh5_to_device_kernel(uint8_t * W, long long pitch, int M, int nblk, int block_bytes, int qh_offset) {
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long) M * nblk) return;
+    const int row = (int) (i / nblk), blk = (int) (i % nblk);
+    unsigned short * p = reinterpret_cast<unsigned short *>(W + (long long) row * pitch + (long long) blk * block_bytes + qh_offset);
+    const uint32_t qh = qh5_to_device((uint32_t) p[0] | ((uint32_t) p[1] << 16));
+    p[0] = (unsigned short) (qh & 0xFFFFu);
+    p[1] = (unsigned short) (qh >> 16);
+}
+}  // namespace
+
+void prefer_max_shared_carveout(const void * kernel) {
+    static const bool on = [] { const char * e = getenv("RWKV_B200_CARVEOUT"); return !e || atoi(e) != 0; }();
+    if (!on) return;
+    static std::mutex mu;
+    static std::set<std::pair<int, const void *>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (!done.insert({dev, kernel}).second) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);      // a preference: failure is harmless
+    cudaGetLastError();
+}
+
+cudaError_t weights_to_device_layout(void * W, long long pitch, int type, int M, int K, cudaStream_t stream) {
+    if (type != DT_Q5_0 && type != DT_Q5_1) return cudaSuccess;
+    const int nblk = K / 32;
+    const long long n = (long long) M * nblk;
+    if (n <= 0) return cudaSuccess;
+    qh5_to_device_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<uint8_t *>(W), pitch, M, nblk, dtype_block_bytes(type), type == DT_Q5_0 ? 2 : 4);
+    return cudaGetLastError();
+}
 
 cudaError_t gemv_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream) {
     if (batch.n <= 0 || batch.T <= 0) return cudaSuccess;

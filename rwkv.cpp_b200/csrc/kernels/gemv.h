@@ -34,10 +34,6 @@ struct GemvProblem {
     long long pitch;
     int type, K, M;
     const float * x;  long long ldx;      // input  column t at x + t*ldx
-    // Single-token launches of the streaming kernel: x[:, 0] already in the staged layout of this problem's (type, K) (act_stage.cuh),
-    // emitted by the kernel that produced x. The consumers copy it instead of quantising x; NULL = stage from x. Ignored by the
-    // generic kernel and the tensor-core path.
-    const unsigned char * xq;
     float * y;        long long ldy;      // output column t at y + t*ldy
     const float * res;  long long ldres;
     const float * gate; long long ldgate;
@@ -94,6 +90,11 @@ cudaError_t gemv_tma_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStrea
 bool gemv_lnmix_supported(const GemvBatch & batch);
 cudaError_t gemv_generic_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream);
 
+// Brings a freshly uploaded matrix (file bytes, rows `pitch` bytes apart) into the device layout of quant_decode.cuh, in place: the
+// fifth-bit word of every Q5_0 / Q5_1 block is bit-transposed (qh5_to_device); every other type is left as it is. Must run before any
+// kernel reads the matrix (including gemm_tc_repack).
+cudaError_t weights_to_device_layout(void * W, long long pitch, int type, int M, int K, cudaStream_t stream);
+
 // Tensor-core (tcgen05) path for chunks of >= 32 tokens (gemm_tc.cu). act16_scratch: device scratch for the fp16 copies of the
 // input matrices (sum over distinct inputs of round16(T) * K halves).
 bool gemm_tc_supported(const GemvProblem & p, int T);
@@ -111,6 +112,12 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
 // Programmatic dependent launch for every kernel of the eval path (RWKV_B200_NO_PDL=1 turns it off).
 extern bool g_use_pdl;
 
+// Every kernel of the eval path asks for the SAME L1 / shared-memory split (all shared): an SM can only change its carve-out when it is
+// idle, so a stream that alternates between 113-225 KB weight-streaming kernels and small glue kernels with the default (L1-heavy)
+// preference makes every kernel boundary wait for the SMs to drain instead of overlapping through programmatic dependent launch.
+// Once per (device, kernel); RWKV_B200_CARVEOUT=0 leaves the driver's default (A/B aid).
+void prefer_max_shared_carveout(const void * kernel);
+
 // Launch with the PDL attribute: the kernel may start while its predecessor in the stream is still running; it must
 // execute griddepcontrol.wait before touching anything the predecessor writes.
 template <typename... KArgs, typename... Args>
@@ -125,6 +132,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 1 : 0;
+    prefer_max_shared_carveout(reinterpret_cast<const void *>(kernel));
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #if defined(__CUDACC__)

@@ -174,16 +174,8 @@ __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch ba
     for (int g = 0; g < n_groups; g++) {
         const int c0 = g * NC, nc = min(NC, batch.T - c0);
         if (g > 0) consumer_barrier();   // everyone finished reading the previous group's activations
-        if (lnmix) {
-            stage_column_lnmix(P, act, sh.slots, blockIdx.x == 0);
-        } else if (P.xq && NC == 1 && batch.T == 1) {
-            // the producer of x left the staged column in global memory (act_stage.cuh): one 16-byte-per-thread copy out of L2
-            const int4 * src = reinterpret_cast<const int4 *>(P.xq);
-            int4 * dst = reinterpret_cast<int4 *>(act);
-            for (int i = threadIdx.x; i < (int) (colb / 16); i += CONSUMER_THREADS) dst[i] = __ldcg(src + i);
-        } else {
-            for (int c = 0; c < nc; c++) stage_column<4, STAGE_V2>(P, c0 + c, act + c * colb, sh.red_d);
-        }
+        if (lnmix) stage_column_lnmix(P, act, sh.slots, blockIdx.x == 0);
+        else for (int c = 0; c < nc; c++) stage_column<4, STAGE_V2>(P, c0 + c, act + c * colb, sh.red_d);
         consumer_barrier();
         trace_mark(batch.trace, 1);
         const int it0 = g * my_tiles;
@@ -267,6 +259,7 @@ cudaError_t launch_tma_nc(const GemvBatch & batch, int grid, size_t smem, cudaSt
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 1 : 0;
     g_kernel_launches++;
+    prefer_max_shared_carveout(reinterpret_cast<const void *>(tma::gemv_tma_kernel<NC, STAGE_V2>));
     return cudaLaunchKernelEx(&cfg, tma::gemv_tma_kernel<NC, STAGE_V2>, batch);
 }
 
@@ -280,9 +273,8 @@ static int assign_tiles_and_ctas(GemvBatch & batch, int total_ctas, long long st
     for (int i = 0; i < batch.n; i++) total_bytes += (double) batch.p[i].M * (double) batch.p[i].pitch;
     for (int i = 0; i < batch.n; i++) {
         GemvProblem & p = batch.p[i];
-        const int wr = CONSUMER_WARPS / p.wk;
+        // as many rows as the ring stage holds (the warps' row slots rotate from tile to tile, gemv_tma_device.cuh: rotated_slot)
         int rows = (int) (stage_bytes / p.pitch);
-        rows -= rows % wr;
         if (rows > MAX_TILE_ROWS) rows = MAX_TILE_ROWS;
         p.tile_rows = rows;
     }

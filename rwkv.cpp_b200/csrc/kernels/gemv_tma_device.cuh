@@ -4,7 +4,6 @@
 #pragma once
 #include "gemv.h"
 #include "quant_decode.cuh"
-#include "act_stage.cuh"
 
 #include <cuda_fp16.h>
 
@@ -15,8 +14,11 @@ constexpr int CONSUMER_WARPS = 8;
 constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
 constexpr int THREADS = CONSUMER_THREADS + 32;      // + one producer warp
 constexpr int NSTAGES = 3;
-constexpr int NOMINAL_STAGE_BYTES = 30 * 1024;      // WK is planned against this size, whatever the launch really gets
-constexpr int CTA_SMEM_BUDGET = 112 * 1024;         // dynamic shared memory per CTA so that two CTAs share an SM
+constexpr int NOMINAL_STAGE_BYTES = 28 * 1024;      // WK is planned against this size, whatever the launch really gets (>= this)
+// Dynamic shared memory per CTA so that TWO CTAs share an SM: 233 472 B per SM, 1 KB reserved per CTA, ~1.9 KB static (Shared) ->
+// at most 113 792 B dynamic. (With 112 KB the K = 14336 launches, whose carve-up rounds differently, came to 114 176 B and ran ONE
+// CTA per SM: the ffn-value GEMV was the slowest launch of the layer, profiles/r2_trace_decode_c4.log.)
+constexpr int CTA_SMEM_BUDGET = 111 * 1024;
 constexpr int MAX_TILE_ROWS = 64;
 constexpr int MAX_BLOCKS_PER_LANE = 4;              // activation blocks a lane keeps in registers
 
@@ -134,9 +136,18 @@ __device__ __forceinline__ float apply_epilogue(const GemvProblem & P, float v, 
 }
 
 // ---- shared-memory layout:  [ ring: NSTAGES x stage_bytes ][ act: NC columns ][ red ] ----------------------------
-// The activation column's layout is act_stage.cuh's (producer kernels can emit it ready-made).
-__host__ __device__ inline int padded_blocks(int type, int K) { return act::padded_blocks(type, K); }
-__host__ __device__ inline size_t act_bytes_per_column(int type, int K) { return act::bytes_per_column(type, K); }
+// Blocks of a quantised activation column rounded up to whole units (pairs for the 2-byte-aligned formats).
+__host__ __device__ inline int padded_blocks(int type, int K) {
+    const int nblk = K / 32;
+    return (type == DT_Q4_1 || type == DT_Q5_1) ? nblk : (nblk + 1) / 2 * 2;
+}
+__host__ __device__ inline size_t act_bytes_per_column(int type, int K) {
+    size_t b;
+    if (type == DT_F32) b = (size_t) K * 4;
+    else if (type == DT_F16) b = (size_t) K * 2;
+    else b = (size_t) padded_blocks(type, K) * (32 + sizeof(ActScale));
+    return (b + 15) & ~(size_t) 15;
+}
 
 struct Shared {
     uint64_t full[NSTAGES];
@@ -338,6 +349,15 @@ __device__ __forceinline__ LaneMap lane_map(const GemvProblem & P) {
     m.WK = P.wk; m.WR = CONSUMER_WARPS / m.WK; m.wk = warp % m.WK; m.wr = warp / m.WK;
     return m;
 }
+// Row slot of this warp row-group in the i-th tile of its CTA. A tile of `rows` rows is walked in steps of WR * RPS rows; when the last
+// step is partial only its first `rem` slots have a row, so the slot a warp group plays rotates by `rem` from tile to tile: over a few
+// tiles every warp gets the same number of rows and tiles can use the whole ring stage instead of a multiple of WR rows. Which warp
+// computes a row has no influence on the row's arithmetic.
+__device__ __forceinline__ int rotated_slot(const LaneMap & m, int rows, int i) {
+    const int per_step = m.WR * m.RPS;
+    const int rem = ((rows % per_step) + m.RPS - 1) / m.RPS;
+    return (m.wr + i * rem) % m.WR;
+}
 __device__ __forceinline__ float group_sum(float v, int G) {
     for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -386,10 +406,11 @@ __device__ void consume_quant_regs(Shared & sh, uint8_t * ring, uint32_t stage_b
         const int row0 = tile * P.tile_rows;
         const int rows = min(P.tile_rows, P.M - row0);
         const int s = it % NSTAGES;
+        const int slot = rotated_slot(m, P.tile_rows, it);      // (full tiles all have tile_rows rows; the ragged last tile just gets some slot)
         // epilogue operands of this tile, requested before we block on the weights
         EpiOperands pre; pre.a = 0.f; pre.b = 0.f;
         if (m.WK == 1) {          // lane l <-> l-th output of this warp in this tile: step l / RPS, row slot l % RPS
-            const int r = ((lane / m.RPS) * m.WR + m.wr) * m.RPS + (lane % m.RPS);
+            const int r = ((lane / m.RPS) * m.WR + slot) * m.RPS + (lane % m.RPS);
             if (r < rows) pre = prefetch_epilogue(P, row0 + r, c0);
         } else if ((int) threadIdx.x < rows) {
             pre = prefetch_epilogue(P, row0 + (int) threadIdx.x, c0);
@@ -398,7 +419,7 @@ __device__ void consume_quant_regs(Shared & sh, uint8_t * ring, uint32_t stage_b
         const uint8_t * stage = ring + (size_t) s * stage_bytes;
         float * red_t = red + (size_t) (it & 1) * MAX_TILE_ROWS * CONSUMER_WARPS;
         int step = 0;
-        for (int rb = m.wr * m.RPS; rb < rows; rb += m.WR * m.RPS, step++) {
+        for (int rb = slot * m.RPS; rb < rows; rb += m.WR * m.RPS, step++) {
             const int r = rb + m.rs;
             const uint8_t * wrow = stage + (size_t) min(r, rows - 1) * (size_t) P.pitch;   // idle row slots recompute the last row
             float acc = 0.f;
@@ -453,7 +474,7 @@ __device__ void consume_smem(Shared & sh, uint8_t * ring, uint32_t stage_bytes, 
         // WK > 1: thread i owns output (row i / nc, column i % nc) of the tile and fetches its epilogue operands now
         EpiOperands pre; pre.a = 0.f; pre.b = 0.f;
         if (m.WK > 1 && (int) threadIdx.x < rows * nc) pre = prefetch_epilogue(P, row0 + (int) threadIdx.x / nc, c0 + (int) threadIdx.x % nc);
-        for (int rb = m.wr * m.RPS; rb < rows; rb += m.WR * m.RPS) {
+        for (int rb = rotated_slot(m, P.tile_rows, it) * m.RPS; rb < rows; rb += m.WR * m.RPS) {
             const int r = rb + m.rs;
             const bool live_row = r < rows;
             const uint8_t * wrow = stage + (size_t) min(r, rows - 1) * (size_t) P.pitch;

@@ -3,7 +3,6 @@
 #include "ops.h"
 #include "gemv.h"          // g_kernel_launches
 #include "../formats.h"
-#include "act_stage.cuh"
 
 #include <cuda_fp16.h>
 
@@ -128,18 +127,18 @@ __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const LnMixParams p)
     for (int j = 0; j < p.n_out; j++) {     // rolled: kernel parameters are indexable in the constant bank
         const float * coef = p.coef[j];
         float * out = p.out[j];
-        const act::StagedOut qo{p.q_out[j], p.q_type[j], C};      // single-token passes: the consumer's staged column as well
+        if (p.formula == 0) {
 #pragma unroll
-        for (int i = 0; i < PER; i++) {
-            const int c = tid + i * LN_THREADS;
-            float val = 0.f;
-            if (c < C) {
-                const float m = coef[c];
-                val = (p.formula == 0) ? __fadd_rn(__fmul_rn(xa[i], m), __fsub_rn(xb[i], __fmul_rn(xb[i], m)))
-                                       : __fadd_rn(__fmul_rn(__fsub_rn(xb[i], xa[i]), m), xa[i]);
-                out[o0 + i * LN_THREADS] = val;
+            for (int i = 0; i < PER; i++) {
+                const int c = tid + i * LN_THREADS;
+                if (c < C) { const float m = coef[c]; out[o0 + i * LN_THREADS] = __fadd_rn(__fmul_rn(xa[i], m), __fsub_rn(xb[i], __fmul_rn(xb[i], m))); }
             }
-            if (qo.dst && (c & ~31) < C) act::warp_emit_block(qo, c >> 5, val);      // warp-uniform: C % 32 == 0, one warp = one block
+        } else {
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int c = tid + i * LN_THREADS;
+                if (c < C) out[o0 + i * LN_THREADS] = __fadd_rn(__fmul_rn(__fsub_rn(xb[i], xa[i]), coef[c]), xa[i]);
+            }
         }
     }
 #pragma unroll
@@ -153,12 +152,11 @@ __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const LnMixParams p)
     trace_end(p.trace);
 }
 
-// Passes of fewer than LERP_TILE_TOKENS tokens (decode): 8 lanes per channel, 32 channels per CTA, one CTA row per token: each (j, channel) row of W2 is `mix` contiguous floats. The W2 rows
+// Passes of fewer than LERP_MIN_TOKENS tokens (decode): 8 lanes per channel, 32 channels per CTA, one CTA row per token: each (j, channel) row of W2 is `mix` contiguous floats. The W2 rows
 // (5.2 MB per layer at 7B, straight from HBM) are pulled into registers before the programmatic-dependency wait.
 constexpr int LERP1_MAX_F4 = 4;   // float4 per lane per j held in registers: mix <= 128
 __global__ void __launch_bounds__(GLUE_THREADS) v6_lerp_decode_kernel(const V6LerpParams p) {
     extern __shared__ float zs[];   // [5*mix]
-    __shared__ float ob[5][32];     // the CTA's 32 channels of each output = one 32-element block of its staged column
     trace_begin(p.trace);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int t = blockIdx.y, mix = p.mix, C = p.C;
@@ -214,108 +212,86 @@ __global__ void __launch_bounds__(GLUE_THREADS) v6_lerp_decode_kernel(const V6Le
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (sub == 0) {
-            const float val = live ? __fadd_rn(__fmul_rn(__fadd_rn(acc, vec ? maa[j] : p.maa[j][c]), sx), xx) : 0.f;
-            if (live) p.out[j][o] = val;
-            ob[j][grp] = val;
-        }
-    }
-    if (p.q_out[0] != nullptr) {       // single-token passes with C % 32 == 0 (the launcher's caller checks): warp j emits block blockIdx.x of out_j
-        __syncthreads();
-        const int warp = threadIdx.x >> 5;
-        if (warp < 5 && p.q_out[warp]) act::warp_emit_block(act::StagedOut{p.q_out[warp], p.q_type[warp], C}, blockIdx.x, ob[warp][threadIdx.x & 31]);
+        if (live && sub == 0) p.out[j][o] = __fadd_rn(__fmul_rn(__fadd_rn(acc, vec ? maa[j] : p.maa[j][c]), sx), xx);
     }
     trace_end(p.trace);
 }
 
 
-// Passes of >= LERP_TILE_TOKENS tokens: one thread per channel, 128 channels x LERP_TILE_TOKENS tokens per CTA. For each of the five mixes the thread holds
-// its W2 row (`mix` contiguous floats, 5.2 MB per layer at 7B) in registers and walks the tile's tokens; z[:, t] of the
-// tile sits in shared memory and is read as broadcasts. The first W2 row is pulled before the programmatic-dependency wait.
+// Passes of >= LERP_MIN_TOKENS tokens: one thread per channel, one CTA = 128 channels x a tile of TILE tokens x ONE of the five mixes
+// (blockIdx.z). The thread holds its W2 row (`mix` contiguous floats) in registers and walks the tile's tokens; z[:, t] of the tile
+// sits in shared memory and is read as broadcasts. TILE = 32 for chunks (each W2 row is fetched once per 32 tokens: 21 MB of L2
+// traffic per 128-token layer pass at 7B instead of 84 MB with tiles of 8, and 5 x more CTAs than one CTA looping over the mixes),
+// 8 for short passes. The W2 row is pulled before the programmatic-dependency wait.
 constexpr int LERP_THREADS = 128;
-constexpr int LERP_TILE_TOKENS = 8;
+constexpr int LERP_MIN_TOKENS = 8;
 constexpr int LERP_MAX_F4 = 16;   // W2 row in registers: mix <= 64
+template <int TILE>
 __global__ void __launch_bounds__(LERP_THREADS) v6_lerp_kernel(const V6LerpParams p) {
-    extern __shared__ __align__(16) float lerp_zs[];        // [tile][5 * mix]
+    extern __shared__ __align__(16) float lerp_zs[];        // [tile][mix]: the z rows of mix j
     trace_begin(p.trace);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int mix = p.mix, C = p.C, tid = threadIdx.x;
+    const int mix = p.mix, C = p.C, tid = threadIdx.x, j = blockIdx.z;
     const int c = blockIdx.x * LERP_THREADS + tid;
     const bool live = c < C;
     const int cc = live ? c : 0;
     const int m4 = mix / 4;
     const bool vec = (mix & 3) == 0 && m4 <= LERP_MAX_F4;
-    const int t0 = blockIdx.y * LERP_TILE_TOKENS, nt = min(LERP_TILE_TOKENS, p.T - t0);
+    const int t0 = blockIdx.y * TILE, nt = min(TILE, p.T - t0);
     float4 w[LERP_MAX_F4];
-    auto load_w = [&](int j) {
+    {
         const float4 * wrow = reinterpret_cast<const float4 *>(p.w2 + ((size_t) j * C + cc) * mix);
 #pragma unroll
         for (int i = 0; i < LERP_MAX_F4; i++) w[i] = (vec && i < m4) ? __ldg(wrow + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    load_w(0);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    {
-        const float * zsrc = p.z + (size_t) t0 * 5 * mix;          // the tile's z columns are contiguous
-        const int nz = nt * 5 * mix;
-        if ((mix & 3) == 0) {
-            for (int i = tid; i < nz / 4; i += LERP_THREADS) reinterpret_cast<float4 *>(lerp_zs)[i] = __ldg(reinterpret_cast<const float4 *>(zsrc) + i);
-        } else {
-            for (int i = tid; i < nz; i += LERP_THREADS) lerp_zs[i] = zsrc[i];
-        }
     }
-    float sx[LERP_TILE_TOKENS], xx[LERP_TILE_TOKENS];
-#pragma unroll
-    for (int tt = 0; tt < LERP_TILE_TOKENS; tt++) {
-        const size_t o = (size_t) (t0 + (tt < nt ? tt : 0)) * C + cc;
-        sx[tt] = __ldg(p.sx + o);
-        xx[tt] = __ldg(p.xx + o);
+    const float maa = p.maa[j][cc];
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int i = tid; i < nt * mix; i += LERP_THREADS) {
+        const int tt = i / mix, k = i % mix;
+        lerp_zs[i] = p.z[(size_t) (t0 + tt) * 5 * mix + j * mix + k];
     }
     __syncthreads();
-#pragma unroll 1
-    for (int j = 0; j < 5; j++) {
-        if (j > 0) load_w(j);
-        const float maa = p.maa[j][cc];
+    float * out = p.out[j];
+#pragma unroll 4
+    for (int tt = 0; tt < nt; tt++) {
+        const size_t o = (size_t) (t0 + tt) * C + cc;
+        const float sx = __ldg(p.sx + o), xx = __ldg(p.xx + o);
+        const float * zj = lerp_zs + (size_t) tt * mix;
+        // the same eight partial sums and the same combination tree as the decode kernel's 8 lanes + shuffles: a chunked
+        // evaluation stays bit-identical to the serial one (tests/test_eval_sequence_in_chunks.c memcmp's them)
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (vec) {
 #pragma unroll
-        for (int tt = 0; tt < LERP_TILE_TOKENS; tt++) {
-            if (tt < nt) {
-                const float * zj = lerp_zs + (size_t) tt * 5 * mix + j * mix;
-                // the same eight partial sums and the same combination tree as the decode kernel's 8 lanes + shuffles: a chunked
-                // evaluation stays bit-identical to the serial one (tests/test_eval_sequence_in_chunks.c memcmp's them)
-                float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (vec) {
+            for (int i = 0; i < LERP_MAX_F4; i++) {
+                if (i < m4) {
+                    const float4 z = reinterpret_cast<const float4 *>(zj)[i];
+                    float & s8 = a[i & 7];
+                    s8 = __fmaf_rn(w[i].x, z.x, s8); s8 = __fmaf_rn(w[i].y, z.y, s8);
+                    s8 = __fmaf_rn(w[i].z, z.z, s8); s8 = __fmaf_rn(w[i].w, z.w, s8);
+                }
+            }
+        } else if ((mix & 3) == 0) {
+            const float4 * wrow = reinterpret_cast<const float4 *>(p.w2 + ((size_t) j * C + cc) * mix);
+            for (int i0 = 0; i0 < m4; i0 += 8) {
 #pragma unroll
-                    for (int i = 0; i < LERP_MAX_F4; i++) {
-                        if (i < m4) {
-                            const float4 z = reinterpret_cast<const float4 *>(zj)[i];
-                            float & s8 = a[i & 7];
-                            s8 = __fmaf_rn(w[i].x, z.x, s8); s8 = __fmaf_rn(w[i].y, z.y, s8);
-                            s8 = __fmaf_rn(w[i].z, z.z, s8); s8 = __fmaf_rn(w[i].w, z.w, s8);
-                        }
-                    }
-                } else if ((mix & 3) == 0) {
-                    const float4 * wrow = reinterpret_cast<const float4 *>(p.w2 + ((size_t) j * C + cc) * mix);
-                    for (int i0 = 0; i0 < m4; i0 += 8) {
-#pragma unroll
-                        for (int u = 0; u < 8; u++) {
-                            if (i0 + u < m4) {
-                                const float4 wv = __ldg(wrow + i0 + u), z = reinterpret_cast<const float4 *>(zj)[i0 + u];
-                                a[u] = __fmaf_rn(wv.x, z.x, a[u]); a[u] = __fmaf_rn(wv.y, z.y, a[u]);
-                                a[u] = __fmaf_rn(wv.z, z.z, a[u]); a[u] = __fmaf_rn(wv.w, z.w, a[u]);
-                            }
-                        }
-                    }
-                } else {
-                    const float * wrow = p.w2 + ((size_t) j * C + cc) * mix;
-                    for (int i0 = 0; i0 < mix; i0 += 8) {
-#pragma unroll
-                        for (int u = 0; u < 8; u++)
-                            if (i0 + u < mix) a[u] = __fmaf_rn(__ldg(wrow + i0 + u), zj[i0 + u], a[u]);
+                for (int u = 0; u < 8; u++) {
+                    if (i0 + u < m4) {
+                        const float4 wv = __ldg(wrow + i0 + u), z = reinterpret_cast<const float4 *>(zj)[i0 + u];
+                        a[u] = __fmaf_rn(wv.x, z.x, a[u]); a[u] = __fmaf_rn(wv.y, z.y, a[u]);
+                        a[u] = __fmaf_rn(wv.z, z.z, a[u]); a[u] = __fmaf_rn(wv.w, z.w, a[u]);
                     }
                 }
-                const float acc = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[4]), __fadd_rn(a[2], a[6])), __fadd_rn(__fadd_rn(a[1], a[5]), __fadd_rn(a[3], a[7])));
-                if (live) p.out[j][(size_t) (t0 + tt) * C + c] = __fadd_rn(__fmul_rn(__fadd_rn(acc, maa), sx[tt]), xx[tt]);
+            }
+        } else {
+            const float * wrow = p.w2 + ((size_t) j * C + cc) * mix;
+            for (int i0 = 0; i0 < mix; i0 += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (i0 + u < mix) a[u] = __fmaf_rn(__ldg(wrow + i0 + u), zj[i0 + u], a[u]);
             }
         }
+        const float acc = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[4]), __fadd_rn(a[2], a[6])), __fadd_rn(__fadd_rn(a[1], a[5]), __fadd_rn(a[3], a[7])));
+        if (live) out[(size_t) (t0 + tt) * C + c] = __fadd_rn(__fmul_rn(__fadd_rn(acc, maa), sx), xx);
     }
     trace_end(p.trace);
 }
@@ -344,16 +320,17 @@ cudaError_t launch_ln_mix(const LnMixParams & p_in, cudaStream_t s) {
 cudaError_t launch_v6_lerp(const V6LerpParams & p_in, cudaStream_t s) {
     V6LerpParams p = p_in;
     p.trace = trace_slot("v6_lerp");
-    if (p.T < LERP_TILE_TOKENS) {
+    if (p.T < LERP_MIN_TOKENS) {
         dim3 grid((p.C + 31) / 32, p.T);
         g_kernel_launches++;
         return launch_pdl(v6_lerp_decode_kernel, grid, dim3(GLUE_THREADS), (size_t) 5 * p.mix * sizeof(float), s, p);
     }
-    const size_t smem = (size_t) LERP_TILE_TOKENS * 5 * p.mix * sizeof(float);
-    if (smem > 48 * 1024) return cudaErrorInvalidValue;
-    dim3 grid((p.C + LERP_THREADS - 1) / LERP_THREADS, (p.T + LERP_TILE_TOKENS - 1) / LERP_TILE_TOKENS);
     g_kernel_launches++;
-    return launch_pdl(v6_lerp_kernel, grid, dim3(LERP_THREADS), smem, s, p);
+    const int tile = (p.T >= 32 && (size_t) 32 * p.mix * sizeof(float) <= 48 * 1024) ? 32 : 8;      // which tile a token falls into does not touch its arithmetic
+    const size_t smem = (size_t) tile * p.mix * sizeof(float);
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    dim3 grid((p.C + LERP_THREADS - 1) / LERP_THREADS, (p.T + tile - 1) / tile, 5);
+    return tile == 32 ? launch_pdl(v6_lerp_kernel<32>, grid, dim3(LERP_THREADS), smem, s, p) : launch_pdl(v6_lerp_kernel<8>, grid, dim3(LERP_THREADS), smem, s, p);
 }
 
 }  // namespace rwkv

@@ -29,9 +29,6 @@ struct LnMixParams {
     float * out[6];           // [C, T] each
     float * out_xx;           // optional [C, T]: LN(x)
     float * out_sx;           // optional [C, T]: prev - xx
-    // T == 1, C % 32 == 0 only: out_j additionally as the staged column (act_stage.cuh) of a consumer with weight type q_type[j]
-    unsigned char * q_out[6];
-    int q_type[6];
 };
 cudaError_t launch_ln_mix(const LnMixParams & p, cudaStream_t s);
 
@@ -45,8 +42,6 @@ struct V6LerpParams {
     const float * maa[5];     // [C]
     float * out[5];           // [C, T]
     int C, T, mix;
-    unsigned char * q_out[5]; // T == 1, C % 32 == 0 only: staged columns (act_stage.cuh) for consumers of weight type q_type[j]
-    int q_type[5];
 };
 cudaError_t launch_v6_lerp(const V6LerpParams & p, cudaStream_t s);
 
@@ -59,7 +54,6 @@ struct Wkv4Params {
     float * aa_out, * bb_out, * pp_out;
     float * y;                        // [C, T] = r * wkv
     int C, T;
-    unsigned char * q_out; int q_type;  // T == 1, C % 32 == 0 only: y as a staged column (act_stage.cuh)
 };
 cudaError_t launch_wkv4(const Wkv4Params & p, cudaStream_t s);
 
@@ -86,7 +80,6 @@ struct Wkv6Params {
     const void * dw2; long long dw2_pitch; int dw2_type, dw2_K;
     const float * dw2_x;              // [dw2_K, T]
     const float * dw2_bias;           // [C] time_decay
-    unsigned char * q_out; int q_type;  // T == 1, S % 32 == 0 only: y as a staged column (act_stage.cuh)
 };
 // largest decay-LoRA rank the fused form takes (activation blocks of a chunk of tokens live in shared memory)
 constexpr int WKV6_FUSED_DECAY_MAX_K = 128;
@@ -107,7 +100,6 @@ struct Wkv7Params {
     float * state_out;
     float * y;                        // [C, T]
     int H, S, T;
-    unsigned char * q_out; int q_type;  // T == 1, S % 32 == 0 only: y as a staged column (act_stage.cuh)
 };
 cudaError_t launch_wkv7(const Wkv7Params & p, cudaStream_t s);
 

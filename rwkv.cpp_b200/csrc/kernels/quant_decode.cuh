@@ -1,7 +1,12 @@
 // Decoding of ggml quant blocks (ggml-common.h:161-221; element order ggml-quants.c:255-347) into
 // int8x4 words ready for dp4a, shared by the decode-GEMV and the prefill GEMM.
 //
-// HBM layout = file layout: rows of 18/20/22/24/34-byte blocks, row pitch padded to 16 B.
+// HBM layout = file layout: rows of 18/20/22/24/34-byte blocks, row pitch padded to 16 B -- with ONE difference: the 32-bit word
+// of fifth bits (qh) of every Q5_0 / Q5_1 block is stored bit-transposed (qh5_to_device, applied once at load time; same bytes,
+// same information). In the file, bit 4w + k of qh belongs to byte k of int8x4 word w; on the device it sits at bit 8k + w, so
+// one shift + one AND drops the four fifth bits of a word onto bit 4 of its four bytes, where the file layout needs a shift, an
+// AND, an integer multiply and another AND per word (spread_bit5). The Q5_1 decode shrinks from ~52 to ~27 instructions per block
+// (the dp4a GEMV is instruction-bound on it: profiles/r2_c4 trace, 0.57 issue slots busy per cycle at 3.5 TB/s).
 // A "unit" is the smallest group of whole blocks that is 4-byte aligned: 2 blocks for the
 // 2-byte-aligned formats (Q4_0 36 B, Q5_0 44 B, Q8_0 68 B), 1 block for Q4_1 (20 B) / Q5_1 (24 B).
 // A lane pulls one unit as 32-bit words and realigns with funnel shifts.
@@ -51,6 +56,20 @@ RWKV_HD float half_bits_to_float(uint32_t h16) {
 // disjoint bit ranges, so the multiply has no carries.
 RWKV_HD uint32_t spread_bit5(uint32_t n4) { return (n4 * 0x02040810u) & 0x10101010u; }
 
+// File order -> device order of a Q5 block's fifth-bit word (an 8 x 4 bit transpose) and back.
+RWKV_HD uint32_t qh5_to_device(uint32_t qh) {
+    uint32_t o = 0;
+    for (int w = 0; w < 8; w++)
+        for (int k = 0; k < 4; k++) o |= ((qh >> (4 * w + k)) & 1u) << (8 * k + w);
+    return o;
+}
+RWKV_HD uint32_t qh5_to_file(uint32_t qd) {
+    uint32_t o = 0;
+    for (int w = 0; w < 8; w++)
+        for (int k = 0; k < 4; k++) o |= ((qd >> (8 * k + w)) & 1u) << (4 * w + k);
+    return o;
+}
+
 template <int TYPE> struct QTraits;
 template <> struct QTraits<DT_Q4_0> { static constexpr int BLOCK_BYTES = 18, UNIT_BLOCKS = 2, UNIT_WORDS = 9,  OFFSET = 8,  HAS_MIN = 0; };
 template <> struct QTraits<DT_Q4_1> { static constexpr int BLOCK_BYTES = 20, UNIT_BLOCKS = 1, UNIT_WORDS = 5,  OFFSET = 0,  HAS_MIN = 1; };
@@ -66,13 +85,14 @@ struct BlockQ {
     float d, m;
 };
 
+// qh: the fifth bits in DEVICE order (qh5_to_device): word w's four bits at positions 8k + w.
 RWKV_HD void nibble_words(const uint32_t qs[4], uint32_t qh, bool five_bit, int q[8]) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         uint32_t lo = qs[i] & 0x0F0F0F0Fu, hi = (qs[i] >> 4) & 0x0F0F0F0Fu;
         if (five_bit) {
-            lo |= spread_bit5((qh >> (4 * i)) & 0xFu);
-            hi |= spread_bit5((qh >> (16 + 4 * i)) & 0xFu);
+            lo |= (qh << (4 - i)) & 0x10101010u;        // word i:     bits 8k + i     -> 8k + 4
+            hi |= (qh >> i) & 0x10101010u;              // word 4 + i: bits 8k + 4 + i -> 8k + 4
         }
         q[i] = (int) lo;
         q[4 + i] = (int) hi;

@@ -324,6 +324,7 @@ Model * load_model(const char * path, int device, int layer_begin, int layer_end
                 ce = cudaMemset(dst, 0, (size_t) d.M * (size_t) d.pitch);
                 if (ce == cudaSuccess) ce = cudaMemcpy2D(dst, (size_t) d.pitch, staging.get(), row_bytes, row_bytes, (size_t) d.M, cudaMemcpyHostToDevice);
             }
+            if (ce == cudaSuccess) ce = weights_to_device_layout(dst, d.pitch, d.type, d.M, d.K, 0);      // Q5 fifth-bit words -> device order
             if (ce == cudaSuccess && r.tiled_bytes) {
                 uint8_t * td = m.arena + r.tiled_offset;
                 ce = gemm_tc_repack(dst, d.pitch, d.type, d.M, d.K, td, 0);

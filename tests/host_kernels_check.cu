@@ -52,8 +52,18 @@ template <int TYPE> static int check_type(const char * name) {
         for (auto & a : act) a = (int8_t) ((int) (rnd() % 255) - 127);
         const int nunits = nblk / TR::UNIT_BLOCKS;
         for (int u = 0; u < nunits; u++) {
+            // what the loader leaves in HBM: the file bytes with every Q5 block's fifth-bit word in device order (qh5_to_device)
+            std::vector<uint8_t> dev(row.begin() + (size_t) u * TR::UNIT_WORDS * 4, row.begin() + (size_t) (u + 1) * TR::UNIT_WORDS * 4);
+            if (TYPE == DT_Q5_0 || TYPE == DT_Q5_1) {
+                for (int b = 0; b < TR::UNIT_BLOCKS; b++) {
+                    uint8_t * qp = dev.data() + (size_t) b * bb + (TYPE == DT_Q5_0 ? 2 : 4);
+                    uint32_t qh; memcpy(&qh, qp, 4);
+                    if (qh5_to_file(qh5_to_device(qh)) != qh) { printf("%s: qh5 round trip\n", name); bad++; }
+                    qh = qh5_to_device(qh); memcpy(qp, &qh, 4);
+                }
+            }
             uint32_t w[TR::UNIT_WORDS];
-            memcpy(w, row.data() + (size_t) u * TR::UNIT_WORDS * 4, sizeof(w));
+            memcpy(w, dev.data(), sizeof(w));
             for (int b = 0; b < TR::UNIT_BLOCKS; b++) {
                 const int blk = u * TR::UNIT_BLOCKS + b;
                 BlockQ bq; decode_block<TYPE>(w, b, bq);
