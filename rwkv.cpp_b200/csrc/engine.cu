@@ -30,6 +30,12 @@ struct Scratch {      // carve-up of ctx->scratch for T tokens
 };
 
 constexpr int BATCH_TC_MIN = 16;
+// smallest batch (in weights) that is worth a tensor-core launch; RWKV_B200_TC_MIN_WEIGHTS overrides (the GPU tests set 0 so that the
+// reference's tiny fixtures still run their >= 32-token passes through the tcgen05 kernel)
+long long tc_min_weights() {
+    static const long long v = [] { const char * e = getenv("RWKV_B200_TC_MIN_WEIGHTS"); return e ? atoll(e) : (long long) (1 << 20); }();
+    return v;
+}
 
 struct Dims { size_t C, F, R; };
 
@@ -79,12 +85,6 @@ Scratch carve(const Model & m, float * base, int T) {
 struct Batch {
     GemvBatch b;
     explicit Batch(int T) { memset(&b, 0, sizeof(b)); b.T = T; }
-    // L2 look-ahead: the matrices of the launch(es) after this one (single-token passes; opt-in RWKV_B200_XPF=1 until measured)
-    void prefetch(const DevMatrix & W) {
-        static const bool on = [] { const char * e = getenv("RWKV_B200_XPF"); return e && atoi(e) != 0; }();
-        if (!on || !W.data || b.T != 1 || b.pf_n >= GEMV_MAX_PREFETCH) return;
-        b.pf_ptr[b.pf_n] = W.data; b.pf_bytes[b.pf_n] = (long long) W.pitch * W.M; b.pf_n++;
-    }
     GemvProblem & add(const DevMatrix & W, const float * x, float * y, int epi = EPI_NONE) {
         GemvProblem & p = b.p[b.n++];
         p.W = W.data; p.Wt = W.tiled; p.pitch = W.pitch; p.type = W.type; p.K = W.K; p.M = W.M;
@@ -110,9 +110,17 @@ bool launch_batch(Context * ctx, GemvBatch & b) {
         GemvBatch tcb, rest;
         memset(&tcb, 0, sizeof(tcb)); memset(&rest, 0, sizeof(rest));
         tcb.T = rest.T = b.T;
+        long long tc_weights = 0;
         for (int i = 0; i < b.n; i++) {
-            if (gemm_tc_supported(b.p[i], b.T)) tcb.p[tcb.n++] = b.p[i];
+            if (gemm_tc_supported(b.p[i], b.T)) { tcb.p[tcb.n++] = b.p[i]; tc_weights += (long long) b.p[i].M * b.p[i].K; }
             else rest.p[rest.n++] = b.p[i];
+        }
+        // A tensor-core launch costs ~40 us whatever it multiplies (TMEM allocation, ring fill, epilogue, K-split reduction: measured
+        // 43 us for the 160 x 4096 LoRA matrix of a v6 layer, profiles/r2_trace_prefill_c7.log); a batch with less than a million
+        // weights is cheaper on the multi-column GEMV, which streams it out of L2 once per group of 4 tokens.
+        if (tc_weights < tc_min_weights()) {
+            for (int i = 0; i < tcb.n; i++) rest.p[rest.n++] = tcb.p[i];
+            tcb.n = 0;
         }
         if (tcb.n) CUDA_OK(ctx, gemm_tc_launch(tcb, ctx->model->dev, ctx->stream, ctx->act16, ctx->act16_bytes));
         if (rest.n) CUDA_OK(ctx, gemv_launch(rest, ctx->model->dev, ctx->stream));
@@ -148,39 +156,16 @@ cudaError_t do_wkv4(Context * ctx, const Wkv4Params & wp) {
     return ctx->batch_stride ? launch_wkv4_batch(wp, ctx->batch_stride, ctx->stream) : launch_wkv4(wp, ctx->stream);
 }
 
-// LayerNorm + token shift + mix in front of a batch of GEMVs. Single-token passes fold it into the GEMV launch itself (PRO_LN_MIX:
-// every CTA recomputes the 16 KB LayerNorm in its prologue; one launch and one dependency hand-off fewer per block); multi-token
-// passes, batch contexts and shapes the streaming kernel cannot take run ln_mix_kernel first. Both produce the same bits.
-// Every problem of `b` must have been added with x = the lp.out[j] it reads.
-bool ln_mix_then(Context * ctx, const LnMixParams & lp, Batch & b) {
-    // Measured on B200 (profiles/r2_c3_ab_*.json, 7B Q5_1): folding the LayerNorm into the consumer costs 4.24 ms per token against 3.14 ms
-    // with the separate ln_mix launch (every CTA's in-kernel LayerNorm sits on the critical path for ~25 us), so it is opt-in only.
-    static const bool want_fuse = [] { const char * e = getenv("RWKV_B200_FUSE_LN"); return e && atoi(e) != 0; }() && getenv("RWKV_B200_GENERIC_GEMV") == nullptr;
-    bool fuse = lp.T == 1 && !ctx->batch_stride && want_fuse && ctx->fuse_ln_mix;
-    if (fuse) {
-        GemvBatch probe = b.b;
-        fuse = gemv_lnmix_supported(probe);
-    }
-    if (!fuse) {
-        CUDA_OK(ctx, do_ln_mix(ctx, lp));
-        return true;
-    }
-    for (int i = 0; i < b.b.n; i++) {
-        GemvProblem & p = b.b.p[i];
-        int j = 0;
-        while (j < lp.n_out && lp.out[j] != p.x) j++;
-        RWKV_CHECK(ctx->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, j < lp.n_out, "internal: GEMV input is not a mix output");
-        p.x = lp.x; p.ldx = lp.C;
-        p.pro = PRO_LN_MIX;
-        p.ln_w = lp.ln_w; p.ln_b = lp.ln_b;
-        p.mix_prev = lp.state_in; p.mix_coef = lp.coef[j]; p.mix_formula = lp.formula;
-        p.ln_state_out = lp.state_out; p.ln_xx_out = lp.out_xx; p.ln_sx_out = lp.out_sx;
-    }
+// LayerNorm + token shift + mix in front of a batch of GEMVs: its own launch (ln_mix_kernel). Folding it into the consuming GEMV
+// (every CTA recomputing the LayerNorm in its prologue) was built and measured in round 2: 4.24 ms per 7B token against 3.14 ms,
+// the in-kernel LayerNorm + staging took 11 us on the critical path of every CTA (profiles/r2_trace_decode_c7_fuseln.log); removed.
+bool ln_mix_then(Context * ctx, const LnMixParams & lp, Batch &) {
+    CUDA_OK(ctx, do_ln_mix(ctx, lp));
     return true;
 }
 
 // Channel mixing, all versions (rwkv_ffn_v4_v5 :484-511, rwkv_ffn_v6 :513-531, rwkv_ffn_v7 :533-543).
-bool ffn(Context * ctx, const Layer & L, const Layer * next, const Scratch & s, int T, const float * st_in, float * st_out) {
+bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
     const Model & m = *ctx->model;
     const int C = m.n_embed;
     LnMixParams lp{};
@@ -201,7 +186,6 @@ bool ffn(Context * ctx, const Layer & L, const Layer * next, const Scratch & s, 
         Batch b(T);
         b.add(L.ffn_key, s.mix[0], s.ffn_k, EPI_RELU_SQR);
         if (m.arch_major != 7) b.add(L.ffn_receptance, s.mix[1], s.ffn_r, EPI_SIGMOID);
-        b.prefetch(L.ffn_value);
         if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     }
     {
@@ -209,12 +193,6 @@ bool ffn(Context * ctx, const Layer & L, const Layer * next, const Scratch & s, 
         GemvProblem & p = b.add(L.ffn_value, s.ffn_k, s.x, m.arch_major == 7 ? EPI_ADD : EPI_MUL_ADD);
         p.res = s.x; p.ldres = C;
         p.gate = s.ffn_r; p.ldgate = C;
-        if (next) {      // the next layer's first big launch
-            b.prefetch(next->att_maa_w1); b.prefetch(next->att_receptance); b.prefetch(next->att_key); b.prefetch(next->att_value); b.prefetch(next->att_gate);
-            b.prefetch(next->att_decay_w1); b.prefetch(next->att_w1);
-        } else if (ctx->model->head.data && ctx->model->layer_end == ctx->model->n_layer) {
-            b.prefetch(ctx->model->head);
-        }
         if (!run_batch(ctx, b)) return false;
     }
     return true;
@@ -224,7 +202,6 @@ bool att_output(Context * ctx, const Layer & L, const Scratch & s, int T) {
     Batch b(T);
     GemvProblem & p = b.add(L.att_output, s.y, s.x, EPI_ADD);   // x + Wo.y  (:182/:291/:384/:481 + residual :667-679)
     p.res = s.x; p.ldres = ctx->model->n_embed;
-    b.prefetch(L.ffn_key); b.prefetch(L.ffn_receptance);
     return run_batch(ctx, b);
 }
 
@@ -241,7 +218,6 @@ bool att_v4(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     b.add(L.att_receptance, s.mix[2], s.r, EPI_SIGMOID);
     b.add(L.att_key, s.mix[0], s.k);
     b.add(L.att_value, s.mix[1], s.v);
-    b.prefetch(L.att_output);
     if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     Wkv4Params wp{};
     wp.k = s.k; wp.v = s.v; wp.r = s.r;
@@ -270,7 +246,6 @@ bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     b.add(L.att_key, s.mix[0], s.k);
     b.add(L.att_value, s.mix[1], s.v);
     if (v52) b.add(L.att_gate, s.mix[3], s.g, EPI_SILU);
-    b.prefetch(L.att_output);
     if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     Wkv6Params wp{};
     wp.r = s.r; wp.k = s.k; wp.v = s.v;
@@ -312,31 +287,17 @@ bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
         b.add(L.att_value, s.mix[3], s.v);
         b.add(L.att_gate, s.mix[5], s.g, EPI_SILU);
         b.add(L.att_decay_w1, s.mix[1], s.lora[1], EPI_TANH);
-        b.prefetch(L.att_decay_w2); b.prefetch(L.att_output);
         if (!run_batch(ctx, b)) return false;
     }
-    // :357-367  w = exp(-exp(Wd2 . tanh(..) + time_decay)): folded into the WKV kernel (every head computes its own rows) unless the
-    // pass takes the tensor-core path or the context is a batch -- the choice depends on the weight type and the pass kind only, so
-    // all passes that must agree bit for bit (T < 32, and every T for F32 weights) use the same arithmetic
-    bool fused_decay;
-    {
+    {   // :357-367  w = exp(-exp(Wd2 . tanh(..) + time_decay))
         Batch b(T);
         GemvProblem & p = b.add(L.att_decay_w2, s.lora[1], s.w, EPI_BIAS_EXPNEGEXP);
         p.bias = L.att_time_decay.data;
-        // opt-in: measured gain 1 % (3.137 vs 3.173 ms per token at 7B), and a batch context (separate decay GEMV) would no longer be
-        // bit-identical to rwkv_eval
-        static const bool no_fuse = [] { const char * e = getenv("RWKV_B200_FUSE_DECAY"); return !(e && atoi(e) != 0); }();
-        const bool tc = (T >= 32 || (ctx->batch_n > 0 && T >= BATCH_TC_MIN)) && ctx->use_tensor_cores && ctx->act16 && gemm_tc_supported(p, T);
-        fused_decay = !no_fuse && !ctx->batch_stride && !tc && L.att_decay_w2.K <= WKV6_FUSED_DECAY_MAX_K && L.att_decay_w2.K % 32 == 0;
-        if (!fused_decay && !run_batch(ctx, b)) return false;
+        if (!run_batch(ctx, b)) return false;
     }
     Wkv6Params wp{};   // :370-382
     wp.r = s.r; wp.k = s.k; wp.v = s.v;
     wp.td = s.w; wp.td_per_token = 1; wp.tf = L.att_time_faaaa.data; wp.per_head_scalars = 0;
-    if (fused_decay) {
-        wp.dw2 = L.att_decay_w2.data; wp.dw2_pitch = L.att_decay_w2.pitch; wp.dw2_type = L.att_decay_w2.type; wp.dw2_K = L.att_decay_w2.K;
-        wp.dw2_x = s.lora[1]; wp.dw2_bias = L.att_time_decay.data;
-    }
     wp.state_in = st_in + 2 * C; wp.state_out = st_out + 2 * C;
     wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
     wp.g = s.g; wp.y = s.y; wp.eps = 64e-5f; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
@@ -363,7 +324,6 @@ bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T,
         b.add(L.att_a1, s.mix[4], s.lora[1]);
         b.add(L.att_g1, s.mix[5], s.lora[2], EPI_SIGMOID);
         if (!first) b.add(L.att_v1, s.mix[3], s.lora[3]);
-        b.prefetch(L.att_w2); b.prefetch(L.att_a2); b.prefetch(L.att_g2); b.prefetch(L.att_v2); b.prefetch(L.att_output);
         if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
     }
     {   // second halves
@@ -448,7 +408,7 @@ bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase, int seg) {
             case 5: ok = att_v5(ctx, L, s, T, st_in, st_out); break;
             default: ok = att_v4(ctx, L, s, T, st_in, st_out); break;
         }
-        if (!ok || !ffn(ctx, L, i + 1 < l1 ? &m.layers[i + 1] : nullptr, s, T, st_in, st_out)) return false;
+        if (!ok || !ffn(ctx, L, s, T, st_in, st_out)) return false;
     }
     if (want_logits && l1 == m.n_layer) {   // :705-708 / :851-854  head . LN(x_last; ln_out); a batch context wants every column
         Batch b(ctx->batch_n ? T : 1);

@@ -40,7 +40,6 @@ struct Context {
     void * act16 = nullptr;          // fp16 copies of GEMM inputs for the tensor-core prefill path
     size_t act16_bytes = 0;
     bool use_tensor_cores = true;
-    bool fuse_ln_mix = true;         // single-token passes: LayerNorm + token shift + mix inside the consuming GEMV (PRO_LN_MIX)
     size_t scratch_floats = 0;
     int capacity_T = 0;
     // Two pinned token slots, used alternately (`phase`): the host may prepare pass n+1 while pass n runs.

@@ -350,7 +350,6 @@ cudaError_t gemv_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t 
 }
 
 cudaError_t gemv_generic_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream) {
-    for (int i = 0; i < batch.n; i++) if (batch.p[i].pro == PRO_LN_MIX) return cudaErrorInvalidValue;   // streaming kernel only
     batch.trace = trace_slot("gemv_generic");
     // CTA budget split over the problems in proportion to their weight bytes.
     const int total_ctas = dev.num_sms * CTAS_PER_SM;

@@ -22,11 +22,7 @@ enum GemvEpilogue : int {
     EPI_BIAS_W7,          // exp(-0.606531*sigmoid(v+bias[row]))  (v7 decay, rwkv_graph.inc:425-430)
 };
 // PRO_LAYERNORM: LN(x; ln_w, ln_b, eps 1e-5) applied while staging x (the head).
-// PRO_LN_MIX (single-token passes only): x is the residual stream; every CTA computes xx = LN(x; ln_w, ln_b) and the token-shift
-// mix of xx with the carried LN(x) of the previous token (rwkv_carry_x + lerp, rwkv_graph.inc:56-82, 94-97, 310-311) and stages
-// THAT as its activation column -- the ln_mix launch of the per-kernel path folded into the GEMV that consumes it. The arithmetic is
-// ln_mix_kernel's (same reduction tree, same roundings), so a token evaluated alone and inside a chunk still agree bit for bit.
-enum GemvPrologue : int { PRO_NONE = 0, PRO_LAYERNORM = 1, PRO_LN_MIX = 2 };
+enum GemvPrologue : int { PRO_NONE = 0, PRO_LAYERNORM = 1 };
 
 struct GemvProblem {
     const void * W;          // device, rows of quant blocks / f16 / f32, `pitch` bytes apart (16-B multiple)
@@ -39,12 +35,6 @@ struct GemvProblem {
     const float * gate; long long ldgate;
     const float * bias;                   // [M]
     const float * ln_w; const float * ln_b;  // [K]
-    // PRO_LN_MIX: formula 0 (v4/v5): xx*m + (prev - prev*m); formula 1 (v6/v7): (prev - xx)*m + xx
-    const float * mix_prev;               // [K] LN(x) of the previous token (att_xx / ffn_xx slot of the input state)
-    const float * mix_coef;               // [K] m
-    float * ln_state_out;                 // [K] <- xx (slot of the output state); written by CTA 0 of the launch
-    float * ln_xx_out; float * ln_sx_out; // optional [K]: xx and prev - xx (inputs of the v6 lerp); CTA 0
-    int mix_formula;
     int epi, pro;
     int first_cta, n_cta;                 // filled by gemv_launch
     int wk, g, tile_rows;                 // streaming kernel only: warps sharing a row along K, lanes per row, rows per TMA tile
@@ -65,17 +55,10 @@ inline TraceRec * trace_slot(const char * name) {
 }
 
 constexpr int GEMV_MAX_PROBLEMS = 8;
-constexpr int GEMV_MAX_PREFETCH = 8;
 struct GemvBatch {
     int n, T;
     TraceRec * trace;
     long long max_col_bytes, stage_bytes; // streaming kernel only: shared-memory carve-up
-    int prefetch_tiles;                   // streaming kernel only: tiles beyond the ring each CTA asks L2 to fetch at kernel start
-    // Weights of the launches that FOLLOW this one (the engine knows the order): every CTA asks L2 for its slice of each region at
-    // kernel start, so HBM keeps streaming through the dependency bubbles between launches and the next launch finds its tiles in L2.
-    int pf_n;
-    const void * pf_ptr[GEMV_MAX_PREFETCH];
-    long long pf_bytes[GEMV_MAX_PREFETCH];
     GemvProblem p[GEMV_MAX_PROBLEMS];
 };
 
@@ -86,8 +69,6 @@ struct DeviceInfo { int device; int num_sms; int max_smem_optin; };
 // direct-load kernel (gemv.cu); the choice depends on the problem shapes only, never on T.
 cudaError_t gemv_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream);
 cudaError_t gemv_tma_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream);      // cudaErrorNotSupported if a shape does not fit
-// Can this single-token batch take the PRO_LN_MIX prologue (streaming kernel, n_embed <= 4096)? Shapes only.
-bool gemv_lnmix_supported(const GemvBatch & batch);
 cudaError_t gemv_generic_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream);
 
 // Brings a freshly uploaded matrix (file bytes, rows `pitch` bytes apart) into the device layout of quant_decode.cuh, in place: the

@@ -19,81 +19,11 @@
 // WK, itself a function of (type, K, pitch) alone -- never of T, the batch composition or the tile size. A token
 // evaluated alone and inside a chunk therefore produces identical bits (tests/test_eval_sequence_in_chunks.c:54).
 #include "gemv_tma_device.cuh"
-#include "decode_steps.cuh"
 
 #include <cstdlib>
 
 namespace rwkv {
 namespace tma {
-
-// PRO_LN_MIX: LayerNorm + token shift + mix of the residual stream, computed by the 256 consumer threads of EVERY CTA of the
-// launch (16 KB of x, out of L2) and staged straight into the activation column -- the ln_mix launch of the multi-token path,
-// folded into its consumer. Loads that do not depend on the previous kernel (LayerNorm weights, the carried LN(x) of the previous
-// token, the mix vector) are issued before the programmatic-dependency wait. Arithmetic = ln_mix_kernel's (glue.cu): statistics
-// through steps::ln_center_scale_256, the same roundings for LN and the mix, and the quantisation of stage_column (block maximum
-// and integer block sum do not depend on the order they are taken in) -- so the staged bytes equal what ln_mix + PRO_NONE stage.
-// Thread t owns channels t + 256 m: block 8 m + warp of the column is one warp's 32 lanes. CTA 0 of the launch writes the new
-// carry (and xx / prev - xx for the v6 lerp).
-static __device__ __noinline__ void stage_column_lnmix(const GemvProblem & P, uint8_t * col, double (* slots)[32], bool leader) {
-    using steps::LN_MAXCH;
-    const int C = P.K, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    float lw[LN_MAXCH], lb[LN_MAXCH], pv[LN_MAXCH], cf[LN_MAXCH];
-#pragma unroll
-    for (int m = 0; m < LN_MAXCH; m++) {
-        const int c = t + 256 * m;
-        const bool live = c < C;
-        lw[m] = live ? P.ln_w[c] : 0.f;
-        lb[m] = live ? P.ln_b[c] : 0.f;
-        pv[m] = live ? P.mix_prev[c] : 0.f;
-        cf[m] = live ? P.mix_coef[c] : 0.f;
-    }
-    grid_dependency_wait();
-    float xa[LN_MAXCH], scale_a;
-    steps::ln_center_scale_256(P.x, C, xa, scale_a, slots);
-    const bool has_min = (P.type == DT_Q4_1 || P.type == DT_Q5_1);
-    const int UB = has_min ? 1 : 2;
-    const int nblk = C / 32, nunits = (nblk + UB - 1) / UB;
-#pragma unroll
-    for (int m = 0; m < LN_MAXCH; m++) {
-        const int c = t + 256 * m;
-        if (256 * m + 32 * warp >= C) break;                        // warp-uniform: C is a multiple of 32
-        const float xx = __fadd_rn(__fmul_rn(__fmul_rn(xa[m], scale_a), lw[m]), lb[m]);     // LN(x)
-        const float v = (P.mix_formula == 0) ? __fadd_rn(__fmul_rn(xx, cf[m]), __fsub_rn(pv[m], __fmul_rn(pv[m], cf[m])))
-                                             : __fadd_rn(__fmul_rn(__fsub_rn(pv[m], xx), cf[m]), xx);
-        if (leader) {
-            P.ln_state_out[c] = xx;
-            if (P.ln_xx_out) P.ln_xx_out[c] = xx;
-            if (P.ln_sx_out) P.ln_sx_out[c] = __fsub_rn(pv[m], xx);
-        }
-        if (P.type == DT_F32) {
-            reinterpret_cast<float *>(col)[c] = v;
-        } else if (P.type == DT_F16) {
-            reinterpret_cast<__half *>(col)[c] = __float2half_rn(v);
-        } else {
-            const int blk = 8 * m + warp;
-            const float amax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fabsf(v))));   // non-negative floats order as integers
-            const float d32 = amax / 127.0f;
-            const float id = (amax != 0.0f) ? 127.0f / amax : 0.0f;
-            const int q = __float2int_rn(v * id);
-            const int isum = __reduce_add_sync(0xffffffffu, q);
-            int word = q & 0xFF;
-            word |= (__shfl_down_sync(0xffffffffu, q, 1) & 0xFF) << 8;
-            word |= (__shfl_down_sync(0xffffffffu, q, 2) & 0xFF) << 16;
-            word |= (__shfl_down_sync(0xffffffffu, q, 3) & 0xFF) << 24;
-            const int u = blk / UB, bi = blk % UB;
-            if ((lane & 3) == 0) {
-                const int i8 = lane >> 2;                               // word i8 = elements 4 i8 .. 4 i8 + 3 of the block
-                *reinterpret_cast<int *>(col + ((size_t) (bi * 2 + (i8 >> 2)) * nunits + u) * 16 + (i8 & 3) * 4) = word;
-            }
-            if (lane == 0) {
-                ActScale a;
-                a.d = round_to_half(d32);
-                a.s = has_min ? round_to_half(d32 * (float) isum) : (float) isum;
-                *reinterpret_cast<ActScale *>(col + (size_t) nunits * UB * 32 + ((size_t) bi * nunits + u) * 8) = a;
-            }
-        }
-    }
-}
 
 template <int NC, bool STAGE_V2 = false>
 __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch batch) {
@@ -131,24 +61,6 @@ __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch ba
         if (threadIdx.x == CONSUMER_THREADS) {
             const uint64_t policy = (n_groups == 1) ? policy_evict_first() : policy_evict_normal();
             const uint8_t * Wb = reinterpret_cast<const uint8_t *>(P.W);
-            // Tiles beyond the ring: ask L2 for them now. While the consumers still wait for the previous kernel and stage their
-            // activations the ring is full and HBM would idle; this way it keeps streaming this launch's weights into L2, and the
-            // ring refills from there.
-            for (int i = NSTAGES; i < my_tiles && i < NSTAGES + batch.prefetch_tiles; i++) {
-                const int row0 = (local_cta + i * P.n_cta) * P.tile_rows;
-                bulk_prefetch_l2(Wb + (size_t) row0 * (size_t) P.pitch, (uint32_t) ((size_t) min(P.tile_rows, P.M - row0) * (size_t) P.pitch));
-            }
-            // ... and for this CTA's slice of the weights of the launches that follow (cross-launch look-ahead through L2)
-            for (int r = 0; r < batch.pf_n; r++) {
-                const long long bytes = batch.pf_bytes[r];
-                long long per = (bytes + gridDim.x - 1) / gridDim.x;
-                per = (per + 127) / 128 * 128;
-                const long long lo = (long long) blockIdx.x * per, hi = lo + per < bytes ? lo + per : bytes;
-                for (long long o = lo; o < hi; o += 16384) {
-                    const long long n = (hi - o < 16384 ? hi - o : 16384) / 16 * 16;
-                    if (n > 0) bulk_prefetch_l2(reinterpret_cast<const uint8_t *>(batch.pf_ptr[r]) + o, (uint32_t) n);
-                }
-            }
             int it = 0;
             for (int g = 0; g < n_groups; g++) {
                 for (int i = 0; i < my_tiles; i++, it++) {
@@ -167,15 +79,13 @@ __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch ba
     }
 
     // ===== consumers =====
-    const bool lnmix = P.pro == PRO_LN_MIX;      // single-token launches only (gemv_tma_launch checks): the prologue waits itself
-    if (!lnmix) grid_dependency_wait();          // activations / residuals come from the previous kernel
+    grid_dependency_wait();          // activations / residuals come from the previous kernel
     trace_mark(batch.trace, 0);
     const bool quant = P.type != DT_F16 && P.type != DT_F32;
     for (int g = 0; g < n_groups; g++) {
         const int c0 = g * NC, nc = min(NC, batch.T - c0);
         if (g > 0) consumer_barrier();   // everyone finished reading the previous group's activations
-        if (lnmix) stage_column_lnmix(P, act, sh.slots, blockIdx.x == 0);
-        else for (int c = 0; c < nc; c++) stage_column<4, STAGE_V2>(P, c0 + c, act + c * colb, sh.red_d);
+        for (int c = 0; c < nc; c++) stage_column<4, STAGE_V2>(P, c0 + c, act + c * colb, sh.red_d);
         consumer_barrier();
         trace_mark(batch.trace, 1);
         const int it0 = g * my_tiles;
@@ -273,8 +183,11 @@ static int assign_tiles_and_ctas(GemvBatch & batch, int total_ctas, long long st
     for (int i = 0; i < batch.n; i++) total_bytes += (double) batch.p[i].M * (double) batch.p[i].pitch;
     for (int i = 0; i < batch.n; i++) {
         GemvProblem & p = batch.p[i];
-        // as many rows as the ring stage holds (the warps' row slots rotate from tile to tile, gemv_tma_device.cuh: rotated_slot)
+        // as many rows as the ring stage holds (the warps' row slots rotate from tile to tile, gemv_tma_device.cuh: rotated_slot);
+        // RWKV_B200_FULL_TILES=0: a multiple of the warp row-groups only (A/B aid)
+        static const bool full_tiles = [] { const char * e = getenv("RWKV_B200_FULL_TILES"); return !e || atoi(e) != 0; }();
         int rows = (int) (stage_bytes / p.pitch);
+        if (!full_tiles) rows -= rows % (CONSUMER_WARPS / p.wk);
         if (rows > MAX_TILE_ROWS) rows = MAX_TILE_ROWS;
         p.tile_rows = rows;
     }
@@ -320,25 +233,9 @@ bool gemv_tma_plan(GemvBatch & batch, int total_ctas, long long stage_bytes, siz
 
 // Returns cudaErrorNotSupported when some problem of the batch does not fit the streaming kernel
 // (the caller then uses the generic kernel for the whole batch).
-bool gemv_lnmix_supported(const GemvBatch & batch) {
-    using namespace tma;
-    if (batch.T != 1 || batch.n < 1) return false;
-    size_t max_col = 0;
-    for (int i = 0; i < batch.n; i++) {
-        GemvProblem p = batch.p[i];
-        if (p.K != batch.p[0].K || p.K > 256 * steps::LN_MAXCH || p.K % 32 != 0 || !plan_wk(p)) return false;
-        const size_t cb = act_bytes_per_column(p.type, p.K);
-        if (cb > max_col) max_col = cb;
-    }
-    const long long rest = (long long) max_col + (long long) 2 * MAX_TILE_ROWS * CONSUMER_WARPS * (long long) sizeof(float);
-    return ((long long) CTA_SMEM_BUDGET - rest) / NSTAGES / 1024 * 1024 >= NOMINAL_STAGE_BYTES;
-}
-
 cudaError_t gemv_tma_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream) {
     using namespace tma;
     size_t max_col = 0;
-    for (int i = 0; i < batch.n; i++)
-        if ((batch.p[i].pro == PRO_LN_MIX) != (batch.p[0].pro == PRO_LN_MIX) || (batch.p[i].pro == PRO_LN_MIX && !gemv_lnmix_supported(batch))) return cudaErrorInvalidValue;
     for (int i = 0; i < batch.n; i++) {
         GemvProblem & p = batch.p[i];
         if (!plan_wk(p)) return cudaErrorNotSupported;
@@ -359,8 +256,6 @@ cudaError_t gemv_tma_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStrea
     const int next = assign_tiles_and_ctas(batch, 2 * dev.num_sms, stage_bytes);
     batch.max_col_bytes = (long long) max_col;
     batch.stage_bytes = stage_bytes;
-    static const int l2_prefetch = [] { const char * e = getenv("RWKV_B200_L2_PREFETCH"); return e ? atoi(e) : 0; }();
-    batch.prefetch_tiles = l2_prefetch;
     batch.trace = trace_slot(batch.n > 1 ? "gemv_tma(batch)" : "gemv_tma");
     const size_t smem = (size_t) NSTAGES * (size_t) stage_bytes + (size_t) nc * max_col + (size_t) 2 * MAX_TILE_ROWS * CONSUMER_WARPS * nc * sizeof(float);
     switch (nc) {

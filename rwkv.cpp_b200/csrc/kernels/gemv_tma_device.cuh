@@ -75,10 +75,6 @@ __device__ __forceinline__ void bulk_copy_g2s(void * dst, const void * src, uint
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
 }
-// fire-and-forget request to bring [src, src + bytes) into L2 (bytes and src multiples of 16)
-__device__ __forceinline__ void bulk_prefetch_l2(const void * src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -153,7 +149,6 @@ struct Shared {
     uint64_t full[NSTAGES];
     uint64_t empty[NSTAGES];
     double red_d[CONSUMER_WARPS + 1];
-    double slots[2][32];      // LayerNorm partials of the PRO_LN_MIX prologue (steps::ln_center_scale_256)
     TraceRec * trace;
     GemvProblem P;
 };

@@ -72,17 +72,7 @@ struct Wkv6Params {
     float * y;                        // [C, T]
     float eps;                        // 1e-5 (v5) or 64e-5 (v6)
     int H, S, T;
-    // v6, passes that do not take the tensor-core path: the decay GEMV (rwkv_graph.inc:357-367) folded into this kernel -- every head
-    // computes its own S rows of  td = exp(-exp(W2 . z + time_decay))  from z = tanh(decay_w1 . xw) [dw2_K, T], one launch fewer per
-    // layer. dw2 != NULL replaces `td` (td_per_token must be 1). Arithmetic per row: the reference's block dot products
-    // (quant_decode.cuh: block_dot) against Q8_0 / Q8_1 blocks of z, accumulated block after block in fp32 (F16: fp16-rounded z,
-    // F32: plain), for every pass size alike -- serial and chunked evaluation stay bit-identical.
-    const void * dw2; long long dw2_pitch; int dw2_type, dw2_K;
-    const float * dw2_x;              // [dw2_K, T]
-    const float * dw2_bias;           // [C] time_decay
 };
-// largest decay-LoRA rank the fused form takes (activation blocks of a chunk of tokens live in shared memory)
-constexpr int WKV6_FUSED_DECAY_MAX_K = 128;
 cudaError_t launch_wkv6(const Wkv6Params & p, cudaStream_t s);
 
 // v7 (rwkv_att_v7, rwkv_graph.inc:432-479 + rwkv_wkv_v7_impl, rwkv_operators_wkv_v7.inc:37-106):

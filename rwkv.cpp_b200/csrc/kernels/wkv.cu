@@ -3,7 +3,6 @@
 // whole chunk; one CTA per head (v5+), one thread per state column (v5/v6) or row (v7).
 #include "ops.h"
 #include "gemv.h"   // g_kernel_launches
-#include "quant_decode.cuh"
 #include "../formats.h"
 
 #include <cuda_fp16.h>
@@ -101,12 +100,6 @@ __global__ void __launch_bounds__(Wkv6Layout<S>::BLOCK) wkv6_kernel(const Wkv6Pa
     __shared__ Wkv6Chunk<S> buf[2];
     __shared__ __align__(16) float sf[S], sdc[S];
     __shared__ __align__(16) float ybuf[2][TB][S];
-    // fused decay GEMV: the chunk's z columns as the operand the reference would multiply (Q8 blocks / fp16-rounded / fp32)
-    constexpr int DMAXB = WKV6_FUSED_DECAY_MAX_K / 32;
-    __shared__ __align__(16) unsigned char zraw[TB * WKV6_FUSED_DECAY_MAX_K * 4];       // one buffer, two views (quantised / float operand)
-    int (* zq)[DMAXB][8] = reinterpret_cast<int (*)[DMAXB][8]>(zraw);
-    ActScale (* zs)[DMAXB] = reinterpret_cast<ActScale (*)[DMAXB]>(zraw + sizeof(int) * TB * DMAXB * 8);
-    float (* zf)[WKV6_FUSED_DECAY_MAX_K] = reinterpret_cast<float (*)[WKV6_FUSED_DECAY_MAX_K]>(zraw);
     trace_begin(p.trace);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int h = blockIdx.x, tid = threadIdx.x, C = p.H * S;
@@ -153,7 +146,7 @@ __global__ void __launch_bounds__(Wkv6Layout<S>::BLOCK) wkv6_kernel(const Wkv6Pa
             wkv_cp16(&B.k[tt][f], p.k + o);
             wkv_cp16(&B.r[tt][f], p.r + o);
             wkv_cp16(&B.v[tt][f], p.v + o);
-            if (p.td_per_token && !p.dw2) wkv_cp16(&B.d[tt][f], p.td + o);
+            if (p.td_per_token) wkv_cp16(&B.d[tt][f], p.td + o);
         }
     };
     // trace marks of CTA 0 (cycles, stored as start + cycles): [0] staging + wait for the chunk, [1] phase A,
@@ -161,102 +154,12 @@ __global__ void __launch_bounds__(Wkv6Layout<S>::BLOCK) wkv6_kernel(const Wkv6Pa
     const bool acct = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
     long long a0 = 0, a1 = 0, a2 = 0, a3 = 0, tq = acct ? clock64() : 0;
     auto tick = [&](long long & a) { if (acct) { const long long now = clock64(); a += now - tq; tq = now; } };
-    // ---- decay rows of this head for the tokens of chunk c -> B.d (fused form) ----
-    const bool fused_decay = p.dw2 != nullptr;
-    const float dbias = (fused_decay && tid < S) ? p.dw2_bias[h * S + tid] : 0.f;
-    auto decay_rows = [&](int c) {
-        Wkv6Chunk<S> & B = buf[c & 1];
-        const int t0 = c * TB, nt = min(TB, p.T - t0);
-        const int K = p.dw2_K, nblk = K / 32, type = p.dw2_type;
-        const bool quant = type != DT_F16 && type != DT_F32;
-        if (quant) {                 // one thread per (token, 32-element block): x86 flavour of quantize_row_q8_0 / q8_1
-            const bool has_min = type == DT_Q4_1 || type == DT_Q5_1;
-            for (int w = tid; w < nt * nblk; w += BLOCK) {
-                const int tt = w / nblk, blk = w % nblk;
-                const float4 * x4 = reinterpret_cast<const float4 *>(p.dw2_x + (size_t) (t0 + tt) * K + blk * 32);
-                float4 v[8];
-                float amax = 0.f;
-#pragma unroll
-                for (int j = 0; j < 8; j++) { v[j] = x4[j]; amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w)))); }
-                const float d32 = amax / 127.0f;
-                const float id = (amax != 0.0f) ? 127.0f / amax : 0.0f;
-                int isum = 0;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int q0 = __float2int_rn(v[j].x * id), q1 = __float2int_rn(v[j].y * id), q2 = __float2int_rn(v[j].z * id), q3 = __float2int_rn(v[j].w * id);
-                    isum += q0 + q1 + q2 + q3;
-                    zq[tt][blk][j] = (q0 & 0xFF) | ((q1 & 0xFF) << 8) | ((q2 & 0xFF) << 16) | ((q3 & 0xFF) << 24);
-                }
-                ActScale a;
-                a.d = __half2float(__float2half_rn(d32));
-                a.s = has_min ? __half2float(__float2half_rn(d32 * (float) isum)) : (float) isum;
-                zs[tt][blk] = a;
-            }
-        } else {
-            for (int w = tid; w < nt * K; w += BLOCK) {
-                const int tt = w / K, k = w % K;
-                const float x = p.dw2_x[(size_t) (t0 + tt) * K + k];
-                zf[tt][k] = type == DT_F16 ? __half2float(__float2half_rn(x)) : x;
-            }
-        }
-        __syncthreads();
-        if (tid < S) {
-            const uint8_t * wrow = reinterpret_cast<const uint8_t *>(p.dw2) + (size_t) (h * S + tid) * (size_t) p.dw2_pitch;
-            float acc[TB];
-#pragma unroll
-            for (int tt = 0; tt < TB; tt++) acc[tt] = 0.f;
-            auto blocks = [&](auto tag) {
-                constexpr int TYPE = decltype(tag)::value;
-                using TR = QTraits<TYPE>;
-                const int nunits = (nblk + TR::UNIT_BLOCKS - 1) / TR::UNIT_BLOCKS;
-                for (int u = 0; u < nunits; u++) {
-                    uint32_t w[TR::UNIT_WORDS];
-#pragma unroll
-                    for (int i = 0; i < TR::UNIT_WORDS; i++) w[i] = reinterpret_cast<const uint32_t *>(wrow)[u * TR::UNIT_WORDS + i];
-#pragma unroll
-                    for (int bi = 0; bi < TR::UNIT_BLOCKS; bi++) {
-                        const int blk = u * TR::UNIT_BLOCKS + bi;
-                        if (blk >= nblk) break;
-                        BlockQ bq;
-                        decode_block<TYPE>(w, bi, bq);
-#pragma unroll
-                        for (int tt = 0; tt < TB; tt++) if (tt < nt) acc[tt] = block_dot<TYPE>(bq, zq[tt][blk], zs[tt][blk], acc[tt]);
-                    }
-                }
-            };
-            switch (type) {
-                case DT_Q4_0: blocks(std::integral_constant<int, DT_Q4_0>{}); break;
-                case DT_Q4_1: blocks(std::integral_constant<int, DT_Q4_1>{}); break;
-                case DT_Q5_0: blocks(std::integral_constant<int, DT_Q5_0>{}); break;
-                case DT_Q5_1: blocks(std::integral_constant<int, DT_Q5_1>{}); break;
-                case DT_Q8_0: blocks(std::integral_constant<int, DT_Q8_0>{}); break;
-                case DT_F16:
-                    for (int k = 0; k < K; k++) {
-                        const float wv = __half2float(reinterpret_cast<const __half *>(wrow)[k]);
-#pragma unroll
-                        for (int tt = 0; tt < TB; tt++) if (tt < nt) acc[tt] = __fmaf_rn(wv, zf[tt][k], acc[tt]);
-                    }
-                    break;
-                default:
-                    for (int k = 0; k < K; k++) {
-                        const float wv = reinterpret_cast<const float *>(wrow)[k];
-#pragma unroll
-                        for (int tt = 0; tt < TB; tt++) if (tt < nt) acc[tt] = __fmaf_rn(wv, zf[tt][k], acc[tt]);
-                    }
-                    break;
-            }
-#pragma unroll
-            for (int tt = 0; tt < TB; tt++) if (tt < nt) B.d[tt][tid] = expf(-expf(__fadd_rn(acc[tt], dbias)));
-        }
-        // B.d becomes visible to phase A through the barrier that follows the cp.async wait
-    };
     float tfr[8];     // time_first of my key rows
     stage(0);
     wkv_cp_commit();
     for (int c = 0; c < nchunks; c++) {
         if (c + 1 < nchunks) stage(c + 1);     // buf[(c+1)&1] was last read by phase A of chunk c-1, two barriers ago
         wkv_cp_commit();
-        if (fused_decay) decay_rows(c);        // zq / zs / zf were last read before the previous iteration's barriers
         wkv_cp_wait<1>();
         __syncthreads();
         tick(a0);
@@ -321,9 +224,10 @@ __global__ void __launch_bounds__(Wkv6Layout<S>::BLOCK) wkv6_kernel(const Wkv6Pa
             }
             s1 = wkv_warp_sum_d(s1);
             s2 = wkv_warp_sum_d(s2);
-            const double mean_d = s1 / S;
+            constexpr double INV_S = 1.0 / S;                          // S is a power of two: x * INV_S == x / S bit for bit, without the
+            const double mean_d = s1 * INV_S;                          // two double-precision divisions per token
             const float mean = (float) mean_d;
-            const float var = (float) fmax(s2 / S - mean_d * mean_d, 0.0);
+            const float var = (float) fmax(s2 * INV_S - mean_d * mean_d, 0.0);
             const float rstd = 1.0f / sqrtf(var + p.eps);
             const size_t o = (size_t) (t0 + tt) * C + h * S;
 #pragma unroll
