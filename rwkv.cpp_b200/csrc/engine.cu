@@ -11,6 +11,7 @@
 #include <new>
 #include <vector>
 
+#include "kernels/act_stage.cuh"
 #include "kernels/gemv.h"
 #include "kernels/ops.h"
 
@@ -30,10 +31,12 @@ struct Scratch {      // carve-up of ctx->scratch for T tokens
 };
 
 constexpr int BATCH_TC_MIN = 16;
-// smallest batch (in weights) that is worth a tensor-core launch; RWKV_B200_TC_MIN_WEIGHTS overrides (the GPU tests set 0 so that the
-// reference's tiny fixtures still run their >= 32-token passes through the tcgen05 kernel)
+// Smallest batch (in weights) that goes to the tensor cores in a pass of >= 32 tokens: 0 = every eligible batch. A tensor-core launch
+// has a fixed cost of ~40 us (43 us for the 160 x 4096 LoRA matrix of a v6 layer), but the multi-column GEMV is worse for such a
+// matrix at T = 128 (200 us: 32 column groups): measured 20.3 ms per 7B chunk with a 2^20 threshold against 15.0 ms with none
+// (profiles/r2_c8_pf_*.json). RWKV_B200_TC_MIN_WEIGHTS overrides (A/B aid).
 long long tc_min_weights() {
-    static const long long v = [] { const char * e = getenv("RWKV_B200_TC_MIN_WEIGHTS"); return e ? atoll(e) : (long long) (1 << 20); }();
+    static const long long v = [] { const char * e = getenv("RWKV_B200_TC_MIN_WEIGHTS"); return e ? atoll(e) : 0ll; }();
     return v;
 }
 
@@ -95,6 +98,41 @@ struct Batch {
     }
 };
 
+// ---- staged activation columns (act_stage.cuh) + LayerNorm as a GEMV tail job (gemv.h: LnTail) ------------------------------------
+// Single-token passes: the kernel that produces a GEMV's input vector (the v6 lerp, a WKV kernel, the LayerNorm tail job) also writes
+// it in the layout the streaming GEMV keeps in shared memory, so the consumer copies ~5 KB instead of quantising 16 KB of fp32 on
+// its critical path. One slot per (producer, output); a slot serves every consumer whose weight type multiplies the same staged format.
+constexpr int XQ_SLOTS = 16;
+enum XqSlot { XQ_ATT_MIX = 0 /* .. 5 */, XQ_LERP = 6 /* .. 10 */, XQ_WKV = 11, XQ_FFN_MIX = 12 /* .. 13 */ };
+
+bool handoff_enabled() {
+    static const bool on = getenv("RWKV_B200_NO_XQ") == nullptr && getenv("RWKV_B200_GENERIC_GEMV") == nullptr;
+    return on;
+}
+// The slot to fill for a consumer matrix W of this pass, or NULL when the pass / shape cannot use the hand-off.
+unsigned char * xq_slot(const Context * ctx, int T, int slot, const DevMatrix & W) {
+    if (!handoff_enabled() || T != 1 || ctx->batch_stride || !ctx->xq || !W.data || W.K % 32 != 0 || W.type == DT_F32 || act::stage_class(W.type) == act::SC_NONE) return nullptr;
+    if (act::bytes_per_column(W.type, W.K) > ctx->xq_slot_bytes) return nullptr;
+    return ctx->xq + (size_t) slot * ctx->xq_slot_bytes;
+}
+// Point problem p at a staged copy of its input that was written for weight type q_type.
+void xq_bind(GemvProblem & p, const unsigned char * q, int q_type) {
+    if (q && act::stage_class(p.type) == act::stage_class(q_type)) p.xq = q;
+}
+// Ask the single-token GEMV launch `b` (which writes the residual stream) to run the next block's LayerNorm + mix as its tail job.
+void attach_tail(Context * ctx, GemvBatch & b, const LnMixParams * next) {
+    static const bool off = getenv("RWKV_B200_NO_LN_TAIL") != nullptr;
+    if (off || !next || b.T != 1 || ctx->batch_stride || !ctx->tail_counter || next->T != 1) return;
+    LnTail & t = b.tail;
+    t.enabled = 1;
+    t.C = next->C; t.formula = next->formula; t.n_out = next->n_out;
+    t.x = next->x; t.ln_w = next->ln_w; t.ln_b = next->ln_b;
+    t.state_in = next->state_in; t.state_out = next->state_out;
+    for (int j = 0; j < 6; j++) { t.coef[j] = next->coef[j]; t.out[j] = next->out[j]; t.q_out[j] = next->q_out[j]; t.q_type[j] = next->q_type[j]; }
+    t.out_xx = next->out_xx; t.out_sx = next->out_sx;
+    t.counter = ctx->tail_counter;
+}
+
 #define CUDA_OK(ctx, call)                                                                               \
     do { cudaError_t _e = (call);                                                                        \
          RWKV_CHECK((ctx)->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, _e == cudaSuccess,       \
@@ -115,9 +153,6 @@ bool launch_batch(Context * ctx, GemvBatch & b) {
             if (gemm_tc_supported(b.p[i], b.T)) { tcb.p[tcb.n++] = b.p[i]; tc_weights += (long long) b.p[i].M * b.p[i].K; }
             else rest.p[rest.n++] = b.p[i];
         }
-        // A tensor-core launch costs ~40 us whatever it multiplies (TMEM allocation, ring fill, epilogue, K-split reduction: measured
-        // 43 us for the 160 x 4096 LoRA matrix of a v6 layer, profiles/r2_trace_prefill_c7.log); a batch with less than a million
-        // weights is cheaper on the multi-column GEMV, which streams it out of L2 once per group of 4 tokens.
         if (tc_weights < tc_min_weights()) {
             for (int i = 0; i < tcb.n; i++) rest.p[rest.n++] = tcb.p[i];
             tcb.n = 0;
@@ -156,21 +191,26 @@ cudaError_t do_wkv4(Context * ctx, const Wkv4Params & wp) {
     return ctx->batch_stride ? launch_wkv4_batch(wp, ctx->batch_stride, ctx->stream) : launch_wkv4(wp, ctx->stream);
 }
 
-// LayerNorm + token shift + mix in front of a batch of GEMVs: its own launch (ln_mix_kernel). Folding it into the consuming GEMV
-// (every CTA recomputing the LayerNorm in its prologue) was built and measured in round 2: 4.24 ms per 7B token against 3.14 ms,
-// the in-kernel LayerNorm + staging took 11 us on the critical path of every CTA (profiles/r2_trace_decode_c7_fuseln.log); removed.
-bool ln_mix_then(Context * ctx, const LnMixParams & lp, Batch &) {
+// LayerNorm + token shift + mix in front of a batch of GEMVs. In a single-token pass the previous GEMV launch (the one that wrote the
+// residual stream) normally ran it as its tail job (attach_tail): then nothing is launched here and the staged columns of the mixed
+// vectors are valid (*staged). Otherwise (first layer of a pass / layer group, multi-token passes, batch contexts, generic GEMV) it is
+// its own launch of ln_mix_kernel. Both produce the same bits. (Folding the LayerNorm into the CONSUMING GEMV instead -- every CTA
+// recomputing it in its prologue -- was built and measured in round 2: 4.24 vs 3.14 ms per 7B token; removed.)
+bool ln_mix_then(Context * ctx, const LnMixParams & lp, bool * staged) {
+    *staged = ctx->ln_done_by_tail;
+    if (ctx->ln_done_by_tail) { ctx->ln_done_by_tail = false; return true; }
     CUDA_OK(ctx, do_ln_mix(ctx, lp));
     return true;
 }
+// After a launch that carried a tail job: did the launcher honour it?
+void note_tail(Context * ctx, const GemvBatch & b) { ctx->ln_done_by_tail = b.tail.enabled != 0; }
 
-// Channel mixing, all versions (rwkv_ffn_v4_v5 :484-511, rwkv_ffn_v6 :513-531, rwkv_ffn_v7 :533-543).
-bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
+// LayerNorm + mix parameters of the channel-mixing block (rwkv_ffn_v4_v5 :484-511, rwkv_ffn_v6 :513-531, rwkv_ffn_v7 :533-543).
+LnMixParams ffn_ln(const Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
     const Model & m = *ctx->model;
-    const int C = m.n_embed;
     LnMixParams lp{};
     lp.x = s.x; lp.ln_w = L.ln2_w.data; lp.ln_b = L.ln2_b.data;
-    lp.state_in = st_in; lp.state_out = st_out; lp.C = C; lp.T = T;
+    lp.state_in = st_in; lp.state_out = st_out; lp.C = m.n_embed; lp.T = T;
     if (m.arch_major == 7) {
         lp.formula = 1; lp.n_out = 1; lp.coef[0] = L.ffn_x_k.data; lp.out[0] = s.mix[0];
     } else if (m.arch_major == 6) {
@@ -182,71 +222,117 @@ bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const float *
         lp.coef[0] = L.ffn_time_mix_k.data; lp.out[0] = s.mix[0];
         lp.coef[1] = L.ffn_time_mix_r.data; lp.out[1] = s.mix[1];
     }
+    lp.q_out[0] = xq_slot(ctx, T, XQ_FFN_MIX, L.ffn_key); lp.q_type[0] = L.ffn_key.type;
+    if (m.arch_major != 7) { lp.q_out[1] = xq_slot(ctx, T, XQ_FFN_MIX + 1, L.ffn_receptance); lp.q_type[1] = L.ffn_receptance.type; }
+    return lp;
+}
+
+// Channel mixing, all versions. `next_ln`: the LayerNorm + mix of the block that follows (next layer's time mixing), run as the tail
+// job of the ffn.value launch when the pass allows it.
+bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const LnMixParams & lp, const LnMixParams * next_ln) {
+    const Model & m = *ctx->model;
+    const int C = m.n_embed;
     {
         Batch b(T);
-        b.add(L.ffn_key, s.mix[0], s.ffn_k, EPI_RELU_SQR);
-        if (m.arch_major != 7) b.add(L.ffn_receptance, s.mix[1], s.ffn_r, EPI_SIGMOID);
-        if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
+        GemvProblem & pk = b.add(L.ffn_key, s.mix[0], s.ffn_k, EPI_RELU_SQR);
+        GemvProblem * pr = (m.arch_major != 7) ? &b.add(L.ffn_receptance, s.mix[1], s.ffn_r, EPI_SIGMOID) : nullptr;
+        bool staged = false;
+        if (!ln_mix_then(ctx, lp, &staged)) return false;
+        if (staged) { xq_bind(pk, lp.q_out[0], lp.q_type[0]); if (pr) xq_bind(*pr, lp.q_out[1], lp.q_type[1]); }
+        if (!run_batch(ctx, b)) return false;
     }
     {
         Batch b(T);
         GemvProblem & p = b.add(L.ffn_value, s.ffn_k, s.x, m.arch_major == 7 ? EPI_ADD : EPI_MUL_ADD);
         p.res = s.x; p.ldres = C;
         p.gate = s.ffn_r; p.ldgate = C;
+        attach_tail(ctx, b.b, next_ln);
         if (!run_batch(ctx, b)) return false;
+        note_tail(ctx, b.b);
     }
     return true;
 }
 
-bool att_output(Context * ctx, const Layer & L, const Scratch & s, int T) {
+// yq: y as a staged column (written by the WKV kernel) or NULL; ffn_lp: the channel-mixing block's LayerNorm + mix = this launch's tail job
+bool att_output(Context * ctx, const Layer & L, const Scratch & s, int T, const unsigned char * yq, const LnMixParams * ffn_lp) {
     Batch b(T);
     GemvProblem & p = b.add(L.att_output, s.y, s.x, EPI_ADD);   // x + Wo.y  (:182/:291/:384/:481 + residual :667-679)
     p.res = s.x; p.ldres = ctx->model->n_embed;
-    return run_batch(ctx, b);
+    xq_bind(p, yq, L.att_output.type);
+    attach_tail(ctx, b.b, ffn_lp);
+    if (!run_batch(ctx, b)) return false;
+    note_tail(ctx, b.b);
+    return true;
 }
 
-bool att_v4(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
-    const int C = ctx->model->n_embed;
+// LayerNorm + mix parameters of the time-mixing block of layer `layer`, per architecture (:94-97, :306-311, :400-413), with the staged
+// columns of the consumers of each mixed vector.
+LnMixParams att_ln(const Context * ctx, const Layer & L, int layer, const Scratch & s, int T, const float * st_in, float * st_out) {
+    const Model & m = *ctx->model;
+    const int C = m.n_embed;
     LnMixParams lp{};
     lp.x = s.x; lp.ln_w = L.ln1_w.data; lp.ln_b = L.ln1_b.data;
     lp.state_in = st_in + C; lp.state_out = st_out + C; lp.C = C; lp.T = T;
-    lp.formula = 0; lp.n_out = 3;
-    lp.coef[0] = L.att_time_mix_k.data; lp.out[0] = s.mix[0];
-    lp.coef[1] = L.att_time_mix_v.data; lp.out[1] = s.mix[1];
-    lp.coef[2] = L.att_time_mix_r.data; lp.out[2] = s.mix[2];
+    const DevMatrix * cons[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};      // first consumer of out[j]
+    if (m.arch_major == 7) {
+        lp.formula = 1; lp.n_out = 6;
+        for (int j = 0; j < 6; j++) { lp.coef[j] = L.att_x_rwkvag.data + (size_t) j * C; lp.out[j] = s.mix[j]; }   // r w k v a g
+        cons[0] = &L.att_receptance; cons[1] = &L.att_w1; cons[2] = &L.att_key; cons[3] = &L.att_value; cons[4] = &L.att_a1; cons[5] = &L.att_g1;
+    } else if (m.arch_major == 6) {
+        lp.formula = 1; lp.n_out = 1; lp.coef[0] = L.att_maa_x.data; lp.out[0] = s.mix[0];
+        lp.out_xx = s.xx; lp.out_sx = s.sx;
+        cons[0] = &L.att_maa_w1;
+    } else {
+        const bool v52 = m.arch_major == 5 && m.arch_minor >= 2;
+        lp.formula = 0; lp.n_out = v52 ? 4 : 3;
+        lp.coef[0] = L.att_time_mix_k.data; lp.out[0] = s.mix[0];
+        lp.coef[1] = L.att_time_mix_v.data; lp.out[1] = s.mix[1];
+        lp.coef[2] = L.att_time_mix_r.data; lp.out[2] = s.mix[2];
+        if (v52) { lp.coef[3] = L.att_time_mix_g.data; lp.out[3] = s.mix[3]; }
+        cons[0] = &L.att_key; cons[1] = &L.att_value; cons[2] = &L.att_receptance; cons[3] = &L.att_gate;
+    }
+    (void) layer;
+    for (int j = 0; j < lp.n_out; j++) if (cons[j]) { lp.q_out[j] = xq_slot(ctx, T, XQ_ATT_MIX + j, *cons[j]); lp.q_type[j] = cons[j]->type; }
+    return lp;
+}
+
+bool att_v4(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out, const LnMixParams & lp, const LnMixParams * ffn_lp) {
+    const int C = ctx->model->n_embed;
     Batch b(T);
-    b.add(L.att_receptance, s.mix[2], s.r, EPI_SIGMOID);
-    b.add(L.att_key, s.mix[0], s.k);
-    b.add(L.att_value, s.mix[1], s.v);
-    if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
+    GemvProblem & pr = b.add(L.att_receptance, s.mix[2], s.r, EPI_SIGMOID);
+    GemvProblem & pk = b.add(L.att_key, s.mix[0], s.k);
+    GemvProblem & pv = b.add(L.att_value, s.mix[1], s.v);
+    bool staged = false;
+    if (!ln_mix_then(ctx, lp, &staged)) return false;
+    if (staged) { xq_bind(pr, lp.q_out[2], lp.q_type[2]); xq_bind(pk, lp.q_out[0], lp.q_type[0]); xq_bind(pv, lp.q_out[1], lp.q_type[1]); }
+    if (!run_batch(ctx, b)) return false;
     Wkv4Params wp{};
     wp.k = s.k; wp.v = s.v; wp.r = s.r;
     wp.time_first = L.att_time_first.data; wp.time_decay = L.att_time_decay.data;
     wp.aa_in = st_in + 2 * C; wp.bb_in = st_in + 3 * C; wp.pp_in = st_in + 4 * C;
     wp.aa_out = st_out + 2 * C; wp.bb_out = st_out + 3 * C; wp.pp_out = st_out + 4 * C;
     wp.y = s.y; wp.C = C; wp.T = T;
+    wp.q_out = (C % 32 == 0) ? xq_slot(ctx, T, XQ_WKV, L.att_output) : nullptr; wp.q_type = L.att_output.type;
     CUDA_OK(ctx, do_wkv4(ctx, wp));
-    return att_output(ctx, L, s, T);
+    return att_output(ctx, L, s, T, wp.q_out, ffn_lp);
 }
 
-bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
+bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out, const LnMixParams & lp, const LnMixParams * ffn_lp) {
     const Model & m = *ctx->model;
     const int C = m.n_embed;
     const bool v52 = m.arch_minor >= 2;
-    LnMixParams lp{};
-    lp.x = s.x; lp.ln_w = L.ln1_w.data; lp.ln_b = L.ln1_b.data;
-    lp.state_in = st_in + C; lp.state_out = st_out + C; lp.C = C; lp.T = T;
-    lp.formula = 0; lp.n_out = v52 ? 4 : 3;
-    lp.coef[0] = L.att_time_mix_k.data; lp.out[0] = s.mix[0];
-    lp.coef[1] = L.att_time_mix_v.data; lp.out[1] = s.mix[1];
-    lp.coef[2] = L.att_time_mix_r.data; lp.out[2] = s.mix[2];
-    if (v52) { lp.coef[3] = L.att_time_mix_g.data; lp.out[3] = s.mix[3]; }
     Batch b(T);
-    b.add(L.att_receptance, s.mix[2], s.r);
-    b.add(L.att_key, s.mix[0], s.k);
-    b.add(L.att_value, s.mix[1], s.v);
-    if (v52) b.add(L.att_gate, s.mix[3], s.g, EPI_SILU);
-    if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
+    GemvProblem & pr = b.add(L.att_receptance, s.mix[2], s.r);
+    GemvProblem & pk = b.add(L.att_key, s.mix[0], s.k);
+    GemvProblem & pv = b.add(L.att_value, s.mix[1], s.v);
+    GemvProblem * pg = v52 ? &b.add(L.att_gate, s.mix[3], s.g, EPI_SILU) : nullptr;
+    bool staged = false;
+    if (!ln_mix_then(ctx, lp, &staged)) return false;
+    if (staged) {
+        xq_bind(pr, lp.q_out[2], lp.q_type[2]); xq_bind(pk, lp.q_out[0], lp.q_type[0]); xq_bind(pv, lp.q_out[1], lp.q_type[1]);
+        if (pg) xq_bind(*pg, lp.q_out[3], lp.q_type[3]);
+    }
+    if (!run_batch(ctx, b)) return false;
     Wkv6Params wp{};
     wp.r = s.r; wp.k = s.k; wp.v = s.v;
     wp.td = L.att_time_decay.data; wp.td_per_token = 0;
@@ -256,22 +342,21 @@ bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
     wp.g = v52 ? s.g : nullptr;
     wp.y = s.y; wp.eps = 1e-5f; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
+    wp.q_out = (m.head_size % 32 == 0) ? xq_slot(ctx, T, XQ_WKV, L.att_output) : nullptr; wp.q_type = L.att_output.type;
     CUDA_OK(ctx, do_wkv6(ctx, wp));
-    return att_output(ctx, L, s, T);
+    return att_output(ctx, L, s, T, wp.q_out, ffn_lp);
 }
 
-bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
+bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out, const LnMixParams & lp, const LnMixParams * ffn_lp) {
     const Model & m = *ctx->model;
     const int C = m.n_embed;
-    LnMixParams lp{};   // :306-311
-    lp.x = s.x; lp.ln_w = L.ln1_w.data; lp.ln_b = L.ln1_b.data;
-    lp.state_in = st_in + C; lp.state_out = st_out + C; lp.C = C; lp.T = T;
-    lp.formula = 1; lp.n_out = 1; lp.coef[0] = L.att_maa_x.data; lp.out[0] = s.mix[0];
-    lp.out_xx = s.xx; lp.out_sx = s.sx;
     {   // :313-321  tanh(W1 . xxx)
         Batch b(T);
-        b.add(L.att_maa_w1, s.mix[0], s.lora[0], EPI_TANH);
-        if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
+        GemvProblem & p1 = b.add(L.att_maa_w1, s.mix[0], s.lora[0], EPI_TANH);
+        bool staged = false;
+        if (!ln_mix_then(ctx, lp, &staged)) return false;
+        if (staged) xq_bind(p1, lp.q_out[0], lp.q_type[0]);
+        if (!run_batch(ctx, b)) return false;
     }
     V6LerpParams vp{};   // :323-346
     vp.w2 = L.att_maa_w2.data; vp.z = s.lora[0]; vp.xx = s.xx; vp.sx = s.sx;
@@ -279,14 +364,20 @@ bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     vp.maa[3] = L.att_maa_r.data; vp.maa[4] = L.att_maa_g.data;
     for (int j = 0; j < 5; j++) vp.out[j] = s.mix[1 + j];   // w, k, v, r, g
     vp.C = C; vp.T = T; vp.mix = L.maa_mix;
+    {   // staged columns for the five consumers (w, k, v, r, g order of the lerp outputs): all or none
+        const DevMatrix * cons[5] = {&L.att_decay_w1, &L.att_key, &L.att_value, &L.att_receptance, &L.att_gate};
+        bool all = C % 32 == 0;
+        for (int j = 0; j < 5; j++) { vp.q_out[j] = xq_slot(ctx, T, XQ_LERP + j, *cons[j]); vp.q_type[j] = cons[j]->type; all = all && vp.q_out[j]; }
+        if (!all) for (int j = 0; j < 5; j++) vp.q_out[j] = nullptr;
+    }
     CUDA_OK(ctx, launch_v6_lerp(vp, ctx->stream));
     {   // :349-363
         Batch b(T);
-        b.add(L.att_receptance, s.mix[4], s.r);
-        b.add(L.att_key, s.mix[2], s.k);
-        b.add(L.att_value, s.mix[3], s.v);
-        b.add(L.att_gate, s.mix[5], s.g, EPI_SILU);
-        b.add(L.att_decay_w1, s.mix[1], s.lora[1], EPI_TANH);
+        xq_bind(b.add(L.att_receptance, s.mix[4], s.r), vp.q_out[3], vp.q_type[3]);
+        xq_bind(b.add(L.att_key, s.mix[2], s.k), vp.q_out[1], vp.q_type[1]);
+        xq_bind(b.add(L.att_value, s.mix[3], s.v), vp.q_out[2], vp.q_type[2]);
+        xq_bind(b.add(L.att_gate, s.mix[5], s.g, EPI_SILU), vp.q_out[4], vp.q_type[4]);
+        xq_bind(b.add(L.att_decay_w1, s.mix[1], s.lora[1], EPI_TANH), vp.q_out[0], vp.q_type[0]);
         if (!run_batch(ctx, b)) return false;
     }
     {   // :357-367  w = exp(-exp(Wd2 . tanh(..) + time_decay))
@@ -301,30 +392,27 @@ bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     wp.state_in = st_in + 2 * C; wp.state_out = st_out + 2 * C;
     wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
     wp.g = s.g; wp.y = s.y; wp.eps = 64e-5f; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
+    wp.q_out = (m.head_size % 32 == 0) ? xq_slot(ctx, T, XQ_WKV, L.att_output) : nullptr; wp.q_type = L.att_output.type;
     CUDA_OK(ctx, do_wkv6(ctx, wp));
-    return att_output(ctx, L, s, T);
+    return att_output(ctx, L, s, T, wp.q_out, ffn_lp);
 }
 
-bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T, const float * st_in, float * st_out) {
+bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T, const float * st_in, float * st_out, const LnMixParams & lp, const LnMixParams * ffn_lp) {
     const Model & m = *ctx->model;
     const int C = m.n_embed;
     const bool first = layer == 0;
-    LnMixParams lp{};   // :400-413
-    lp.x = s.x; lp.ln_w = L.ln1_w.data; lp.ln_b = L.ln1_b.data;
-    lp.state_in = st_in + C; lp.state_out = st_out + C; lp.C = C; lp.T = T;
-    lp.formula = 1; lp.n_out = 6;
-    for (int j = 0; j < 6; j++) { lp.coef[j] = L.att_x_rwkvag.data + (size_t) j * C; lp.out[j] = s.mix[j]; }   // r w k v a g
     float * v_dst = first ? s.v_first : s.v;
-    {   // :415-432, 439, 447 -- first halves of the LoRA pairs
+    {   // :415-432, 439, 447 -- first halves of the LoRA pairs. The staged column of a mix output was written for its first consumer;
+        // att_v1 shares x_v with att_value only if both multiply the same staged format (in quantised files the LoRA matrices stay fp16)
         Batch b(T);
-        b.add(L.att_receptance, s.mix[0], s.r);
-        b.add(L.att_key, s.mix[2], s.k);
-        b.add(L.att_value, s.mix[3], v_dst);
-        b.add(L.att_w1, s.mix[1], s.lora[0], EPI_TANH);
-        b.add(L.att_a1, s.mix[4], s.lora[1]);
-        b.add(L.att_g1, s.mix[5], s.lora[2], EPI_SIGMOID);
-        if (!first) b.add(L.att_v1, s.mix[3], s.lora[3]);
-        if (!ln_mix_then(ctx, lp, b) || !run_batch(ctx, b)) return false;
+        GemvProblem * ps[7] = {&b.add(L.att_receptance, s.mix[0], s.r), &b.add(L.att_key, s.mix[2], s.k), &b.add(L.att_value, s.mix[3], v_dst),
+                               &b.add(L.att_w1, s.mix[1], s.lora[0], EPI_TANH), &b.add(L.att_a1, s.mix[4], s.lora[1]), &b.add(L.att_g1, s.mix[5], s.lora[2], EPI_SIGMOID),
+                               first ? nullptr : &b.add(L.att_v1, s.mix[3], s.lora[3])};
+        const int src[7] = {0, 2, 3, 1, 4, 5, 3};      // which mix output each problem reads
+        bool staged = false;
+        if (!ln_mix_then(ctx, lp, &staged)) return false;
+        if (staged) for (int i = 0; i < 7; i++) if (ps[i]) xq_bind(*ps[i], lp.q_out[src[i]], lp.q_type[src[i]]);
+        if (!run_batch(ctx, b)) return false;
     }
     {   // second halves
         Batch b(T);
@@ -341,8 +429,9 @@ bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T,
     wp.lnx_w = L.att_ln_x_w.data; wp.lnx_b = L.att_ln_x_b.data;
     wp.state_in = st_in + 2 * C; wp.state_out = st_out + 2 * C;
     wp.y = s.y; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
+    wp.q_out = (m.head_size % 32 == 0) ? xq_slot(ctx, T, XQ_WKV, L.att_output) : nullptr; wp.q_type = L.att_output.type;
     CUDA_OK(ctx, ctx->batch_stride ? launch_wkv7_batch(wp, ctx->batch_stride, ctx->stream) : launch_wkv7(wp, ctx->stream));
-    return att_output(ctx, L, s, T);
+    return att_output(ctx, L, s, T, wp.q_out, ffn_lp);
 }
 
 bool ensure_capacity(Context * ctx, int T) {
@@ -397,18 +486,23 @@ bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase, int seg) {
         CUDA_OK(ctx, launch_embed_ln0(m.emb.data, m.emb.type, m.emb.pitch, ctx->tokens, T, C, m.ln0_w.data, m.ln0_b.data, s.x, ctx->stream));
     }   // a later pipeline stage / layer group finds x (and v_first) already in place
     const size_t per_layer = m.state_floats_per_layer();
+    ctx->ln_done_by_tail = false;
     for (int i = l0; i < l1; i++) {
         const Layer & L = m.layers[i];
         const float * st_in = ctx->state_a + (size_t) i * per_layer;
         float * st_out = ctx->state_b + (size_t) i * per_layer;
+        const LnMixParams alp = att_ln(ctx, L, i, s, T, st_in, st_out), flp = ffn_ln(ctx, L, s, T, st_in, st_out);
+        LnMixParams next_alp{};
+        const bool has_next = i + 1 < l1;
+        if (has_next) next_alp = att_ln(ctx, m.layers[i + 1], i + 1, s, T, ctx->state_a + (size_t) (i + 1) * per_layer, ctx->state_b + (size_t) (i + 1) * per_layer);
         bool ok;
         switch (m.arch_major) {
-            case 7: ok = att_v7(ctx, L, i, s, T, st_in, st_out); break;
-            case 6: ok = att_v6(ctx, L, s, T, st_in, st_out); break;
-            case 5: ok = att_v5(ctx, L, s, T, st_in, st_out); break;
-            default: ok = att_v4(ctx, L, s, T, st_in, st_out); break;
+            case 7: ok = att_v7(ctx, L, i, s, T, st_in, st_out, alp, &flp); break;
+            case 6: ok = att_v6(ctx, L, s, T, st_in, st_out, alp, &flp); break;
+            case 5: ok = att_v5(ctx, L, s, T, st_in, st_out, alp, &flp); break;
+            default: ok = att_v4(ctx, L, s, T, st_in, st_out, alp, &flp); break;
         }
-        if (!ok || !ffn(ctx, L, s, T, st_in, st_out)) return false;
+        if (!ok || !ffn(ctx, L, s, T, flp, has_next ? &next_alp : nullptr)) return false;
     }
     if (want_logits && l1 == m.n_layer) {   // :705-708 / :851-854  head . LN(x_last; ln_out); a batch context wants every column
         Batch b(ctx->batch_n ? T : 1);
@@ -544,6 +638,11 @@ Context * create_context(Model * model, ErrorSink sink, int batch_n) {
         && cudaMalloc(reinterpret_cast<void **>(&ctx->state_b), seqs * n * sizeof(float)) == cudaSuccess
         && cudaMalloc(reinterpret_cast<void **>(&ctx->state_init), n * sizeof(float)) == cudaSuccess
         && cudaMalloc(reinterpret_cast<void **>(&ctx->logits), seqs * (size_t) model->n_vocab * sizeof(float)) == cudaSuccess;
+    if (ok && batch_n == 0) {      // staged-column hand-off slots (every handed-off vector has n_embed elements, at most 2 bytes each) + the tail-job ticket
+        ctx->xq_slot_bytes = ((size_t) 2 * model->n_embed + 64 + 255) / 256 * 256;
+        ok = cudaMalloc(reinterpret_cast<void **>(&ctx->xq), (size_t) XQ_SLOTS * ctx->xq_slot_bytes) == cudaSuccess
+            && cudaMalloc(reinterpret_cast<void **>(&ctx->tail_counter), 256) == cudaSuccess && cudaMemset(ctx->tail_counter, 0, 256) == cudaSuccess;
+    }
     if (ok) {
         std::vector<float> init(n);
         fill_init_state(*model, init.data());
@@ -574,7 +673,7 @@ void destroy_context(Context * ctx) {
     if (model) cudaSetDevice(model->dev.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->state_a); cudaFree(ctx->state_b); cudaFree(ctx->state_init); cudaFree(ctx->logits);
-    cudaFree(ctx->tokens); cudaFree(ctx->scratch); cudaFree(ctx->trace_buf); cudaFree(ctx->act16);
+    cudaFree(ctx->tokens); cudaFree(ctx->scratch); cudaFree(ctx->trace_buf); cudaFree(ctx->act16); cudaFree(ctx->xq); cudaFree(ctx->tail_counter);
     for (int i = 0; i < 2; i++) {
         if (ctx->tokens_host[i]) cudaFreeHost(ctx->tokens_host[i]);
         if (ctx->slot_free[i]) cudaEventDestroy(ctx->slot_free[i]);
@@ -583,6 +682,7 @@ void destroy_context(Context * ctx) {
     if (ctx->copy_in) { cudaStreamSynchronize(ctx->copy_in); cudaStreamDestroy(ctx->copy_in); }
     if (ctx->copy_out) { cudaStreamSynchronize(ctx->copy_out); cudaStreamDestroy(ctx->copy_out); }
     if (ctx->pass_begin) cudaEventDestroy(ctx->pass_begin);
+    if (ctx->pipe_done) cudaEventDestroy(ctx->pipe_done);
     for (int i = 0; i < Context::MAX_SEGMENTS; i++) { if (ctx->seg_in[i]) cudaEventDestroy(ctx->seg_in[i]); if (ctx->seg_out[i]) cudaEventDestroy(ctx->seg_out[i]); }
     cudaFree(ctx->sample_token); cudaFree(ctx->sample_scratch); cudaFree(ctx->bias_ids); cudaFree(ctx->bias_values);
     if (ctx->sample_token_host) cudaFreeHost(ctx->sample_token_host);
@@ -949,11 +1049,16 @@ bool pipeline_eval_host(Context * head, const uint32_t * tokens, size_t T, size_
             const size_t so = (size_t) m.layer_begin * per_layer, cnt = (size_t) (m.layer_end - m.layer_begin) * per_layer;
             if (state_out) CUDA_OK(head, cudaMemcpyAsync(state_out + so, c->state_a + so, cnt * sizeof(float), cudaMemcpyDefault, g.streams[r]));
             if (logits_out && r + 1 == n) CUDA_OK(head, cudaMemcpyAsync(logits_out, c->logits, (size_t) m.n_vocab * sizeof(float), cudaMemcpyDefault, g.streams[r]));
+            // completion marker of THIS evaluation on stage r. Waiting on the stream itself (cudaStreamSynchronize) outside the lock
+            // would be illegal whenever another host thread is capturing its stage graph on the same stream at that moment (found by
+            // compute-sanitizer's slower timing: cudaErrorStreamCaptureInvalidated); an event recorded before that capture began is fine.
+            if (!c->pipe_done) CUDA_OK(head, cudaEventCreateWithFlags(&c->pipe_done, cudaEventDisableTiming));
+            CUDA_OK(head, cudaEventRecord(c->pipe_done, g.streams[r]));
         }
     }
     for (size_t r = 0; r < n; r++) {
         CUDA_OK(head, cudaSetDevice(g.devices[r]));
-        CUDA_OK(head, cudaStreamSynchronize(g.streams[r]));
+        CUDA_OK(head, cudaEventSynchronize(stage_of(head, r)->pipe_done));
     }
     return true;
 }

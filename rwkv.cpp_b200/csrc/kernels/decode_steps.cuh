@@ -30,7 +30,7 @@ __device__ __forceinline__ void ln_center_scale_256(const float * x, int C, floa
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int m = q + 4 * i, c = t + 256 * m;
-            xa[m] = (c < C) ? x[c] : 0.f;
+            xa[m] = (c < C) ? __ldcg(x + c) : 0.f;       // L2, not L1: as a GEMV tail job x was written by OTHER SMs during this very kernel
             sa[q] += (double) xa[m];
         }
     }

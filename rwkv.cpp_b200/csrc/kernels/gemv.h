@@ -30,6 +30,10 @@ struct GemvProblem {
     long long pitch;
     int type, K, M;
     const float * x;  long long ldx;      // input  column t at x + t*ldx
+    // Single-token launches of the streaming kernel: x[:, 0] already in the staged layout of this problem's (type, K) (act_stage.cuh),
+    // emitted by the kernel that produced x. The consumers copy it instead of quantising x; NULL = stage from x. Ignored by the
+    // generic kernel and the tensor-core path.
+    const unsigned char * xq;
     float * y;        long long ldy;      // output column t at y + t*ldy
     const float * res;  long long ldres;
     const float * gate; long long ldgate;
@@ -54,11 +58,32 @@ inline TraceRec * trace_slot(const char * name) {
     return g_trace_base + g_trace_next++;
 }
 
+// Tail job of a single-token streaming launch that writes the residual stream x (att.output / ffn.value): the CTA that finishes LAST
+// (device-side ticket) runs the LayerNorm + token shift + mix of the NEXT block on the finished x, i.e. what ln_mix_kernel would do as
+// a separate launch -- one launch boundary, one dependency release and one single-SM kernel less per block. Arithmetic = ln_mix_kernel's
+// (steps::ln_center_scale_256 reproduces its reduction tree), so results do not change. The mixed vectors also leave in the staged
+// layout of their consumers (q_out, act_stage.cuh).
+struct LnTail {
+    int enabled;
+    int C, formula, n_out;
+    const float * x;          // [C] residual stream (written by this launch)
+    const float * ln_w, * ln_b;
+    const float * state_in;   // [C] previous token's LN(x)
+    float * state_out;        // [C] <- LN(x)
+    const float * coef[6];
+    float * out[6];
+    float * out_xx, * out_sx; // optional
+    unsigned char * q_out[6]; // optional staged columns
+    int q_type[6];
+    int * counter;            // device int, zero between launches
+};
+
 constexpr int GEMV_MAX_PROBLEMS = 8;
 struct GemvBatch {
     int n, T;
     TraceRec * trace;
     long long max_col_bytes, stage_bytes; // streaming kernel only: shared-memory carve-up
+    LnTail tail;                          // streaming kernel, T == 1 only; the launcher clears tail.enabled when it cannot honour it
     GemvProblem p[GEMV_MAX_PROBLEMS];
 };
 

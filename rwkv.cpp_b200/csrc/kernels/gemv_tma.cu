@@ -19,11 +19,49 @@
 // WK, itself a function of (type, K, pitch) alone -- never of T, the batch composition or the tile size. A token
 // evaluated alone and inside a chunk therefore produces identical bits (tests/test_eval_sequence_in_chunks.c:54).
 #include "gemv_tma_device.cuh"
+#include "decode_steps.cuh"
+#include "act_stage.cuh"
 
 #include <cstdlib>
 
 namespace rwkv {
 namespace tma {
+
+// The tail job (gemv.h: LnTail), run by the 256 consumer threads of the launch's last CTA: LayerNorm + token shift + mix of the next
+// block. Thread t owns channels t + 256 m, so warp w's 32 lanes hold 32-element block w + 8 m of every vector: the staged columns of
+// the consumers come out of warp-level reductions (act::warp_emit_block). Same per-element operations and reduction trees as
+// ln_mix_kernel<PER> (glue.cu) for T = 1.
+static __device__ __noinline__ void ln_mix_tail(const LnTail & p, double (* slots)[32]) {
+    using steps::LN_MAXCH;
+    const int C = p.C, t = threadIdx.x, warp = t >> 5;
+    float lw[LN_MAXCH], lb[LN_MAXCH], pv[LN_MAXCH];
+#pragma unroll
+    for (int m = 0; m < LN_MAXCH; m++) {
+        const int c = t + 256 * m;
+        const bool live = c < C;
+        lw[m] = live ? p.ln_w[c] : 0.f;
+        lb[m] = live ? p.ln_b[c] : 0.f;
+        pv[m] = live ? p.state_in[c] : 0.f;
+    }
+    float xa[LN_MAXCH], scale_a;
+    steps::ln_center_scale_256(p.x, C, xa, scale_a, slots);
+#pragma unroll
+    for (int m = 0; m < LN_MAXCH; m++) {
+        const int c = t + 256 * m;
+        if (256 * m + 32 * warp >= C) break;                        // warp-uniform: C is a multiple of 32
+        const float xx = __fadd_rn(__fmul_rn(__fmul_rn(xa[m], scale_a), lw[m]), lb[m]);     // LN(x)
+        p.state_out[c] = xx;
+        if (p.out_xx) p.out_xx[c] = xx;
+        if (p.out_sx) p.out_sx[c] = __fsub_rn(pv[m], xx);
+        for (int j = 0; j < p.n_out; j++) {
+            const float cf = p.coef[j][c];
+            const float v = (p.formula == 0) ? __fadd_rn(__fmul_rn(xx, cf), __fsub_rn(pv[m], __fmul_rn(pv[m], cf)))
+                                             : __fadd_rn(__fmul_rn(__fsub_rn(pv[m], xx), cf), xx);
+            p.out[j][c] = v;
+            if (p.q_out[j]) act::warp_emit_block(act::StagedOut{p.q_out[j], p.q_type[j], C}, 8 * m + warp, v);
+        }
+    }
+}
 
 template <int NC, bool STAGE_V2 = false>
 __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch batch) {
@@ -85,7 +123,14 @@ __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch ba
     for (int g = 0; g < n_groups; g++) {
         const int c0 = g * NC, nc = min(NC, batch.T - c0);
         if (g > 0) consumer_barrier();   // everyone finished reading the previous group's activations
-        for (int c = 0; c < nc; c++) stage_column<4, STAGE_V2>(P, c0 + c, act + c * colb, sh.red_d);
+        if (NC == 1 && P.xq && batch.T == 1) {
+            // the producer of x left the staged column in global memory (act_stage.cuh): one 16-byte-per-thread copy out of L2
+            const int4 * src = reinterpret_cast<const int4 *>(P.xq);
+            int4 * dst = reinterpret_cast<int4 *>(act);
+            for (int i = threadIdx.x; i < (int) (colb / 16); i += CONSUMER_THREADS) dst[i] = __ldcg(src + i);
+        } else {
+            for (int c = 0; c < nc; c++) stage_column<4, STAGE_V2>(P, c0 + c, act + c * colb, sh.red_d);
+        }
         consumer_barrier();
         trace_mark(batch.trace, 1);
         const int it0 = g * my_tiles;
@@ -112,6 +157,19 @@ __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch ba
         }
 #undef RWKV_CONSUME_REGS
 #undef RWKV_CONSUME_SMEM
+    }
+    if (NC == 1 && batch.tail.enabled) {
+        // every consumer thread's stores -> visible device-wide -> one ticket per CTA; the CTA that draws the last ticket knows that
+        // all of x has been written and is visible to it
+        __threadfence();
+        consumer_barrier();
+        if (threadIdx.x == 0) sh.ticket = atomicAdd(batch.tail.counter, 1);
+        consumer_barrier();
+        if (sh.ticket == (int) gridDim.x - 1) {
+            __threadfence();
+            ln_mix_tail(batch.tail, sh.slots);
+            if (threadIdx.x == 0) *batch.tail.counter = 0;      // ready for the next launch (ordered by kernel completion)
+        }
     }
     trace_end(batch.trace);
 }
@@ -183,11 +241,12 @@ static int assign_tiles_and_ctas(GemvBatch & batch, int total_ctas, long long st
     for (int i = 0; i < batch.n; i++) total_bytes += (double) batch.p[i].M * (double) batch.p[i].pitch;
     for (int i = 0; i < batch.n; i++) {
         GemvProblem & p = batch.p[i];
-        // as many rows as the ring stage holds (the warps' row slots rotate from tile to tile, gemv_tma_device.cuh: rotated_slot);
-        // RWKV_B200_FULL_TILES=0: a multiple of the warp row-groups only (A/B aid)
-        static const bool full_tiles = [] { const char * e = getenv("RWKV_B200_FULL_TILES"); return !e || atoi(e) != 0; }();
+        // a multiple of the warp row-groups: every warp gets the same number of rows per tile. (Filling the whole ring stage -- 12 rows
+        // instead of 8 at K = 4096 Q5_1, warps' row slots rotating from tile to tile -- raised the steady-state rate per CTA by 39 % but
+        // cost more in the first tile and the tail: 3.096 vs 3.008 ms per 7B token, profiles/r2_c8_ab_*.json. Not kept.)
+        const int wr = CONSUMER_WARPS / p.wk;
         int rows = (int) (stage_bytes / p.pitch);
-        if (!full_tiles) rows -= rows % (CONSUMER_WARPS / p.wk);
+        rows -= rows % wr;
         if (rows > MAX_TILE_ROWS) rows = MAX_TILE_ROWS;
         p.tile_rows = rows;
     }
@@ -252,6 +311,7 @@ cudaError_t gemv_tma_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStrea
     else if (batch.T >= 2 && stage_for(2) >= NOMINAL_STAGE_BYTES) nc = 2;
     const long long stage_bytes = stage_for(nc);
     if (stage_bytes < NOMINAL_STAGE_BYTES) return cudaErrorNotSupported;
+    if (batch.T != 1 || nc != 1 || batch.tail.C > 256 * steps::LN_MAXCH || batch.tail.C % 32 != 0 || !batch.tail.counter) batch.tail.enabled = 0;
     // two CTAs per SM
     const int next = assign_tiles_and_ctas(batch, 2 * dev.num_sms, stage_bytes);
     batch.max_col_bytes = (long long) max_col;

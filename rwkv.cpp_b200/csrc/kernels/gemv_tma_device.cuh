@@ -149,6 +149,8 @@ struct Shared {
     uint64_t full[NSTAGES];
     uint64_t empty[NSTAGES];
     double red_d[CONSUMER_WARPS + 1];
+    double slots[2][32];      // LayerNorm partials of the tail job (steps::ln_center_scale_256)
+    int ticket;               // arrival order of this CTA at the end of the launch (tail job)
     TraceRec * trace;
     GemvProblem P;
 };
@@ -344,15 +346,6 @@ __device__ __forceinline__ LaneMap lane_map(const GemvProblem & P) {
     m.WK = P.wk; m.WR = CONSUMER_WARPS / m.WK; m.wk = warp % m.WK; m.wr = warp / m.WK;
     return m;
 }
-// Row slot of this warp row-group in the i-th tile of its CTA. A tile of `rows` rows is walked in steps of WR * RPS rows; when the last
-// step is partial only its first `rem` slots have a row, so the slot a warp group plays rotates by `rem` from tile to tile: over a few
-// tiles every warp gets the same number of rows and tiles can use the whole ring stage instead of a multiple of WR rows. Which warp
-// computes a row has no influence on the row's arithmetic.
-__device__ __forceinline__ int rotated_slot(const LaneMap & m, int rows, int i) {
-    const int per_step = m.WR * m.RPS;
-    const int rem = ((rows % per_step) + m.RPS - 1) / m.RPS;
-    return (m.wr + i * rem) % m.WR;
-}
 __device__ __forceinline__ float group_sum(float v, int G) {
     for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -401,11 +394,10 @@ __device__ void consume_quant_regs(Shared & sh, uint8_t * ring, uint32_t stage_b
         const int row0 = tile * P.tile_rows;
         const int rows = min(P.tile_rows, P.M - row0);
         const int s = it % NSTAGES;
-        const int slot = rotated_slot(m, P.tile_rows, it);      // (full tiles all have tile_rows rows; the ragged last tile just gets some slot)
         // epilogue operands of this tile, requested before we block on the weights
         EpiOperands pre; pre.a = 0.f; pre.b = 0.f;
         if (m.WK == 1) {          // lane l <-> l-th output of this warp in this tile: step l / RPS, row slot l % RPS
-            const int r = ((lane / m.RPS) * m.WR + slot) * m.RPS + (lane % m.RPS);
+            const int r = ((lane / m.RPS) * m.WR + m.wr) * m.RPS + (lane % m.RPS);
             if (r < rows) pre = prefetch_epilogue(P, row0 + r, c0);
         } else if ((int) threadIdx.x < rows) {
             pre = prefetch_epilogue(P, row0 + (int) threadIdx.x, c0);
@@ -414,7 +406,7 @@ __device__ void consume_quant_regs(Shared & sh, uint8_t * ring, uint32_t stage_b
         const uint8_t * stage = ring + (size_t) s * stage_bytes;
         float * red_t = red + (size_t) (it & 1) * MAX_TILE_ROWS * CONSUMER_WARPS;
         int step = 0;
-        for (int rb = slot * m.RPS; rb < rows; rb += m.WR * m.RPS, step++) {
+        for (int rb = m.wr * m.RPS; rb < rows; rb += m.WR * m.RPS, step++) {
             const int r = rb + m.rs;
             const uint8_t * wrow = stage + (size_t) min(r, rows - 1) * (size_t) P.pitch;   // idle row slots recompute the last row
             float acc = 0.f;
@@ -469,7 +461,7 @@ __device__ void consume_smem(Shared & sh, uint8_t * ring, uint32_t stage_bytes, 
         // WK > 1: thread i owns output (row i / nc, column i % nc) of the tile and fetches its epilogue operands now
         EpiOperands pre; pre.a = 0.f; pre.b = 0.f;
         if (m.WK > 1 && (int) threadIdx.x < rows * nc) pre = prefetch_epilogue(P, row0 + (int) threadIdx.x / nc, c0 + (int) threadIdx.x % nc);
-        for (int rb = rotated_slot(m, P.tile_rows, it) * m.RPS; rb < rows; rb += m.WR * m.RPS) {
+        for (int rb = m.wr * m.RPS; rb < rows; rb += m.WR * m.RPS) {
             const int r = rb + m.rs;
             const bool live_row = r < rows;
             const uint8_t * wrow = stage + (size_t) min(r, rows - 1) * (size_t) P.pitch;

@@ -3,6 +3,7 @@
 #include "ops.h"
 #include "gemv.h"          // g_kernel_launches
 #include "../formats.h"
+#include "act_stage.cuh"
 
 #include <cuda_fp16.h>
 
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const LnMixParams p)
 constexpr int LERP1_MAX_F4 = 4;   // float4 per lane per j held in registers: mix <= 128
 __global__ void __launch_bounds__(GLUE_THREADS) v6_lerp_decode_kernel(const V6LerpParams p) {
     extern __shared__ float zs[];   // [5*mix]
+    __shared__ float ob[5][32];     // the CTA's 32 channels of each output = one 32-element block of its staged column
     trace_begin(p.trace);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int t = blockIdx.y, mix = p.mix, C = p.C;
@@ -212,7 +214,16 @@ __global__ void __launch_bounds__(GLUE_THREADS) v6_lerp_decode_kernel(const V6Le
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (live && sub == 0) p.out[j][o] = __fadd_rn(__fmul_rn(__fadd_rn(acc, vec ? maa[j] : p.maa[j][c]), sx), xx);
+        if (sub == 0) {
+            const float val = live ? __fadd_rn(__fmul_rn(__fadd_rn(acc, vec ? maa[j] : p.maa[j][c]), sx), xx) : 0.f;
+            if (live) p.out[j][o] = val;
+            ob[j][grp] = val;
+        }
+    }
+    if (p.q_out[0] != nullptr) {       // single-token passes with C % 32 == 0 (the caller checks): warp j emits block blockIdx.x of out_j
+        __syncthreads();
+        const int warp = threadIdx.x >> 5;
+        if (warp < 5 && p.q_out[warp]) act::warp_emit_block(act::StagedOut{p.q_out[warp], p.q_type[warp], C}, blockIdx.x, ob[warp][threadIdx.x & 31]);
     }
     trace_end(p.trace);
 }

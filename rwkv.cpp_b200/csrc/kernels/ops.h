@@ -29,6 +29,10 @@ struct LnMixParams {
     float * out[6];           // [C, T] each
     float * out_xx;           // optional [C, T]: LN(x)
     float * out_sx;           // optional [C, T]: prev - xx
+    // T == 1, C % 32 == 0, LN done as the tail job of the GEMV that wrote x (gemv.h: LnTail) only: out_j additionally as the staged column
+    // (act_stage.cuh) of a consumer with weight type q_type[j]; ln_mix_kernel itself ignores these
+    unsigned char * q_out[6];
+    int q_type[6];
 };
 cudaError_t launch_ln_mix(const LnMixParams & p, cudaStream_t s);
 
@@ -42,6 +46,8 @@ struct V6LerpParams {
     const float * maa[5];     // [C]
     float * out[5];           // [C, T]
     int C, T, mix;
+    unsigned char * q_out[5]; // T == 1, C % 32 == 0 only: staged columns (act_stage.cuh) for consumers of weight type q_type[j]; all or none
+    int q_type[5];
 };
 cudaError_t launch_v6_lerp(const V6LerpParams & p, cudaStream_t s);
 
@@ -54,6 +60,7 @@ struct Wkv4Params {
     float * aa_out, * bb_out, * pp_out;
     float * y;                        // [C, T] = r * wkv
     int C, T;
+    unsigned char * q_out; int q_type;  // T == 1, C % 32 == 0 only: y as a staged column (act_stage.cuh)
 };
 cudaError_t launch_wkv4(const Wkv4Params & p, cudaStream_t s);
 
@@ -72,6 +79,7 @@ struct Wkv6Params {
     float * y;                        // [C, T]
     float eps;                        // 1e-5 (v5) or 64e-5 (v6)
     int H, S, T;
+    unsigned char * q_out; int q_type;  // T == 1, S % 32 == 0 only: y as a staged column (act_stage.cuh)
 };
 cudaError_t launch_wkv6(const Wkv6Params & p, cudaStream_t s);
 
@@ -90,6 +98,7 @@ struct Wkv7Params {
     float * state_out;
     float * y;                        // [C, T]
     int H, S, T;
+    unsigned char * q_out; int q_type;  // T == 1, S % 32 == 0 only: y as a staged column (act_stage.cuh)
 };
 cudaError_t launch_wkv7(const Wkv7Params & p, cudaStream_t s);
 

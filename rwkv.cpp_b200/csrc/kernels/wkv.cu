@@ -3,6 +3,7 @@
 // whole chunk; one CTA per head (v5+), one thread per state column (v5/v6) or row (v7).
 #include "ops.h"
 #include "gemv.h"   // g_kernel_launches
+#include "act_stage.cuh"
 #include "../formats.h"
 
 #include <cuda_fp16.h>
@@ -36,7 +37,9 @@ __global__ void wkv4_kernel(const Wkv4Params p) {
         aa = __fadd_rn(__fmul_rn(e1, aa), __fmul_rn(e2, v));
         bb = __fadd_rn(__fmul_rn(e1, bb), e2);
         pp = qq;
-        p.y[o] = __fmul_rn(p.r[o], __fdiv_rn(a, b));
+        const float yv = __fmul_rn(p.r[o], __fdiv_rn(a, b));
+        p.y[o] = yv;
+        if (p.q_out) act::warp_emit_block(act::StagedOut{p.q_out, p.q_type, p.C}, c >> 5, yv);      // T == 1, C % 32 == 0: whole warps only
     }
     p.aa_out[c] = aa; p.bb_out[c] = bb; p.pp_out[c] = pp;
     trace_end(p.trace);
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(Wkv6Layout<S>::BLOCK) wkv6_kernel(const Wkv6Pa
                     n = __fadd_rn(__fmul_rn(n, lw[i]), lb[i]);
                     if (p.g) n = __fmul_rn(n, p.g[o + col]);
                     p.y[o + col] = n;
+                    if (p.q_out) act::warp_emit_block(act::StagedOut{p.q_out, p.q_type, C}, (h * S) / 32 + i, n);   // T == 1, S % 32 == 0: col < S for all lanes
                 }
             }
         }
@@ -321,7 +325,9 @@ __global__ void __launch_bounds__(S) wkv7_kernel(const Wkv7Params p, const long 
 #pragma unroll 8
         for (int j = 0; j < S; j++) rk += (double) red[j];
         n = __fadd_rn(n, __fmul_rn(v, (float) rk));
-        p.y[o] = __fmul_rn(n, p.g[o]);
+        const float yv = __fmul_rn(n, p.g[o]);
+        p.y[o] = yv;
+        if (p.q_out) act::warp_emit_block(act::StagedOut{p.q_out, p.q_type, C}, c >> 5, yv);       // T == 1, S % 32 == 0: whole warps only
     }
 #pragma unroll
     for (int j = 0; j < S; j++) p.state_out[so + ((size_t) h * S + i) * S + j] = st[j];

@@ -42,10 +42,6 @@ DIFF_SUM_CHECKED_IN = {"4v0-660K": (-0.170404, 0.278034), "5v1-730K": (-163.4394
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    # The engine sends batches of fewer than 2^20 weights to the batch-invariant GEMV even in passes of >= 32 tokens (a tensor-core
-    # launch has a fixed cost a LoRA-sized matrix cannot amortise). The reference's fixtures are ALL that small, so the tests switch the
-    # threshold off: their >= 32-token passes keep running through the tcgen05 kernel, which is what pins it to the reference.
-    os.environ.setdefault("RWKV_B200_TC_MIN_WEIGHTS", "0")
 
 
 def model_path(ver, fmt):
