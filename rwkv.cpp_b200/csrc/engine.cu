@@ -98,8 +98,8 @@ struct Batch {
     }
 };
 
-// ---- staged activation columns (act_stage.cuh) + LayerNorm as a GEMV tail job (gemv.h: LnTail) ------------------------------------
-// Single-token passes: the kernel that produces a GEMV's input vector (the v6 lerp, a WKV kernel, the LayerNorm tail job) also writes
+// ---- staged activation columns (act_stage.cuh) --------------------------------------------------------------------------------------
+// Single-token passes: the kernel that produces a GEMV's input vector (LayerNorm + mix, the v6 lerp, a WKV kernel) also writes
 // it in the layout the streaming GEMV keeps in shared memory, so the consumer copies ~5 KB instead of quantising 16 KB of fp32 on
 // its critical path. One slot per (producer, output); a slot serves every consumer whose weight type multiplies the same staged format.
 constexpr int XQ_SLOTS = 16;
@@ -119,20 +119,6 @@ unsigned char * xq_slot(const Context * ctx, int T, int slot, const DevMatrix & 
 void xq_bind(GemvProblem & p, const unsigned char * q, int q_type) {
     if (q && act::stage_class(p.type) == act::stage_class(q_type)) p.xq = q;
 }
-// Ask the single-token GEMV launch `b` (which writes the residual stream) to run the next block's LayerNorm + mix as its tail job.
-void attach_tail(Context * ctx, GemvBatch & b, const LnMixParams * next) {
-    static const bool off = getenv("RWKV_B200_NO_LN_TAIL") != nullptr;
-    if (off || !next || b.T != 1 || ctx->batch_stride || !ctx->tail_counter || next->T != 1) return;
-    LnTail & t = b.tail;
-    t.enabled = 1;
-    t.C = next->C; t.formula = next->formula; t.n_out = next->n_out;
-    t.x = next->x; t.ln_w = next->ln_w; t.ln_b = next->ln_b;
-    t.state_in = next->state_in; t.state_out = next->state_out;
-    for (int j = 0; j < 6; j++) { t.coef[j] = next->coef[j]; t.out[j] = next->out[j]; t.q_out[j] = next->q_out[j]; t.q_type[j] = next->q_type[j]; }
-    t.out_xx = next->out_xx; t.out_sx = next->out_sx;
-    t.counter = ctx->tail_counter;
-}
-
 #define CUDA_OK(ctx, call)                                                                               \
     do { cudaError_t _e = (call);                                                                        \
          RWKV_CHECK((ctx)->sink(), RWKV_ERROR_CTX | RWKV_ERROR_UNSUPPORTED, false, _e == cudaSuccess,       \
@@ -191,19 +177,18 @@ cudaError_t do_wkv4(Context * ctx, const Wkv4Params & wp) {
     return ctx->batch_stride ? launch_wkv4_batch(wp, ctx->batch_stride, ctx->stream) : launch_wkv4(wp, ctx->stream);
 }
 
-// LayerNorm + token shift + mix in front of a batch of GEMVs. In a single-token pass the previous GEMV launch (the one that wrote the
-// residual stream) normally ran it as its tail job (attach_tail): then nothing is launched here and the staged columns of the mixed
-// vectors are valid (*staged). Otherwise (first layer of a pass / layer group, multi-token passes, batch contexts, generic GEMV) it is
-// its own launch of ln_mix_kernel. Both produce the same bits. (Folding the LayerNorm into the CONSUMING GEMV instead -- every CTA
-// recomputing it in its prologue -- was built and measured in round 2: 4.24 vs 3.14 ms per 7B token; removed.)
+// LayerNorm + token shift + mix in front of a batch of GEMVs: its own launch (ln_mix_kernel), which in single-token passes also
+// leaves the mixed vectors as staged columns for their consumers (*staged). Two fusions were built, measured at 7B Q5_1 and removed
+// in round 2: (a) into the CONSUMING GEMV, every CTA recomputing the LayerNorm in its prologue: 4.24 vs 3.14 ms per token
+// (profiles/r2_trace_decode_c7_fuseln.log); (b) as the tail job of the PRODUCING GEMV (att.output / ffn.value), run by the CTA that
+// draws the last ticket: 3.62 vs 2.86 ms (profiles/r2_c11_ab_*.json) -- every CTA pays a device-wide fence + ticket before it may
+// retire, and the one CTA left behind does the LayerNorm of 4096 channels with 256 threads where this kernel uses 1024 and has its
+// parameter loads in flight before the dependency wait.
 bool ln_mix_then(Context * ctx, const LnMixParams & lp, bool * staged) {
-    *staged = ctx->ln_done_by_tail;
-    if (ctx->ln_done_by_tail) { ctx->ln_done_by_tail = false; return true; }
+    *staged = lp.T == 1 && !ctx->batch_stride && lp.C % 32 == 0 && lp.q_out[0] != nullptr;
     CUDA_OK(ctx, do_ln_mix(ctx, lp));
     return true;
 }
-// After a launch that carried a tail job: did the launcher honour it?
-void note_tail(Context * ctx, const GemvBatch & b) { ctx->ln_done_by_tail = b.tail.enabled != 0; }
 
 // LayerNorm + mix parameters of the channel-mixing block (rwkv_ffn_v4_v5 :484-511, rwkv_ffn_v6 :513-531, rwkv_ffn_v7 :533-543).
 LnMixParams ffn_ln(const Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out) {
@@ -227,9 +212,8 @@ LnMixParams ffn_ln(const Context * ctx, const Layer & L, const Scratch & s, int 
     return lp;
 }
 
-// Channel mixing, all versions. `next_ln`: the LayerNorm + mix of the block that follows (next layer's time mixing), run as the tail
-// job of the ffn.value launch when the pass allows it.
-bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const LnMixParams & lp, const LnMixParams * next_ln) {
+// Channel mixing, all versions.
+bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const LnMixParams & lp) {
     const Model & m = *ctx->model;
     const int C = m.n_embed;
     {
@@ -246,23 +230,18 @@ bool ffn(Context * ctx, const Layer & L, const Scratch & s, int T, const LnMixPa
         GemvProblem & p = b.add(L.ffn_value, s.ffn_k, s.x, m.arch_major == 7 ? EPI_ADD : EPI_MUL_ADD);
         p.res = s.x; p.ldres = C;
         p.gate = s.ffn_r; p.ldgate = C;
-        attach_tail(ctx, b.b, next_ln);
         if (!run_batch(ctx, b)) return false;
-        note_tail(ctx, b.b);
     }
     return true;
 }
 
-// yq: y as a staged column (written by the WKV kernel) or NULL; ffn_lp: the channel-mixing block's LayerNorm + mix = this launch's tail job
-bool att_output(Context * ctx, const Layer & L, const Scratch & s, int T, const unsigned char * yq, const LnMixParams * ffn_lp) {
+// yq: y as a staged column (written by the WKV kernel) or NULL
+bool att_output(Context * ctx, const Layer & L, const Scratch & s, int T, const unsigned char * yq) {
     Batch b(T);
     GemvProblem & p = b.add(L.att_output, s.y, s.x, EPI_ADD);   // x + Wo.y  (:182/:291/:384/:481 + residual :667-679)
     p.res = s.x; p.ldres = ctx->model->n_embed;
     xq_bind(p, yq, L.att_output.type);
-    attach_tail(ctx, b.b, ffn_lp);
-    if (!run_batch(ctx, b)) return false;
-    note_tail(ctx, b.b);
-    return true;
+    return run_batch(ctx, b);
 }
 
 // LayerNorm + mix parameters of the time-mixing block of layer `layer`, per architecture (:94-97, :306-311, :400-413), with the staged
@@ -296,7 +275,7 @@ LnMixParams att_ln(const Context * ctx, const Layer & L, int layer, const Scratc
     return lp;
 }
 
-bool att_v4(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out, const LnMixParams & lp, const LnMixParams * ffn_lp) {
+bool att_v4(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out, const LnMixParams & lp) {
     const int C = ctx->model->n_embed;
     Batch b(T);
     GemvProblem & pr = b.add(L.att_receptance, s.mix[2], s.r, EPI_SIGMOID);
@@ -314,10 +293,10 @@ bool att_v4(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     wp.y = s.y; wp.C = C; wp.T = T;
     wp.q_out = (C % 32 == 0) ? xq_slot(ctx, T, XQ_WKV, L.att_output) : nullptr; wp.q_type = L.att_output.type;
     CUDA_OK(ctx, do_wkv4(ctx, wp));
-    return att_output(ctx, L, s, T, wp.q_out, ffn_lp);
+    return att_output(ctx, L, s, T, wp.q_out);
 }
 
-bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out, const LnMixParams & lp, const LnMixParams * ffn_lp) {
+bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out, const LnMixParams & lp) {
     const Model & m = *ctx->model;
     const int C = m.n_embed;
     const bool v52 = m.arch_minor >= 2;
@@ -344,10 +323,10 @@ bool att_v5(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     wp.y = s.y; wp.eps = 1e-5f; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
     wp.q_out = (m.head_size % 32 == 0) ? xq_slot(ctx, T, XQ_WKV, L.att_output) : nullptr; wp.q_type = L.att_output.type;
     CUDA_OK(ctx, do_wkv6(ctx, wp));
-    return att_output(ctx, L, s, T, wp.q_out, ffn_lp);
+    return att_output(ctx, L, s, T, wp.q_out);
 }
 
-bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out, const LnMixParams & lp, const LnMixParams * ffn_lp) {
+bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const float * st_in, float * st_out, const LnMixParams & lp) {
     const Model & m = *ctx->model;
     const int C = m.n_embed;
     {   // :313-321  tanh(W1 . xxx)
@@ -394,10 +373,10 @@ bool att_v6(Context * ctx, const Layer & L, const Scratch & s, int T, const floa
     wp.g = s.g; wp.y = s.y; wp.eps = 64e-5f; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
     wp.q_out = (m.head_size % 32 == 0) ? xq_slot(ctx, T, XQ_WKV, L.att_output) : nullptr; wp.q_type = L.att_output.type;
     CUDA_OK(ctx, do_wkv6(ctx, wp));
-    return att_output(ctx, L, s, T, wp.q_out, ffn_lp);
+    return att_output(ctx, L, s, T, wp.q_out);
 }
 
-bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T, const float * st_in, float * st_out, const LnMixParams & lp, const LnMixParams * ffn_lp) {
+bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T, const float * st_in, float * st_out, const LnMixParams & lp) {
     const Model & m = *ctx->model;
     const int C = m.n_embed;
     const bool first = layer == 0;
@@ -431,7 +410,7 @@ bool att_v7(Context * ctx, const Layer & L, int layer, const Scratch & s, int T,
     wp.y = s.y; wp.H = m.head_count; wp.S = m.head_size; wp.T = T;
     wp.q_out = (m.head_size % 32 == 0) ? xq_slot(ctx, T, XQ_WKV, L.att_output) : nullptr; wp.q_type = L.att_output.type;
     CUDA_OK(ctx, ctx->batch_stride ? launch_wkv7_batch(wp, ctx->batch_stride, ctx->stream) : launch_wkv7(wp, ctx->stream));
-    return att_output(ctx, L, s, T, wp.q_out, ffn_lp);
+    return att_output(ctx, L, s, T, wp.q_out);
 }
 
 bool ensure_capacity(Context * ctx, int T) {
@@ -486,23 +465,19 @@ bool enqueue_pass(Context * ctx, int T, bool want_logits, int phase, int seg) {
         CUDA_OK(ctx, launch_embed_ln0(m.emb.data, m.emb.type, m.emb.pitch, ctx->tokens, T, C, m.ln0_w.data, m.ln0_b.data, s.x, ctx->stream));
     }   // a later pipeline stage / layer group finds x (and v_first) already in place
     const size_t per_layer = m.state_floats_per_layer();
-    ctx->ln_done_by_tail = false;
     for (int i = l0; i < l1; i++) {
         const Layer & L = m.layers[i];
         const float * st_in = ctx->state_a + (size_t) i * per_layer;
         float * st_out = ctx->state_b + (size_t) i * per_layer;
         const LnMixParams alp = att_ln(ctx, L, i, s, T, st_in, st_out), flp = ffn_ln(ctx, L, s, T, st_in, st_out);
-        LnMixParams next_alp{};
-        const bool has_next = i + 1 < l1;
-        if (has_next) next_alp = att_ln(ctx, m.layers[i + 1], i + 1, s, T, ctx->state_a + (size_t) (i + 1) * per_layer, ctx->state_b + (size_t) (i + 1) * per_layer);
         bool ok;
         switch (m.arch_major) {
-            case 7: ok = att_v7(ctx, L, i, s, T, st_in, st_out, alp, &flp); break;
-            case 6: ok = att_v6(ctx, L, s, T, st_in, st_out, alp, &flp); break;
-            case 5: ok = att_v5(ctx, L, s, T, st_in, st_out, alp, &flp); break;
-            default: ok = att_v4(ctx, L, s, T, st_in, st_out, alp, &flp); break;
+            case 7: ok = att_v7(ctx, L, i, s, T, st_in, st_out, alp); break;
+            case 6: ok = att_v6(ctx, L, s, T, st_in, st_out, alp); break;
+            case 5: ok = att_v5(ctx, L, s, T, st_in, st_out, alp); break;
+            default: ok = att_v4(ctx, L, s, T, st_in, st_out, alp); break;
         }
-        if (!ok || !ffn(ctx, L, s, T, flp, has_next ? &next_alp : nullptr)) return false;
+        if (!ok || !ffn(ctx, L, s, T, flp)) return false;
     }
     if (want_logits && l1 == m.n_layer) {   // :705-708 / :851-854  head . LN(x_last; ln_out); a batch context wants every column
         Batch b(ctx->batch_n ? T : 1);
@@ -638,10 +613,9 @@ Context * create_context(Model * model, ErrorSink sink, int batch_n) {
         && cudaMalloc(reinterpret_cast<void **>(&ctx->state_b), seqs * n * sizeof(float)) == cudaSuccess
         && cudaMalloc(reinterpret_cast<void **>(&ctx->state_init), n * sizeof(float)) == cudaSuccess
         && cudaMalloc(reinterpret_cast<void **>(&ctx->logits), seqs * (size_t) model->n_vocab * sizeof(float)) == cudaSuccess;
-    if (ok && batch_n == 0) {      // staged-column hand-off slots (every handed-off vector has n_embed elements, at most 2 bytes each) + the tail-job ticket
+    if (ok && batch_n == 0) {      // staged-column hand-off slots (every handed-off vector has n_embed elements, at most 2 bytes each) 
         ctx->xq_slot_bytes = ((size_t) 2 * model->n_embed + 64 + 255) / 256 * 256;
-        ok = cudaMalloc(reinterpret_cast<void **>(&ctx->xq), (size_t) XQ_SLOTS * ctx->xq_slot_bytes) == cudaSuccess
-            && cudaMalloc(reinterpret_cast<void **>(&ctx->tail_counter), 256) == cudaSuccess && cudaMemset(ctx->tail_counter, 0, 256) == cudaSuccess;
+        ok = cudaMalloc(reinterpret_cast<void **>(&ctx->xq), (size_t) XQ_SLOTS * ctx->xq_slot_bytes) == cudaSuccess;
     }
     if (ok) {
         std::vector<float> init(n);
@@ -673,7 +647,7 @@ void destroy_context(Context * ctx) {
     if (model) cudaSetDevice(model->dev.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->state_a); cudaFree(ctx->state_b); cudaFree(ctx->state_init); cudaFree(ctx->logits);
-    cudaFree(ctx->tokens); cudaFree(ctx->scratch); cudaFree(ctx->trace_buf); cudaFree(ctx->act16); cudaFree(ctx->xq); cudaFree(ctx->tail_counter);
+    cudaFree(ctx->tokens); cudaFree(ctx->scratch); cudaFree(ctx->trace_buf); cudaFree(ctx->act16); cudaFree(ctx->xq);
     for (int i = 0; i < 2; i++) {
         if (ctx->tokens_host[i]) cudaFreeHost(ctx->tokens_host[i]);
         if (ctx->slot_free[i]) cudaEventDestroy(ctx->slot_free[i]);

@@ -40,8 +40,6 @@ struct Context {
     unsigned char * xq = nullptr;    // staged activation columns handed from producer kernels to single-token GEMVs (act_stage.cuh)
     size_t xq_slot_bytes = 0;
     cudaEvent_t pipe_done = nullptr; // in-process pipeline: end of this context's latest evaluation on its stage's stream
-    int * tail_counter = nullptr;    // device ticket of the GEMV tail job (gemv.h: LnTail); zero between launches
-    bool ln_done_by_tail = false;    // enqueue-time: the previous GEMV launch ran the next block's LayerNorm + mix as its tail job
     void * act16 = nullptr;          // fp16 copies of GEMM inputs for the tensor-core prefill path
     size_t act16_bytes = 0;
     bool use_tensor_cores = true;

@@ -16,8 +16,12 @@
 //     stage, no __syncthreads in the K loop.
 //   * At T = 128 the contraction is HBM-bound on the fp16 weights (128 FLOP per weight byte, ridge 221): the target is the
 //     copy bandwidth, i.e. 17 GB / 6.5 TB/s = 2.6 ms per 7B chunk = 58 % of the sustained bf16 peak, not the tensor peak.
-//   * Launches whose tiles would leave most SMs idle (4096-row matrices: 32 tiles; LoRA matrices: 1-2) are cut along K;
-//     the CTA that arrives last at a tile's counter adds the partial tiles up in split order (deterministic).
+//   * Launches whose tiles would leave most SMs idle (4096-row matrices: 32 tiles; LoRA matrices: 1-2) are cut along K over a
+//     thread-block CLUSTER of 2 / 4 / 8 CTAs per tile: every CTA parks its fp32 accumulator in its own (by then idle) ring memory,
+//     and after a cluster barrier CTA r adds up columns [r * npad / c, ...) of all c accumulators through distributed shared
+//     memory, in rank order (deterministic), and runs the fused epilogue on them. (First version: partial tiles through global
+//     memory, the last-arriving CTA adding all of them: 128 threads x up to 512 dependent L2 round trips, 60-100 us per launch --
+//     99 us on the critical path of every v6 layer for the 160 x 4096 LoRA matrix alone, profiles/r2_trace_prefill_c7_gemm_marks.log.)
 //
 // Numerics: weights exactly as the file stores them, rounded once to fp16 after dequantisation; activations are fp16 of the
 // reference's own operand values (convert_f16_kernel below); fp32 accumulation in the tensor core. Not bit-identical to the
@@ -139,7 +143,6 @@ struct TcShared {
     uint32_t tmem_base;
     GemvProblem P;
     float colscale[MAX_N];
-    int split_rank;          // arrival order of this CTA among the K-splits of its tile (split-K epilogue)
 };
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
@@ -176,13 +179,9 @@ template <int EPI> __device__ __forceinline__ void store_cols(const EpiRow & e, 
         e.y[(long long) col * e.ldy] = v;
     }
 }
-// Epilogue warp w owns TMEM lanes 32 (w % 4) .. + 31 = rows row0 + 32 (w % 4) + lane and walks all 32-column groups of the accumulator.
-//   MODE 0  single split: accumulator -> fused epilogue -> y
-//   MODE 1  one of several K-splits: accumulator -> this split's slot of the partial buffer (row-major [128][npad rounded up to 32], full-line stores)
-//   MODE 2  the split that arrived last: partials of ALL splits, added in split order from the buffer -> fused epilogue -> y
-template <int MODE>
-__device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, const float * cs, uint32_t tmem_base, int row0, int npad, int T,
-                                              float * part0, int nsplit, size_t slot_floats) {
+// Epilogue warp w owns TMEM lanes 32 (w % 4) .. + 31 = rows row0 + 32 (w % 4) + lane and walks all 32-column groups of the accumulator:
+// accumulator -> fused epilogue -> y (a tile that was not cut along K).
+__device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, const float * cs, uint32_t tmem_base, int row0, int npad, int T) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3;
     const int row = row0 + q * 32 + lane;
@@ -192,35 +191,11 @@ __device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, const flo
     e.y = Psh.y + row; e.ldy = Psh.ldy;
     e.res = Psh.res ? Psh.res + row : nullptr; e.ldres = Psh.ldres;
     e.gate = Psh.gate ? Psh.gate + row : nullptr; e.ldgate = Psh.ldgate;
-    e.bias = (MODE != 1 && live && Psh.bias) ? Psh.bias[row] : 0.f;
-    // partial rows are (npad rounded up to 32) floats apart: the loop below moves whole 32-column groups, and with a stride of npad the
-    // last group of a row would spill into the next row's partial whenever npad is not a multiple of 32
-    float * prow = part0 + (size_t) (q * 32 + lane) * (size_t) ((npad + 31) & ~31);
+    e.bias = (live && Psh.bias) ? Psh.bias[row] : 0.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < npad; c0 += 32) {
         uint32_t acc[32];
-        if constexpr (MODE == 2) {
-#pragma unroll
-            for (int j = 0; j < 32; j++) acc[j] = 0u;          // +0.0f
-            for (int sp = 0; sp < nsplit; sp++) {
-                const float4 * src = reinterpret_cast<const float4 *>(prow + (size_t) sp * slot_floats + c0);
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float4 v = __ldcg(src + j);            // written by other SMs: L2, not L1
-                    acc[4 * j] = __float_as_uint(__uint_as_float(acc[4 * j]) + v.x); acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + v.y);
-                    acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + v.z); acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + v.w);
-                }
-            }
-        } else {
-            tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) c0, acc);
-        }
-        if constexpr (MODE == 1) {
-            float4 * dst = reinterpret_cast<float4 *>(prow + c0);
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                __stcg(dst + j, make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3])));
-            continue;
-        }
+        tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) c0, acc);
         if (!live) continue;
         switch (epi) {
             case EPI_SIGMOID: store_cols<EPI_SIGMOID>(e, acc, cs, c0, T); break;
@@ -233,6 +208,83 @@ __device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, const flo
             case EPI_BIAS_SIGMOID: store_cols<EPI_BIAS_SIGMOID>(e, acc, cs, c0, T); break;
             case EPI_BIAS_W7: store_cols<EPI_BIAS_W7>(e, acc, cs, c0, T); break;
             default: store_cols<EPI_NONE>(e, acc, cs, c0, T); break;
+        }
+    }
+}
+
+// ---- K-split over a thread-block cluster --------------------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_sync_all() {      // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ float ld_dsmem(uint32_t addr) { float v; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+
+// Step 1 (epilogue warps): this CTA's accumulator -> its own ring memory, column-major [npad][128] fp32 (thread = tile row: a warp
+// writes 32 consecutive floats per column, conflict-free).
+__device__ __noinline__ void tc_park_accumulator(uint32_t tmem_base, float * park, int npad) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3;
+    const int r = q * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < npad; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) c0, acc);
+#pragma unroll
+        for (int j = 0; j < 32; j++) if (c0 + j < npad) park[(size_t) (c0 + j) * TILE_M + r] = __uint_as_float(acc[j]);
+    }
+}
+__device__ __forceinline__ float tc_epilogue_value(int epi, float v, float res, float gate, float bias) {
+    switch (epi) {
+        case EPI_SIGMOID: return sigmoidf_(v);
+        case EPI_SILU: return v / (1.0f + expf(-v));
+        case EPI_TANH: return tanhf(v);
+        case EPI_RELU_SQR: { const float r = fmaxf(v, 0.0f); return r * r; }
+        case EPI_ADD: return res + v;
+        case EPI_MUL_ADD: return res + gate * v;
+        case EPI_BIAS_EXPNEGEXP: return expf(-expf(v + bias));
+        case EPI_BIAS_SIGMOID: return sigmoidf_(v + bias);
+        case EPI_BIAS_W7: return expf(sigmoidf_(v + bias) * -0.606531f);
+        default: return v;
+    }
+}
+// Step 2 (epilogue warps, after the cluster barrier): columns [rank * cpr, (rank + 1) * cpr) of the tile = sum over the cluster's
+// accumulators in rank order -> fused epilogue -> y. Thread = tile row: loads from a peer and the stores to y are 128-byte runs.
+__device__ __noinline__ void tc_reduce_columns(const GemvProblem & Psh, const float * cs, const float * park, int row0, int npad, int T, int csize) {
+    const int r = (int) threadIdx.x - EPI_WARP0 * 32;            // 0..127
+    const int row = row0 + r;
+    const bool live = row < Psh.M;
+    const uint32_t rank = cluster_ctarank();
+    const int cpr = (npad + csize - 1) / csize;
+    const int c_lo = (int) rank * cpr, c_hi = min(min(npad, T), c_lo + cpr);
+    const int epi = Psh.epi;
+    const float bias = (live && Psh.bias) ? Psh.bias[row] : 0.f;
+    const uint32_t park0 = smem_u32(park) + (uint32_t) r * 4u;
+    uint32_t peer[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) peer[p] = map_to_cta(park0, (uint32_t) (p < csize ? p : 0));
+    constexpr int CB = 4;                                        // columns in flight per thread
+#pragma unroll 1
+    for (int c0 = c_lo; c0 < c_hi; c0 += CB) {
+        float part[CB][8], res[CB], gate[CB];
+#pragma unroll
+        for (int j = 0; j < CB; j++) {
+            const int c = min(c0 + j, c_hi - 1);
+            res[j] = (live && Psh.res) ? Psh.res[(long long) c * Psh.ldres + row] : 0.f;
+            gate[j] = (live && Psh.gate) ? Psh.gate[(long long) c * Psh.ldgate + row] : 0.f;
+#pragma unroll
+            for (int p = 0; p < 8; p++) part[j][p] = p < csize ? ld_dsmem(peer[p] + (uint32_t) c * (TILE_M * 4u)) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < CB; j++) {
+            const int c = c0 + j;
+            if (c >= c_hi || !live) continue;
+            float v = 0.f;
+#pragma unroll
+            for (int p = 0; p < 8; p++) if (p < csize) v += part[j][p];
+            Psh.y[(long long) c * Psh.ldy + row] = tc_epilogue_value(epi, v * cs[c], res[j], gate[j], bias);
         }
     }
 }
@@ -308,13 +360,11 @@ struct TcBatch {
     const __half * act16[GEMV_MAX_PROBLEMS];   // canonical-layout fp16 activations per problem (convert_f16_kernel)
     const float * colscale[GEMV_MAX_PROBLEMS]; // [npad] power-of-two factor per token that the epilogue multiplies back in
     GemvProblem p[GEMV_MAX_PROBLEMS];          // first_cta / n_cta: CTA range of the problem = splits x tiles
-    // Work decomposition: a problem's CTAs are [split][tile]. With splits > 1 every CTA contracts `steps_per_split` K-steps and
-    // leaves its 128 x npad partial tile in `partial`; the CTA that arrives last at the tile's counter adds the partials up in split
-    // order (a fixed order: deterministic) and runs the epilogue.
+    // Work decomposition. The launch runs in clusters of `cluster` CTAs (1, 2, 4 or 8). A problem is either cut along K into exactly
+    // `cluster` splits -- its CTA (tile, split) = (local / cluster, local % cluster): the cluster IS the tile, split = cluster rank --
+    // or not cut at all (splits = 1, CTA local = tile; its CTA range is padded to a multiple of the cluster size, the padding exits).
+    int cluster;
     int tiles[GEMV_MAX_PROBLEMS], splits[GEMV_MAX_PROBLEMS], steps_per_split[GEMV_MAX_PROBLEMS];
-    int slot0[GEMV_MAX_PROBLEMS];              // first partial slot / counter of the problem (slot = slot0 + tile * splits + split)
-    float * partial;                           // [slots][128][npad rounded up to 32] fp32
-    int * counters;                            // one per (problem, tile) with splits > 1, at index slot0 + tile * splits; zero between launches
     TraceRec * trace;
 };
 
@@ -326,6 +376,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int pi = 0;
     for (int i = 1; i < batch.n; i++) if ((int) blockIdx.x >= batch.p[i].first_cta) pi = i;
+    // padding CTAs of an un-split problem (its CTA range is rounded up to whole clusters): nothing to do, and nobody in their
+    // cluster talks to them (cluster barriers and distributed shared memory are used by K-split tiles only)
+    if (batch.splits[pi] == 1 && (int) blockIdx.x - batch.p[pi].first_cta >= batch.tiles[pi]) return;
     const int nst = batch.stages;
     if (tid == 0) {
         sh.P = batch.p[pi];
@@ -342,8 +395,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
     const uint32_t b_bytes = (uint32_t) NPAD * KSTEP * 2, stage_bytes = A_BYTES + b_bytes;
     const int nsteps_total = P.K / KSTEP;
     const int local = (int) blockIdx.x - P.first_cta, ntiles = batch.tiles[pi];
-    const int split = local / ntiles, tile = local % ntiles;
     const int nsplit = batch.splits[pi];
+    const int split = nsplit > 1 ? local % nsplit : 0, tile = nsplit > 1 ? local / nsplit : local;
+    (void) ntiles;
     const int ks0 = split * batch.steps_per_split[pi], ks1 = min(nsteps_total, ks0 + batch.steps_per_split[pi]);
     const int n = ks1 - ks0;                   // K-steps of this CTA (>= 1 by construction)
     const int row0 = tile * TILE_M;
@@ -413,7 +467,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
             }
         }
     } else {
-        // ===== epilogue (warps 2-5): residual / gate inputs (and, with K-splits, the partial buffer) belong to the previous kernels
+        // ===== epilogue (warps 2-5): residual / gate inputs belong to the previous kernels
         // until the programmatic-dependency wait
         asm volatile("griddepcontrol.wait;" ::: "memory");
         const int et = tid - EPI_WARP0 * 32;
@@ -421,23 +475,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
         asm volatile("bar.sync 2, 128;" ::: "memory");
         mbar_wait(&sh.acc_done, 0);
         tc_fence_after_sync();
-        if (nsplit == 1) {
-            tc_epilogue_rows<0>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, nullptr, 1, 0);
-        } else {
-            const size_t slot_floats = (size_t) TILE_M * (size_t) ((NPAD + 31) & ~31);
-            const int slot_first = batch.slot0[pi] + tile * nsplit;
-            float * part0 = batch.partial + (size_t) slot_first * slot_floats;
-            tc_epilogue_rows<1>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, part0 + (size_t) split * slot_floats, nsplit, slot_floats);
-            __threadfence();                                    // my partial is visible device-wide before I take a ticket
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (et == 0) sh.split_rank = atomicAdd(batch.counters + slot_first, 1);
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (sh.split_rank == nsplit - 1) {                  // every other split's partial has been published before its ticket
-                __threadfence();
-                tc_epilogue_rows<2>(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T, part0, nsplit, slot_floats);
-                if (et == 0) batch.counters[slot_first] = 0;    // ready for the next launch (ordered by kernel completion)
-            }
-        }
+        if (nsplit == 1) tc_epilogue_rows(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T);
+        else tc_park_accumulator(sh.tmem_base, reinterpret_cast<float *>(smem), NPAD);      // acc_done: every MMA has finished reading the ring
+    }
+    if (nsplit > 1) {
+        // every thread of the cluster: accumulators parked -> [barrier] -> each CTA reduces its column slice out of all of them ->
+        // [barrier] so that no CTA retires (and frees its shared memory) while a peer still reads it
+        __syncwarp();
+        cluster_sync_all();
+        if (warp >= EPI_WARP0) tc_reduce_columns(P, sh.colscale, reinterpret_cast<const float *>(smem), row0, NPAD, batch.T, nsplit);
+        __syncwarp();
+        cluster_sync_all();
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -603,8 +651,7 @@ bool gemm_tc_supported(const GemvProblem & p, int T) {
            (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.Wt) & 15) == 0;
 }
 
-// Workspace layout (gemm_tc_workspace_bytes): [split-K tile counters, zero between launches][split-K partial tiles][fp16 operands +
-// per-token scales of the batch's distinct inputs]. The caller zeroes the counter block once after allocating.
+// Workspace layout (gemm_tc_workspace_bytes): [reserved header][fp16 operands + per-token scales of the batch's distinct inputs].
 size_t gemm_tc_workspace_bytes(int T, size_t operand_halves) {
     const size_t npad = (size_t) (T + 15) / 16 * 16;
     return GEMM_TC_COUNTER_BYTES + GEMM_TC_PARTIAL_BYTES + operand_halves * 2 + (size_t) GEMV_MAX_PROBLEMS * (npad * 4 + 512);
@@ -618,8 +665,6 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
     tb.npad = (batch.T + 15) / 16 * 16;
     tb.tmem_cols = 32;
     while (tb.tmem_cols < tb.npad) tb.tmem_cols *= 2;      // the accumulator
-    tb.counters = reinterpret_cast<int *>(workspace);
-    tb.partial = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(workspace) + GEMM_TC_COUNTER_BYTES);
 
     uint8_t * scratch = reinterpret_cast<uint8_t *>(workspace) + GEMM_TC_COUNTER_BYTES + GEMM_TC_PARTIAL_BYTES;
     const size_t scratch_bytes = workspace_bytes - GEMM_TC_COUNTER_BYTES - GEMM_TC_PARTIAL_BYTES;
@@ -650,32 +695,33 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
         tb.colscale[i] = cvt.colscale[shared];
     }
     // ---- work decomposition: one CTA per (row tile, K-split). Every CTA streams its share of the weights from HBM, so what matters
-    // is that close to all SMs have a CTA: launches with few tiles (4096-row matrices: 32; LoRA: 1-2) are cut along K.
+    // is that close to all SMs have a CTA: launches with few tiles (4096-row matrices: 32; LoRA: 1-2) are cut along K over clusters
+    // of c = 2 / 4 / 8 CTAs (a problem is cut c ways or not at all: the cluster size is one per launch).
     static const int force_split = [] { const char * e = getenv("RWKV_B200_TC_SPLITK"); return e ? atoi(e) : -1; }();
     int total = 0;
     for (int i = 0; i < batch.n; i++) { tb.tiles[i] = (batch.p[i].M + tc::TILE_M - 1) / tc::TILE_M; total += tb.tiles[i]; }
     const int sms = dev.num_sms > 0 ? dev.num_sms : 148;
     int want = total * 4 < sms * 3 ? sms / total : 1;      // below 75 % of the SMs: split, but never into a second wave
     if (force_split >= 0) want = force_split < 1 ? 1 : force_split;
-    const size_t slot_bytes = (size_t) tc::TILE_M * (size_t) ((tb.npad + 31) & ~31) * sizeof(float);
-    const int slot_cap = (int) (GEMM_TC_PARTIAL_BYTES / slot_bytes), ctr_cap = (int) (GEMM_TC_COUNTER_BYTES / sizeof(int));
-    int next = 0, slots = 0;
+    int cluster = 1;
+    while (cluster * 2 <= want && cluster < 8) cluster *= 2;
+    bool any_split = false;
+    for (int i = 0; i < batch.n; i++) {
+        const int nsteps = batch.p[i].K / tc::KSTEP;
+        const int per = (nsteps + cluster - 1) / cluster;
+        // at least four K-steps per split, and the last split must not come out empty
+        const bool cut = cluster > 1 && nsteps >= 4 * cluster && (cluster - 1) * per < nsteps;
+        tb.splits[i] = cut ? cluster : 1;
+        tb.steps_per_split[i] = cut ? per : nsteps;
+        any_split = any_split || cut;
+    }
+    if (!any_split) cluster = 1;
+    tb.cluster = cluster;
+    int next = 0;
     for (int i = 0; i < batch.n; i++) {
         GemvProblem & p = batch.p[i];
-        const int nsteps = p.K / tc::KSTEP;
-        int splits = want;
-        if (splits > 32) splits = 32;
-        if (splits > nsteps / 4) splits = nsteps / 4;                   // at least four K-steps per split
-        if (splits < 1) splits = 1;
-        int per = (nsteps + splits - 1) / splits;
-        splits = (nsteps + per - 1) / per;
-        if (splits > 1 && (slots + tb.tiles[i] * splits > slot_cap || slots + tb.tiles[i] * splits > ctr_cap)) { splits = 1; per = nsteps; }
-        tb.splits[i] = splits;
-        tb.steps_per_split[i] = splits == 1 ? nsteps : per;
-        tb.slot0[i] = slots;
-        if (splits > 1) slots += tb.tiles[i] * splits;
-        p.first_cta = next;
-        p.n_cta = tb.tiles[i] * splits;
+        p.first_cta = next;                                               // a multiple of the cluster size
+        p.n_cta = tb.splits[i] > 1 ? tb.tiles[i] * cluster : (tb.tiles[i] + cluster - 1) / cluster * cluster;
         next += p.n_cta;
         tb.p[i] = p;
     }
@@ -700,7 +746,27 @@ cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream
     if (ae != cudaSuccess) return ae;
     tb.trace = trace_slot("gemm_tc");
     g_kernel_launches++;
-    return launch_pdl(tc::gemm_tc_kernel, dim3((unsigned) next), dim3(tc::THREADS), smem, stream, tb);      // (launch_pdl also pins the carve-out)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned) next);
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned) cluster; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        na++;
+    }
+    if (g_use_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = (unsigned) na;
+    prefer_max_shared_carveout(reinterpret_cast<const void *>(tc::gemm_tc_kernel));
+    return cudaLaunchKernelEx(&cfg, tc::gemm_tc_kernel, tb);
 }
 
 }  // namespace rwkv

@@ -350,7 +350,6 @@ cudaError_t gemv_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t 
 }
 
 cudaError_t gemv_generic_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream) {
-    batch.tail.enabled = 0;           // the tail job exists in the streaming kernel only: the caller launches ln_mix itself
     batch.trace = trace_slot("gemv_generic");
     // CTA budget split over the problems in proportion to their weight bytes.
     const int total_ctas = dev.num_sms * CTAS_PER_SM;

@@ -58,32 +58,11 @@ inline TraceRec * trace_slot(const char * name) {
     return g_trace_base + g_trace_next++;
 }
 
-// Tail job of a single-token streaming launch that writes the residual stream x (att.output / ffn.value): the CTA that finishes LAST
-// (device-side ticket) runs the LayerNorm + token shift + mix of the NEXT block on the finished x, i.e. what ln_mix_kernel would do as
-// a separate launch -- one launch boundary, one dependency release and one single-SM kernel less per block. Arithmetic = ln_mix_kernel's
-// (steps::ln_center_scale_256 reproduces its reduction tree), so results do not change. The mixed vectors also leave in the staged
-// layout of their consumers (q_out, act_stage.cuh).
-struct LnTail {
-    int enabled;
-    int C, formula, n_out;
-    const float * x;          // [C] residual stream (written by this launch)
-    const float * ln_w, * ln_b;
-    const float * state_in;   // [C] previous token's LN(x)
-    float * state_out;        // [C] <- LN(x)
-    const float * coef[6];
-    float * out[6];
-    float * out_xx, * out_sx; // optional
-    unsigned char * q_out[6]; // optional staged columns
-    int q_type[6];
-    int * counter;            // device int, zero between launches
-};
-
 constexpr int GEMV_MAX_PROBLEMS = 8;
 struct GemvBatch {
     int n, T;
     TraceRec * trace;
     long long max_col_bytes, stage_bytes; // streaming kernel only: shared-memory carve-up
-    LnTail tail;                          // streaming kernel, T == 1 only; the launcher clears tail.enabled when it cannot honour it
     GemvProblem p[GEMV_MAX_PROBLEMS];
 };
 
@@ -111,7 +90,7 @@ cudaError_t gemm_tc_repack(const void * W, long long pitch, int type, int M, int
 // workspace: gemm_tc_workspace_bytes(T, sum over the batch's distinct inputs of round16(T) * K) bytes of device memory whose first
 // GEMM_TC_COUNTER_BYTES were zeroed once after the allocation (split-K tile counters; every launch leaves them zero again).
 constexpr size_t GEMM_TC_COUNTER_BYTES = 4096;
-constexpr size_t GEMM_TC_PARTIAL_BYTES = (size_t) 24 << 20;      // split-K partial tiles: 384 slots of 128 x 128 fp32
+constexpr size_t GEMM_TC_PARTIAL_BYTES = 0;                      // (K-splits are reduced through distributed shared memory: no global partials)
 size_t gemm_tc_workspace_bytes(int T, size_t operand_halves);
 cudaError_t gemm_tc_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStream_t stream, void * workspace, size_t workspace_bytes);
 

@@ -19,49 +19,12 @@
 // WK, itself a function of (type, K, pitch) alone -- never of T, the batch composition or the tile size. A token
 // evaluated alone and inside a chunk therefore produces identical bits (tests/test_eval_sequence_in_chunks.c:54).
 #include "gemv_tma_device.cuh"
-#include "decode_steps.cuh"
 #include "act_stage.cuh"
 
 #include <cstdlib>
 
 namespace rwkv {
 namespace tma {
-
-// The tail job (gemv.h: LnTail), run by the 256 consumer threads of the launch's last CTA: LayerNorm + token shift + mix of the next
-// block. Thread t owns channels t + 256 m, so warp w's 32 lanes hold 32-element block w + 8 m of every vector: the staged columns of
-// the consumers come out of warp-level reductions (act::warp_emit_block). Same per-element operations and reduction trees as
-// ln_mix_kernel<PER> (glue.cu) for T = 1.
-static __device__ __noinline__ void ln_mix_tail(const LnTail & p, double (* slots)[32]) {
-    using steps::LN_MAXCH;
-    const int C = p.C, t = threadIdx.x, warp = t >> 5;
-    float lw[LN_MAXCH], lb[LN_MAXCH], pv[LN_MAXCH];
-#pragma unroll
-    for (int m = 0; m < LN_MAXCH; m++) {
-        const int c = t + 256 * m;
-        const bool live = c < C;
-        lw[m] = live ? p.ln_w[c] : 0.f;
-        lb[m] = live ? p.ln_b[c] : 0.f;
-        pv[m] = live ? p.state_in[c] : 0.f;
-    }
-    float xa[LN_MAXCH], scale_a;
-    steps::ln_center_scale_256(p.x, C, xa, scale_a, slots);
-#pragma unroll
-    for (int m = 0; m < LN_MAXCH; m++) {
-        const int c = t + 256 * m;
-        if (256 * m + 32 * warp >= C) break;                        // warp-uniform: C is a multiple of 32
-        const float xx = __fadd_rn(__fmul_rn(__fmul_rn(xa[m], scale_a), lw[m]), lb[m]);     // LN(x)
-        p.state_out[c] = xx;
-        if (p.out_xx) p.out_xx[c] = xx;
-        if (p.out_sx) p.out_sx[c] = __fsub_rn(pv[m], xx);
-        for (int j = 0; j < p.n_out; j++) {
-            const float cf = p.coef[j][c];
-            const float v = (p.formula == 0) ? __fadd_rn(__fmul_rn(xx, cf), __fsub_rn(pv[m], __fmul_rn(pv[m], cf)))
-                                             : __fadd_rn(__fmul_rn(__fsub_rn(pv[m], xx), cf), xx);
-            p.out[j][c] = v;
-            if (p.q_out[j]) act::warp_emit_block(act::StagedOut{p.q_out[j], p.q_type[j], C}, 8 * m + warp, v);
-        }
-    }
-}
 
 template <int NC, bool STAGE_V2 = false>
 __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch batch) {
@@ -157,19 +120,6 @@ __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch ba
         }
 #undef RWKV_CONSUME_REGS
 #undef RWKV_CONSUME_SMEM
-    }
-    if (NC == 1 && batch.tail.enabled) {
-        // every consumer thread's stores -> visible device-wide -> one ticket per CTA; the CTA that draws the last ticket knows that
-        // all of x has been written and is visible to it
-        __threadfence();
-        consumer_barrier();
-        if (threadIdx.x == 0) sh.ticket = atomicAdd(batch.tail.counter, 1);
-        consumer_barrier();
-        if (sh.ticket == (int) gridDim.x - 1) {
-            __threadfence();
-            ln_mix_tail(batch.tail, sh.slots);
-            if (threadIdx.x == 0) *batch.tail.counter = 0;      // ready for the next launch (ordered by kernel completion)
-        }
     }
     trace_end(batch.trace);
 }
@@ -311,7 +261,6 @@ cudaError_t gemv_tma_launch(GemvBatch & batch, const DeviceInfo & dev, cudaStrea
     else if (batch.T >= 2 && stage_for(2) >= NOMINAL_STAGE_BYTES) nc = 2;
     const long long stage_bytes = stage_for(nc);
     if (stage_bytes < NOMINAL_STAGE_BYTES) return cudaErrorNotSupported;
-    if (batch.T != 1 || nc != 1 || batch.tail.C > 256 * steps::LN_MAXCH || batch.tail.C % 32 != 0 || !batch.tail.counter) batch.tail.enabled = 0;
     // two CTAs per SM
     const int next = assign_tiles_and_ctas(batch, 2 * dev.num_sms, stage_bytes);
     batch.max_col_bytes = (long long) max_col;

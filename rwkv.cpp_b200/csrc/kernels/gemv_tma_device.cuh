@@ -15,10 +15,11 @@ constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
 constexpr int THREADS = CONSUMER_THREADS + 32;      // + one producer warp
 constexpr int NSTAGES = 3;
 constexpr int NOMINAL_STAGE_BYTES = 28 * 1024;      // WK is planned against this size, whatever the launch really gets (>= this)
-// Dynamic shared memory per CTA so that TWO CTAs share an SM: 233 472 B per SM, 1 KB reserved per CTA, ~1.9 KB static (Shared) ->
-// at most 113 792 B dynamic. (With 112 KB the K = 14336 launches, whose carve-up rounds differently, came to 114 176 B and ran ONE
-// CTA per SM: the ffn-value GEMV was the slowest launch of the layer, profiles/r2_trace_decode_c4.log.)
-constexpr int CTA_SMEM_BUDGET = 111 * 1024;
+// Dynamic shared memory per CTA so that TWO CTAs share an SM: 233 472 B per SM, 1 KB reserved per CTA, ~1.4 KB static (Shared).
+// 110 KB gives the same tile heights as 111 KB for every shape of the BASELINE configurations (8 rows at K = 4096 Q5_1, 2 at
+// K = 14336) and leaves 1 KB of slack: at 111 KB half a kilobyte more of static shared memory would silently halve the occupancy.
+// (With 112 KB the K = 14336 launches came to 114 176 B and ran ONE CTA per SM, profiles/r2_trace_decode_c4.log.)
+constexpr int CTA_SMEM_BUDGET = 110 * 1024;
 constexpr int MAX_TILE_ROWS = 64;
 constexpr int MAX_BLOCKS_PER_LANE = 4;              // activation blocks a lane keeps in registers
 
@@ -149,8 +150,6 @@ struct Shared {
     uint64_t full[NSTAGES];
     uint64_t empty[NSTAGES];
     double red_d[CONSUMER_WARPS + 1];
-    double slots[2][32];      // LayerNorm partials of the tail job (steps::ln_center_scale_256)
-    int ticket;               // arrival order of this CTA at the end of the launch (tail job)
     TraceRec * trace;
     GemvProblem P;
 };

@@ -124,21 +124,23 @@ __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const LnMixParams p)
         xb[i] = (t > 0) ? __fadd_rn(__fmul_rn(__fmul_rn(xb[i], scale_b), lw[i]), lb[i]) : pv[i];          // LN(x[:, t-1]) or the carry
     }
     const size_t o0 = (size_t) t * C + tid;
+    // single-token passes with C % 32 == 0 (the caller checks): the 32 lanes of a warp hold one 32-element block of every mixed vector,
+    // which also leaves as a staged column (act_stage.cuh) for the GEMV that consumes it
+    const bool emit = p.T == 1;
 #pragma unroll 1
     for (int j = 0; j < p.n_out; j++) {     // rolled: kernel parameters are indexable in the constant bank
         const float * coef = p.coef[j];
         float * out = p.out[j];
-        if (p.formula == 0) {
+        const act::StagedOut so{emit ? p.q_out[j] : nullptr, p.q_type[j], C};
 #pragma unroll
-            for (int i = 0; i < PER; i++) {
-                const int c = tid + i * LN_THREADS;
-                if (c < C) { const float m = coef[c]; out[o0 + i * LN_THREADS] = __fadd_rn(__fmul_rn(xa[i], m), __fsub_rn(xb[i], __fmul_rn(xb[i], m))); }
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < PER; i++) {
-                const int c = tid + i * LN_THREADS;
-                if (c < C) out[o0 + i * LN_THREADS] = __fadd_rn(__fmul_rn(__fsub_rn(xb[i], xa[i]), coef[c]), xa[i]);
+        for (int i = 0; i < PER; i++) {
+            const int c = tid + i * LN_THREADS;
+            if (c < C) {
+                const float m = coef[c];
+                const float v = (p.formula == 0) ? __fadd_rn(__fmul_rn(xa[i], m), __fsub_rn(xb[i], __fmul_rn(xb[i], m)))
+                                                 : __fadd_rn(__fmul_rn(__fsub_rn(xb[i], xa[i]), m), xa[i]);
+                out[o0 + i * LN_THREADS] = v;
+                if (so.dst) act::warp_emit_block(so, c >> 5, v);      // c < C is warp-uniform here
             }
         }
     }

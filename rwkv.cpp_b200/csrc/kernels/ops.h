@@ -29,8 +29,8 @@ struct LnMixParams {
     float * out[6];           // [C, T] each
     float * out_xx;           // optional [C, T]: LN(x)
     float * out_sx;           // optional [C, T]: prev - xx
-    // T == 1, C % 32 == 0, LN done as the tail job of the GEMV that wrote x (gemv.h: LnTail) only: out_j additionally as the staged column
-    // (act_stage.cuh) of a consumer with weight type q_type[j]; ln_mix_kernel itself ignores these
+    // T == 1, C % 32 == 0 only: out_j additionally as the staged column (act_stage.cuh) of a consumer with weight type q_type[j]
+    // (NULL: not wanted); the batch kernel ignores these
     unsigned char * q_out[6];
     int q_type[6];
 };
