@@ -151,6 +151,11 @@ RWKV_API void rwkv_b200_set_tensor_cores(struct rwkv_context * ctx, bool enabled
  * upload - evaluate - download order. On by default; RWKV_B200_OVERLAP=0/1 sets the default of new contexts. rwkv_eval_sequence_in_chunks
  * pipelines the upload against its first chunk and the download against its last one. */
 RWKV_API void rwkv_b200_set_overlap(struct rwkv_context * ctx, bool enabled);
+/* Pageable caller buffers (what the reference's bindings pass: python/rwkv_cpp/rwkv_cpp_model.py:330-351): with overlap on, a host
+ * state of at least `bytes` bytes (default 4 MiB; process-wide) that is neither pinned nor device memory is copied slice by slice
+ * through pinned bounce buffers of the context by two helper threads, in step with the layer groups, instead of by the driver's
+ * synchronous pageable staging. Same bytes either way. RWKV_B200_NO_BOUNCE=1 turns the bounce path off. */
+RWKV_API void rwkv_b200_set_bounce_min_bytes(size_t bytes);
 /* Number of layer groups the overlapped path uses for this context (0 = overlap off or a single group). */
 RWKV_API int rwkv_b200_overlap_groups(const struct rwkv_context * ctx);
 

@@ -494,6 +494,7 @@ bool rwkv_b200_profile_pass(struct rwkv_context * ctx, const uint32_t * tokens, 
 void rwkv_b200_set_graphs(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_graphs = enabled; }
 void rwkv_b200_set_tensor_cores(struct rwkv_context * ctx, bool enabled) { C(ctx)->use_tensor_cores = enabled; }
 void rwkv_b200_set_overlap(struct rwkv_context * ctx, bool enabled) { C(ctx)->overlap_copies = enabled; }
+void rwkv_b200_set_bounce_min_bytes(size_t bytes) { g_bounce_min_bytes.store(bytes); }
 int rwkv_b200_overlap_groups(const struct rwkv_context * ctx) { return C(ctx)->overlap_copies && C(ctx)->n_segments > 1 ? C(ctx)->n_segments : 0; }
 static bool trace_rearm(Context * c) {
     std::vector<TraceRec> init(1024);

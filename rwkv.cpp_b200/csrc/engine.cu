@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "kernels/act_stage.cuh"
@@ -177,15 +179,17 @@ cudaError_t do_wkv4(Context * ctx, const Wkv4Params & wp) {
     return ctx->batch_stride ? launch_wkv4_batch(wp, ctx->batch_stride, ctx->stream) : launch_wkv4(wp, ctx->stream);
 }
 
-// LayerNorm + token shift + mix in front of a batch of GEMVs: its own launch (ln_mix_kernel), which in single-token passes also
-// leaves the mixed vectors as staged columns for their consumers (*staged). Two fusions were built, measured at 7B Q5_1 and removed
-// in round 2: (a) into the CONSUMING GEMV, every CTA recomputing the LayerNorm in its prologue: 4.24 vs 3.14 ms per token
-// (profiles/r2_trace_decode_c7_fuseln.log); (b) as the tail job of the PRODUCING GEMV (att.output / ffn.value), run by the CTA that
-// draws the last ticket: 3.62 vs 2.86 ms (profiles/r2_c11_ab_*.json) -- every CTA pays a device-wide fence + ticket before it may
-// retire, and the one CTA left behind does the LayerNorm of 4096 channels with 256 threads where this kernel uses 1024 and has its
-// parameter loads in flight before the dependency wait.
+// LayerNorm + token shift + mix in front of a batch of GEMVs: its own launch (ln_mix_kernel); *staged = the mixed vectors also left
+// as staged columns (never, today). Three variations were built, measured at 7B Q5_1 and removed in round 2:
+// (a) fused into the CONSUMING GEMV, every CTA recomputing the LayerNorm in its prologue: 4.24 vs 3.14 ms per token
+//     (profiles/r2_trace_decode_c7_fuseln.log);
+// (b) as the tail job of the PRODUCING GEMV (att.output / ffn.value), run by the CTA that draws the last ticket: 3.62 vs 2.86 ms
+//     (profiles/r2_c11_ab_*.json) -- every CTA pays a device-wide fence + ticket before it may retire, and the one CTA left behind does
+//     the LayerNorm of 4096 channels with 256 threads where this kernel uses 1024 and has its parameter loads in flight before the
+//     dependency wait;
+// (c) ln_mix_kernel emitting the staged columns of its consumers: 2.95 vs 2.86 ms (profiles/r2_c12_ab_default.json).
 bool ln_mix_then(Context * ctx, const LnMixParams & lp, bool * staged) {
-    *staged = lp.T == 1 && !ctx->batch_stride && lp.C % 32 == 0 && lp.q_out[0] != nullptr;
+    *staged = false;
     CUDA_OK(ctx, do_ln_mix(ctx, lp));
     return true;
 }
@@ -653,6 +657,8 @@ void destroy_context(Context * ctx) {
         if (ctx->slot_free[i]) cudaEventDestroy(ctx->slot_free[i]);
     }
     for (auto & g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (ctx->bounce_in) { cudaFreeHost(ctx->bounce_in); cudaFreeHost(ctx->bounce_out); cudaFreeHost(ctx->bounce_logits); }
+    for (int i = 0; i < Context::MAX_SEGMENTS; i++) if (ctx->seg_d2h[i]) cudaEventDestroy(ctx->seg_d2h[i]);
     if (ctx->copy_in) { cudaStreamSynchronize(ctx->copy_in); cudaStreamDestroy(ctx->copy_in); }
     if (ctx->copy_out) { cudaStreamSynchronize(ctx->copy_out); cudaStreamDestroy(ctx->copy_out); }
     if (ctx->pass_begin) cudaEventDestroy(ctx->pass_begin);
@@ -684,6 +690,54 @@ bool download_outputs(Context * ctx, float * state_out, float * logits_out) {
     return true;
 }
 
+// ---- pageable caller buffers ----------------------------------------------------------------------------------------------------
+// The reference's bindings hand over ordinary (pageable) memory (python/rwkv_cpp/rwkv_cpp_model.py:330-351: fresh torch / numpy buffers per
+// call). A cudaMemcpyAsync from pageable memory is staged by the driver on the calling thread, synchronously and at ~6 GB/s: the
+// eight slice copies of a 7B state took 5.8 ms before the first kernel was even enqueued (121 tok/s against 303 with pinned buffers,
+// profiles/r2_c8_*.json). Registering the caller's pages (cudaHostRegister) would be as fast as pinned memory, but a registration
+// outlives a free(): the next buffer malloc() places at the same address would be DMA'd from the OLD pages. So the state travels
+// through pinned bounce buffers owned by the context, copied by two helper threads (one per direction) slice by slice, in step with
+// the layer groups: memcpy of slice g+1 || H2D of slice g || kernels of group g-1 ... and the mirror image on the way out.
+static bool is_pageable_host(const void * p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+static bool bounce_enabled() {
+    static const bool on = getenv("RWKV_B200_NO_BOUNCE") == nullptr;
+    return on;
+}
+// states below this size go the plain way (two helper threads cost ~0.1 ms); rwkv_b200_set_bounce_min_bytes moves the bar (tests)
+std::atomic<size_t> g_bounce_min_bytes{(size_t) 4 << 20};
+static bool ensure_bounce(Context * ctx) {
+    if (ctx->bounce_in) return true;
+    const size_t bytes = ctx->model->state_len() * sizeof(float);
+    if (cudaMallocHost(reinterpret_cast<void **>(&ctx->bounce_in), bytes) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void **>(&ctx->bounce_out), bytes) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void **>(&ctx->bounce_logits), (size_t) ctx->model->n_vocab * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        if (ctx->bounce_in) cudaFreeHost(ctx->bounce_in);
+        if (ctx->bounce_out) cudaFreeHost(ctx->bounce_out);
+        ctx->bounce_in = ctx->bounce_out = ctx->bounce_logits = nullptr;
+        return false;                      // not an error: the caller falls back to plain copies
+    }
+    for (int i = 0; i < Context::MAX_SEGMENTS; i++)
+        if (cudaEventCreateWithFlags(&ctx->seg_d2h[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    return true;
+}
+// Joins the helper threads of one pass whatever way the pass ends.
+struct BounceThreads {
+    std::thread in, out;
+    std::atomic<int> in_done{0};        // slices memcpy'd into bounce_in
+    std::atomic<int> out_posted{0};     // slices whose D2H copy + event have been enqueued
+    std::atomic<bool> abort{false};
+    ~BounceThreads() {
+        abort.store(true);
+        if (in.joinable()) in.join();
+        if (out.joinable()) out.join();
+    }
+};
+
 // One pass with the caller's host state pipelined against the layer groups: H2D of group g+1 and D2H of group g-1 run on their
 // own streams while group g computes (the state layout is layer-major, rwkv_graph.inc:545-606, so a group is one contiguous
 // slice). state_in == NULL starts from the init image (a device copy); state_out / logits_out may be NULL.
@@ -692,40 +746,85 @@ static bool eval_host_overlapped(Context * ctx, const uint32_t * tokens, int T, 
     const int G = ctx->n_segments;
     if (!ensure_copy_streams(ctx)) return false;
     const size_t per_layer = m.state_floats_per_layer();
+    const size_t state_bytes = m.state_len() * sizeof(float);
+    // pageable caller memory takes the bounce path (worth two threads from a few MB on)
+    const bool big = state_bytes >= g_bounce_min_bytes.load() && bounce_enabled();
+    bool b_in = big && state_in && is_pageable_host(state_in);
+    bool b_out = big && state_out && is_pageable_host(state_out);
+    if ((b_in || b_out) && !ensure_bounce(ctx)) b_in = b_out = false;
+    const bool b_log = b_out && logits_out && is_pageable_host(logits_out);
+    const int dev = m.dev.device;
+    auto slice = [&](int g, size_t & off, size_t & cnt) { int l0, l1; segment_range(ctx, g, l0, l1); off = (size_t) l0 * per_layer; cnt = (size_t) (l1 - l0) * per_layer; };
+    BounceThreads bt;
+    if (b_in) bt.in = std::thread([&] {
+        for (int g = 1; g <= G && !bt.abort.load(); g++) {
+            size_t off, cnt; slice(g, off, cnt);
+            memcpy(ctx->bounce_in + off, state_in + off, cnt * sizeof(float));
+            bt.in_done.store(g, std::memory_order_release);
+        }
+    });
+    if (b_out) bt.out = std::thread([&] {
+        cudaSetDevice(dev);
+        for (int g = 1; g <= G; g++) {
+            while (bt.out_posted.load(std::memory_order_acquire) < g) { if (bt.abort.load()) return; std::this_thread::yield(); }
+            if (cudaEventSynchronize(ctx->seg_d2h[g - 1]) != cudaSuccess) return;
+            size_t off, cnt; slice(g, off, cnt);
+            memcpy(state_out + off, ctx->bounce_out + off, cnt * sizeof(float));
+        }
+    });
     // nothing of this pass may start before everything enqueued earlier on the context's stream has finished with the state
     CUDA_OK(ctx, cudaEventRecord(ctx->pass_begin, ctx->stream));
     CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->pass_begin, 0));
-    if (state_in) {
+    if (state_in && !b_in) {
         for (int g = 1; g <= G; g++) {
-            int l0, l1;
-            segment_range(ctx, g, l0, l1);
-            const size_t off = (size_t) l0 * per_layer, cnt = (size_t) (l1 - l0) * per_layer;
+            size_t off, cnt; slice(g, off, cnt);
             CUDA_OK(ctx, cudaMemcpyAsync(ctx->state_a + off, state_in + off, cnt * sizeof(float), cudaMemcpyDefault, ctx->copy_in));
             CUDA_OK(ctx, cudaEventRecord(ctx->seg_in[g - 1], ctx->copy_in));
         }
-    } else if (!resident_in) {
+    } else if (!state_in && !resident_in) {
         CUDA_OK(ctx, cudaMemcpyAsync(ctx->state_a, ctx->state_init, m.state_len() * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     }
     if (!begin_pass(ctx, tokens, T)) return false;
     const bool want_logits = logits_out != nullptr;
     for (int g = 1; g <= G; g++) {
+        if (b_in) {      // the slice is in pinned memory once the helper thread says so
+            while (bt.in_done.load(std::memory_order_acquire) < g) std::this_thread::yield();
+            size_t off, cnt; slice(g, off, cnt);
+            CUDA_OK(ctx, cudaMemcpyAsync(ctx->state_a + off, ctx->bounce_in + off, cnt * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in));
+            CUDA_OK(ctx, cudaEventRecord(ctx->seg_in[g - 1], ctx->copy_in));
+        }
         if (state_in) CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->seg_in[g - 1], 0));
         if (!run_layers(ctx, T, want_logits, g)) return false;
         CUDA_OK(ctx, cudaEventRecord(ctx->seg_out[g - 1], ctx->stream));
+        if (b_out && g > 1) {      // one group behind: the copy-out stream never waits for something that has not been enqueued
+            size_t off, cnt; slice(g - 1, off, cnt);
+            // the new state of group g-1 is in state_b until end_pass swaps the buffers
+            CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->seg_out[g - 2], 0));
+            CUDA_OK(ctx, cudaMemcpyAsync(ctx->bounce_out + off, ctx->state_b + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
+            CUDA_OK(ctx, cudaEventRecord(ctx->seg_d2h[g - 2], ctx->copy_out));
+            bt.out_posted.store(g - 1, std::memory_order_release);
+        }
     }
     if (!end_pass(ctx, T, want_logits)) return false;      // the new state is ctx->state_a from here on
-    if (logits_out) CUDA_OK(ctx, cudaMemcpyAsync(logits_out, ctx->logits, (size_t) m.n_vocab * sizeof(float), cudaMemcpyDefault, ctx->stream));
-    if (state_out) {
+    if (logits_out) CUDA_OK(ctx, cudaMemcpyAsync(b_log ? ctx->bounce_logits : logits_out, ctx->logits, (size_t) m.n_vocab * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    if (state_out && b_out) {
+        size_t off, cnt; slice(G, off, cnt);
+        CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->seg_out[G - 1], 0));
+        CUDA_OK(ctx, cudaMemcpyAsync(ctx->bounce_out + off, ctx->state_a + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
+        CUDA_OK(ctx, cudaEventRecord(ctx->seg_d2h[G - 1], ctx->copy_out));
+        bt.out_posted.store(G, std::memory_order_release);
+    } else if (state_out) {
         for (int g = 1; g <= G; g++) {
-            int l0, l1;
-            segment_range(ctx, g, l0, l1);
-            const size_t off = (size_t) l0 * per_layer, cnt = (size_t) (l1 - l0) * per_layer;
+            size_t off, cnt; slice(g, off, cnt);
             CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->seg_out[g - 1], 0));
             CUDA_OK(ctx, cudaMemcpyAsync(state_out + off, ctx->state_a + off, cnt * sizeof(float), cudaMemcpyDefault, ctx->copy_out));
         }
     }
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (b_log) memcpy(logits_out, ctx->bounce_logits, (size_t) m.n_vocab * sizeof(float));
     if (state_out) CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy_out));
+    if (bt.out.joinable()) bt.out.join();                  // the last slices have been copied to the caller
+    if (bt.in.joinable()) bt.in.join();
     return true;
 }
 

@@ -62,6 +62,9 @@ struct Context {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t seg_in[MAX_SEGMENTS] = {}, seg_out[MAX_SEGMENTS] = {};
     cudaEvent_t pass_begin = nullptr;
+    // pinned bounce buffers for pageable caller memory (engine.cu: eval_host_overlapped), allocated on first need
+    float * bounce_in = nullptr, * bounce_out = nullptr, * bounce_logits = nullptr;
+    cudaEvent_t seg_d2h[MAX_SEGMENTS] = {};          // slice g has arrived in bounce_out
 
     // CUDA graphs for single-token passes; captured on the second use of a slot.
     struct GraphSlot { cudaGraphExec_t exec = nullptr; int uses = 0; unsigned long long launches = 0; };
@@ -106,6 +109,7 @@ struct Context {
 // Largest number of tokens pushed through the kernels in one go; longer sequences are cut into
 // pieces of this size with the state staying on the device.
 constexpr int MAX_TOKENS_PER_PASS = 256;
+extern std::atomic<size_t> g_bounce_min_bytes;   // pageable caller states of at least this many bytes travel through pinned bounce buffers
 
 Context * create_context(Model * model, ErrorSink sink, int batch_n = 0);   // batch_n > 0: a batch context for that many sequences
 void destroy_context(Context * ctx);

@@ -124,23 +124,20 @@ __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const LnMixParams p)
         xb[i] = (t > 0) ? __fadd_rn(__fmul_rn(__fmul_rn(xb[i], scale_b), lw[i]), lb[i]) : pv[i];          // LN(x[:, t-1]) or the carry
     }
     const size_t o0 = (size_t) t * C + tid;
-    // single-token passes with C % 32 == 0 (the caller checks): the 32 lanes of a warp hold one 32-element block of every mixed vector,
-    // which also leaves as a staged column (act_stage.cuh) for the GEMV that consumes it
-    const bool emit = p.T == 1;
+    // (Emitting the mixed vectors as staged columns here as well -- act_stage.cuh, as the lerp and WKV kernels do -- was measured: it
+    // adds 2.5 us to every launch of this single-CTA, latency-bound kernel and takes 1.4 us out of the consumer: 2.95 vs 2.86 ms per
+    // 7B token, profiles/r2_c12_ab_default.json vs r2_c11_ab_notail.json. Not kept: its consumers quantise the column themselves.)
 #pragma unroll 1
     for (int j = 0; j < p.n_out; j++) {     // rolled: kernel parameters are indexable in the constant bank
         const float * coef = p.coef[j];
         float * out = p.out[j];
-        const act::StagedOut so{emit ? p.q_out[j] : nullptr, p.q_type[j], C};
 #pragma unroll
         for (int i = 0; i < PER; i++) {
             const int c = tid + i * LN_THREADS;
             if (c < C) {
                 const float m = coef[c];
-                const float v = (p.formula == 0) ? __fadd_rn(__fmul_rn(xa[i], m), __fsub_rn(xb[i], __fmul_rn(xb[i], m)))
-                                                 : __fadd_rn(__fmul_rn(__fsub_rn(xb[i], xa[i]), m), xa[i]);
-                out[o0 + i * LN_THREADS] = v;
-                if (so.dst) act::warp_emit_block(so, c >> 5, v);      // c < C is warp-uniform here
+                out[o0 + i * LN_THREADS] = (p.formula == 0) ? __fadd_rn(__fmul_rn(xa[i], m), __fsub_rn(xb[i], __fmul_rn(xb[i], m)))
+                                                           : __fadd_rn(__fmul_rn(__fsub_rn(xb[i], xa[i]), m), xa[i]);
             }
         }
     }
@@ -265,8 +262,8 @@ __global__ void __launch_bounds__(LERP_THREADS) v6_lerp_kernel(const V6LerpParam
     }
     __syncthreads();
     float * out = p.out[j];
-#pragma unroll 4
-    for (int tt = 0; tt < nt; tt++) {
+#pragma unroll 8
+    for (int tt = 0; tt < nt; tt++) {       // eight tokens' loads in flight: the loop is latency-bound (4-5 CTAs of 4 warps per SM)
         const size_t o = (size_t) (t0 + tt) * C + cc;
         const float sx = __ldg(p.sx + o), xx = __ldg(p.xx + o);
         const float * zj = lerp_zs + (size_t) tt * mix;

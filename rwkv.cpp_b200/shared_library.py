@@ -136,6 +136,8 @@ class RWKVSharedLibrary:
         lib.rwkv_b200_set_tensor_cores.restype = None
         lib.rwkv_b200_set_overlap.argtypes = [vp, ctypes.c_bool]
         lib.rwkv_b200_set_overlap.restype = None
+        lib.rwkv_b200_set_bounce_min_bytes.argtypes = [ctypes.c_size_t]
+        lib.rwkv_b200_set_bounce_min_bytes.restype = None
         lib.rwkv_b200_overlap_groups.argtypes = [vp]
         lib.rwkv_b200_overlap_groups.restype = ctypes.c_int
         lib.rwkv_b200_batch_create.argtypes = [vp, ctypes.c_size_t]

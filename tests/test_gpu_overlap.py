@@ -59,6 +59,37 @@ def test_overlapped_copies_bitwise(lib, ver, fmt):
         lib.rwkv_free(ctx)
 
 
+@pytest.mark.parametrize("ver", VERSIONS)
+def test_pageable_buffers_through_the_bounce_path_bitwise(lib, ver):
+    """Pageable caller memory (numpy arrays) of any size through the pinned bounce buffers + helper threads (engine.cu:
+    eval_host_overlapped; normally from 4 MiB of state on): the same bytes as the plain order, with aliased state_in == state_out,
+    NULL state_in, logits skipped, serial and sequence calls."""
+    ctx = lib.rwkv_init_from_file(model_path(ver, "Q5_1"), 1, 0)
+    try:
+        n_state, n_logits = lib.rwkv_get_state_buffer_element_count(ctx), lib.rwkv_get_logits_buffer_element_count(ctx)
+        toks = LONG_PROMPT[:24]
+        want = run(lib, ctx, toks, False, n_state, n_logits)
+        want_seq = run(lib, ctx, toks, False, n_state, n_logits, seq=9)
+        lib.library.rwkv_b200_set_bounce_min_bytes(0)
+        try:
+            for skip in (False, True):
+                got = run(lib, ctx, toks, True, n_state, n_logits, skip_logits=skip)
+                assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes(), (ver, skip)
+            got_seq = run(lib, ctx, toks, True, n_state, n_logits, seq=9)
+            assert got_seq[0].tobytes() == want_seq[0].tobytes() and got_seq[1].tobytes() == want_seq[1].tobytes()
+            # distinct in / out buffers, and a state handed back without logits
+            s_in, s_out = want[1].copy(), np.zeros(n_state, dtype=np.float32)
+            assert lib.library.rwkv_eval(ctx.ptr, toks[0], s_in.ctypes.data_as(P_F), s_out.ctypes.data_as(P_F), None)
+            lib.library.rwkv_b200_set_overlap(ctx.ptr, False)
+            s_ref = np.zeros(n_state, dtype=np.float32)
+            assert lib.library.rwkv_eval(ctx.ptr, toks[0], s_in.ctypes.data_as(P_F), s_ref.ctypes.data_as(P_F), None)
+            assert s_out.tobytes() == s_ref.tobytes() and s_in.tobytes() == want[1].tobytes()
+        finally:
+            lib.library.rwkv_b200_set_bounce_min_bytes(4 << 20)
+    finally:
+        lib.rwkv_free(ctx)
+
+
 def test_overlap_with_pinned_buffers_real_head_size(pkg, lib, tmp_path):
     import torch
     import synthetic_model as sm
