@@ -649,15 +649,30 @@ def run_pipeline(args, rank, world, dist):
     log("rank %d: layers [%d, %d) loaded in %.1fs" % (rank, begin, end, load_s))
     n_vocab = lib.rwkv_get_logits_len(ctxs[0])
     first, last = rank == 0, rank == world - 1
-    # ---- connect the stages: 64-byte CUDA IPC handles of the mailboxes, all_gathered once ----
-    hsz = int(L.rwkv_b200_pipe_handle_size())
-    hbuf = ctypes.create_string_buffer(hsz)
-    assert L.rwkv_b200_pipe_export(ctxs[0].ptr, hbuf), "pipe_export failed"
-    mine = torch.frombuffer(bytearray(hbuf.raw), dtype=torch.uint8).to(f"cuda:{local}")
-    gathered = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine)
-    handles = [bytes(g.cpu().numpy().tobytes()) for g in gathered]
-    assert L.rwkv_b200_pipe_connect(ctxs[0].ptr, None if first else handles[rank - 1], None if last else handles[rank + 1]), "pipe_connect failed"
+    # ---- connect the stages: 64-byte CUDA IPC handles of the mailboxes, all_gathered once. Should a box refuse CUDA IPC / peer
+    # access between its GPUs (or RWKV_B200_PIPE_TRANSPORT=nccl ask for it), every rank falls back to the round-1 transport: the
+    # stage API (rwkv_b200_stage_eval) with x handed on by NCCL send / recv on the stage's stream. The line says which one ran.
+    transport = os.environ.get("RWKV_B200_PIPE_TRANSPORT", "peer")
+    if transport == "peer":
+        ok = 1
+        try:
+            hsz = int(L.rwkv_b200_pipe_handle_size())
+            hbuf = ctypes.create_string_buffer(hsz)
+            ok = 1 if L.rwkv_b200_pipe_export(ctxs[0].ptr, hbuf) else 0
+            mine = torch.frombuffer(bytearray(hbuf.raw), dtype=torch.uint8).to(f"cuda:{local}")
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine)
+            handles = [bytes(g.cpu().numpy().tobytes()) for g in gathered]
+            if ok and not L.rwkv_b200_pipe_connect(ctxs[0].ptr, None if first else handles[rank - 1], None if last else handles[rank + 1]):
+                ok = 0
+        except Exception as exc:      # noqa: BLE001 -- any failure of the set-up means "use the fallback", on every rank
+            log("rank %d: peer-memory set-up failed: %r" % (rank, exc))
+            ok = 0
+        flag = torch.tensor([ok], device=f"cuda:{local}", dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            log("rank %d: peer-memory mailboxes unavailable on this box -> NCCL send/recv transport" % rank)
+            transport = "nccl"
     dist.barrier()
     for c in ctxs:
         L.rwkv_b200_state_load(c.ptr, None)
@@ -683,11 +698,24 @@ def run_pipeline(args, rank, world, dist):
         toks = sm.synthetic_tokens(n_items * T + T, n_vocab)
         arr = (ctypes.c_uint32 * len(toks))(*toks)
 
+        n_hidden = int(L.rwkv_b200_stage_hidden_len(ctxs[0].ptr, T))
+        hin = torch.empty(n_hidden, dtype=torch.float32, device=f"cuda:{local}") if transport == "nccl" and not first else None
+        hout = torch.empty(n_hidden, dtype=torch.float32, device=f"cuda:{local}") if transport == "nccl" and not last else None
+
         def run(u0, u1):
             for u in range(u0, u1):
                 seq = u % n_seq
-                ok = L.rwkv_b200_pipe_eval(ctxs[seq].ptr, ctypes.cast(ctypes.byref(arr, 4 * u * T), PU) if first else None, T, True, sp)
-                assert ok, "pipe_eval failed"
+                tok_p = ctypes.cast(ctypes.byref(arr, 4 * u * T), PU) if first else None
+                if transport == "peer":
+                    ok = L.rwkv_b200_pipe_eval(ctxs[seq].ptr, tok_p, T, True, sp)
+                else:       # every rank walks the items in the same order, so sends and receives pair up; all of it is stream-ordered
+                    if hin is not None:
+                        dist.recv(hin, src=rank - 1)
+                    ok = L.rwkv_b200_stage_eval(ctxs[seq].ptr, tok_p, T, ctypes.c_void_p(hin.data_ptr()) if hin is not None else None,
+                                                ctypes.c_void_p(hout.data_ptr()) if hout is not None else None, True, sp)
+                    if hout is not None:
+                        dist.send(hout, dst=rank + 1)
+                assert ok, "pipeline stage evaluation failed"
                 if read_logits and last:
                     assert L.rwkv_b200_stage_logits(ctxs[seq].ptr, ctypes.cast(logits_host.data_ptr(), PF), sp)
                     if keep is not None and seq == 0 and len(keep) < 4:
@@ -760,8 +788,10 @@ def run_pipeline(args, rank, world, dist):
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype_label(args.workload), "data": "synthetic",
             "config": {"workload": workload_label(args, preset),
                        "parallelism": f"pp{world}: layer blocks {blocks} balanced by bytes (head = {head_bytes / layer_bytes:.1f} layers) + their state slice per GPU, "
-                                      f"{world} sequences in flight (one per stage), x f32[{preset['C']}] per token by NVLink peer stores + flags inside the library "
-                                      f"(csrc/kernels/pipe.cu); one step = {world} tokens",
+                                      f"{world} sequences in flight (one per stage), x f32[{preset['C']}] per token by "
+                                      + ("NVLink peer stores + flags inside the library (csrc/kernels/pipe.cu)" if transport == "peer" else "NCCL send/recv on the stage's stream (fallback transport)")
+                                      + f"; one step = {world} tokens",
+                       "transport": transport,
                        "l2": "each stage streams its share of the weights per token >> 126 MB L2, no flush needed", "load_s": round(load_s, 2), "cuda_graph": True},
             "clocks": clocks,
             "e2e": {"value": world * K / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": 4 * world, "d2h_bytes_per_step": 4 * n_vocab * world,

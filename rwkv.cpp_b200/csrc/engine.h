@@ -23,6 +23,9 @@ struct PipeGroup {
     std::atomic<int> refs{0};
 };
 
+struct CopyPool;                        // helper threads of the pageable-buffer bounce path (engine.cu)
+void destroy_copy_pool(CopyPool * p);
+
 struct Context {
     Model * model = nullptr;
     PipeGroup * group = nullptr;           // set on the stage-0 context of an in-process pipeline
@@ -65,6 +68,7 @@ struct Context {
     // pinned bounce buffers for pageable caller memory (engine.cu: eval_host_overlapped), allocated on first need
     float * bounce_in = nullptr, * bounce_out = nullptr, * bounce_logits = nullptr;
     cudaEvent_t seg_d2h[MAX_SEGMENTS] = {};          // slice g has arrived in bounce_out
+    CopyPool * copy_pool = nullptr;
 
     // CUDA graphs for single-token passes; captured on the second use of a slot.
     struct GraphSlot { cudaGraphExec_t exec = nullptr; int uses = 0; unsigned long long launches = 0; };

@@ -437,34 +437,22 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
             const uint64_t a_fixed = make_desc(0, A_LBO, 128), b_fixed = make_desc(0, (uint32_t) NG * 128, 128);
             const uint32_t smem0 = smem_u32(smem) >> 4, stage16 = stage_bytes >> 4;
             const uint32_t a_k16 = (2 * A_LBO) >> 4, b_k16 = (uint32_t) (2 * NG * 128) >> 4;
-            // trace marks of CTA 0 (cycles, stored as start + cycles): [0] MMA thread waiting for operands, [1] issuing the MMAs,
-            // [2] issuing the commits, [3] whole K loop
+            // trace marks of CTA 0 (%globaltimer): [0] first stage complete = first MMA issued, [1] last MMA issued
             const bool acct = batch.trace != nullptr && blockIdx.x == 0;
-            long long waited = 0, t_mma = 0, t_commit = 0;
-            const long long loop0 = acct ? clock64() : 0;
             for (int it = 0; it < n; it++) {
                 const int s = it % nst;
                 const uint32_t a0 = smem0 + (uint32_t) s * stage16, b0 = a0 + (A_BYTES >> 4);
-                const long long w0 = acct ? clock64() : 0;
                 mbar_wait(&sh.full[s], (uint32_t) ((it / nst) & 1));
-                const long long w1 = acct ? clock64() : 0;
-                if (acct) waited += w1 - w0;
+                if (acct && it == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); batch.trace->mark[0] = g; }
                 tc_fence_after_sync();
 #pragma unroll
                 for (int k = 0; k < KSTEP / 16; k++)
                     umma_f16(tmem_d, a_fixed | (uint64_t) ((a0 + (uint32_t) k * a_k16) & 0x3FFFu), b_fixed | (uint64_t) ((b0 + (uint32_t) k * b_k16) & 0x3FFFu), idesc,
                              (it > 0 || k > 0) ? 1u : 0u);
-                const long long w2 = acct ? clock64() : 0;
                 umma_commit(&sh.empty[s]);                 // the stage is free once these MMAs have read it
-                if (acct) { t_mma += w2 - w1; t_commit += clock64() - w2; }
             }
             umma_commit(&sh.acc_done);                     // ... and the accumulator is final
-            if (acct) {
-                batch.trace->mark[0] = batch.trace->start + (unsigned long long) waited;
-                batch.trace->mark[1] = batch.trace->start + (unsigned long long) t_mma;
-                batch.trace->mark[2] = batch.trace->start + (unsigned long long) t_commit;
-                batch.trace->mark[3] = batch.trace->start + (unsigned long long) (clock64() - loop0);
-            }
+            if (acct) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); batch.trace->mark[1] = g; }
         }
     } else {
         // ===== epilogue (warps 2-5): residual / gate inputs belong to the previous kernels
@@ -474,6 +462,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
         for (int i = et; i < NPAD; i += EPI_THREADS) sh.colscale[i] = batch.colscale[pi][i];
         asm volatile("bar.sync 2, 128;" ::: "memory");
         mbar_wait(&sh.acc_done, 0);
+        if (batch.trace != nullptr && blockIdx.x == 0 && et == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); batch.trace->mark[2] = g; }
         tc_fence_after_sync();
         if (nsplit == 1) tc_epilogue_rows(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T);
         else tc_park_accumulator(sh.tmem_base, reinterpret_cast<float *>(smem), NPAD);      // acc_done: every MMA has finished reading the ring
@@ -487,6 +476,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
         __syncwarp();
         cluster_sync_all();
     }
+    if (batch.trace != nullptr && blockIdx.x == 0 && tid == EPI_WARP0 * 32) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); batch.trace->mark[3] = g; }
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(sh.tmem_base, (uint32_t) batch.tmem_cols);

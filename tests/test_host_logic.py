@@ -203,3 +203,17 @@ def test_quantize_cli_matches_library_call(lib, tmp_path):
     assert a.read_bytes() == b.read_bytes()
     r = subprocess.run([os.sys.executable, os.path.join(ROOT, "rwkv.cpp_b200", "quantize.py"), src, str(a), "Q9_9"], capture_output=True, text=True)
     assert r.returncode != 0
+
+
+def test_no_kernel_spills_its_parameters(lib):
+    """Round 2, GPU call 10: a `const LnTail &` taken INTO the kernel parameter made nvcc copy the 1.6 KB GemvBatch into every
+    thread's local memory at kernel entry (a 1624-byte stack frame): every GEMV launch 2-4x slower, found only on the GPU. This reads
+    the resource usage of the built library on the CPU: no kernel of the eval path may have a stack frame above 256 bytes
+    (the sampling kernel, one launch per sampled token, keeps its sorted candidate list in local memory on purpose)."""
+    r = subprocess.run(["cuobjdump", "--dump-resource-usage", lib.path], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    names = re.findall(r"Function ([^:\s]+):\s*\n\s*REG:(\d+) STACK:(\d+)", r.stdout)
+    assert len(names) > 20, "no kernels found in %s" % lib.path
+    fat = [(n, int(st)) for n, _, st in names if int(st) > 256 and "sample_kernel" not in n]
+    assert not fat, fat
