@@ -117,6 +117,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t * r) {   // 3
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t * r) {    // 32 lanes x 8 consecutive columns
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp:98-123;
 // canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units, mma_traits_sm100.hpp:273-303):
 //   element (row, k) lives at  start + (row % 8) * 16 + (row / 8) * SBO + (k / 8) * LBO   bytes
@@ -147,23 +154,26 @@ struct TcShared {
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
 
-// 32 accumulator columns of one row -> fused epilogue -> column-major store. Everything the loop needs sits in registers
-// (the problem record lives in shared memory: re-reading it per element made the unrolled body 250 instructions long).
+// Epilogue of a tile that was not cut along K: accumulator -> fused epilogue -> y, column-major stores (a warp writes 32 consecutive
+// rows of a column: 128-byte runs). Epilogue warp w owns TMEM lanes 32 (w % 4) .. + 31 = rows row0 + 32 (w % 4) + lane.
+// The accumulator is walked in a ROLLED loop of 8-column groups. The first version unrolled 32 columns per group for each of the ten
+// epilogue kinds: 143 KB of straight-line code of which every launch executed 4-16 KB exactly once per group, cold -- instruction
+// fetch from L2 at one cache line per ~300 cycles, i.e. 4-10 us of the ~15 us a launch spent outside its K loop
+// (profiles/r2_trace_prefill_c15.log marks). Eight columns per trip keeps a kind's body at 0.5-4 KB, fetched once, run 16 times.
 struct EpiRow { float * y; long long ldy; const float * res; long long ldres; const float * gate; long long ldgate; float bias; };
-template <int EPI> __device__ __forceinline__ void store_cols(const EpiRow & e, const uint32_t (&acc)[32], const float * cs, int c0, int T) {
-    // the residual / gate inputs of all 32 columns are requested before the first store: the output may alias the residual
-    // (x += ...), so a load placed after a store would have to wait for it, one L2 round trip per column
-    float rv[32], gv[32];
+template <int EPI> __device__ __forceinline__ void store_cols8(const EpiRow & e, const uint32_t (&acc)[8], const float * cs, int c0, int T) {
+    // the residual / gate inputs of the group are requested before the first store: the output may alias the residual (x += ...)
+    float rv[8], gv[8];
     if constexpr (EPI == EPI_ADD || EPI == EPI_MUL_ADD) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) rv[j] = c0 + j < T ? e.res[(long long) (c0 + j) * e.ldres] : 0.f;
+        for (int j = 0; j < 8; j++) rv[j] = c0 + j < T ? e.res[(long long) (c0 + j) * e.ldres] : 0.f;
     }
     if constexpr (EPI == EPI_MUL_ADD) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) gv[j] = c0 + j < T ? e.gate[(long long) (c0 + j) * e.ldgate] : 0.f;
+        for (int j = 0; j < 8; j++) gv[j] = c0 + j < T ? e.gate[(long long) (c0 + j) * e.ldgate] : 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
+    for (int j = 0; j < 8; j++) {
         const int col = c0 + j;
         if (col >= T) break;
         float v = __uint_as_float(acc[j]) * cs[col];
@@ -179,8 +189,6 @@ template <int EPI> __device__ __forceinline__ void store_cols(const EpiRow & e, 
         e.y[(long long) col * e.ldy] = v;
     }
 }
-// Epilogue warp w owns TMEM lanes 32 (w % 4) .. + 31 = rows row0 + 32 (w % 4) + lane and walks all 32-column groups of the accumulator:
-// accumulator -> fused epilogue -> y (a tile that was not cut along K).
 __device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, const float * cs, uint32_t tmem_base, int row0, int npad, int T) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3;
@@ -193,21 +201,21 @@ __device__ __noinline__ void tc_epilogue_rows(const GemvProblem & Psh, const flo
     e.gate = Psh.gate ? Psh.gate + row : nullptr; e.ldgate = Psh.ldgate;
     e.bias = (live && Psh.bias) ? Psh.bias[row] : 0.f;
 #pragma unroll 1
-    for (int c0 = 0; c0 < npad; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) c0, acc);
+    for (int c0 = 0; c0 < npad && c0 < T; c0 += 8) {
+        uint32_t acc[8];
+        tmem_ld8(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) c0, acc);      // warp-collective: before any lane drops out
         if (!live) continue;
         switch (epi) {
-            case EPI_SIGMOID: store_cols<EPI_SIGMOID>(e, acc, cs, c0, T); break;
-            case EPI_SILU: store_cols<EPI_SILU>(e, acc, cs, c0, T); break;
-            case EPI_TANH: store_cols<EPI_TANH>(e, acc, cs, c0, T); break;
-            case EPI_RELU_SQR: store_cols<EPI_RELU_SQR>(e, acc, cs, c0, T); break;
-            case EPI_ADD: store_cols<EPI_ADD>(e, acc, cs, c0, T); break;
-            case EPI_MUL_ADD: store_cols<EPI_MUL_ADD>(e, acc, cs, c0, T); break;
-            case EPI_BIAS_EXPNEGEXP: store_cols<EPI_BIAS_EXPNEGEXP>(e, acc, cs, c0, T); break;
-            case EPI_BIAS_SIGMOID: store_cols<EPI_BIAS_SIGMOID>(e, acc, cs, c0, T); break;
-            case EPI_BIAS_W7: store_cols<EPI_BIAS_W7>(e, acc, cs, c0, T); break;
-            default: store_cols<EPI_NONE>(e, acc, cs, c0, T); break;
+            case EPI_SIGMOID: store_cols8<EPI_SIGMOID>(e, acc, cs, c0, T); break;
+            case EPI_SILU: store_cols8<EPI_SILU>(e, acc, cs, c0, T); break;
+            case EPI_TANH: store_cols8<EPI_TANH>(e, acc, cs, c0, T); break;
+            case EPI_RELU_SQR: store_cols8<EPI_RELU_SQR>(e, acc, cs, c0, T); break;
+            case EPI_ADD: store_cols8<EPI_ADD>(e, acc, cs, c0, T); break;
+            case EPI_MUL_ADD: store_cols8<EPI_MUL_ADD>(e, acc, cs, c0, T); break;
+            case EPI_BIAS_EXPNEGEXP: store_cols8<EPI_BIAS_EXPNEGEXP>(e, acc, cs, c0, T); break;
+            case EPI_BIAS_SIGMOID: store_cols8<EPI_BIAS_SIGMOID>(e, acc, cs, c0, T); break;
+            case EPI_BIAS_W7: store_cols8<EPI_BIAS_W7>(e, acc, cs, c0, T); break;
+            default: store_cols8<EPI_NONE>(e, acc, cs, c0, T); break;
         }
     }
 }
@@ -252,6 +260,22 @@ __device__ __forceinline__ float tc_epilogue_value(int epi, float v, float res, 
 }
 // Step 2 (epilogue warps, after the cluster barrier): columns [rank * cpr, (rank + 1) * cpr) of the tile = sum over the cluster's
 // accumulators in rank order -> fused epilogue -> y. Thread = tile row: loads from a peer and the stores to y are 128-byte runs.
+// A ROLLED, software-pipelined loop over groups of four columns: the loads of group g + 1 (residual / gate out of L2, the peers'
+// partial sums out of distributed shared memory) are in flight while group g is summed and stored. (Two variants measured in
+// profiles/r2_trace_prefill_c15.log / _c16_unrolled_reduce_regression.log: loads and use in the same trip, an L2 round trip per
+// group: 11-19 us from the last MMA to the end of the epilogue; residual / gate prefetched into registers before the barrier with the
+// loop fully unrolled: 37 us -- 4 000 straight-line instructions executed once are fetched from L2 one cache line at a time.)
+struct ReduceGroup { float part[4][8], res[4], gate[4]; };
+__device__ __forceinline__ void tc_load_group(const GemvProblem & Psh, const uint32_t (&peer)[8], int csize, int row, bool live, int c0, int c_hi, ReduceGroup & g) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int c = min(c0 + j, c_hi - 1);
+        g.res[j] = (live && Psh.res) ? Psh.res[(long long) c * Psh.ldres + row] : 0.f;
+        g.gate[j] = (live && Psh.gate) ? Psh.gate[(long long) c * Psh.ldgate + row] : 0.f;
+#pragma unroll
+        for (int p = 0; p < 8; p++) g.part[j][p] = p < csize ? ld_dsmem(peer[p] + (uint32_t) c * (TILE_M * 4u)) : 0.f;
+    }
+}
 __device__ __noinline__ void tc_reduce_columns(const GemvProblem & Psh, const float * cs, const float * park, int row0, int npad, int T, int csize) {
     const int r = (int) threadIdx.x - EPI_WARP0 * 32;            // 0..127
     const int row = row0 + r;
@@ -259,33 +283,28 @@ __device__ __noinline__ void tc_reduce_columns(const GemvProblem & Psh, const fl
     const uint32_t rank = cluster_ctarank();
     const int cpr = (npad + csize - 1) / csize;
     const int c_lo = (int) rank * cpr, c_hi = min(min(npad, T), c_lo + cpr);
+    if (c_lo >= c_hi) return;
     const int epi = Psh.epi;
     const float bias = (live && Psh.bias) ? Psh.bias[row] : 0.f;
     const uint32_t park0 = smem_u32(park) + (uint32_t) r * 4u;
     uint32_t peer[8];
 #pragma unroll
     for (int p = 0; p < 8; p++) peer[p] = map_to_cta(park0, (uint32_t) (p < csize ? p : 0));
-    constexpr int CB = 4;                                        // columns in flight per thread
+    ReduceGroup cur, nxt;
+    tc_load_group(Psh, peer, csize, row, live, c_lo, c_hi, cur);
 #pragma unroll 1
-    for (int c0 = c_lo; c0 < c_hi; c0 += CB) {
-        float part[CB][8], res[CB], gate[CB];
+    for (int c0 = c_lo; c0 < c_hi; c0 += 4) {
+        if (c0 + 4 < c_hi) tc_load_group(Psh, peer, csize, row, live, c0 + 4, c_hi, nxt);
 #pragma unroll
-        for (int j = 0; j < CB; j++) {
-            const int c = min(c0 + j, c_hi - 1);
-            res[j] = (live && Psh.res) ? Psh.res[(long long) c * Psh.ldres + row] : 0.f;
-            gate[j] = (live && Psh.gate) ? Psh.gate[(long long) c * Psh.ldgate + row] : 0.f;
-#pragma unroll
-            for (int p = 0; p < 8; p++) part[j][p] = p < csize ? ld_dsmem(peer[p] + (uint32_t) c * (TILE_M * 4u)) : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < CB; j++) {
+        for (int j = 0; j < 4; j++) {
             const int c = c0 + j;
             if (c >= c_hi || !live) continue;
             float v = 0.f;
 #pragma unroll
-            for (int p = 0; p < 8; p++) if (p < csize) v += part[j][p];
-            Psh.y[(long long) c * Psh.ldy + row] = tc_epilogue_value(epi, v * cs[c], res[j], gate[j], bias);
+            for (int p = 0; p < 8; p++) if (p < csize) v += cur.part[j][p];
+            Psh.y[(long long) c * Psh.ldy + row] = tc_epilogue_value(epi, v * cs[c], cur.res[j], cur.gate[j], bias);
         }
+        cur = nxt;
     }
 }
 
@@ -461,18 +480,28 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
         const int et = tid - EPI_WARP0 * 32;
         for (int i = et; i < NPAD; i += EPI_THREADS) sh.colscale[i] = batch.colscale[pi][i];
         asm volatile("bar.sync 2, 128;" ::: "memory");
-        mbar_wait(&sh.acc_done, 0);
-        if (batch.trace != nullptr && blockIdx.x == 0 && et == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); batch.trace->mark[2] = g; }
-        tc_fence_after_sync();
-        if (nsplit == 1) tc_epilogue_rows(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T);
-        else tc_park_accumulator(sh.tmem_base, reinterpret_cast<float *>(smem), NPAD);      // acc_done: every MMA has finished reading the ring
+        if (nsplit == 1) {
+            mbar_wait(&sh.acc_done, 0);
+            if (batch.trace != nullptr && blockIdx.x == 0 && et == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); batch.trace->mark[2] = g; }
+            tc_fence_after_sync();
+            tc_epilogue_rows(P, sh.colscale, sh.tmem_base, row0, NPAD, batch.T);
+        } else {
+            mbar_wait(&sh.acc_done, 0);
+            if (batch.trace != nullptr && blockIdx.x == 0 && et == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); batch.trace->mark[2] = g; }
+            tc_fence_after_sync();
+            tc_park_accumulator(sh.tmem_base, reinterpret_cast<float *>(smem), NPAD);      // acc_done: every MMA has finished reading the ring
+            // every thread of the cluster: accumulators parked -> [barrier] -> each CTA reduces its column slice out of all of them ->
+            // [barrier] so that no CTA retires (and frees its shared memory) while a peer still reads it
+            __syncwarp();
+            cluster_sync_all();
+            tc_reduce_columns(P, sh.colscale, reinterpret_cast<const float *>(smem), row0, NPAD, batch.T, nsplit);
+            __syncwarp();
+            cluster_sync_all();
+        }
     }
-    if (nsplit > 1) {
-        // every thread of the cluster: accumulators parked -> [barrier] -> each CTA reduces its column slice out of all of them ->
-        // [barrier] so that no CTA retires (and frees its shared memory) while a peer still reads it
+    if (nsplit > 1 && warp < EPI_WARP0) {      // the producer and MMA warps take part in both cluster barriers
         __syncwarp();
         cluster_sync_all();
-        if (warp >= EPI_WARP0) tc_reduce_columns(P, sh.colscale, reinterpret_cast<const float *>(smem), row0, NPAD, batch.T, nsplit);
         __syncwarp();
         cluster_sync_all();
     }

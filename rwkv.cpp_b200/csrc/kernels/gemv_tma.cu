@@ -26,7 +26,12 @@
 namespace rwkv {
 namespace tma {
 
-template <int NC, bool STAGE_V2 = false>
+// ONLY: the weight type of EVERY problem of the launch (a single-token launch of a model whose matrices share one format: all of a
+// v4 / v5 / v6 layer), or -1 for launches that mix formats. The one-kernel-for-everything instantiation is 15 500 instructions
+// (248 KB) of which a launch runs ~1 500 scattered ones; ncu attributes 34 % of the warp stall cycles of a 12 MB launch, and 50-64 %
+// of the LoRA launches', to instruction fetch (profiles/r2_ncu_hot_gemv_gemm_details.txt). A per-format instantiation is ~2 000
+// instructions, contiguous.
+template <int NC, bool STAGE_V2 = false, int ONLY = -1>
 __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch batch) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ Shared sh;
@@ -52,7 +57,8 @@ __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch ba
     const uint32_t stage_bytes = (uint32_t) batch.stage_bytes;
 
     uint8_t * ring = smem;
-    const size_t colb = act_bytes_per_column(P.type, P.K);
+    const int ptype = ONLY >= 0 ? ONLY : P.type;
+    const size_t colb = act_bytes_per_column(ptype, P.K);
     uint8_t * act = smem + (size_t) NSTAGES * stage_bytes;
     float * red = reinterpret_cast<float *>(act + (size_t) NC * batch.max_col_bytes);
 
@@ -82,7 +88,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch ba
     // ===== consumers =====
     grid_dependency_wait();          // activations / residuals come from the previous kernel
     trace_mark(batch.trace, 0);
-    const bool quant = P.type != DT_F16 && P.type != DT_F32;
+    const bool quant = ptype != DT_F16 && ptype != DT_F32;
     for (int g = 0; g < n_groups; g++) {
         const int c0 = g * NC, nc = min(NC, batch.T - c0);
         if (g > 0) consumer_barrier();   // everyone finished reading the previous group's activations
@@ -92,23 +98,28 @@ __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch ba
             int4 * dst = reinterpret_cast<int4 *>(act);
             for (int i = threadIdx.x; i < (int) (colb / 16); i += CONSUMER_THREADS) dst[i] = __ldcg(src + i);
         } else {
-            for (int c = 0; c < nc; c++) stage_column<4, STAGE_V2>(P, c0 + c, act + c * colb, sh.red_d);
+            for (int c = 0; c < nc; c++) stage_column<4, STAGE_V2, ONLY>(P, c0 + c, act + c * colb, sh.red_d);
         }
         consumer_barrier();
         trace_mark(batch.trace, 1);
         const int it0 = g * my_tiles;
 #define RWKV_CONSUME_REGS(T_) consume_quant_regs<T_>(sh, ring, stage_bytes, act, c0, red, it0, my_tiles, local_cta, P.n_cta)
 #define RWKV_CONSUME_SMEM(T_) consume_smem<T_, NC>(sh, ring, stage_bytes, act, colb, c0, nc, red, it0, my_tiles, local_cta, P.n_cta)
-        if (NC == 1 && quant) {
-            switch (P.type) {
+        if constexpr (ONLY >= 0) {
+            if constexpr (NC == 1 && ONLY != DT_F16 && ONLY != DT_F32) RWKV_CONSUME_REGS(ONLY);
+            else RWKV_CONSUME_SMEM(ONLY);
+        } else if (NC == 1 && quant) {
+            switch (ptype) {
                 case DT_Q4_0: RWKV_CONSUME_REGS(DT_Q4_0); break;
                 case DT_Q4_1: RWKV_CONSUME_REGS(DT_Q4_1); break;
                 case DT_Q5_0: RWKV_CONSUME_REGS(DT_Q5_0); break;
                 case DT_Q5_1: RWKV_CONSUME_REGS(DT_Q5_1); break;
                 default: RWKV_CONSUME_REGS(DT_Q8_0); break;
             }
+        } else if constexpr (NC == 1) {      // quantised columns of a single-column launch never come here
+            if (ptype == DT_F16) RWKV_CONSUME_SMEM(DT_F16); else RWKV_CONSUME_SMEM(DT_F32);
         } else {
-            switch (P.type) {
+            switch (ptype) {
                 case DT_Q4_0: RWKV_CONSUME_SMEM(DT_Q4_0); break;
                 case DT_Q4_1: RWKV_CONSUME_SMEM(DT_Q4_1); break;
                 case DT_Q5_0: RWKV_CONSUME_SMEM(DT_Q5_0); break;
@@ -155,16 +166,32 @@ bool plan_wk(GemvProblem & p) {
     return false;
 }
 
-template <int NC, bool STAGE_V2 = false>
+template <int NC, bool STAGE_V2 = false, int ONLY = -1>
 cudaError_t launch_tma_nc(const GemvBatch & batch, int grid, size_t smem, cudaStream_t stream) {
-    if constexpr (NC == 1 && !STAGE_V2) {
+    if constexpr (NC == 1 && !STAGE_V2 && ONLY < 0) {
         // single-column launches stage their activation column one thread per 32-element block (gemv_tma_device.cuh: stage_column
         // PER_BLOCK; bit-identical bytes, -0.36 ms per 7B token); RWKV_B200_STAGE_V2=0 selects the 8-lanes-per-block variant
         static const bool stage_v2 = [] { const char * e = getenv("RWKV_B200_STAGE_V2"); return !e || atoi(e) != 0; }();
-        if (stage_v2) return launch_tma_nc<1, true>(batch, grid, smem, stream);
+        if (stage_v2) {
+            // ... and run the instantiation of their weight format when the launch has only one (RWKV_B200_GEMV_PER_TYPE=0: never)
+            static const bool per_type = [] { const char * e = getenv("RWKV_B200_GEMV_PER_TYPE"); return !e || atoi(e) != 0; }();
+            int only = batch.p[0].type;
+            for (int i = 1; i < batch.n; i++) if (batch.p[i].type != only) only = -1;
+            if (per_type) switch (only) {
+                case DT_Q4_0: return launch_tma_nc<1, true, DT_Q4_0>(batch, grid, smem, stream);
+                case DT_Q4_1: return launch_tma_nc<1, true, DT_Q4_1>(batch, grid, smem, stream);
+                case DT_Q5_0: return launch_tma_nc<1, true, DT_Q5_0>(batch, grid, smem, stream);
+                case DT_Q5_1: return launch_tma_nc<1, true, DT_Q5_1>(batch, grid, smem, stream);
+                case DT_Q8_0: return launch_tma_nc<1, true, DT_Q8_0>(batch, grid, smem, stream);
+                case DT_F16: return launch_tma_nc<1, true, DT_F16>(batch, grid, smem, stream);
+                case DT_F32: return launch_tma_nc<1, true, DT_F32>(batch, grid, smem, stream);
+                default: break;
+            }
+            return launch_tma_nc<1, true>(batch, grid, smem, stream);
+        }
     }
     static PerDeviceOnce once;                // the shared-memory opt-in is per device
-    const cudaError_t ae = once.run([&] { return cudaFuncSetAttribute(tma::gemv_tma_kernel<NC, STAGE_V2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::CTA_SMEM_BUDGET); });
+    const cudaError_t ae = once.run([&] { return cudaFuncSetAttribute(tma::gemv_tma_kernel<NC, STAGE_V2, ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::CTA_SMEM_BUDGET); });
     if (ae != cudaSuccess) return ae;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned) grid);
@@ -177,8 +204,8 @@ cudaError_t launch_tma_nc(const GemvBatch & batch, int grid, size_t smem, cudaSt
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 1 : 0;
     g_kernel_launches++;
-    prefer_max_shared_carveout(reinterpret_cast<const void *>(tma::gemv_tma_kernel<NC, STAGE_V2>));
-    return cudaLaunchKernelEx(&cfg, tma::gemv_tma_kernel<NC, STAGE_V2>, batch);
+    prefer_max_shared_carveout(reinterpret_cast<const void *>(tma::gemv_tma_kernel<NC, STAGE_V2, ONLY>));
+    return cudaLaunchKernelEx(&cfg, tma::gemv_tma_kernel<NC, STAGE_V2, ONLY>, batch);
 }
 
 }  // namespace

@@ -188,9 +188,11 @@ template <int TYPE> __device__ __forceinline__ void load_unit(const uint8_t * ro
 // the two IEEE divisions, the scale and the sums once per 32 elements instead of once per 4, no shuffles; ~4x fewer instructions for
 // a stage that is instruction-bound. The staged bytes are identical: the maximum and the integer sum of a block do
 // not depend on the order they are taken in.
-template <int UNR = 4, bool PER_BLOCK = false>     // UNR: float4 loads a thread keeps in flight per round of the quantising loop
+// TYPE_HINT: the weight type when the whole launch has one (a compile-time constant: the other formats' code is not generated), else -1.
+template <int UNR = 4, bool PER_BLOCK = false, int TYPE_HINT = -1>     // UNR: float4 loads a thread keeps in flight per round of the quantising loop
 static __device__ void stage_column(const GemvProblem & P, int col_index, uint8_t * col, double * red_d) {
     const int K = P.K, tid = threadIdx.x;
+    const int ptype = TYPE_HINT >= 0 ? TYPE_HINT : P.type;
     const float * x = P.x + (long long) col_index * P.ldx;
     float mean = 0.f, rstd = 1.f;
     const bool ln = P.pro == PRO_LAYERNORM;
@@ -217,14 +219,14 @@ static __device__ void stage_column(const GemvProblem & P, int col_index, uint8_
     auto norm = [&](float v, int k) -> float {
         return ln ? __fadd_rn(__fmul_rn(__fmul_rn(v - mean, rstd), P.ln_w[k]), P.ln_b[k]) : v;
     };
-    if (P.type == DT_F32) {
+    if (ptype == DT_F32) {
         float * d = reinterpret_cast<float *>(col);
         for (int k = tid; k < K; k += CONSUMER_THREADS) d[k] = norm(x[k], k);
-    } else if (P.type == DT_F16) {
+    } else if (ptype == DT_F16) {
         __half * d = reinterpret_cast<__half *>(col);
         for (int k = tid; k < K; k += CONSUMER_THREADS) d[k] = __float2half_rn(norm(x[k], k));
     } else {
-        const bool has_min = (P.type == DT_Q4_1 || P.type == DT_Q5_1);
+        const bool has_min = (ptype == DT_Q4_1 || ptype == DT_Q5_1);
         const int UB = has_min ? 1 : 2;
         const int nblk = K / 32, nunits = (nblk + UB - 1) / UB;
         if constexpr (PER_BLOCK) {

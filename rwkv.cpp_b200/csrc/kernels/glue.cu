@@ -93,6 +93,22 @@ __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const LnMixParams p)
         lb[i] = live ? p.ln_b[c] : 0.f;
         pv[i] = (live && t == 0) ? p.state_in[c] : 0.f;   // written by the previous token's pass: safe before the wait
     }
+    // the mix coefficients too (up to 6 vectors): last read one token ago, i.e. an HBM round trip each -- and the output loop below
+    // used to take them one vector after the other, AFTER the statistics (1-2 us of a 7 us kernel that runs 64 times per 7B token)
+    // (the first PRE_N vectors: 1024 threads leave 64 registers each)
+    constexpr bool PRE = PER <= 4;
+    constexpr int PRE_N = 3;
+    float cf[PRE ? PRE_N : 1][PER];
+    if constexpr (PRE) {
+#pragma unroll
+        for (int j = 0; j < PRE_N; j++) {
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int c = tid + i * LN_THREADS;
+                cf[j][i] = (j < p.n_out && c < C) ? p.coef[j][c] : 0.f;
+            }
+        }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     double sa = 0, sb = 0;
 #pragma unroll
@@ -127,17 +143,35 @@ __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const LnMixParams p)
     // (Emitting the mixed vectors as staged columns here as well -- act_stage.cuh, as the lerp and WKV kernels do -- was measured: it
     // adds 2.5 us to every launch of this single-CTA, latency-bound kernel and takes 1.4 us out of the consumer: 2.95 vs 2.86 ms per
     // 7B token, profiles/r2_c12_ab_default.json vs r2_c11_ab_notail.json. Not kept: its consumers quantise the column themselves.)
-#pragma unroll 1
-    for (int j = 0; j < p.n_out; j++) {     // rolled: kernel parameters are indexable in the constant bank
-        const float * coef = p.coef[j];
-        float * out = p.out[j];
+    if constexpr (PRE) {
 #pragma unroll
-        for (int i = 0; i < PER; i++) {
-            const int c = tid + i * LN_THREADS;
-            if (c < C) {
-                const float m = coef[c];
-                out[o0 + i * LN_THREADS] = (p.formula == 0) ? __fadd_rn(__fmul_rn(xa[i], m), __fsub_rn(xb[i], __fmul_rn(xb[i], m)))
-                                                           : __fadd_rn(__fmul_rn(__fsub_rn(xb[i], xa[i]), m), xa[i]);
+        for (int j = 0; j < PRE_N; j++) {
+            if (j >= p.n_out) break;
+            float * out = p.out[j];
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int c = tid + i * LN_THREADS;
+                if (c < C) {
+                    const float m = cf[j][i];
+                    out[o0 + i * LN_THREADS] = (p.formula == 0) ? __fadd_rn(__fmul_rn(xa[i], m), __fsub_rn(xb[i], __fmul_rn(xb[i], m)))
+                                                               : __fadd_rn(__fmul_rn(__fsub_rn(xb[i], xa[i]), m), xa[i]);
+                }
+            }
+        }
+    }
+    {
+#pragma unroll 1
+        for (int j = PRE ? PRE_N : 0; j < p.n_out; j++) {     // rolled: kernel parameters are indexable in the constant bank
+            const float * coef = p.coef[j];
+            float * out = p.out[j];
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int c = tid + i * LN_THREADS;
+                if (c < C) {
+                    const float m = coef[c];
+                    out[o0 + i * LN_THREADS] = (p.formula == 0) ? __fadd_rn(__fmul_rn(xa[i], m), __fsub_rn(xb[i], __fmul_rn(xb[i], m)))
+                                                               : __fadd_rn(__fmul_rn(__fsub_rn(xb[i], xa[i]), m), xa[i]);
+                }
             }
         }
     }
@@ -236,7 +270,10 @@ __global__ void __launch_bounds__(GLUE_THREADS) v6_lerp_decode_kernel(const V6Le
 constexpr int LERP_THREADS = 128;
 constexpr int LERP_MIN_TOKENS = 8;
 constexpr int LERP_MAX_F4 = 16;   // W2 row in registers: mix <= 64
-template <int TILE>
+// M4 > 0: mix == 4 * M4 known at compile time (32 and 64 in the released models): the dot product is M4 float4 steps with no
+// predication and no other code path in the loop -- the generic body ran ~270 instructions per token where 60 do the work
+// (ncu: 44 % of the issue slots busy for 43 us on a kernel that moves 25 MB). M4 == 0: any mix.
+template <int TILE, int M4>
 __global__ void __launch_bounds__(LERP_THREADS) v6_lerp_kernel(const V6LerpParams p) {
     extern __shared__ __align__(16) float lerp_zs[];        // [tile][mix]: the z rows of mix j
     trace_begin(p.trace);
@@ -245,8 +282,8 @@ __global__ void __launch_bounds__(LERP_THREADS) v6_lerp_kernel(const V6LerpParam
     const int c = blockIdx.x * LERP_THREADS + tid;
     const bool live = c < C;
     const int cc = live ? c : 0;
-    const int m4 = mix / 4;
-    const bool vec = (mix & 3) == 0 && m4 <= LERP_MAX_F4;
+    const int m4 = M4 > 0 ? M4 : mix / 4;
+    const bool vec = M4 > 0 || ((mix & 3) == 0 && m4 <= LERP_MAX_F4);
     const int t0 = blockIdx.y * TILE, nt = min(TILE, p.T - t0);
     float4 w[LERP_MAX_F4];
     {
@@ -270,7 +307,15 @@ __global__ void __launch_bounds__(LERP_THREADS) v6_lerp_kernel(const V6LerpParam
         // the same eight partial sums and the same combination tree as the decode kernel's 8 lanes + shuffles: a chunked
         // evaluation stays bit-identical to the serial one (tests/test_eval_sequence_in_chunks.c memcmp's them)
         float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (vec) {
+        if constexpr (M4 > 0) {
+#pragma unroll
+            for (int i = 0; i < M4; i++) {
+                const float4 z = reinterpret_cast<const float4 *>(zj)[i];
+                float & s8 = a[i & 7];
+                s8 = __fmaf_rn(w[i].x, z.x, s8); s8 = __fmaf_rn(w[i].y, z.y, s8);
+                s8 = __fmaf_rn(w[i].z, z.z, s8); s8 = __fmaf_rn(w[i].w, z.w, s8);
+            }
+        } else if (vec) {
 #pragma unroll
             for (int i = 0; i < LERP_MAX_F4; i++) {
                 if (i < m4) {
@@ -340,7 +385,9 @@ cudaError_t launch_v6_lerp(const V6LerpParams & p_in, cudaStream_t s) {
     const size_t smem = (size_t) tile * p.mix * sizeof(float);
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
     dim3 grid((p.C + LERP_THREADS - 1) / LERP_THREADS, (p.T + tile - 1) / tile, 5);
-    return tile == 32 ? launch_pdl(v6_lerp_kernel<32>, grid, dim3(LERP_THREADS), smem, s, p) : launch_pdl(v6_lerp_kernel<8>, grid, dim3(LERP_THREADS), smem, s, p);
+    if (p.mix == 32) return tile == 32 ? launch_pdl(v6_lerp_kernel<32, 8>, grid, dim3(LERP_THREADS), smem, s, p) : launch_pdl(v6_lerp_kernel<8, 8>, grid, dim3(LERP_THREADS), smem, s, p);
+    if (p.mix == 64) return tile == 32 ? launch_pdl(v6_lerp_kernel<32, 16>, grid, dim3(LERP_THREADS), smem, s, p) : launch_pdl(v6_lerp_kernel<8, 16>, grid, dim3(LERP_THREADS), smem, s, p);
+    return tile == 32 ? launch_pdl(v6_lerp_kernel<32, 0>, grid, dim3(LERP_THREADS), smem, s, p) : launch_pdl(v6_lerp_kernel<8, 0>, grid, dim3(LERP_THREADS), smem, s, p);
 }
 
 }  // namespace rwkv
