@@ -31,7 +31,7 @@ namespace tma {
 // (248 KB) of which a launch runs ~1 500 scattered ones; ncu attributes 34 % of the warp stall cycles of a 12 MB launch, and 50-64 %
 // of the LoRA launches', to instruction fetch (profiles/r2_ncu_hot_gemv_gemm_details.txt). A per-format instantiation is ~2 000
 // instructions, contiguous.
-template <int NC, bool STAGE_V2 = false, int ONLY = -1>
+template <int NC, bool STAGE_V2 = false, int ONLY = -1, bool HAS_LN = true>
 __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch batch) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ Shared sh;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemv_tma_kernel(const GemvBatch ba
             int4 * dst = reinterpret_cast<int4 *>(act);
             for (int i = threadIdx.x; i < (int) (colb / 16); i += CONSUMER_THREADS) dst[i] = __ldcg(src + i);
         } else {
-            for (int c = 0; c < nc; c++) stage_column<4, STAGE_V2, ONLY>(P, c0 + c, act + c * colb, sh.red_d);
+            for (int c = 0; c < nc; c++) stage_column<4, STAGE_V2, ONLY, HAS_LN>(P, c0 + c, act + c * colb, sh.red_d);
         }
         consumer_barrier();
         trace_mark(batch.trace, 1);
@@ -166,7 +166,7 @@ bool plan_wk(GemvProblem & p) {
     return false;
 }
 
-template <int NC, bool STAGE_V2 = false, int ONLY = -1>
+template <int NC, bool STAGE_V2 = false, int ONLY = -1, bool HAS_LN = true>
 cudaError_t launch_tma_nc(const GemvBatch & batch, int grid, size_t smem, cudaStream_t stream) {
     if constexpr (NC == 1 && !STAGE_V2 && ONLY < 0) {
         // single-column launches stage their activation column one thread per 32-element block (gemv_tma_device.cuh: stage_column
@@ -177,21 +177,19 @@ cudaError_t launch_tma_nc(const GemvBatch & batch, int grid, size_t smem, cudaSt
             static const bool per_type = [] { const char * e = getenv("RWKV_B200_GEMV_PER_TYPE"); return !e || atoi(e) != 0; }();
             int only = batch.p[0].type;
             for (int i = 1; i < batch.n; i++) if (batch.p[i].type != only) only = -1;
+            bool has_ln = false;
+            for (int i = 0; i < batch.n; i++) has_ln = has_ln || batch.p[i].pro == PRO_LAYERNORM;
+#define RWKV_PER_TYPE(T_) case T_: return has_ln ? launch_tma_nc<1, true, T_, true>(batch, grid, smem, stream) : launch_tma_nc<1, true, T_, false>(batch, grid, smem, stream);
             if (per_type) switch (only) {
-                case DT_Q4_0: return launch_tma_nc<1, true, DT_Q4_0>(batch, grid, smem, stream);
-                case DT_Q4_1: return launch_tma_nc<1, true, DT_Q4_1>(batch, grid, smem, stream);
-                case DT_Q5_0: return launch_tma_nc<1, true, DT_Q5_0>(batch, grid, smem, stream);
-                case DT_Q5_1: return launch_tma_nc<1, true, DT_Q5_1>(batch, grid, smem, stream);
-                case DT_Q8_0: return launch_tma_nc<1, true, DT_Q8_0>(batch, grid, smem, stream);
-                case DT_F16: return launch_tma_nc<1, true, DT_F16>(batch, grid, smem, stream);
-                case DT_F32: return launch_tma_nc<1, true, DT_F32>(batch, grid, smem, stream);
+                RWKV_PER_TYPE(DT_Q4_0) RWKV_PER_TYPE(DT_Q4_1) RWKV_PER_TYPE(DT_Q5_0) RWKV_PER_TYPE(DT_Q5_1) RWKV_PER_TYPE(DT_Q8_0) RWKV_PER_TYPE(DT_F16) RWKV_PER_TYPE(DT_F32)
                 default: break;
             }
+#undef RWKV_PER_TYPE
             return launch_tma_nc<1, true>(batch, grid, smem, stream);
         }
     }
     static PerDeviceOnce once;                // the shared-memory opt-in is per device
-    const cudaError_t ae = once.run([&] { return cudaFuncSetAttribute(tma::gemv_tma_kernel<NC, STAGE_V2, ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::CTA_SMEM_BUDGET); });
+    const cudaError_t ae = once.run([&] { return cudaFuncSetAttribute(tma::gemv_tma_kernel<NC, STAGE_V2, ONLY, HAS_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::CTA_SMEM_BUDGET); });
     if (ae != cudaSuccess) return ae;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned) grid);
@@ -204,8 +202,8 @@ cudaError_t launch_tma_nc(const GemvBatch & batch, int grid, size_t smem, cudaSt
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 1 : 0;
     g_kernel_launches++;
-    prefer_max_shared_carveout(reinterpret_cast<const void *>(tma::gemv_tma_kernel<NC, STAGE_V2, ONLY>));
-    return cudaLaunchKernelEx(&cfg, tma::gemv_tma_kernel<NC, STAGE_V2, ONLY>, batch);
+    prefer_max_shared_carveout(reinterpret_cast<const void *>(tma::gemv_tma_kernel<NC, STAGE_V2, ONLY, HAS_LN>));
+    return cudaLaunchKernelEx(&cfg, tma::gemv_tma_kernel<NC, STAGE_V2, ONLY, HAS_LN>, batch);
 }
 
 }  // namespace

@@ -189,13 +189,15 @@ template <int TYPE> __device__ __forceinline__ void load_unit(const uint8_t * ro
 // a stage that is instruction-bound. The staged bytes are identical: the maximum and the integer sum of a block do
 // not depend on the order they are taken in.
 // TYPE_HINT: the weight type when the whole launch has one (a compile-time constant: the other formats' code is not generated), else -1.
-template <int UNR = 4, bool PER_BLOCK = false, int TYPE_HINT = -1>     // UNR: float4 loads a thread keeps in flight per round of the quantising loop
+// HAS_LN = false: the launch has no PRO_LAYERNORM problem (every launch but the head): the LayerNorm code, ~1 500 of the 4 200
+// instructions of a per-format instantiation, is not generated.
+template <int UNR = 4, bool PER_BLOCK = false, int TYPE_HINT = -1, bool HAS_LN = true>     // UNR: float4 loads a thread keeps in flight per round of the quantising loop
 static __device__ void stage_column(const GemvProblem & P, int col_index, uint8_t * col, double * red_d) {
     const int K = P.K, tid = threadIdx.x;
     const int ptype = TYPE_HINT >= 0 ? TYPE_HINT : P.type;
     const float * x = P.x + (long long) col_index * P.ldx;
     float mean = 0.f, rstd = 1.f;
-    const bool ln = P.pro == PRO_LAYERNORM;
+    const bool ln = HAS_LN && P.pro == PRO_LAYERNORM;
     if (ln) {
         const int lane = tid & 31, warp = tid >> 5;
         double s = 0;
