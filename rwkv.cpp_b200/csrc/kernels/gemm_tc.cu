@@ -244,7 +244,7 @@ __device__ __noinline__ void tc_park_accumulator(uint32_t tmem_base, float * par
         for (int j = 0; j < 32; j++) if (c0 + j < npad) park[(size_t) (c0 + j) * TILE_M + r] = __uint_as_float(acc[j]);
     }
 }
-__device__ __noinline__ float tc_epilogue_value(int epi, float v, float res, float gate, float bias) {      // one shared copy: the callers loop is small
+__device__ __forceinline__ float tc_epilogue_value(int epi, float v, float res, float gate, float bias) {
     switch (epi) {
         case EPI_SIGMOID: return sigmoidf_(v);
         case EPI_SILU: return v / (1.0f + expf(-v));
@@ -260,84 +260,56 @@ __device__ __noinline__ float tc_epilogue_value(int epi, float v, float res, flo
 }
 // Step 2 (epilogue warps, after the cluster barrier): columns [rank * cpr, (rank + 1) * cpr) of the tile = sum over the cluster's
 // accumulators in rank order -> fused epilogue -> y. Thread = tile row: loads from a peer and the stores to y are 128-byte runs.
-// What the versions of this step taught (profiles/r2_trace_prefill_c15 / c16 / c17.log, ncu source view of call 18):
-//   * residual / gate loads inside the loop: an L2 round trip per group of four columns behind the barrier (11-19 us per launch);
-//   * the same inputs prefetched into registers with the loop fully unrolled: 37 us -- 4 000 straight-line instructions executed
-//     once are fetched from L2 one cache line at a time;
-//   * rolled and software-pipelined, cluster size a run-time value: 17 us, a third of the samples "no instruction" in a 1 000-
-//     instruction body, a fifth waiting for the first load.
-// So: the loop is ROLLED and SMALL (cluster size a template parameter, four columns per trip), and its global inputs are staged
-// through this CTA's own shared memory by tc_stage_slice, which issues all of its loads at once right after the accumulator is
-// complete -- they are in flight while the accumulator is parked and the cluster barrier is crossed.
-__device__ __forceinline__ void tc_slice(int npad, int T, int csize, int & c_lo, int & c_hi) {
-    const int cpr = (npad + csize - 1) / csize;
-    c_lo = (int) cluster_ctarank() * cpr;
-    c_hi = min(min(npad, T), c_lo + cpr);
-}
-// residual / gate of my slice -> rg[0 / 1][column - c_lo][row] (shared memory behind the parked accumulator)
-__device__ __noinline__ void tc_stage_slice(const GemvProblem & Psh, float * rg, int row0, int npad, int T, int csize) {
-    const int r = (int) threadIdx.x - EPI_WARP0 * 32;
-    const int row = row0 + r;
-    if (row >= Psh.M) return;
-    int c_lo, c_hi;
-    tc_slice(npad, T, csize, c_lo, c_hi);
-    const int cpr = (npad + csize - 1) / csize;
-    // eight loads, then eight stores: written as "store each value as it is loaded" the compiler must assume that a store through
-    // rg may change what the next load reads and serialises 32-64 L2 round trips (29-41 us per launch,
-    // profiles/r2_trace_prefill_c19_aliased_staging_regression.log)
-    const float * res = Psh.res, * gate = Psh.gate;
-    const long long ldres = Psh.ldres, ldgate = Psh.ldgate;
-    for (int half = 0; half < 2; half++) {
-        const float * src = half == 0 ? res : gate;
-        if (!src) continue;
-        const long long ld = half == 0 ? ldres : ldgate;
-        float * dst = rg + (size_t) half * cpr * TILE_M + r;
-#pragma unroll 1
-        for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
-            float t[8];
+// A ROLLED, software-pipelined loop over groups of four columns: the loads of group g + 1 (residual / gate out of L2, the peers'
+// partial sums out of distributed shared memory) are in flight while group g is summed and stored. From the last MMA to the end of this
+// step a launch spends 10-18 us (park, two cluster barriers, the reduction); variants measured, all under profiles/:
+//   loads and use in the same trip (r2_trace_prefill_c15.log): 11-19 us;
+//   residual / gate prefetched into registers before the barrier, loop fully unrolled (_c16_unrolled_reduce_regression.log): 37 us --
+//     4 000 straight-line instructions executed once are fetched from L2 one cache line at a time;
+//   this version (r2_trace_prefill_c17.log): 10-18 us;
+//   cluster size as a template parameter + residual / gate staged through shared memory right after the last MMA
+//     (_c19_aliased_staging_regression.log: 29-41 us with "store each value as it is loaded", the compiler serialising the loads
+//     behind the possibly-aliasing stores; r2_trace_prefill_c20.log with batched loads: 11-19 us, no better than this one).
+struct ReduceGroup { float part[4][8], res[4], gate[4]; };
+__device__ __forceinline__ void tc_load_group(const GemvProblem & Psh, const uint32_t (&peer)[8], int csize, int row, bool live, int c0, int c_hi, ReduceGroup & g) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) t[j] = c0 + j < c_hi ? src[(long long) (c0 + j) * ld + row] : 0.f;
+    for (int j = 0; j < 4; j++) {
+        const int c = min(c0 + j, c_hi - 1);
+        g.res[j] = (live && Psh.res) ? Psh.res[(long long) c * Psh.ldres + row] : 0.f;
+        g.gate[j] = (live && Psh.gate) ? Psh.gate[(long long) c * Psh.ldgate + row] : 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; j++) if (c0 + j < c_hi) dst[(size_t) (c0 + j - c_lo) * TILE_M] = t[j];
-        }
+        for (int p = 0; p < 8; p++) g.part[j][p] = p < csize ? ld_dsmem(peer[p] + (uint32_t) c * (TILE_M * 4u)) : 0.f;
     }
 }
-template <int CSIZE>
-__device__ __noinline__ void tc_reduce_columns(const GemvProblem & Psh, const float * cs, const float * park, const float * rg, int row0, int npad, int T) {
+__device__ __noinline__ void tc_reduce_columns(const GemvProblem & Psh, const float * cs, const float * park, int row0, int npad, int T, int csize) {
     const int r = (int) threadIdx.x - EPI_WARP0 * 32;            // 0..127
     const int row = row0 + r;
-    if (row >= Psh.M) return;
-    int c_lo, c_hi;
-    tc_slice(npad, T, CSIZE, c_lo, c_hi);
-    const int cpr = (npad + CSIZE - 1) / CSIZE;
+    const bool live = row < Psh.M;
+    const uint32_t rank = cluster_ctarank();
+    const int cpr = (npad + csize - 1) / csize;
+    const int c_lo = (int) rank * cpr, c_hi = min(min(npad, T), c_lo + cpr);
+    if (c_lo >= c_hi) return;
     const int epi = Psh.epi;
-    const float bias = Psh.bias ? Psh.bias[row] : 0.f;
-    const bool has_res = Psh.res != nullptr && rg != nullptr, has_gate = Psh.gate != nullptr && rg != nullptr;
-    const float * res_s = rg + r, * gate_s = rg + (size_t) cpr * TILE_M + r;
+    const float bias = (live && Psh.bias) ? Psh.bias[row] : 0.f;
     const uint32_t park0 = smem_u32(park) + (uint32_t) r * 4u;
-    uint32_t peer[CSIZE];
+    uint32_t peer[8];
 #pragma unroll
-    for (int p = 0; p < CSIZE; p++) peer[p] = map_to_cta(park0, (uint32_t) p);
+    for (int p = 0; p < 8; p++) peer[p] = map_to_cta(park0, (uint32_t) (p < csize ? p : 0));
+    ReduceGroup cur, nxt;
+    tc_load_group(Psh, peer, csize, row, live, c_lo, c_hi, cur);
 #pragma unroll 1
     for (int c0 = c_lo; c0 < c_hi; c0 += 4) {
-        float part[4][CSIZE], res[4], gate[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int c = min(c0 + j, c_hi - 1);
-#pragma unroll
-            for (int p = 0; p < CSIZE; p++) part[j][p] = ld_dsmem(peer[p] + (uint32_t) c * (TILE_M * 4u));
-            res[j] = has_res ? res_s[(size_t) (c - c_lo) * TILE_M] : ((Psh.res && rg == nullptr) ? Psh.res[(long long) c * Psh.ldres + row] : 0.f);
-            gate[j] = has_gate ? gate_s[(size_t) (c - c_lo) * TILE_M] : ((Psh.gate && rg == nullptr) ? Psh.gate[(long long) c * Psh.ldgate + row] : 0.f);
-        }
+        if (c0 + 4 < c_hi) tc_load_group(Psh, peer, csize, row, live, c0 + 4, c_hi, nxt);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int c = c0 + j;
-            if (c >= c_hi) break;
+            if (c >= c_hi || !live) continue;
             float v = 0.f;
 #pragma unroll
-            for (int p = 0; p < CSIZE; p++) v += part[j][p];
-            Psh.y[(long long) c * Psh.ldy + row] = tc_epilogue_value(epi, v * cs[c], res[j], gate[j], bias);
+            for (int p = 0; p < 8; p++) if (p < csize) v += cur.part[j][p];
+            Psh.y[(long long) c * Psh.ldy + row] = tc_epilogue_value(epi, v * cs[c], cur.res[j], cur.gate[j], bias);
         }
+        cur = nxt;
     }
 }
 
@@ -522,20 +494,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const TcBatch batch
             mbar_wait(&sh.acc_done, 0);
             if (batch.trace != nullptr && blockIdx.x == 0 && et == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); batch.trace->mark[2] = g; }
             tc_fence_after_sync();
-            // acc_done: every MMA has finished reading the ring, which now holds [parked accumulator | residual / gate of my slice]
-            float * park = reinterpret_cast<float *>(smem);
-            const int cpr = (NPAD + nsplit - 1) / nsplit;
-            const size_t park_floats = (size_t) NPAD * TILE_M, rg_floats = (size_t) 2 * cpr * TILE_M;
-            float * rg = (park_floats + rg_floats) * sizeof(float) <= (size_t) nst * stage_bytes ? park + park_floats : nullptr;
-            if (rg) tc_stage_slice(P, rg, row0, NPAD, batch.T, nsplit);      // all loads in flight, landing during the park + barrier
-            tc_park_accumulator(sh.tmem_base, park, NPAD);
+            tc_park_accumulator(sh.tmem_base, reinterpret_cast<float *>(smem), NPAD);      // acc_done: every MMA has finished reading the ring
             // every thread of the cluster: accumulators parked -> [barrier] -> each CTA reduces its column slice out of all of them ->
             // [barrier] so that no CTA retires (and frees its shared memory) while a peer still reads it
             __syncwarp();
             cluster_sync_all();
-            if (nsplit == 2) tc_reduce_columns<2>(P, sh.colscale, park, rg, row0, NPAD, batch.T);
-            else if (nsplit == 4) tc_reduce_columns<4>(P, sh.colscale, park, rg, row0, NPAD, batch.T);
-            else tc_reduce_columns<8>(P, sh.colscale, park, rg, row0, NPAD, batch.T);
+            tc_reduce_columns(P, sh.colscale, reinterpret_cast<const float *>(smem), row0, NPAD, batch.T, nsplit);
             __syncwarp();
             cluster_sync_all();
         }

@@ -193,17 +193,22 @@ __global__ void __launch_bounds__(Wkv6Layout<S>::BLOCK) wkv6_kernel(const Wkv6Pa
                 const float4 g = *reinterpret_cast<const float4 *>(&B.v[tt][j0]);
                 v_[0] = g.x; v_[1] = g.y; v_[2] = g.z; v_[3] = g.w;
             };
-            // one token: 32 x 4 multiply-adds on the 8 x 4 patch, the head's partial outputs combined over the octants by shuffles
-            auto token = [&](int tt, const float (&k_)[8], const float (&r_)[8], const float (&d_)[8], const float (&v_)[4]) {
+            // two tokens per trip where the register file allows it: the shuffles and the shared-memory loads of one token then
+            // overlap the multiply-adds of its neighbour (a warp is alone on its scheduler: nothing else hides their latency).
+            // (A full chunk written out as ONE basic block with two explicit operand sets, loads of token t + 1 ahead of the arithmetic
+            // of token t, was slower: 93k vs 83k cycles per 128 tokens, profiles/r2_trace_prefill_c20.log.)
+#pragma unroll(S <= 64 ? 2 : 1)
+            for (int tt = 0; tt < nt; tt++) {
+                fetch(tt, kk, rr, dv, vv);
                 float y[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int ii = 0; ii < 8; ii++) {
 #pragma unroll
                     for (int jj = 0; jj < 4; jj++) {
-                        const float kv = __fmul_rn(v_[jj], k_[ii]);
+                        const float kv = __fmul_rn(vv[jj], kk[ii]);
                         const float temp = __fmaf_rn(kv, tfr[ii], st[ii][jj]);
-                        y[jj] = __fmaf_rn(temp, r_[ii], y[jj]);
-                        st[ii][jj] = __fmaf_rn(st[ii][jj], d_[ii], kv);
+                        y[jj] = __fmaf_rn(temp, rr[ii], y[jj]);
+                        st[ii][jj] = __fmaf_rn(st[ii][jj], dv[ii], kv);
                     }
                 }
 #pragma unroll
@@ -212,25 +217,6 @@ __global__ void __launch_bounds__(Wkv6Layout<S>::BLOCK) wkv6_kernel(const Wkv6Pa
                     for (int jj = 0; jj < 4; jj++) y[jj] += __shfl_xor_sync(0xffffffffu, y[jj], o);
                 }
                 if (worker && oct == 0) *reinterpret_cast<float4 *>(&yb[tt][j0]) = make_float4(y[0], y[1], y[2], y[3]);
-            };
-            if (nt == TB && S <= 64) {
-                // a full chunk as ONE basic block with two operand sets: token t + 1's shared-memory loads are issued before token t's
-                // arithmetic, and nothing but the 32 state updates ties a token to its predecessor -- the shuffle trees and the loads
-                // of one token overlap the multiply-adds of the next (a warp is alone on its scheduler: nothing else hides them)
-                float k2[8], r2[8], d2[8], v2[4];
-                fetch(0, kk, rr, dv, vv);
-#pragma unroll
-                for (int tt = 0; tt < TB; tt += 2) {
-                    fetch(tt + 1, k2, r2, d2, v2);
-                    token(tt, kk, rr, dv, vv);
-                    if (tt + 2 < TB) fetch(tt + 2, kk, rr, dv, vv);
-                    token(tt + 1, k2, r2, d2, v2);
-                }
-            } else {
-                for (int tt = 0; tt < nt; tt++) {
-                    fetch(tt, kk, rr, dv, vv);
-                    token(tt, kk, rr, dv, vv);
-                }
             }
             tick(a1);
             wkv_bar_arrive(BAR_FULL + (c & 1), BLOCK);     // the chunk's output rows are complete: over to the normalising warps
