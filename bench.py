@@ -798,8 +798,12 @@ def run_pipeline(args, rank, world, dist):
                     "host_buffers": "pinned", "ms_per_step": e2e_ms / K,
                     "note": "token ids enter on stage 0, logits leave from the last stage; the recurrent state stays resident on its stage"},
             "gpu_launches": int(launches),
-            "single_stream": {"tokens_per_s": lat_steps / (lat_ms / 1e3), "ms_per_token": lat_ms / lat_steps,
-                              "note": "ONE sequence through all stages (layer i+1 needs layer i: a pipeline cannot speed a single stream up; this is its latency)"},
+            "single_stream": {"ms_per_token": dev_ms / K, "tokens_per_s": K / (dev_ms / 1e3),
+                              "note": "latency of ONE sampled stream (the next token comes out of the logits): a token crosses all `world` stages, i.e. "
+                                      "`world` ticks = one step of the loaded pipeline (layer i+1 needs layer i: a pipeline cannot speed a single stream up)",
+                              "teacher_forced_ms_per_token": lat_ms / lat_steps,
+                              "teacher_forced_note": "ONE sequence whose tokens are known in advance (prompt ingestion token by token): stage 0 already works on "
+                                                     "token u+1 while the last stage finishes token u"},
             "pipeline_check": chk[0],
             "prefill": {"tokens_per_s": world * P * PREFILL_TOKENS / (pdev_ms / 1e3), "ms_per_chunk": pdev_ms / (P * world), "chunk": PREFILL_TOKENS, "steps": P,
                         "e2e_tokens_per_s": world * P * PREFILL_TOKENS / (pe2e_ms / 1e3)},
