@@ -65,8 +65,21 @@ void segment_range(const Context * ctx, int seg, int & l0, int & l1) {
     l0 = m.layer_begin; l1 = m.layer_end;
     if (seg <= 0) return;
     const int n = m.layer_end - m.layer_begin, G = ctx->n_segments;
-    l0 = m.layer_begin + (int) ((long long) n * (seg - 1) / G);
-    l1 = m.layer_begin + (int) ((long long) n * seg / G);
+    // Graded groups: 1, 2, 3, 5, 10, 6, 3, 2 thirty-seconds of the layers. The upload of the first group's state slice and the download
+    // of the last group's are the two copies nothing can overlap, so those groups are small; a group may grow by about the ratio of
+    // compute time to copy time per layer (1.7 at 7B: 75 us vs 43 us) over its predecessor without starving the kernels, and shrink
+    // the same way towards the end without queueing the downloads. A pipeline model with those two rates puts a 7B token at 2.60 ms
+    // against 2.81 ms for eight even groups (2.46 ms: kernels alone). RWKV_B200_EVEN_SEGMENTS=1: the even split of round 1 (A/B aid).
+    static const bool even = getenv("RWKV_B200_EVEN_SEGMENTS") != nullptr;
+    static const int cum32[9] = {0, 1, 3, 6, 11, 21, 27, 30, 32};
+    if (even || G != 8 || n < 16) {
+        l0 = m.layer_begin + (int) ((long long) n * (seg - 1) / G);
+        l1 = m.layer_begin + (int) ((long long) n * seg / G);
+        return;
+    }
+    auto cut = [&](int s) -> int { return (int) (((long long) cum32[s] * n + 16) / 32); };      // strictly increasing for n >= 16
+    l0 = m.layer_begin + cut(seg - 1);
+    l1 = m.layer_begin + cut(seg);
 }
 
 size_t scratch_floats_for(const Model & m, int T) {
@@ -191,6 +204,10 @@ cudaError_t do_wkv4(Context * ctx, const Wkv4Params & wp) {
 //     the LayerNorm of 4096 channels with 256 threads where this kernel uses 1024 and has its parameter loads in flight before the
 //     dependency wait;
 // (c) ln_mix_kernel emitting the staged columns of its consumers: 2.95 vs 2.86 ms (profiles/r2_c12_ab_default.json).
+// And for passes of >= 32 tokens: (d) ln_mix_kernel writing the fp16 GEMM operands of its consumers itself, so that two of the six
+//     convert_f16 launches of a v6 layer disappear: 10.74 vs 10.85 ms per 7B chunk (profiles/r2_c21_pf_ln16.json / _noln16.json), and
+//     the tail of the state went NaN in the shift-state-3e5 robustness test of the 64-channel fixture
+//     (profiles/r2_c21_parity_ln16_nan_at_3e5.log; not understood). 1 % was not worth an unexplained failure: not kept.
 bool ln_mix_then(Context * ctx, const LnMixParams & lp, bool * staged) {
     *staged = false;
     CUDA_OK(ctx, do_ln_mix(ctx, lp));
