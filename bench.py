@@ -9,7 +9,8 @@ One "step" = one single-token evaluation (with logits) of the whole model. Print
   value        decode tokens/s, state resident in HBM, CUDA-event timed on the library's own stream
   e2e          the same metric through rwkv_eval() with HOST state/logits buffers (H2D + D2H inside the timed region)
   prefill      128-token rwkv_eval_sequence chunk: device-timed and e2e tokens/s
-  roofline     dominant kernel (fused dequant-GEMV): algorithmic weight bytes / CUDA-event time vs MEASURED_PEAKS.json
+  roofline     dominant kernel (fused dequant-GEMV): algorithmic weight bytes / its share of the graph-replayed step (critical-path
+               attribution of the in-kernel %globaltimer timeline x the CUDA-event step time) vs MEASURED_PEAKS.json
   cpu_baseline the UNMODIFIED reference (oracle/_ref) timed on this box's host cores on a bounded sample
 Weights are synthetic (random-init, exact shapes/dtypes; tools/synthetic_model.py); no checkpoints exist offline.
 The 6 GB of weights streamed per token exceed the 126 MB L2 48x, so no explicit L2 flush is needed between steps.
