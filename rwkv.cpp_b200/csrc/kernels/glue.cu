@@ -78,7 +78,9 @@ __device__ __forceinline__ double block_sum_ln(double v, double * slots) {
 // weights, the carried state of the previous token) issued BEFORE the programmatic-dependency wait, the x loads
 // right after it, two barrier-separated reductions, rolled output loop (small code: instruction fetch is the other
 // cost of a run-once kernel). Statistics as ggml_compute_forward_norm_f32 (ggml-cpu.c:6906-6925, sums in double).
-template <int PER>
+// PRE_N: how many of the mix-coefficient vectors are requested before the dependency wait (3 for blocks with up to three mixed
+// vectors -- every v6 block --, 6 for v4 / v5.2 / v7 time mixing: a few spilled registers there against one HBM round trip per vector).
+template <int PER, int PRE_N>
 __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const LnMixParams p) {
     __shared__ double slots[4][LN_WARPS];
     trace_begin(p.trace);
@@ -95,9 +97,8 @@ __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const LnMixParams p)
     }
     // the mix coefficients too (up to 6 vectors): last read one token ago, i.e. an HBM round trip each -- and the output loop below
     // used to take them one vector after the other, AFTER the statistics (1-2 us of a 7 us kernel that runs 64 times per 7B token)
-    // (the first PRE_N vectors: 1024 threads leave 64 registers each)
+    // (1024 threads leave 64 registers each: PER <= 4 only)
     constexpr bool PRE = PER <= 4;
-    constexpr int PRE_N = 3;
     float cf[PRE ? PRE_N : 1][PER];
     if constexpr (PRE) {
 #pragma unroll
@@ -364,11 +365,13 @@ cudaError_t launch_ln_mix(const LnMixParams & p_in, cudaStream_t s) {
     p.trace = trace_slot("ln_mix");
     g_kernel_launches++;
     const int per = (p.C + LN_THREADS - 1) / LN_THREADS;
-    if (per <= 1) return launch_pdl(ln_mix_kernel<1>, dim3(p.T), dim3(LN_THREADS), 0, s, p);
-    if (per <= 2) return launch_pdl(ln_mix_kernel<2>, dim3(p.T), dim3(LN_THREADS), 0, s, p);
-    if (per <= 4) return launch_pdl(ln_mix_kernel<4>, dim3(p.T), dim3(LN_THREADS), 0, s, p);
-    if (per <= 8) return launch_pdl(ln_mix_kernel<8>, dim3(p.T), dim3(LN_THREADS), 0, s, p);
-    if (per <= 16) return launch_pdl(ln_mix_kernel<16>, dim3(p.T), dim3(LN_THREADS), 0, s, p);
+#define RWKV_LN(PER_) return p.n_out > 3 ? launch_pdl(ln_mix_kernel<PER_, 6>, dim3(p.T), dim3(LN_THREADS), 0, s, p) : launch_pdl(ln_mix_kernel<PER_, 3>, dim3(p.T), dim3(LN_THREADS), 0, s, p);
+    if (per <= 1) { RWKV_LN(1) }
+    if (per <= 2) { RWKV_LN(2) }
+    if (per <= 4) { RWKV_LN(4) }
+    if (per <= 8) { RWKV_LN(8) }
+    if (per <= 16) { RWKV_LN(16) }
+#undef RWKV_LN
     return cudaErrorInvalidValue;   // n_embed > 16384
 }
 
