@@ -217,3 +217,26 @@ def test_no_kernel_spills_its_parameters(lib):
     assert len(names) > 20, "no kernels found in %s" % lib.path
     fat = [(n, int(st)) for n, _, st in names if int(st) > 256 and "sample_kernel" not in n]
     assert not fat, fat
+
+
+def test_bench_reference_arm_line(tmp_path):
+    """`bench.py --impl reference` (the driver's reference arm) on a tiny synthetic workload, on the CPU: ONE JSON line on stdout with
+    the keys the contract names, timed through the UNMODIFIED reference library (oracle/_ref) -- no CUDA needed for this arm."""
+    import json
+    import ref_lib
+    import sys
+    if ref_lib.reference_library_path() is None:
+        pytest.skip("oracle/_ref not built")
+    env = dict(os.environ, RWKV_B200_BENCH_DIR=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "rwkv6-small:Q5_1", "--steps", "4", "--warmup", "1",
+                        "--cpu-budget-s", "5"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "decode_tokens_per_sec" and line["unit"] == "tokens/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert "workload" in line["config"] and "model" not in line["config"]
